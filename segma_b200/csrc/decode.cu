@@ -1,0 +1,379 @@
+// Stitching of per-window frame logits and threshold + run-length decoding into interval tables.
+//
+// Replaces torch.concat (src/segma/inference.py:209-211), apply_thresholds (214-234) and the host
+// NumPy/Python run extraction of create_intervals (237-263).  All three are HBM-bound streaming
+// passes: one coalesced read of the logits, warp-shuffle/ballot run-boundary detection, a block
+// offset scan, and a compacted int32 table write.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace segma {
+
+// ---------------------------------------------------------------------------------------------
+// stitch: gather-mean over covering windows
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stitch_kernel(const float* __restrict__ win, int n_windows, int F, int sf,
+                                                      int tail_frames, int C, float* __restrict__ out,
+                                                      long long n_frames) {
+  const long long total = n_frames * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long g = idx / C;
+    const int c = static_cast<int>(idx - g * C);
+    // windows i with i*sf <= g < i*sf + F_i ; the tail is window n_windows with tail_frames frames
+    long long lo = (g - F + sf) / sf;  // ceil((g - F + 1) / sf) for g-F+1 >= 0
+    if (g - F + 1 <= 0) lo = 0;
+    long long hi = g / sf;
+    float acc = 0.f;
+    int cnt = 0;
+    for (long long i = lo; i <= hi; ++i) {
+      const long long k = g - i * sf;
+      if (i < n_windows) {
+        acc += __ldg(win + (i * F + k) * C + c);
+        ++cnt;
+      } else if (i == n_windows && k < tail_frames) {
+        acc += __ldg(win + ((long long)n_windows * F + k) * C + c);
+        ++cnt;
+      }
+    }
+    out[idx] = cnt > 0 ? acc / static_cast<float>(cnt) : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// threshold + run-length decode
+// ---------------------------------------------------------------------------------------------
+struct DecodeParams {
+  float thr[SEGMA_MAX_LABELS];
+  int C;
+  int mode;
+};
+
+constexpr int kDecodeBlock = 1024;  // frames (= threads) per block
+
+__device__ __forceinline__ bool is_active(float x, float thr, int mode) {
+  if (mode == SEGMA_DECODE_SIGMOID) {
+    // fp32 sigmoid exactly as written in the reference: 1 / (1 + exp(-x)), strict '>'
+    const float s = 1.0f / (1.0f + expf(-x));
+    return s > thr;
+  }
+  return x > thr;
+}
+
+__device__ __forceinline__ uint32_t frame_bits(const float* __restrict__ logits, long long frame,
+                                               const DecodeParams& p) {
+  uint32_t bits = 0;
+  const float* row = logits + frame * p.C;
+  if (p.C == 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row));
+    bits |= is_active(v.x, p.thr[0], p.mode) ? 1u : 0u;
+    bits |= is_active(v.y, p.thr[1], p.mode) ? 2u : 0u;
+    bits |= is_active(v.z, p.thr[2], p.mode) ? 4u : 0u;
+    bits |= is_active(v.w, p.thr[3], p.mode) ? 8u : 0u;
+  } else {
+    for (int c = 0; c < p.C; ++c) bits |= is_active(__ldg(row + c), p.thr[c], p.mode) ? (1u << c) : 0u;
+  }
+  return bits;
+}
+
+__global__ void __launch_bounds__(256) mask_kernel(const float* __restrict__ logits, long long n_frames,
+                                                    DecodeParams p, uint8_t* __restrict__ mask) {
+  const long long total = n_frames * p.C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = static_cast<int>(idx % p.C);
+    mask[idx] = is_active(__ldg(logits + idx), p.thr[c], p.mode) ? 1 : 0;
+  }
+}
+
+// Block -> (file, first frame) lookup: block_offsets[f] = first block of file f.
+__device__ __forceinline__ int find_file(const int* __restrict__ block_offsets, int n_files, int block) {
+  int lo = 0, hi = n_files - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(block_offsets + mid) <= block) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// Pass 1: per-frame activity bits (stored for pass 3) and per-(file,label,block) counts of run
+// starts and run ends.  counts index = C*block_offsets[file] + c*nblk_file + local_block.
+__global__ void __launch_bounds__(kDecodeBlock) decode_count_kernel(
+    const float* __restrict__ logits, const long long* __restrict__ file_offsets,
+    const int* __restrict__ block_offsets, int n_files, DecodeParams p, uint32_t* __restrict__ bits_out,
+    int* __restrict__ start_counts, int* __restrict__ end_counts) {
+  __shared__ uint32_t s_bits[kDecodeBlock + 2];
+  __shared__ int s_cnt[2][SEGMA_MAX_LABELS];
+  const int file = find_file(block_offsets, n_files, blockIdx.x);
+  const int local_block = blockIdx.x - block_offsets[file];
+  const int nblk_file = block_offsets[file + 1] - block_offsets[file];
+  const long long f_begin = file_offsets[file], f_end = file_offsets[file + 1];
+  const long long frame = f_begin + (long long)local_block * kDecodeBlock + threadIdx.x;
+  const bool valid = frame < f_end;
+
+  if (threadIdx.x < 2 * SEGMA_MAX_LABELS) (&s_cnt[0][0])[threadIdx.x] = 0;
+  uint32_t bits = valid ? frame_bits(logits, frame, p) : 0u;
+  s_bits[threadIdx.x + 1] = bits;
+  if (threadIdx.x == 0) {
+    const long long prev = frame - 1;
+    s_bits[0] = (prev >= f_begin) ? frame_bits(logits, prev, p) : 0u;
+    const long long next = f_begin + (long long)(local_block + 1) * kDecodeBlock;
+    s_bits[kDecodeBlock + 1] = (next < f_end) ? frame_bits(logits, next, p) : 0u;
+  }
+  if (valid) bits_out[frame] = bits;
+  __syncthreads();
+  const uint32_t prev = s_bits[threadIdx.x], next = s_bits[threadIdx.x + 2];
+  const uint32_t starts = bits & ~prev, ends = bits & ~next;
+  for (int c = 0; c < p.C; ++c) {
+    const unsigned bs = __ballot_sync(0xffffffffu, (starts >> c) & 1u);
+    const unsigned be = __ballot_sync(0xffffffffu, (ends >> c) & 1u);
+    if (lane_id() == 0) {
+      if (bs) atomicAdd(&s_cnt[0][c], __popc(bs));
+      if (be) atomicAdd(&s_cnt[1][c], __popc(be));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < p.C) {
+    const long long idx = (long long)p.C * block_offsets[file] + (long long)threadIdx.x * nblk_file + local_block;
+    start_counts[idx] = s_cnt[0][threadIdx.x];
+    end_counts[idx] = s_cnt[1][threadIdx.x];
+  }
+}
+
+// Pass 2: exclusive scan (single block) of both count arrays in place; total -> *count.
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 8;
+__global__ void __launch_bounds__(kScanThreads) decode_scan_kernel(int* __restrict__ a, int* __restrict__ b,
+                                                                    long long n, int* __restrict__ count) {
+  __shared__ int s_warp[2][32];
+  __shared__ int s_carry[2];
+  if (threadIdx.x == 0) s_carry[0] = s_carry[1] = 0;
+  __syncthreads();
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  for (long long base = 0; base < n; base += (long long)kScanThreads * kScanItems) {
+    int va[kScanItems], vb[kScanItems];
+    int sa = 0, sb = 0;
+    const long long t0 = base + (long long)threadIdx.x * kScanItems;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+      const long long j = t0 + i;
+      va[i] = j < n ? a[j] : 0;
+      vb[i] = j < n ? b[j] : 0;
+      sa += va[i];
+      sb += vb[i];
+    }
+    int ia = sa, ib = sb;  // inclusive warp scan of per-thread sums
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+      if (lane >= o) { ia += ta; ib += tb; }
+    }
+    if (lane == 31) { s_warp[0][warp] = ia; s_warp[1][warp] = ib; }
+    __syncthreads();
+    if (warp == 0) {
+      int wa = s_warp[0][lane], wb = s_warp[1][lane];
+      int xa = wa, xb = wb;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ta = __shfl_up_sync(0xffffffffu, xa, o), tb = __shfl_up_sync(0xffffffffu, xb, o);
+        if (lane >= o) { xa += ta; xb += tb; }
+      }
+      s_warp[0][lane] = xa - wa;  // exclusive warp offsets
+      s_warp[1][lane] = xb - wb;
+    }
+    __syncthreads();
+    int ea = s_carry[0] + s_warp[0][warp] + ia - sa;
+    int eb = s_carry[1] + s_warp[1][warp] + ib - sb;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+      const long long j = t0 + i;
+      if (j < n) { a[j] = ea; b[j] = eb; }
+      ea += va[i];
+      eb += vb[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == kScanThreads - 1) { s_carry[0] = ea; s_carry[1] = eb; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = s_carry[0];
+}
+
+// Pass 3: recompute boundary flags from the stored bits, rank them inside the block and write the
+// (file, label, start, end) rows.  The k-th start and the k-th end of a (file,label) pair form one run.
+__global__ void __launch_bounds__(kDecodeBlock) decode_write_kernel(
+    const uint32_t* __restrict__ bits_in, const long long* __restrict__ file_offsets,
+    const int* __restrict__ block_offsets, int n_files, int C, const int* __restrict__ start_base,
+    const int* __restrict__ end_base, int32_t* __restrict__ table, long long capacity) {
+  __shared__ uint32_t s_bits[kDecodeBlock + 2];
+  __shared__ int s_warp[2][kDecodeBlock / 32];
+  const int file = find_file(block_offsets, n_files, blockIdx.x);
+  const int local_block = blockIdx.x - block_offsets[file];
+  const int nblk_file = block_offsets[file + 1] - block_offsets[file];
+  const long long f_begin = file_offsets[file], f_end = file_offsets[file + 1];
+  const long long frame = f_begin + (long long)local_block * kDecodeBlock + threadIdx.x;
+  const bool valid = frame < f_end;
+  const uint32_t bits = valid ? bits_in[frame] : 0u;
+  s_bits[threadIdx.x + 1] = bits;
+  if (threadIdx.x == 0) {
+    s_bits[0] = (frame - 1 >= f_begin) ? bits_in[frame - 1] : 0u;
+    const long long next = f_begin + (long long)(local_block + 1) * kDecodeBlock;
+    s_bits[kDecodeBlock + 1] = (next < f_end) ? bits_in[next] : 0u;
+  }
+  __syncthreads();
+  const uint32_t starts = bits & ~s_bits[threadIdx.x], ends = bits & ~s_bits[threadIdx.x + 2];
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int rel = static_cast<int>(frame - f_begin);
+  for (int c = 0; c < C; ++c) {
+    const bool is_s = (starts >> c) & 1u, is_e = (ends >> c) & 1u;
+    const unsigned bs = __ballot_sync(0xffffffffu, is_s), be = __ballot_sync(0xffffffffu, is_e);
+    if (lane == 0) { s_warp[0][warp] = __popc(bs); s_warp[1][warp] = __popc(be); }
+    __syncthreads();
+    if (warp == 0) {
+      int a = s_warp[0][lane], b = s_warp[1][lane];
+      int xa = a, xb = b;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ta = __shfl_up_sync(0xffffffffu, xa, o), tb = __shfl_up_sync(0xffffffffu, xb, o);
+        if (lane >= o) { xa += ta; xb += tb; }
+      }
+      s_warp[0][lane] = xa - a;
+      s_warp[1][lane] = xb - b;
+    }
+    __syncthreads();
+    const long long cidx = (long long)C * block_offsets[file] + (long long)c * nblk_file + local_block;
+    const unsigned lt = (1u << lane) - 1u;
+    if (is_s) {
+      const long long row = (long long)start_base[cidx] + s_warp[0][warp] + __popc(bs & lt);
+      if (row < capacity) {
+        table[row * 4 + 0] = file;
+        table[row * 4 + 1] = c;
+        table[row * 4 + 2] = rel * SEGMA_FRAME_SAMPLES;
+      }
+    }
+    if (is_e) {
+      const long long row = (long long)end_base[cidx] + s_warp[1][warp] + __popc(be & lt);
+      if (row < capacity) table[row * 4 + 3] = (rel + 1) * SEGMA_FRAME_SAMPLES;
+    }
+    __syncthreads();
+  }
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct DecodeLayout {
+  size_t bits_off, starts_off, ends_off, file_off, block_off, total;
+  long long n_count;
+};
+
+static DecodeLayout decode_layout(long long n_frames, int n_files, int C) {
+  DecodeLayout L;
+  const long long max_blocks = ceil_div_ll(n_frames, kDecodeBlock) + n_files;
+  L.n_count = max_blocks * C;
+  size_t off = 0;
+  L.bits_off = off; off = align_up(off + sizeof(uint32_t) * (size_t)n_frames, 256);
+  L.starts_off = off; off = align_up(off + sizeof(int) * (size_t)L.n_count, 256);
+  L.ends_off = off; off = align_up(off + sizeof(int) * (size_t)L.n_count, 256);
+  L.file_off = off; off = align_up(off + sizeof(long long) * (size_t)(n_files + 1), 256);
+  L.block_off = off; off = align_up(off + sizeof(int) * (size_t)(n_files + 1), 256);
+  L.total = off;
+  return L;
+}
+
+static int fill_params(DecodeParams& p, int C, const float* thr, int mode) {
+  SEGMA_REQUIRE(C >= 1 && C <= SEGMA_MAX_LABELS, "n_labels must be in [1, %d], got %d", SEGMA_MAX_LABELS, C);
+  SEGMA_REQUIRE(mode == SEGMA_DECODE_SIGMOID || mode == SEGMA_DECODE_LOGIT, "unknown decode mode %d", mode);
+  SEGMA_REQUIRE(thr != nullptr, "thresholds is NULL");
+  p.C = C;
+  p.mode = mode;
+  for (int c = 0; c < SEGMA_MAX_LABELS; ++c) p.thr[c] = c < C ? thr[c] : 0.f;
+  return SEGMA_OK;
+}
+
+}  // namespace segma
+
+using namespace segma;
+
+extern "C" {
+
+int segma_stitch(const float* window_logits, int n_windows, int frames_per_window, int step_frames, int tail_frames,
+                 int n_labels, float* out, int64_t n_frames, void* stream) {
+  SEGMA_REQUIRE(n_windows >= 0 && frames_per_window > 0 && step_frames > 0 && tail_frames >= 0 && n_labels > 0,
+                "segma_stitch: bad geometry");
+  SEGMA_REQUIRE(step_frames <= frames_per_window, "segma_stitch: step_frames %d leaves gaps (frames_per_window %d)",
+                step_frames, frames_per_window);
+  if (n_frames == 0) return SEGMA_OK;
+  SEGMA_REQUIRE(window_logits && out, "segma_stitch: NULL buffer");
+  const long long total = (long long)n_frames * n_labels;
+  const int grid = (int)std::min<long long>(ceil_div_ll(total, 256), (long long)device_sm_count() * 16);
+  stitch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(window_logits, n_windows, frames_per_window, step_frames,
+                                                        tail_frames, n_labels, out, n_frames);
+  return launch_status("stitch_kernel");
+}
+
+int segma_threshold_mask(const float* logits, int64_t n_frames, int n_labels, const float* thresholds, int mode,
+                         uint8_t* mask, void* stream) {
+  DecodeParams p;
+  int rc = fill_params(p, n_labels, thresholds, mode);
+  if (rc != SEGMA_OK) return rc;
+  if (n_frames == 0) return SEGMA_OK;
+  SEGMA_REQUIRE(logits && mask, "segma_threshold_mask: NULL buffer");
+  const long long total = (long long)n_frames * n_labels;
+  const int grid = (int)std::min<long long>(ceil_div_ll(total, 256), (long long)device_sm_count() * 16);
+  mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, n_frames, p, mask);
+  return launch_status("mask_kernel");
+}
+
+size_t segma_decode_workspace_bytes(int64_t n_frames, int n_files, int n_labels) {
+  if (n_frames < 0 || n_files < 1 || n_labels < 1) return 0;
+  return decode_layout(n_frames, n_files, n_labels).total;
+}
+
+int segma_decode_intervals(const float* logits, const int64_t* file_offsets, int n_files, int n_labels,
+                           const float* thresholds, int mode, int32_t* table, int64_t capacity, int32_t* count,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  DecodeParams p;
+  int rc = fill_params(p, n_labels, thresholds, mode);
+  if (rc != SEGMA_OK) return rc;
+  SEGMA_REQUIRE(n_files >= 1 && file_offsets, "segma_decode_intervals: need at least one file");
+  SEGMA_REQUIRE(count && workspace, "segma_decode_intervals: NULL count/workspace");
+  SEGMA_REQUIRE(capacity >= 0 && (capacity == 0 || table), "segma_decode_intervals: NULL table");
+  SEGMA_REQUIRE(file_offsets[0] == 0, "segma_decode_intervals: file_offsets[0] must be 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n_frames = file_offsets[n_files];
+  std::vector<int> block_offsets(n_files + 1, 0);
+  for (int f = 0; f < n_files; ++f) {
+    const long long len = file_offsets[f + 1] - file_offsets[f];
+    SEGMA_REQUIRE(len >= 0, "segma_decode_intervals: file_offsets must be non-decreasing");
+    SEGMA_REQUIRE(len * SEGMA_FRAME_SAMPLES < (1ll << 31), "segma_decode_intervals: file %d exceeds int32 samples", f);
+    block_offsets[f + 1] = block_offsets[f] + (int)ceil_div_ll(len, kDecodeBlock);
+  }
+  const int total_blocks = block_offsets[n_files];
+  const DecodeLayout L = decode_layout(n_frames, n_files, n_labels);
+  SEGMA_REQUIRE(workspace_bytes >= L.total, "segma_decode_intervals: workspace too small (%zu < %zu)",
+                workspace_bytes, L.total);
+  if (total_blocks == 0) return check_cuda(cudaMemsetAsync(count, 0, sizeof(int32_t), st), "memset count");
+  SEGMA_REQUIRE(logits, "segma_decode_intervals: NULL logits");
+  char* ws = static_cast<char*>(workspace);
+  uint32_t* bits = reinterpret_cast<uint32_t*>(ws + L.bits_off);
+  int* starts = reinterpret_cast<int*>(ws + L.starts_off);
+  int* ends = reinterpret_cast<int*>(ws + L.ends_off);
+  long long* d_file = reinterpret_cast<long long*>(ws + L.file_off);
+  int* d_block = reinterpret_cast<int*>(ws + L.block_off);
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+  SEGMA_CUDA_OK(cudaMemcpyAsync(d_file, file_offsets, sizeof(int64_t) * (n_files + 1), cudaMemcpyHostToDevice, st));
+  SEGMA_CUDA_OK(cudaMemcpyAsync(d_block, block_offsets.data(), sizeof(int) * (n_files + 1), cudaMemcpyHostToDevice, st));
+  // pageable-source async copies are staged before returning, so block_offsets may go out of scope
+  decode_count_kernel<<<total_blocks, kDecodeBlock, 0, st>>>(logits, d_file, d_block, n_files, p, bits, starts, ends);
+  rc = launch_status("decode_count_kernel");
+  if (rc != SEGMA_OK) return rc;
+  decode_scan_kernel<<<1, kScanThreads, 0, st>>>(starts, ends, (long long)total_blocks * n_labels, count);
+  rc = launch_status("decode_scan_kernel");
+  if (rc != SEGMA_OK) return rc;
+  decode_write_kernel<<<total_blocks, kDecodeBlock, 0, st>>>(bits, d_file, d_block, n_files, n_labels, starts, ends,
+                                                             table, capacity);
+  return launch_status("decode_write_kernel");
+}
+
+}  // extern "C"

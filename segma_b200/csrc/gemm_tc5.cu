@@ -1,0 +1,387 @@
+// bf16 GEMM / implicit-GEMM Conv1d on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// C[M, N] = epilogue(A[M, K] * W[N, K]^T) with fp32 accumulation.  Replaces torch's dispatch of
+// nn.Linear (q/k/v/out projections, fc1/fc2; site-packages/transformers/models/whisper/modeling_whisper.py:
+// 279-282,310,331-332,355,376-377 and site-packages/torchaudio/models/wav2vec2/components.py:265-268,324-326)
+// and nn.Conv1d of the Whisper stem (modeling_whisper.py:619-625) / wav2vec2 feature extractor
+// (components.py:77-99) to cuBLASLt / cuDNN.
+//
+// Structure (persistent, warp-specialised, one CTA per SM):
+//   warp 0      TMA producer: 128B-swizzled A (128 x 64) and W (BN x 64) tiles into a multi-stage ring
+//   warp 1      allocates TMEM, one elected lane issues tcgen05.mma (M=128, N=BN, K=16) per 32 bytes of K
+//   warps 2-5   epilogue: tcgen05.ld of the fp32 accumulator (double-buffered in TMEM so the next tile's
+//               MMAs overlap), + bias, exact-erf GELU, + fp32 residual / position table, bf16 or fp32 store
+// A strided Conv1d is the same loop with the K axis split into taps: tap j of a stride-s convolution reads
+// the activation map (rows merged s at a time) at column block (j % s) * C and row offset j / s, so no
+// im2col buffer is ever written.
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace segma {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;  // 128 bytes of bf16: one swizzle row
+constexpr int kGemmThreads = 192;
+
+struct GemmKernelArgs {
+  int batch, rows_per_batch, tiles_per_batch;
+  int n, n_tiles;
+  // K axis: taps * kb_per_tap blocks of 64
+  int taps, kb_per_tap, conv_stride;
+  int a_tap_elems;   // channels per tap in the A map (column offset of tap j = (j % s) * a_tap_elems)
+  int w_tap_elems;   // K extent of one tap in the W map
+  int a_ntile_off;   // extra A column offset per N tile (grouped convolution), else 0
+  const float* bias;
+  const float* add_src;
+  long long add_period;
+  void* out;
+  long long out_batch_rows, out_row_offset, ldo;
+  int flags;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 192 ? 5 : 6);
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = BN == 128 ? 256 : 512;
+  static constexpr int kAccStride = BN == 192 ? 256 : BN;  // column offset between the two accumulators
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                const GemmKernelArgs p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + ((1024 - (raw_addr & 1023)) & 1023);
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = lane_id();
+  const int num_tiles = p.batch * p.tiles_per_batch * p.n_tiles;
+  const int num_kb = p.taps * p.kb_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_w);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(full_bar + i, 1);
+      mbar_init(empty_bar + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tmem_full + i, 1);
+      mbar_init(tmem_empty + i, 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc5_fence_before();
+  __syncthreads();
+  tc5_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int b = m_tile / p.tiles_per_batch;
+        const int r0 = (m_tile - b * p.tiles_per_batch) * kBM;
+        const int n0 = n_tile * BN;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int a_col = (tap % p.conv_stride) * p.a_tap_elems + n_tile * p.a_ntile_off;
+          const int a_row = r0 + tap / p.conv_stride;
+          const int w_col = tap * p.w_tap_elems;
+          for (int kk = 0; kk < p.kb_per_tap; ++kk) {
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
+            tma_load_3d(smem_a + stage * Cfg::kABytes, &map_a, full_bar + stage, a_col + kk * kBK, a_row, b);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &map_w, full_bar + stage, w_col + kk * kBK, n0);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(tmem_empty + as, aphase ^ 1);
+        tc5_fence_after();
+        const uint32_t d_tmem = tmem_base + as * Cfg::kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + stage, phase);
+          tc5_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t da = umma_desc_k_sw128(a_addr + k * 32);
+            const uint64_t db = umma_desc_k_sw128(b_addr + k * 32);
+            tc5_mma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc5_commit(empty_bar + stage);  // frees the smem stage once these MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        tc5_commit(tmem_full + as);  // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const bool out_f32 = (p.flags & SEGMA_GEMM_OUT_F32) != 0;
+    const bool do_gelu = (p.flags & SEGMA_GEMM_GELU) != 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int b = m_tile / p.tiles_per_batch;
+      const int r = (m_tile - b * p.tiles_per_batch) * kBM + quad * 32 + lane;
+      const int n0 = n_tile * BN;
+      const bool row_ok = r < p.rows_per_batch;
+      const long long out_row = (long long)b * p.out_batch_rows + p.out_row_offset + r;
+      const long long src_row = p.add_src ? ((long long)b * p.rows_per_batch + r) % p.add_period : 0;
+      mbar_wait(tmem_full + as, aphase);
+      tc5_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::kAccStride;
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        const int nc = n0 + chunk * 32;
+        if (nc >= p.n) break;  // warp-uniform
+        uint32_t acc[32];
+        tmem_ld_32x32(t_addr + chunk * 32, acc);
+        tmem_ld_wait();
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nc + i));
+              v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
+            }
+          }
+          if (do_gelu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+          }
+          if (p.add_src) {
+            const float4* s4 = reinterpret_cast<const float4*>(p.add_src + src_row * p.n + nc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 sv = s4[i];
+              v[4 * i] += sv.x; v[4 * i + 1] += sv.y; v[4 * i + 2] += sv.z; v[4 * i + 3] += sv.w;
+            }
+          }
+          if (out_f32) {
+            float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_row * p.ldo + nc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + nc);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 q;
+              q.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);
+              q.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+              q.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+              q.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+              o4[i] = q;
+            }
+          }
+        }
+      }
+      tc5_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + as);
+    }
+  }
+
+  tc5_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc5_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// bf16 tensor map with a (64 x box_rows [x 1]) box and 128B swizzle
+int make_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                  int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return SEGMA_ERR_CUDA;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t box[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    estr[i] = 1;
+    box[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_elems[i] * 2;
+  }
+  box[0] = kBK;
+  box[1] = box_rows;
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu, stride %llu B)", (int)r,
+                   rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                   (unsigned long long)(rank > 1 ? strides_elems[1] * 2 : 0));
+    return SEGMA_ERR_CUDA;
+  }
+  return SEGMA_OK;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, GemmKernelArgs& ka, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SEGMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc5_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  ka.n_tiles = ceil_div(ka.n, BN);
+  const long long tiles = (long long)ka.batch * ka.tiles_per_batch * ka.n_tiles;
+  if (tiles > 0x7fffffffll) {
+    set_last_error("segma_gemm_bf16: too many tiles");
+    return SEGMA_ERR_INVALID_ARGUMENT;
+  }
+  const int grid = (int)std::min<long long>(tiles, device_sm_count());
+  gemm_tc5_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ma, mw, ka);
+  return launch_status("gemm_tc5_kernel");
+}
+
+}  // namespace segma
+
+using namespace segma;
+
+extern "C" {
+
+int segma_gemm_bf16(const segma_gemm_args* a, void* stream) {
+  SEGMA_REQUIRE(a != nullptr, "segma_gemm_bf16: NULL args");
+  SEGMA_REQUIRE(a->batch >= 0 && a->rows_per_batch >= 0, "segma_gemm_bf16: negative shape");
+  if (a->batch == 0 || a->rows_per_batch == 0) return SEGMA_OK;
+  SEGMA_REQUIRE(a->a && a->w && a->out, "segma_gemm_bf16: NULL buffer");
+  SEGMA_REQUIRE(a->n > 0 && a->n % 32 == 0, "segma_gemm_bf16: n=%d must be a positive multiple of 32", a->n);
+  SEGMA_REQUIRE(a->a_row_stride % 8 == 0 && a->a_batch_stride % 8 == 0,
+                "segma_gemm_bf16: A strides must be multiples of 8 elements (16 bytes)");
+  SEGMA_REQUIRE((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0,
+                "segma_gemm_bf16: A and W must be 16-byte aligned");
+  SEGMA_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && a->ldo % 8 == 0,
+                "segma_gemm_bf16: out must be 16-byte aligned with ldo a multiple of 8");
+  const int taps = a->conv_taps > 0 ? a->conv_taps : 1;
+  const int s = a->conv_stride > 0 ? a->conv_stride : 1;
+  SEGMA_REQUIRE(a->k > 0 && a->k % taps == 0, "segma_gemm_bf16: k=%d must be a positive multiple of conv_taps=%d",
+                a->k, taps);
+  const int c = a->k / taps;  // channels per tap
+  SEGMA_REQUIRE(c % 8 == 0, "segma_gemm_bf16: channels per tap (%d) must be a multiple of 8", c);
+  SEGMA_REQUIRE(taps == 1 || s == 1 || c % kBK == 0,
+                "segma_gemm_bf16: strided conv needs channels per tap (%d) to be a multiple of 64", c);
+  SEGMA_REQUIRE(a->a_row_stride >= (int64_t)c, "segma_gemm_bf16: a_row_stride smaller than the row");
+  if (a->add_src) SEGMA_REQUIRE(a->add_period > 0, "segma_gemm_bf16: add_period must be positive");
+
+  GemmKernelArgs ka{};
+  ka.batch = a->batch;
+  ka.rows_per_batch = a->rows_per_batch;
+  ka.tiles_per_batch = ceil_div(a->rows_per_batch, kBM);
+  ka.n = a->n;
+  ka.taps = taps;
+  ka.kb_per_tap = ceil_div(c, kBK);
+  ka.conv_stride = s;
+  ka.a_tap_elems = c;
+  ka.w_tap_elems = c;
+  ka.a_ntile_off = a->a_col_per_ntile;
+  ka.bias = a->bias;
+  ka.add_src = a->add_src;
+  ka.add_period = a->add_period;
+  ka.out = a->out;
+  ka.out_batch_rows = a->out_batch_rows;
+  ka.out_row_offset = a->out_row_offset;
+  ka.ldo = a->ldo;
+  ka.flags = a->flags;
+
+  // A map: stride-s convolutions view s consecutive input rows as one map row of s*c channels
+  const int in_rows = a->a_rows_per_batch > 0 ? a->a_rows_per_batch : a->rows_per_batch;
+  SEGMA_REQUIRE(in_rows % s == 0, "segma_gemm_bf16: a_rows_per_batch=%d must be a multiple of conv_stride=%d", in_rows, s);
+  CUtensorMap ma, mw;
+  {
+    uint64_t dims[3] = {(uint64_t)s * c, (uint64_t)(in_rows / s), (uint64_t)a->batch};
+    uint64_t strides[3] = {1, (uint64_t)a->a_row_stride * s, (uint64_t)a->a_batch_stride};
+    if (a->batch == 1 && strides[2] == 0) strides[2] = strides[1] * dims[1];
+    int rc = make_bf16_map(&ma, a->a, 3, dims, strides, kBM);
+    if (rc != SEGMA_OK) return rc;
+  }
+  int bn = 256;
+  if (a->n % 256 != 0 && a->n < 512) bn = 128;
+  if (a->n % 256 != 0 && a->n % 128 != 0 && a->n % 192 == 0) bn = 192;
+  if (a->force_bn) {
+    SEGMA_REQUIRE(a->force_bn == 128 || a->force_bn == 192 || a->force_bn == 256, "segma_gemm_bf16: bad force_bn");
+    bn = a->force_bn;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a->k, (uint64_t)a->n};
+    uint64_t strides[2] = {1, (uint64_t)a->k};
+    int rc = make_bf16_map(&mw, a->w, 2, dims, strides, bn);
+    if (rc != SEGMA_OK) return rc;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (bn) {
+    case 128: return launch_gemm<128>(ma, mw, ka, st);
+    case 192: return launch_gemm<192>(ma, mw, ka, st);
+    default: return launch_gemm<256>(ma, mw, ka, st);
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,481 @@
+// Fused windowing + Whisper log-mel front end (fp32).
+//
+// Replaces `unfold` (src/segma/inference.py:148-152) + WhisperFeatureExtractor
+// (site-packages/transformers/models/whisper/feature_extraction_whisper.py:135-164): for every 4 s window,
+// STFT frames of 400 samples at hop 160 (periodic Hann, centre + reflect padding of the 30 s padded window)
+// -> 201-bin power spectrum -> 80 slaney mel bins (391 non-zeros) -> log10(max(., 1e-10))
+// -> max(., window_max - 8) -> (. + 4) / 4, padded with the constant value to 3000 frames.
+//
+// HBM-bound: per window 256 KB of PCM in, 960 KB of features out.  Kernel A stages the overlapping
+// samples of 32 consecutive frames once in shared memory (128-bit loads; each sample is used by 2.5
+// frames), runs a packed real FFT (200-point complex Stockham, radix 8*5*5, in shared memory/registers),
+// applies the sparse mel filters and the log, and reduces the window maximum with one atomic per
+// block.  Kernel B applies the window-global clamp, scales, and streams out the 3000-frame rows
+// (constant beyond the last frame that touches audio), optionally also as the bf16 time-major tile
+// the conv-stem GEMM consumes.
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace segma {
+
+constexpr int kNfft = 400;
+constexpr int kHop = 160;
+constexpr int kHalf = 200;          // complex FFT length (packed real FFT)
+constexpr int kBins = 201;
+constexpr int kMels = SEGMA_MEL_BINS;
+constexpr int kFramesOut = SEGMA_MEL_FRAMES;
+constexpr int kPadSamples = 480000;  // 30 s
+constexpr int kGroup = 32;           // frames per block
+constexpr int kThreadsA = 160;
+constexpr int kMaxTaps = 32;         // max contiguous FFT bins per mel filter
+constexpr int kStage = (kGroup - 1) * kHop + kNfft;  // 5360 staged samples per group
+
+struct MelTables {
+  float hann[kNfft];
+  float2 tw200[kHalf];       // exp(-2 pi i k / 200)
+  float2 tw400[kBins];       // exp(-2 pi i k / 400)
+  int mel_k0[kMels];
+  int mel_len[kMels];
+  float mel_w[kMels][kMaxTaps];
+};
+
+__device__ MelTables g_tab;
+
+static std::mutex g_tab_mutex;
+static bool g_tab_ready = false;
+static std::vector<float> g_mel_dense;  // (201, 80) row-major, active filterbank
+
+static double hz_to_mel(double f) {
+  return f >= 1000.0 ? 15.0 + std::log(f / 1000.0) * (27.0 / std::log(6.4)) : 3.0 * f / 200.0;
+}
+static double mel_to_hz(double m) {
+  return m >= 15.0 ? 1000.0 * std::exp((std::log(6.4) / 27.0) * (m - 15.0)) : 200.0 * m / 3.0;
+}
+
+// slaney-scale, slaney-normalised triangular filters, 0-8 kHz, 16 kHz sampling (float64, then fp32)
+static void default_mel(std::vector<float>& dense) {
+  dense.assign((size_t)kBins * kMels, 0.f);
+  double edges[kMels + 2];
+  const double m_lo = hz_to_mel(0.0), m_hi = hz_to_mel(8000.0);
+  for (int i = 0; i < kMels + 2; ++i) edges[i] = mel_to_hz(m_lo + (m_hi - m_lo) * i / (kMels + 1));
+  for (int k = 0; k < kBins; ++k) {
+    const double f = 8000.0 * k / (kBins - 1);
+    for (int m = 0; m < kMels; ++m) {
+      const double down = (f - edges[m]) / (edges[m + 1] - edges[m]);
+      const double up = (edges[m + 2] - f) / (edges[m + 2] - edges[m + 1]);
+      const double v = std::max(0.0, std::min(down, up)) * (2.0 / (edges[m + 2] - edges[m]));
+      dense[(size_t)k * kMels + m] = (float)v;
+    }
+  }
+}
+
+static int upload_tables_locked() {
+  static MelTables h;  // large: keep off the stack
+  std::memset(&h, 0, sizeof(h));
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int n = 0; n < kNfft; ++n) h.hann[n] = (float)(0.5 - 0.5 * std::cos(two_pi * n / kNfft));
+  for (int k = 0; k < kHalf; ++k) h.tw200[k] = make_float2((float)std::cos(two_pi * k / kHalf), (float)-std::sin(two_pi * k / kHalf));
+  for (int k = 0; k < kBins; ++k) h.tw400[k] = make_float2((float)std::cos(two_pi * k / kNfft), (float)-std::sin(two_pi * k / kNfft));
+  for (int m = 0; m < kMels; ++m) {
+    int first = -1, last = -1;
+    for (int k = 0; k < kBins; ++k)
+      if (g_mel_dense[(size_t)k * kMels + m] != 0.f) {
+        if (first < 0) first = k;
+        last = k;
+      }
+    if (first < 0) { first = 0; last = -1; }
+    const int len = last - first + 1;
+    if (len > kMaxTaps) {
+      set_last_error("mel filter %d spans %d FFT bins (max %d)", m, len, kMaxTaps);
+      return SEGMA_ERR_UNSUPPORTED;
+    }
+    h.mel_k0[m] = first;
+    h.mel_len[m] = len;
+    for (int i = 0; i < len; ++i) h.mel_w[m][i] = g_mel_dense[(size_t)(first + i) * kMels + m];
+  }
+  SEGMA_CUDA_OK(cudaMemcpyToSymbol(g_tab, &h, sizeof(h)));
+  g_tab_ready = true;
+  return SEGMA_OK;
+}
+
+static int ensure_tables() {
+  std::lock_guard<std::mutex> lock(g_tab_mutex);
+  if (g_tab_ready) return SEGMA_OK;
+  if (g_mel_dense.empty()) default_mel(g_mel_dense);
+  return upload_tables_locked();
+}
+
+// ---- device helpers --------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -i (forward-transform rotation by -90 degrees)
+__device__ __forceinline__ float2 mul_neg_i(float2 a) { return make_float2(a.y, -a.x); }
+
+__device__ __forceinline__ void dft2(float2& a, float2& b) {
+  const float2 t = a;
+  a = cadd(t, b);
+  b = csub(t, b);
+}
+
+// in-place forward DFT of length 8, natural order in and out
+__device__ __forceinline__ void dft8(float2 (&v)[8]) {
+  const float r = 0.70710678118654752440f;
+  // stage 1: pairs (k, k+4)
+  dft2(v[0], v[4]); dft2(v[1], v[5]); dft2(v[2], v[6]); dft2(v[3], v[7]);
+  v[5] = cmul(v[5], make_float2(r, -r));
+  v[6] = mul_neg_i(v[6]);
+  v[7] = cmul(v[7], make_float2(-r, -r));
+  // stage 2
+  dft2(v[0], v[2]); dft2(v[1], v[3]); dft2(v[4], v[6]); dft2(v[5], v[7]);
+  v[3] = mul_neg_i(v[3]);
+  v[7] = mul_neg_i(v[7]);
+  // stage 3
+  dft2(v[0], v[1]); dft2(v[2], v[3]); dft2(v[4], v[5]); dft2(v[6], v[7]);
+  // bit-reversed -> natural: outputs currently at [0,4,2,6,1,5,3,7]
+  float2 t;
+  t = v[1]; v[1] = v[4]; v[4] = t;
+  t = v[3]; v[3] = v[6]; v[6] = t;
+}
+
+// in-place forward DFT of length 5
+__device__ __forceinline__ void dft5(float2 (&v)[5]) {
+  const float c1 = 0.30901699437494742410f;   // cos(2pi/5)
+  const float c2 = -0.80901699437494742410f;  // cos(4pi/5)
+  const float s1 = 0.95105651629515357212f;   // sin(2pi/5)
+  const float s2 = 0.58778525229247312917f;   // sin(4pi/5)
+  const float2 a1 = cadd(v[1], v[4]), b1 = csub(v[1], v[4]);
+  const float2 a2 = cadd(v[2], v[3]), b2 = csub(v[2], v[3]);
+  const float2 x0 = v[0];
+  v[0] = make_float2(x0.x + a1.x + a2.x, x0.y + a1.y + a2.y);
+  const float2 p1 = make_float2(x0.x + c1 * a1.x + c2 * a2.x, x0.y + c1 * a1.y + c2 * a2.y);
+  const float2 p2 = make_float2(x0.x + c2 * a1.x + c1 * a2.x, x0.y + c2 * a1.y + c1 * a2.y);
+  // q = -i * (s1*b1 + s2*b2) etc. (forward transform: exp(-i theta))
+  const float2 q1 = make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
+  const float2 q2 = make_float2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
+  // X1 = p1 - i q1, X4 = p1 + i q1, X2 = p2 - i q2, X3 = p2 + i q2
+  v[1] = make_float2(p1.x + q1.y, p1.y - q1.x);
+  v[4] = make_float2(p1.x - q1.y, p1.y + q1.x);
+  v[2] = make_float2(p2.x + q2.y, p2.y - q2.x);
+  v[3] = make_float2(p2.x - q2.y, p2.y + q2.x);
+}
+
+__device__ __forceinline__ uint32_t float_order_key(float v) {
+  const uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_key(uint32_t k) {
+  const uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+  return __uint_as_float(b);
+}
+
+// padded-window sample n (after torch.stft's reflect padding of the 480000-sample buffer)
+__device__ __forceinline__ float sample_at(const float* __restrict__ w, long long n, long long avail) {
+  if (n < 0) n = -n;
+  if (n >= kPadSamples) n = 2ll * (kPadSamples - 1) - n;
+  return (n < avail) ? __ldg(w + n) : 0.f;
+}
+
+// ---- kernel A: log10 mel power of the frames that touch audio + window max ---------------------------
+__global__ void __launch_bounds__(kThreadsA) logmel_power_kernel(const float* __restrict__ pcm, long long pcm_len,
+                                                                 int win_len, long long step, int n_valid_max,
+                                                                 int nvp, float* __restrict__ logspec,
+                                                                 uint32_t* __restrict__ win_max) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* Z = reinterpret_cast<float2*>(smem_raw);                              // [kGroup][kHalf]
+  float* stage = reinterpret_cast<float*>(smem_raw + sizeof(float2) * kGroup * kHalf);  // samples, later power
+  __shared__ float s_red[kThreadsA / 32];
+
+  const int win = blockIdx.y;
+  const int t0 = blockIdx.x * kGroup;
+  const long long w_off = (long long)win * step;
+  long long avail = pcm_len - w_off;
+  if (avail > win_len) avail = win_len;
+  if (avail < 0) avail = 0;
+  // frames >= n_valid see only zeros
+  int n_valid = (int)((avail + 200 + kHop - 1) / kHop);
+  if (avail == 0) n_valid = 0;
+  if (n_valid > kFramesOut) n_valid = kFramesOut;
+  if (t0 >= n_valid) return;  // whole group is silent padding (uniform per block)
+  const float* w = pcm + w_off;
+  const int tid = threadIdx.x;
+
+  // 1. stage samples [160*t0 - 200, +5360) with 128-bit loads where possible
+  {
+    const long long s0 = (long long)kHop * t0 - 200;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
+    for (int q = tid; q < kStage / 4; q += kThreadsA) {
+      const long long n = s0 + 4 * q;
+      float4 v;
+      if (aligned && n >= 0 && n + 3 < avail) {
+        v = __ldg(reinterpret_cast<const float4*>(w + n));
+      } else {
+        v.x = sample_at(w, n, avail);
+        v.y = sample_at(w, n + 1, avail);
+        v.z = sample_at(w, n + 2, avail);
+        v.w = sample_at(w, n + 3, avail);
+      }
+      reinterpret_cast<float4*>(stage)[q] = v;
+    }
+  }
+  __syncthreads();
+
+  // 2. FFT stage 1 (radix 8, Ns = 1): z[n] = (x[2n] h[2n], x[2n+1] h[2n+1]); butterfly j takes n = j + 25 t
+  {
+#pragma unroll 1
+    for (int it = 0; it < (kGroup * 25) / kThreadsA; ++it) {
+      const int id = tid + it * kThreadsA;
+      const int f = id / 25, j = id - f * 25;
+      float2 v[8];
+      const float* s = stage + f * kHop;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int n = j + 25 * t;
+        const float2 x = *reinterpret_cast<const float2*>(s + 2 * n);
+        v[t] = make_float2(x.x * g_tab.hann[2 * n], x.y * g_tab.hann[2 * n + 1]);
+      }
+      dft8(v);
+      float2* z = Z + f * kHalf + j * 8;  // expand(j, 1, 8) = 8 j
+#pragma unroll
+      for (int t = 0; t < 8; ++t) z[t] = v[t];
+    }
+  }
+  __syncthreads();
+
+  // 3. FFT stages 2 and 3 (radix 5; Ns = 8 then 40), in place: read all, barrier, write all
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const int Ns = pass == 0 ? 8 : 40;
+    constexpr int kIter = (kGroup * 40) / kThreadsA;  // 8 butterflies per thread
+    float2 v[kIter][5];
+#pragma unroll
+    for (int it = 0; it < kIter; ++it) {
+      const int id = tid + it * kThreadsA;
+      const int f = id / 40, j = id - f * 40;
+      const int k = j % Ns;
+      const float2* z = Z + f * kHalf;
+      v[it][0] = z[j];
+#pragma unroll
+      for (int t = 1; t < 5; ++t) {
+        // twiddle exp(-2 pi i t k / (5 Ns)) = tw200[t * k * (200 / (5 Ns))]
+        const int tw = t * k * (kHalf / (5 * Ns));
+        v[it][t] = cmul(z[j + 40 * t], g_tab.tw200[tw]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kIter; ++it) {
+      const int id = tid + it * kThreadsA;
+      const int f = id / 40, j = id - f * 40;
+      const int k = j % Ns;
+      dft5(v[it]);
+      float2* z = Z + f * kHalf + (j / Ns) * Ns * 5 + k;
+#pragma unroll
+      for (int t = 0; t < 5; ++t) z[t * Ns] = v[it][t];
+    }
+    __syncthreads();
+  }
+
+  // 4. unpack the real FFT and take the power: P[f][k], k = 0..200 (stage buffer is reused)
+  float* P = stage;
+  for (int id = tid; id < kGroup * kBins; id += kThreadsA) {
+    const int f = id / kBins, k = id - f * kBins;
+    const float2* z = Z + f * kHalf;
+    const float2 a = z[k == kHalf ? 0 : k];
+    const float2 bq = z[(kHalf - k) % kHalf];
+    const float2 b = make_float2(bq.x, -bq.y);                       // conj(Z[200-k])
+    const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
+    const float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
+    const float2 o = mul_neg_i(d);                                   // (Zk - conj(Z[N-k])) / (2i)
+    const float2 x = cadd(e, cmul(g_tab.tw400[k], o));
+    P[f * kBins + k] = fmaf(x.x, x.x, x.y * x.y);
+  }
+  __syncthreads();
+
+  // 5. sparse mel filters + log10; frame index fastest so global stores coalesce along time
+  float local_max = -INFINITY;
+  for (int id = tid; id < kGroup * kMels; id += kThreadsA) {
+    const int m = id / kGroup, f = id - m * kGroup;
+    const int t = t0 + f;
+    if (t < n_valid) {
+      const float* p = P + f * kBins + g_tab.mel_k0[m];
+      const int len = g_tab.mel_len[m];
+      float acc = 0.f;
+      for (int i = 0; i < len; ++i) acc = fmaf(g_tab.mel_w[m][i], p[i], acc);
+      const float v = log10f(fmaxf(acc, 1e-10f));
+      logspec[((long long)win * kMels + m) * nvp + t] = v;
+      local_max = fmaxf(local_max, v);
+    }
+  }
+  local_max = warp_max(local_max);
+  if (lane_id() == 0) s_red[tid >> 5] = local_max;
+  __syncthreads();
+  if (tid == 0) {
+    float m = s_red[0];
+    for (int i = 1; i < kThreadsA / 32; ++i) m = fmaxf(m, s_red[i]);
+    atomicMax(win_max + win, float_order_key(m));
+  }
+}
+
+// ---- kernel B: window-global clamp, scale, constant tail ----------------------------------------------
+__device__ __forceinline__ int window_n_valid(long long pcm_len, int win, long long step, int win_len) {
+  long long avail = pcm_len - (long long)win * step;
+  if (avail > win_len) avail = win_len;
+  if (avail <= 0) return 0;
+  long long nv = (avail + 200 + kHop - 1) / kHop;
+  return nv > kFramesOut ? kFramesOut : (int)nv;
+}
+
+__global__ void __launch_bounds__(256) logmel_finish_f32_kernel(const float* __restrict__ logspec,
+                                                                 const uint32_t* __restrict__ win_max,
+                                                                 long long pcm_len, int win_len, long long step,
+                                                                 int nvp, float* __restrict__ out) {
+  const int win = blockIdx.y;
+  const int n_valid = window_n_valid(pcm_len, win, step, win_len);
+  const uint32_t key = win_max[win];
+  float gmax = key ? float_from_key(key) : -10.f;
+  if (n_valid < kFramesOut) gmax = fmaxf(gmax, -10.f);
+  const float floor_v = gmax - 8.0f;
+  const float fill = (fmaxf(-10.f, floor_v) + 4.0f) / 4.0f;
+  constexpr int kQuads = kMels * kFramesOut / 4;
+  float4* o = reinterpret_cast<float4*>(out + (long long)win * kMels * kFramesOut);
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < kQuads; q += gridDim.x * blockDim.x) {
+    const int m = q / (kFramesOut / 4);
+    const int t = (q - m * (kFramesOut / 4)) * 4;
+    float4 v = make_float4(fill, fill, fill, fill);
+    if (t < n_valid) {
+      const float* src = logspec + ((long long)win * kMels + m) * nvp + t;
+      float r[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = (t + i < n_valid) ? (fmaxf(__ldg(src + i), floor_v) + 4.0f) / 4.0f : fill;
+      v = make_float4(r[0], r[1], r[2], r[3]);
+    }
+    o[q] = v;
+  }
+}
+
+// bf16 time-major (3002, 80) per window: row 0 and row 3001 are the conv padding (zeros)
+constexpr int kTmTile = 32;
+__global__ void __launch_bounds__(256) logmel_finish_tm_kernel(const float* __restrict__ logspec,
+                                                                const uint32_t* __restrict__ win_max,
+                                                                long long pcm_len, int win_len, long long step,
+                                                                int nvp, __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[kMels][kTmTile + 1];
+  const int win = blockIdx.y;
+  const int n_valid = window_n_valid(pcm_len, win, step, win_len);
+  const uint32_t key = win_max[win];
+  float gmax = key ? float_from_key(key) : -10.f;
+  if (n_valid < kFramesOut) gmax = fmaxf(gmax, -10.f);
+  const float floor_v = gmax - 8.0f;
+  const float fill = (fmaxf(-10.f, floor_v) + 4.0f) / 4.0f;
+  __nv_bfloat16* o = out + (long long)win * (kFramesOut + 2) * kMels;
+  const int t0 = blockIdx.x * kTmTile;
+  if (blockIdx.x == 0 && threadIdx.x < kMels) {
+    o[threadIdx.x] = __float2bfloat16(0.f);
+    o[(long long)(kFramesOut + 1) * kMels + threadIdx.x] = __float2bfloat16(0.f);
+  }
+  if (t0 < n_valid) {
+    for (int id = threadIdx.x; id < kMels * kTmTile; id += blockDim.x) {
+      const int m = id / kTmTile, f = id - m * kTmTile;
+      const int t = t0 + f;
+      tile[m][f] = (t < n_valid) ? (fmaxf(__ldg(logspec + ((long long)win * kMels + m) * nvp + t), floor_v) + 4.0f) / 4.0f
+                                 : fill;
+    }
+    __syncthreads();
+  }
+  for (int id = threadIdx.x; id < kTmTile * kMels / 2; id += blockDim.x) {
+    const int f = id / (kMels / 2), m = (id - f * (kMels / 2)) * 2;
+    const int t = t0 + f;
+    if (t >= kFramesOut) continue;
+    float a = fill, b = fill;
+    if (t0 < n_valid) { a = tile[m][f]; b = tile[m + 1][f]; }
+    *reinterpret_cast<uint32_t*>(o + (long long)(t + 1) * kMels + m) = pack_bf16x2(a, b);
+  }
+}
+
+static int max_valid_frames(int win_len) {
+  long long nv = ((long long)win_len + 200 + kHop - 1) / kHop;
+  if (nv > kFramesOut) nv = kFramesOut;
+  return (int)nv;
+}
+static int padded_valid(int win_len) { return ceil_div(max_valid_frames(win_len), kGroup) * kGroup; }
+
+}  // namespace segma
+
+using namespace segma;
+
+extern "C" {
+
+size_t segma_logmel_scratch_bytes(int n_windows, int win_len) {
+  if (n_windows <= 0 || win_len <= 0) return 0;
+  const size_t head = ((size_t)n_windows * sizeof(uint32_t) + 255) / 256 * 256;
+  return head + (size_t)n_windows * kMels * padded_valid(win_len) * sizeof(float);
+}
+
+int segma_logmel_set_filters(const float* mel_201x80) {
+  SEGMA_REQUIRE(mel_201x80 != nullptr, "segma_logmel_set_filters: NULL matrix");
+  std::lock_guard<std::mutex> lock(g_tab_mutex);
+  g_mel_dense.assign(mel_201x80, mel_201x80 + (size_t)kBins * kMels);
+  return upload_tables_locked();
+}
+
+int segma_logmel_get_filters(float* mel_201x80) {
+  SEGMA_REQUIRE(mel_201x80 != nullptr, "segma_logmel_get_filters: NULL matrix");
+  std::lock_guard<std::mutex> lock(g_tab_mutex);
+  if (g_mel_dense.empty()) default_mel(g_mel_dense);
+  std::memcpy(mel_201x80, g_mel_dense.data(), sizeof(float) * kBins * kMels);
+  return SEGMA_OK;
+}
+
+int segma_logmel(const float* pcm, int64_t pcm_len, int n_windows, int win_len, int64_t step, float* out_f32,
+                 void* out_tm, void* scratch, void* stream) {
+  SEGMA_REQUIRE(n_windows >= 0, "segma_logmel: negative n_windows");
+  if (n_windows == 0) return SEGMA_OK;
+  SEGMA_REQUIRE(pcm && scratch, "segma_logmel: NULL pcm/scratch");
+  SEGMA_REQUIRE(win_len > 0 && win_len <= kPadSamples - kNfft, "segma_logmel: win_len %d outside (0, %d]", win_len,
+                kPadSamples - kNfft);
+  SEGMA_REQUIRE(step >= 0 && pcm_len >= 0, "segma_logmel: negative step/pcm_len");
+  SEGMA_REQUIRE(out_f32 || out_tm, "segma_logmel: no output requested");
+  SEGMA_REQUIRE(n_windows <= 65535, "segma_logmel: at most 65535 windows per call");
+  int rc = ensure_tables();
+  if (rc != SEGMA_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nvp = padded_valid(win_len);
+  const size_t head = ((size_t)n_windows * sizeof(uint32_t) + 255) / 256 * 256;
+  uint32_t* win_max = static_cast<uint32_t*>(scratch);
+  float* logspec = reinterpret_cast<float*>(static_cast<char*>(scratch) + head);
+  SEGMA_CUDA_OK(cudaMemsetAsync(win_max, 0, (size_t)n_windows * sizeof(uint32_t), st));
+  const size_t smem = sizeof(float2) * kGroup * kHalf + sizeof(float) * std::max(kStage, kGroup * kBins);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SEGMA_CUDA_OK(cudaFuncSetAttribute(logmel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid_a(nvp / kGroup, n_windows);
+  logmel_power_kernel<<<grid_a, kThreadsA, smem, st>>>(pcm, pcm_len, win_len, step, max_valid_frames(win_len), nvp,
+                                                       logspec, win_max);
+  rc = launch_status("logmel_power_kernel");
+  if (rc != SEGMA_OK) return rc;
+  if (out_f32) {
+    dim3 grid_b(ceil_div(kMels * kFramesOut / 4, 256 * 4), n_windows);
+    logmel_finish_f32_kernel<<<grid_b, 256, 0, st>>>(logspec, win_max, pcm_len, win_len, step, nvp, out_f32);
+    rc = launch_status("logmel_finish_f32_kernel");
+    if (rc != SEGMA_OK) return rc;
+  }
+  if (out_tm) {
+    dim3 grid_c(ceil_div(kFramesOut, kTmTile), n_windows);
+    logmel_finish_tm_kernel<<<grid_c, 256, 0, st>>>(logspec, win_max, pcm_len, win_len, step, nvp,
+                                                    static_cast<__nv_bfloat16*>(out_tm));
+    rc = launch_status("logmel_finish_tm_kernel");
+    if (rc != SEGMA_OK) return rc;
+  }
+  return SEGMA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+// LSTM recurrence over the window axis and the per-label linear heads.
+//
+// The reference builds nn.LSTM without batch_first (src/segma/models/whisper/hydra.py:48-51,
+// surgical_hydra.py:57-60), so the (B, T, d) encoder output is consumed as (seq = B windows, batch = T
+// frames): the recurrence runs across the <= batch_size windows of one forward call and the kept frames
+// are independent rows (SURVEY.md finding 6).  The input projection x W_ih^T + b is a tcgen05 GEMM
+// (gemm_tc5.cu); this kernel runs the sequential part: each CTA owns R frames of one direction, keeps
+// h in shared memory and c in registers, and walks the n_steps windows.  fp32 throughout.
+#include "common.cuh"
+
+namespace segma {
+
+constexpr int kLstmRows = 8;  // frames per CTA
+
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int H>
+__global__ void __launch_bounds__(4 * H) lstm_layer_kernel(const float* __restrict__ pre,
+                                                            const float* __restrict__ w_hh_t, int n_steps,
+                                                            int n_rows, int n_dirs, float* __restrict__ out,
+                                                            __nv_bfloat16* __restrict__ out_bf16) {
+  constexpr int R = kLstmRows;
+  constexpr int G = 4 * H;
+  constexpr int kItems = (R * H) / G;  // pointwise items per thread
+  __shared__ float s_h[R][H];
+  __shared__ float s_g[R][G];
+  const int dir = blockIdx.y;
+  const int r0 = blockIdx.x * R;
+  const int j = threadIdx.x;
+  const float* w = w_hh_t + (long long)dir * H * G + j;
+  float c_state[kItems];
+#pragma unroll
+  for (int i = 0; i < kItems; ++i) c_state[i] = 0.f;
+  for (int i = j; i < R * H; i += G) (&s_h[0][0])[i] = 0.f;
+  __syncthreads();
+
+  for (int step = 0; step < n_steps; ++step) {
+    const int s = dir == 0 ? step : n_steps - 1 - step;
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = r0 + r;
+      acc[r] = row < n_rows ? __ldg(pre + ((long long)s * n_rows + row) * (n_dirs * G) + dir * G + j) : 0.f;
+    }
+#pragma unroll 8
+    for (int k = 0; k < H; ++k) {
+      const float wk = __ldg(w + (long long)k * G);
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = fmaf(wk, s_h[r][k], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) s_g[r][j] = acc[r];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+      const int idx = j + i * G;
+      const int r = idx / H, u = idx - r * H;
+      const float ig = sigmoid_acc(s_g[r][u]);
+      const float fg = sigmoid_acc(s_g[r][H + u]);
+      const float gg = tanhf(s_g[r][2 * H + u]);
+      const float og = sigmoid_acc(s_g[r][3 * H + u]);
+      const float c = fmaf(fg, c_state[i], ig * gg);
+      c_state[i] = c;
+      const float h = og * tanhf(c);
+      s_h[r][u] = h;
+      const int row = r0 + r;
+      if (row < n_rows) {
+        const long long o = ((long long)s * n_rows + row) * (n_dirs * H) + dir * H + u;
+        out[o] = h;
+        if (out_bf16) out_bf16[o] = __float2bfloat16(h);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// one warp per (step, frame) row: C dot products of length n_feat
+__global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ feat, int n_steps, int n_rows,
+                                                     int n_feat, int n_keep, const float* __restrict__ w,
+                                                     const float* __restrict__ b, int C, float* __restrict__ logits,
+                                                     long long frame_offset, int step_frames) {
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (long long)n_steps * n_keep) return;
+  const int s = (int)(wid / n_keep), r = (int)(wid - (long long)s * n_keep);
+  const int lane = lane_id();
+  const float* f = feat + ((long long)s * n_rows + r) * n_feat;
+  float* dst = logits + (frame_offset + (long long)s * step_frames + r) * C;
+  for (int c = 0; c < C; ++c) {
+    float acc = 0.f;
+    for (int k = lane; k < n_feat; k += 32) acc = fmaf(__ldg(f + k), __ldg(w + (long long)c * n_feat + k), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) dst[c] = acc + __ldg(b + c);
+  }
+}
+
+}  // namespace segma
+
+using namespace segma;
+
+extern "C" {
+
+int segma_lstm_layer(const float* pre, const float* w_hh_t, int n_steps, int n_rows, int hidden, int n_dirs,
+                     float* out, void* out_bf16, void* stream) {
+  SEGMA_REQUIRE(n_steps >= 0 && n_rows >= 0 && (n_dirs == 1 || n_dirs == 2), "segma_lstm_layer: bad shape");
+  if (n_steps == 0 || n_rows == 0) return SEGMA_OK;
+  SEGMA_REQUIRE(pre && w_hh_t && out, "segma_lstm_layer: NULL buffer");
+  dim3 grid(ceil_div(n_rows, kLstmRows), n_dirs);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out_bf16);
+  switch (hidden) {
+    case 64: lstm_layer_kernel<64><<<grid, 256, 0, st>>>(pre, w_hh_t, n_steps, n_rows, n_dirs, out, ob); break;
+    case 128: lstm_layer_kernel<128><<<grid, 512, 0, st>>>(pre, w_hh_t, n_steps, n_rows, n_dirs, out, ob); break;
+    case 256: lstm_layer_kernel<256><<<grid, 1024, 0, st>>>(pre, w_hh_t, n_steps, n_rows, n_dirs, out, ob); break;
+    default:
+      set_last_error("segma_lstm_layer: hidden size %d not supported (64, 128, 256)", hidden);
+      return SEGMA_ERR_UNSUPPORTED;
+  }
+  return launch_status("lstm_layer_kernel");
+}
+
+int segma_heads(const float* feat, int n_steps, int n_rows, int n_feat, int n_keep, const float* w, const float* b,
+                int n_labels, float* logits, int64_t frame_offset, int step_frames, void* stream) {
+  SEGMA_REQUIRE(n_steps >= 0 && n_rows > 0 && n_feat > 0 && n_keep >= 0 && n_keep <= n_rows && n_labels > 0,
+                "segma_heads: bad shape");
+  if (n_steps == 0 || n_keep == 0) return SEGMA_OK;
+  SEGMA_REQUIRE(feat && w && b && logits, "segma_heads: NULL buffer");
+  const long long warps = (long long)n_steps * n_keep;
+  heads_kernel<<<(unsigned)ceil_div_ll(warps, 8), 256, 0, (cudaStream_t)stream>>>(
+      feat, n_steps, n_rows, n_feat, n_keep, w, b, n_labels, logits, frame_offset, step_frames);
+  return launch_status("heads_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,262 @@
+"""Torch-tensor front of the C ABI: shape/dtype/device checks, raw pointers, the current CUDA stream.
+
+PyTorch is only the allocator and stream provider here; all arithmetic happens in libsegma_b200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import GemmArgs, SegmaNativeError, check
+
+GEMM_GELU = 1
+GEMM_OUT_F32 = 2
+DECODE_SIGMOID = 0
+DECODE_LOGIT = 1
+
+
+def _lib():
+    return _native.load()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t: torch.Tensor, dtype, name: str) -> int:
+    if not t.is_cuda:
+        raise SegmaNativeError(f"{name} must be a CUDA tensor (segma_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def _ptr(t, dtype, name):
+    return None if t is None else _dev(t, dtype, name)
+
+
+def device_check() -> None:
+    check(_lib().segma_device_check(), "segma_device_check")
+
+
+# ---- log-mel -------------------------------------------------------------------------------------
+def logmel(pcm: torch.Tensor, n_windows: int, win_len: int, step: int, out_f32: bool = True, out_tm: bool = False,
+           pcm_offset: int = 0):
+    """Windows ``pcm[pcm_offset + i*step : ... + win_len]`` -> Whisper log-mel.
+    Returns ``(f32 (n,80,3000) | None, bf16 time-major (n,3002,80) | None)``."""
+    lib = _lib()
+    _dev(pcm, torch.float32, "pcm")
+    assert pcm.dim() == 1 and pcm.is_contiguous()
+    f32 = torch.empty((n_windows, 80, 3000), dtype=torch.float32, device=pcm.device) if out_f32 else None
+    tm = torch.empty((n_windows, 3002, 80), dtype=torch.bfloat16, device=pcm.device) if out_tm else None
+    nbytes = lib.segma_logmel_scratch_bytes(n_windows, win_len)
+    scratch = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=pcm.device)
+    view = pcm[pcm_offset:]
+    check(
+        lib.segma_logmel(view.data_ptr(), view.numel(), n_windows, win_len, step,
+                         None if f32 is None else f32.data_ptr(), None if tm is None else tm.data_ptr(),
+                         scratch.data_ptr(), _stream()),
+        "segma_logmel",
+    )
+    return f32, tm
+
+
+def logmel_into(pcm_view: torch.Tensor, n_windows: int, win_len: int, step: int, tm: torch.Tensor,
+                scratch: torch.Tensor) -> None:
+    check(
+        _lib().segma_logmel(pcm_view.data_ptr(), pcm_view.numel(), n_windows, win_len, step, None, tm.data_ptr(),
+                            scratch.data_ptr(), _stream()),
+        "segma_logmel",
+    )
+
+
+def logmel_scratch_bytes(n_windows: int, win_len: int) -> int:
+    return _lib().segma_logmel_scratch_bytes(n_windows, win_len)
+
+
+def mel_filters() -> np.ndarray:
+    out = np.empty((201, 80), dtype=np.float32)
+    check(_lib().segma_logmel_get_filters(out.ctypes.data), "segma_logmel_get_filters")
+    return out
+
+
+def set_mel_filters(mel: np.ndarray) -> None:
+    m = np.ascontiguousarray(mel, dtype=np.float32)
+    assert m.shape == (201, 80)
+    check(_lib().segma_logmel_set_filters(m.ctypes.data), "segma_logmel_set_filters")
+
+
+# ---- GEMM / conv ---------------------------------------------------------------------------------
+def gemm_raw(a_ptr, a_batch_stride, a_row_stride, batch, rows_per_batch, k, w, n, out_ptr, ldo, *, bias=None,
+             add_src_ptr=None, add_period=0, out_batch_rows=None, out_row_offset=0, flags=0, conv_taps=0,
+             conv_stride=0, a_rows_per_batch=0, a_col_per_ntile=0, force_bn=0) -> None:
+    args = GemmArgs(
+        a=a_ptr, a_batch_stride=a_batch_stride, a_row_stride=a_row_stride, batch=batch,
+        rows_per_batch=rows_per_batch, a_rows_per_batch=a_rows_per_batch, k=k, conv_taps=conv_taps,
+        conv_stride=conv_stride, w=_dev(w, torch.bfloat16, "w"), n=n, bias=_ptr(bias, torch.float32, "bias"),
+        add_src=add_src_ptr, add_period=add_period, out=out_ptr,
+        out_batch_rows=rows_per_batch if out_batch_rows is None else out_batch_rows,
+        out_row_offset=out_row_offset, ldo=ldo, flags=flags, a_col_per_ntile=a_col_per_ntile, force_bn=force_bn,
+    )
+    check(_lib().segma_gemm_bf16(C.byref(args), _stream()), "segma_gemm_bf16")
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, gelu=False, add_src=None, add_period=None, out=None,
+           out_f32=False, force_bn=0) -> torch.Tensor:
+    """out = epilogue(a @ w.T); a (M, K) bf16, w (N, K) bf16."""
+    _dev(a, torch.bfloat16, "a")
+    assert a.dim() == 2 and a.stride(1) == 1 and w.is_contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32 if out_f32 else torch.bfloat16, device=a.device)
+    out_f32 = out.dtype == torch.float32
+    flags = (GEMM_GELU if gelu else 0) | (GEMM_OUT_F32 if out_f32 else 0)
+    gemm_raw(a.data_ptr(), 0, a.stride(0), 1, M, K, w, N, out.data_ptr(), out.stride(0), bias=bias,
+             add_src_ptr=None if add_src is None else _dev(add_src, torch.float32, "add_src"),
+             add_period=(M if add_period is None else add_period) if add_src is not None else 0, flags=flags,
+             force_bn=force_bn)
+    return out
+
+
+def conv1d_tm(x_tm: torch.Tensor, w_tap_major: torch.Tensor, bias, taps: int, stride: int, out_rows: int, *,
+              gelu=True, add_src=None, add_period=0, out=None, out_batch_rows=None, out_row_offset=0, out_f32=False):
+    """Implicit-GEMM Conv1d on a padded time-major activation x_tm (B, rows_in, C) bf16;
+    w_tap_major (N, taps*C) bf16.  Output (B, out_batch_rows, N) rows [out_row_offset, +out_rows)."""
+    B, rows_in, Cc = x_tm.shape
+    assert x_tm.is_contiguous()
+    N = w_tap_major.shape[0]
+    obr = out_rows if out_batch_rows is None else out_batch_rows
+    if out is None:
+        out = torch.zeros((B, obr, N), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x_tm.device)
+    flags = (GEMM_GELU if gelu else 0) | (GEMM_OUT_F32 if out.dtype == torch.float32 else 0)
+    gemm_raw(_dev(x_tm, torch.bfloat16, "x_tm"), rows_in * Cc, Cc, B, out_rows, taps * Cc, w_tap_major, N,
+             out.data_ptr(), N, bias=bias,
+             add_src_ptr=None if add_src is None else _dev(add_src, torch.float32, "add_src"), add_period=add_period,
+             out_batch_rows=obr, out_row_offset=out_row_offset, flags=flags, conv_taps=taps, conv_stride=stride,
+             a_rows_per_batch=rows_in)
+    return out
+
+
+# ---- layernorm / cast / attention ----------------------------------------------------------------
+def layernorm(x: torch.Tensor, gamma, beta, *, out_bf16=None, out_f32=None, mix=None, period=1, n_keep=0, w_in=0.0,
+              w_out=0.0, mix_init=False) -> None:
+    rows, d = x.shape
+    assert x.is_contiguous()
+    check(
+        _lib().segma_layernorm(_dev(x, torch.float32, "x"), _dev(gamma, torch.float32, "gamma"),
+                               _dev(beta, torch.float32, "beta"), rows, d, _ptr(out_bf16, torch.bfloat16, "out_bf16"),
+                               _ptr(out_f32, torch.float32, "out_f32"), _ptr(mix, torch.float32, "mix"), period,
+                               n_keep, float(w_in), float(w_out), int(mix_init), _stream()),
+        "segma_layernorm",
+    )
+
+
+def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
+    rows, cols = src.shape
+    check(
+        _lib().segma_cast_bf16(_dev(src, torch.float32, "src"), src.stride(0), _dev(dst, torch.bfloat16, "dst"),
+                               dst.stride(0), rows, cols, _stream()),
+        "segma_cast_bf16",
+    )
+
+
+def attention(qkv: torch.Tensor, n_windows: int, T: int, n_heads: int, *, n_query=None, gate=None, pos_bias=None,
+              out=None) -> torch.Tensor:
+    assert qkv.is_contiguous() and qkv.shape == (n_windows * T, 3 * n_heads * 64)
+    if out is None:
+        out = torch.zeros((n_windows * T, n_heads * 64), dtype=torch.bfloat16, device=qkv.device)
+    check(
+        _lib().segma_attention(_dev(qkv, torch.bfloat16, "qkv"), n_windows, T, n_heads, T if n_query is None else n_query,
+                               _ptr(gate, torch.float32, "gate"), _ptr(pos_bias, torch.float32, "pos_bias"),
+                               _dev(out, torch.bfloat16, "out"), _stream()),
+        "segma_attention",
+    )
+    return out
+
+
+# ---- LSTM / heads ------------------------------------------------------------------------------
+def lstm_layer(pre: torch.Tensor, w_hh_t: torch.Tensor, hidden: int, *, out=None, out_bf16=None) -> torch.Tensor:
+    n_steps, n_rows, g = pre.shape
+    n_dirs = g // (4 * hidden)
+    assert pre.is_contiguous() and w_hh_t.is_contiguous() and w_hh_t.shape == (n_dirs, hidden, 4 * hidden)
+    if out is None:
+        out = torch.empty((n_steps, n_rows, n_dirs * hidden), dtype=torch.float32, device=pre.device)
+    check(
+        _lib().segma_lstm_layer(_dev(pre, torch.float32, "pre"), _dev(w_hh_t, torch.float32, "w_hh_t"), n_steps, n_rows,
+                                hidden, n_dirs, _dev(out, torch.float32, "out"),
+                                _ptr(out_bf16, torch.bfloat16, "out_bf16"), _stream()),
+        "segma_lstm_layer",
+    )
+    return out
+
+
+def heads(feat: torch.Tensor, w: torch.Tensor, b: torch.Tensor, logits: torch.Tensor, frame_offset: int,
+          step_frames: int, n_keep: int) -> None:
+    n_steps, n_rows, n_feat = feat.shape
+    assert feat.is_contiguous() and w.is_contiguous() and logits.is_contiguous()
+    check(
+        _lib().segma_heads(_dev(feat, torch.float32, "feat"), n_steps, n_rows, n_feat, n_keep,
+                           _dev(w, torch.float32, "w"), _dev(b, torch.float32, "b"), w.shape[0],
+                           _dev(logits, torch.float32, "logits"), frame_offset, step_frames, _stream()),
+        "segma_heads",
+    )
+
+
+# ---- stitch / decode -----------------------------------------------------------------------------
+def stitch(window_logits: torch.Tensor, n_windows: int, frames_per_window: int, step_frames: int, tail_frames: int,
+           n_frames: int) -> torch.Tensor:
+    C_ = window_logits.shape[-1]
+    assert window_logits.is_contiguous()
+    out = torch.empty((n_frames, C_), dtype=torch.float32, device=window_logits.device)
+    check(
+        _lib().segma_stitch(_dev(window_logits, torch.float32, "window_logits"), n_windows, frames_per_window,
+                            step_frames, tail_frames, C_, out.data_ptr(), n_frames, _stream()),
+        "segma_stitch",
+    )
+    return out
+
+
+def threshold_mask(logits: torch.Tensor, thresholds, mode: int = DECODE_SIGMOID) -> torch.Tensor:
+    n, C_ = logits.shape
+    assert logits.is_contiguous()
+    thr = (C.c_float * C_)(*[float(t) for t in thresholds])
+    mask = torch.empty((n, C_), dtype=torch.uint8, device=logits.device)
+    check(
+        _lib().segma_threshold_mask(_dev(logits, torch.float32, "logits"), n, C_, thr, mode, mask.data_ptr(), _stream()),
+        "segma_threshold_mask",
+    )
+    return mask.bool()
+
+
+def decode_intervals(logits: torch.Tensor, thresholds, *, file_offsets=None, mode: int = DECODE_SIGMOID,
+                     capacity: int | None = None) -> torch.Tensor:
+    """(n_frames, C) logits -> int32 (n_intervals, 4) table (file, label, start_sample, end_sample) on the device.
+    Reads the interval count back once (the only synchronisation); retries if ``capacity`` was too small."""
+    lib = _lib()
+    n, C_ = logits.shape
+    assert logits.is_contiguous()
+    offs = [0, n] if file_offsets is None else [int(v) for v in file_offsets]
+    n_files = len(offs) - 1
+    assert offs[-1] == n
+    off_arr = (C.c_int64 * len(offs))(*offs)
+    thr = (C.c_float * C_)(*[float(t) for t in thresholds])
+    ws_bytes = lib.segma_decode_workspace_bytes(n, n_files, C_)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=logits.device)
+    count = torch.zeros(1, dtype=torch.int32, device=logits.device)
+    cap = max(1024, n // 16) if capacity is None else capacity
+    while True:
+        table = torch.empty((cap, 4), dtype=torch.int32, device=logits.device)
+        check(
+            lib.segma_decode_intervals(_dev(logits, torch.float32, "logits"), off_arr, n_files, C_, thr, mode,
+                                       table.data_ptr(), cap, count.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
+            "segma_decode_intervals",
+        )
+        total = int(count.item())
+        if total <= cap:
+            return table[:total]
+        cap = total

@@ -1,0 +1,269 @@
+"""Per-kernel parity on the GPU: every C-ABI entry point against the oracle / a torch fp32 restatement
+of the same op on the same seeded inputs.  Integer / boolean outputs are bit-exact; floating-point
+tolerances are stated per test."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import segma_oracle as O
+from segma_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g) * scale
+
+
+def _close(got, ref, rtol, atol, what=""):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    err = (got - ref).abs()
+    bound = atol + rtol * ref.abs()
+    bad = err > bound
+    assert not bad.any(), f"{what}: {int(bad.sum())} / {bad.numel()} out of tolerance, max err {err.max():.4g} (ref max {ref.abs().max():.4g})"
+
+
+# ---- GEMM -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,K,N", [(128, 64, 128), (300, 768, 768), (1500, 768, 2304), (257, 3072, 768), (199, 256, 1024),
+                                   (1000, 128, 384), (130, 512, 192)])
+def test_gemm_plain(cuda, M, K, N):
+    a = _rand((M, K), 1).to(cuda, torch.bfloat16)
+    w = _rand((N, K), 2, K**-0.5).to(cuda, torch.bfloat16)
+    bias = _rand((N,), 3).to(cuda)
+    out = ops.linear(a, w, bias)
+    ref = a.float() @ w.float().T + bias
+    # bf16 output rounding: 2^-8 relative
+    _close(out, ref, 1e-2, 1e-2, f"gemm {M}x{K}x{N}")
+
+
+def test_gemm_epilogues(cuda):
+    M, K, N = 700, 256, 512
+    a = _rand((M, K), 4).to(cuda, torch.bfloat16)
+    w = _rand((N, K), 5, K**-0.5).to(cuda, torch.bfloat16)
+    bias = _rand((N,), 6).to(cuda)
+    ref = a.float() @ w.float().T + bias
+    out = ops.linear(a, w, bias, gelu=True)
+    _close(out, F.gelu(ref), 1e-2, 1e-2, "gelu epilogue")
+    out32 = ops.linear(a, w, bias, out_f32=True)
+    _close(out32, ref, 1e-4, 1e-4, "fp32 out")
+    gelu32 = ops.linear(a, w, bias, gelu=True, out_f32=True)
+    _close(gelu32, F.gelu(ref), 1e-4, 1e-4, "gelu fp32 (A&S erf vs libm erf)")
+    # residual update in place
+    x = _rand((M, N), 7).to(cuda)
+    want = x + ref
+    ops.linear(a, w, bias, add_src=x, out=x)
+    _close(x, want, 1e-4, 1e-4, "residual in place")
+    # periodic table (position embedding) added after GELU
+    pos = _rand((100, N), 8).to(cuda)
+    out = ops.linear(a, w, bias, gelu=True, add_src=pos, add_period=100, out_f32=True)
+    idx = torch.arange(M, device=cuda) % 100
+    _close(out, F.gelu(ref) + pos[idx], 1e-4, 1e-4, "gelu + periodic add")
+    # no bias
+    out = ops.linear(a, w, None, out_f32=True)
+    _close(out, a.float() @ w.float().T, 1e-4, 1e-4, "no bias")
+
+
+@pytest.mark.parametrize("C,N,taps,stride,T_in,pad", [(80, 128, 3, 1, 3000, 1), (128, 128, 3, 2, 3000, 1), (768, 768, 3, 2, 3000, 1),
+                                                      (64, 64, 3, 2, 12799, 0), (64, 64, 2, 2, 399, 0)])
+def test_gemm_conv(cuda, C, N, taps, stride, T_in, pad):
+    B = 3
+    x = _rand((B, C, T_in), 9)
+    wt = _rand((N, C, taps), 10, (C * taps) ** -0.5)
+    bias = _rand((N,), 11)
+    xb, wb = x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float()
+    ref = F.gelu(F.conv1d(xb, wb, bias, stride=stride, padding=pad)).transpose(1, 2)  # (B, T_out, N)
+    T_out = ref.shape[1]
+    rows_in = T_in + 2 * pad
+    rows_in += (-rows_in) % stride
+    x_tm = torch.zeros((B, rows_in, C), dtype=torch.bfloat16)
+    x_tm[:, pad:pad + T_in] = x.transpose(1, 2).to(torch.bfloat16)
+    w_tm = wt.permute(0, 2, 1).reshape(N, taps * C).contiguous().to(torch.bfloat16)
+    out = ops.conv1d_tm(x_tm.to(cuda), w_tm.to(cuda), bias.to(cuda), taps, stride, T_out, gelu=True, out_f32=True)
+    _close(out, ref, 2e-3, 2e-3, f"conv C={C} N={N} k={taps} s={stride}")
+
+
+# ---- layernorm ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [128, 384, 768])
+def test_layernorm(cuda, d):
+    rows, period, keep = 1000, 250, 199
+    x = _rand((rows, d), 12, 2.0).to(cuda) + 0.5
+    g = (1 + 0.1 * _rand((d,), 13)).to(cuda)
+    b = (0.1 * _rand((d,), 14)).to(cuda)
+    ref = F.layer_norm(x, (d,), g, b, 1e-5)
+    ob = torch.empty((rows, d), dtype=torch.bfloat16, device=cuda)
+    of = torch.empty((rows, d), dtype=torch.float32, device=cuda)
+    mix = torch.zeros((rows // period, keep, d), device=cuda)
+    ops.layernorm(x, g, b, out_bf16=ob, out_f32=of, mix=mix, period=period, n_keep=keep, w_in=0.25, w_out=0.0, mix_init=True)
+    ops.layernorm(x, g, b, mix=mix, period=period, n_keep=keep, w_in=0.0, w_out=0.5)
+    _close(of, ref, 1e-5, 1e-5, "layernorm fp32")
+    _close(ob, ref, 8e-3, 8e-3, "layernorm bf16")
+    want = 0.25 * x.view(-1, period, d)[:, :keep] + 0.5 * ref.view(-1, period, d)[:, :keep]
+    _close(mix, want, 1e-5, 1e-5, "layer mix")
+
+
+def test_cast_bf16(cuda):
+    x = _rand((77, 256), 15).to(cuda)
+    dst = torch.empty((77, 256), dtype=torch.bfloat16, device=cuda)
+    ops.cast_bf16(x, dst)
+    assert torch.equal(dst, x.to(torch.bfloat16))
+
+
+# ---- attention -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,H,B,nq", [(199, 2, 3, 199), (1500, 2, 2, 1500), (1500, 12, 1, 199), (64, 1, 1, 64), (65, 3, 2, 65)])
+def test_attention(cuda, T, H, B, nq):
+    d = H * 64
+    qkv = _rand((B * T, 3 * d), 16).to(torch.bfloat16)
+    qkv[:, :d] *= 0.35
+    out = ops.attention(qkv.to(cuda), B, T, H, n_query=nq)
+    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = (torch.softmax(q @ k.transpose(-1, -2), -1) @ v).permute(0, 2, 1, 3).reshape(B, T, d)
+    got = out.view(B, T, d)[:, :nq]
+    _close(got, ref[:, :nq], 2e-2, 2e-2, f"attention T={T}")
+
+
+def test_attention_wavlm_bias(cuda):
+    T, H, B = 199, 2, 2
+    d = H * 64
+    qkv = _rand((B * T, 3 * d), 17).to(torch.bfloat16)
+    qkv[:, :d] *= 0.35
+    gate = (1.0 + 0.3 * _rand((B, H, T), 18)).contiguous()
+    pos = _rand((H, T, T), 19).contiguous()
+    out = ops.attention(qkv.to(cuda), B, T, H, gate=gate.to(cuda), pos_bias=pos.to(cuda))
+    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) + gate[..., None] * pos[None]
+    ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * T, d)
+    _close(out, ref, 2e-2, 2e-2, "attention + gated bias")
+
+
+# ---- LSTM + heads -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H,dirs", [(128, 2), (64, 1)])
+def test_lstm_layer(cuda, H, dirs):
+    S, N, D = 9, 21, 96
+    sd = {}
+    synth._lstm(sd, "lstm_shared.", D, synth.LSTMDims(H, 1, dirs == 2), 3)
+    x = _rand((S, N, D), 20)
+    ref = O.lstm_seq_first(sd, x)
+    pres, whh = [], []
+    for suffix in ("", "_reverse")[:dirs]:
+        w_ih, w_hh = sd[f"lstm_shared.weight_ih_l0{suffix}"], sd[f"lstm_shared.weight_hh_l0{suffix}"]
+        b = sd[f"lstm_shared.bias_ih_l0{suffix}"] + sd[f"lstm_shared.bias_hh_l0{suffix}"]
+        pres.append(x @ w_ih.T + b)
+        whh.append(w_hh.T.contiguous())
+    pre = torch.cat(pres, dim=-1).contiguous().to(cuda)
+    out = ops.lstm_layer(pre, torch.stack(whh).contiguous().to(cuda), H)
+    _close(out, ref, 1e-4, 1e-5, "lstm layer")
+
+
+def test_heads(cuda):
+    S, N, Fd, C, keep = 5, 30, 256, 4, 19
+    feat = _rand((S, N, Fd), 21).to(cuda)
+    w = _rand((C, Fd), 22, 0.1).to(cuda)
+    b = _rand((C,), 23).to(cuda)
+    logits = torch.full((7 + S * keep, C), float("nan"), device=cuda)
+    ops.heads(feat, w, b, logits, 7, keep, keep)
+    ref = (feat[:, :keep] @ w.T + b).reshape(-1, C)
+    _close(logits[7:], ref, 1e-5, 1e-5, "heads")
+    assert torch.isnan(logits[:7]).all()
+
+
+# ---- log-mel -----------------------------------------------------------------------------------------------
+def _logmel_close(got, ref, what):
+    # |a-b| <= 1e-4 * max(1, |b|)
+    err = (got.cpu() - ref).abs()
+    bound = 1e-4 * torch.clamp(ref.abs(), min=1.0)
+    assert (err <= bound).all(), f"{what}: max err {err.max():.3g}, {(err > bound).sum()} elements out"
+
+
+def test_mel_filters_match_oracle(cuda):
+    assert np.array_equal(ops.mel_filters(), O.whisper_mel_filters().astype(np.float32))
+
+
+def test_logmel_windows(cuda):
+    n = 63680 * 3 + 64000
+    pcm = torch.from_numpy(synth.synth_audio(n, 5))
+    f32, tm = ops.logmel(pcm.to(cuda), 4, 64000, 63680, out_f32=True, out_tm=True)
+    for i in range(4):
+        ref = O.whisper_logmel(pcm[i * 63680: i * 63680 + 64000])
+        _logmel_close(f32[i], ref, f"window {i}")
+        assert torch.equal(tm[i, 1:3001].float().cpu(), f32[i].T.to(torch.bfloat16).float().cpu())
+        assert (tm[i, 0] == 0).all() and (tm[i, 3001] == 0).all()
+
+
+@pytest.mark.parametrize("L", [400, 1000, 33280, 63999])
+def test_logmel_tail_and_silence(cuda, L):
+    pcm = torch.from_numpy(synth.synth_audio(L, 6))
+    f32, _ = ops.logmel(pcm.to(cuda), 1, L, 63680)
+    _logmel_close(f32[0], O.whisper_logmel(pcm), f"tail L={L}")
+    z = torch.zeros(64000)
+    f32, _ = ops.logmel(z.to(cuda), 1, 64000, 63680)
+    _logmel_close(f32[0], O.whisper_logmel(z), "all-zero window")
+
+
+# ---- stitch + decode ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("F_,sf,nw,tail", [(199, 199, 5, 103), (199, 100, 7, 0), (99, 10, 12, 37), (399, 40, 3, 399)])
+def test_stitch(cuda, F_, sf, nw, tail):
+    C = 4
+    wins = [_rand((F_, C), 30 + i) for i in range(nw)]
+    offs = [i * sf for i in range(nw)]
+    if tail:
+        wins.append(_rand((tail, C), 99))
+        offs.append(nw * sf)
+    n_frames = max(o + w.shape[0] for o, w in zip(offs, wins))
+    ref = O.stitch_mean(wins, offs, n_frames)
+    got = ops.stitch(torch.cat(wins).to(cuda), nw, F_, sf, tail, n_frames)
+    if sf == F_:
+        assert torch.equal(got.cpu(), ref)  # concatenation is exact
+    else:
+        _close(got, ref, 1e-6, 1e-6, "stitch")
+
+
+@pytest.mark.parametrize("n,C,p", [(1, 4, 1.0), (5, 4, 0.5), (1024, 4, 0.5), (1025, 4, 0.3), (100_000, 4, 0.5), (4097, 3, 0.9),
+                                   (3000, 7, 0.1), (2048, 4, 0.0), (2048, 4, 1.0)])
+def test_decode_intervals_bit_exact(cuda, n, C, p):
+    rng = np.random.default_rng(n + C)
+    # blocky logits so that runs of every length occur
+    base = rng.standard_normal((n // 7 + 1, C)).repeat(7, axis=0)[:n] + 0.3 * rng.standard_normal((n, C))
+    logits = torch.from_numpy((base + (2 * p - 1) * 3).astype(np.float32))
+    thr = [0.5, 0.3, 0.7, 0.5, 0.45, 0.55, 0.6][:C]
+    mask_ref = O.apply_thresholds(logits, thr)
+    mask = ops.threshold_mask(logits.to(cuda), thr)
+    assert torch.equal(mask.cpu(), mask_ref)
+    table = ops.decode_intervals(logits.to(cuda), thr).cpu().numpy()
+    ref = O.interval_table(mask_ref.numpy(), C)
+    assert table.shape[0] == ref.shape[0]
+    assert np.array_equal(table[:, 1:], ref)
+    assert (table[:, 0] == 0).all()
+
+
+def test_decode_multi_file_and_overflow(cuda):
+    rng = np.random.default_rng(1)
+    lens = [1500, 0, 1, 1024, 5000]
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    logits = torch.from_numpy(rng.standard_normal((int(offs[-1]), 4)).astype(np.float32))
+    thr = [0.5] * 4
+    table = ops.decode_intervals(logits.to(cuda), thr, file_offsets=offs, capacity=8).cpu().numpy()
+    rows = []
+    for f, (a, b) in enumerate(zip(offs[:-1], offs[1:])):
+        t = O.interval_table(O.apply_thresholds(logits[a:b], thr).numpy(), 4)
+        rows.append(np.concatenate([np.full((t.shape[0], 1), f), t], axis=1))
+    assert np.array_equal(table, np.concatenate(rows))
+
+
+def test_decode_logit_cut_mode(cuda):
+    from segma_b200.thresholds import logit_cut
+
+    thr = [0.5, 0.3, 0.7, 0.9]
+    cuts = [logit_cut(t) for t in thr]
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn((50_000, 4), generator=g) * 2
+    # plant values straddling the cut by one ulp
+    for c, cut in enumerate(cuts):
+        v = torch.tensor(cut)
+        logits[c * 10 + 0, c] = v
+        logits[c * 10 + 1, c] = torch.nextafter(v, torch.tensor(float("inf")))
+        logits[c * 10 + 2, c] = torch.nextafter(v, torch.tensor(float("-inf")))
+    ref = O.apply_thresholds(logits, thr)
+    got = ops.threshold_mask(logits.to(cuda), cuts, mode=ops.DECODE_LOGIT)
+    assert torch.equal(got.cpu(), ref)

@@ -1,0 +1,76 @@
+"""Multi-GPU sharding of the path: one process per GPU, files partitioned statically, no collective on the
+data path, one exchange step at the end -- an all-gather of the int32 interval tables.
+
+The reference is single-process, single-device (inference.py:442-458); this module is new work.  The
+atomic work item is a file (the LSTM couples the windows of a forward call, so a file's batches stay on
+one rank); files are assigned longest-processing-time-first so ranks finish together.
+"""
+from __future__ import annotations
+
+import heapq
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def assign_files(sizes: list[int], world_size: int) -> list[list[int]]:
+    """Longest-processing-time-first assignment of file indices to ranks; deterministic on every rank.
+    Each rank's list is returned in ascending file order."""
+    heap = [(0, r) for r in range(world_size)]
+    heapq.heapify(heap)
+    out: list[list[int]] = [[] for _ in range(world_size)]
+    for idx in sorted(range(len(sizes)), key=lambda i: (-sizes[i], i)):
+        load, r = heapq.heappop(heap)
+        out[r].append(idx)
+        heapq.heappush(heap, (load + max(int(sizes[idx]), 1), r))
+    return [sorted(v) for v in out]
+
+
+def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
+    """Initialise torch.distributed from RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun contract).
+    Returns (rank, world_size, local_rank); a single process needs no initialisation."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def all_gather_tables(table: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather variable-length int32 ``(n_i, 4)`` interval tables: one count exchange, then one padded
+    ``all_gather_into_tensor``; rows come back ordered by rank, then in each rank's own order.
+    ``table[:, 0]`` must already hold *global* file indices."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return table
+    world = dist.get_world_size(group)
+    dev = table.device
+    n = torch.tensor([table.shape[0]], dtype=torch.int64, device=dev)
+    counts = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, n, group=group)
+    cmax = int(counts.max().item())
+    padded = torch.zeros((max(cmax, 1), 4), dtype=torch.int32, device=dev)
+    padded[: table.shape[0]] = table
+    gathered = torch.empty((world * max(cmax, 1), 4), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(gathered, padded, group=group)
+    parts = [gathered[r * max(cmax, 1): r * max(cmax, 1) + int(counts[r])] for r in range(world)]
+    return torch.cat(parts, dim=0)
+
+
+def gather_file_tables(local_table: torch.Tensor, group=None) -> torch.Tensor:
+    """``all_gather_tables`` followed by a stable sort on the global file index, so every rank ends up
+    with the same table ordered by file, then label, then time."""
+    full = all_gather_tables(local_table, group)
+    if full.shape[0] == 0:
+        return full
+    order = torch.sort(full[:, 0].to(torch.int64), stable=True).indices
+    return full[order]

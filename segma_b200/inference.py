@@ -1,0 +1,276 @@
+"""Sliding-window inference driver with the reference's prediction API.
+
+Same entry points and signatures as /root/reference/src/segma/inference.py -- ``apply_model_on_audio``
+(119-211), ``apply_thresholds`` (214-234), ``create_intervals`` (237-263), ``write_intervals`` (266-283),
+``infer_file`` (286-357), ``get_list_of_files_to_process`` (360-395), ``run_inference_on_audios`` (398-459)
+and the ``python -m`` CLI (462-501) -- but the whole path from PCM to the interval table runs in
+libsegma_b200 on the GPU: the file is staged to HBM once, windows are cut by the front-end kernel's
+addressing (no ``unfold`` copy), frame logits are written straight onto the file timeline, and thresholds
++ run-length decoding happen on the device; only the (small) interval table crosses back.
+
+Extensions over the reference (all default to its behaviour): ``window_step`` for overlapping windows
+(logit-domain mean), in-memory audio instead of a path, and batched multi-file decoding.
+"""
+from __future__ import annotations
+
+import argparse
+from logging import Logger
+from pathlib import Path
+from typing import Literal
+
+import numpy as np
+import torch
+import yaml
+
+from . import ops
+from .annotation import rttm_line
+from .config import Config, load_config
+from .encoders import MultiLabelEncoder
+from .geometry import FRAME_SAMPLES, INFERENCE_SETTINGS, Chunkyfier, ConvolutionSettings, conv_frames, plan_windows
+from .io import get_audio_info, get_samples_in_range
+from .models import BaseSegmentationModel, Models
+from .thresholds import logit_cut
+
+__all__ = [
+    "Chunkyfier", "prepare_audio", "apply_model_on_audio", "apply_thresholds", "create_intervals",
+    "decode_logits", "write_intervals", "infer_file", "get_list_of_files_to_process", "run_inference_on_audios",
+]
+
+
+def _cuda_device(device) -> torch.device:
+    dev = torch.device("cuda" if device in ("gpu", None) else device)
+    if dev.type != "cuda":
+        raise ops.SegmaNativeError(f"device '{device}': segma_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+    return dev
+
+
+def prepare_audio(audio_path, model: BaseSegmentationModel, device, start_f: int, end_f: int | None = None):
+    """Samples ``[start_f, end_f)`` of the file as a 1-D fp32 device tensor (inference.py:92-116).
+    The Whisper hook is *not* applied here: the reference applies it to the whole span, which cannot
+    work (SURVEY.md finding 5); the log-mel is computed per window by the front-end kernel instead."""
+    num = end_f - start_f if end_f else -1
+    t = get_samples_in_range(audio_path, start_f=start_f, duration_f=num)
+    if t.shape[0] != 1:
+        raise ValueError(f"only mono audio is supported, got {t.shape[0]} channels")
+    host = t.reshape(-1)
+    if torch.cuda.is_available():
+        host = host.pin_memory()
+    return host.to(_cuda_device(device), non_blocking=True)
+
+
+def apply_model_on_audio(
+    audio_path,
+    model: BaseSegmentationModel,
+    conv_settings: ConvolutionSettings,
+    device: Literal["cuda", "gpu"] = "cuda",
+    batch_size: int = 128,
+    chunk_duration_s: float = 4.0,
+    sample_rate: int = 16_000,
+    window_step: int | None = None,
+) -> torch.Tensor:
+    """Apply model on audio, return a ``(n_frames, n_classes)`` fp32 tensor of raw logits on the device.
+
+    Windows and batches are exactly the reference's (inference.py:129-206): ``batch_size`` consecutive
+    windows per forward call, one remainder batch, then the tail alone -- the LSTM of the Whisper-family
+    models couples the windows of a call, so batch boundaries are part of the result (SURVEY.md finding 6).
+    ``audio_path`` may also be a 1-D float32 array / tensor (host or device).
+    """
+    dev = _cuda_device(device)
+    chunk_f = int(chunk_duration_s * sample_rate)
+    chunky = Chunkyfier(batch_size, chunk_f, conv_settings)  # same derived quantities as the reference
+    step = chunky.step if window_step is None else int(window_step)
+    if isinstance(audio_path, torch.Tensor) and audio_path.is_cuda:
+        pcm = audio_path.reshape(-1).to(torch.float32).contiguous()
+    else:
+        pcm = prepare_audio(audio_path, model, dev, 0, None)
+    n_samples = pcm.numel()
+    engine = model._require_engine()
+    frames_per_window = model.n_keep if model.family == "whisper" else conv_frames(chunk_f)
+    plan = plan_windows(n_samples, chunk_f, batch_size, step, frames_per_window)
+    n_labels = model.label_encoder.n_labels
+    sf = plan.step_frames
+    tiled = sf == frames_per_window  # windows tile the frame grid: stitching is concatenation
+    if plan.n_frames == 0:
+        return torch.zeros((0, n_labels), dtype=torch.float32, device=dev)
+    if tiled:
+        logits = torch.empty((plan.n_frames, n_labels), dtype=torch.float32, device=dev)
+    else:
+        n_full = sum(b.n_windows for b in plan.batches if not b.is_tail)
+        tail = next((b for b in plan.batches if b.is_tail), None)
+        win_logits = torch.empty((n_full * frames_per_window + (tail.frames_per_window if tail else 0), n_labels),
+                                 dtype=torch.float32, device=dev)
+    for b in plan.batches:
+        if tiled:
+            engine.forward_pcm(pcm, b.start_sample, b.n_windows, b.win_len, step, logits, b.first_window * sf, sf,
+                               b.frames_per_window)
+        else:
+            engine.forward_pcm(pcm, b.start_sample, b.n_windows, b.win_len, step, win_logits,
+                               b.first_window * frames_per_window, frames_per_window, b.frames_per_window)
+    if tiled:
+        return logits
+    n_full = sum(b.n_windows for b in plan.batches if not b.is_tail)
+    tail_frames = next((b.frames_per_window for b in plan.batches if b.is_tail), 0)
+    return ops.stitch(win_logits, n_full, frames_per_window, sf, tail_frames, plan.n_frames)
+
+
+def _lower_bounds(thresholds: dict, n_labels: int) -> list[float]:
+    assert n_labels == len(thresholds)
+    return [float(lab["lower_bound"]) for lab in thresholds.values()]
+
+
+def apply_thresholds(feature_tensor: torch.Tensor, thresholds: dict[str, dict[str, float]], device="cuda") -> torch.Tensor:
+    """``sigmoid(logits) > lower_bound`` per label (dict order = label order), as a bool tensor.
+    Evaluated in the logit domain against cuts derived from torch's fp32 sigmoid, so the result is
+    bit-identical to the reference's (inference.py:214-234)."""
+    bounds = _lower_bounds(thresholds, feature_tensor.shape[-1])
+    x = feature_tensor.to(_cuda_device(device), torch.float32).contiguous()
+    return ops.threshold_mask(x, [logit_cut(t) for t in bounds], mode=ops.DECODE_LOGIT)
+
+
+def _table_to_intervals(table: np.ndarray, conv_settings: ConvolutionSettings, labels) -> list[tuple[int, int, str]]:
+    if table.shape[0] == 0:
+        return []
+    s_frame = table[:, 2].astype(np.int64) // FRAME_SAMPLES
+    e_frame = table[:, 3].astype(np.int64) // FRAME_SAMPLES  # one past the last active frame
+    starts = np.maximum(0, np.array([conv_settings.rf_start_i(int(s)) for s in s_frame], dtype=np.int64)) \
+        if conv_settings != INFERENCE_SETTINGS else np.maximum(0, s_frame * FRAME_SAMPLES)
+    ends = np.array([conv_settings.rf_end_i(int(e) - 1) + 1 for e in e_frame], dtype=np.int64) \
+        if conv_settings != INFERENCE_SETTINGS else e_frame * FRAME_SAMPLES
+    return [(int(s), int(e), labels[int(c)]) for s, e, c in zip(starts, ends, table[:, 1])]
+
+
+def create_intervals(thresholded_features: torch.Tensor, conv_settings: ConvolutionSettings,
+                     label_encoder: MultiLabelEncoder) -> list[tuple[int, int, str]]:
+    """Per-label maximal runs of True -> ``(start_sample, end_sample, label)``, label-major
+    (inference.py:237-263), extracted by the run-length kernel instead of NumPy + a Python loop."""
+    m = torch.as_tensor(thresholded_features)
+    if m.numel() == 0:
+        return []
+    x = m.to("cuda", torch.float32).contiguous()
+    table = ops.decode_intervals(x, [0.5] * x.shape[-1], mode=ops.DECODE_LOGIT).cpu().numpy()
+    return _table_to_intervals(table, conv_settings, label_encoder.base_labels)
+
+
+def decode_logits(logits: torch.Tensor, thresholds: dict, label_encoder: MultiLabelEncoder,
+                  conv_settings: ConvolutionSettings = INFERENCE_SETTINGS, file_offsets=None):
+    """Fused ``apply_thresholds`` + ``create_intervals`` on device logits (one pass, no boolean tensor).
+    With ``file_offsets`` the frames of several files are decoded at once; returns one list per file."""
+    bounds = _lower_bounds(thresholds, logits.shape[-1])
+    if logits.shape[0] == 0:
+        return [] if file_offsets is None else [[] for _ in range(len(file_offsets) - 1)]
+    table = ops.decode_intervals(logits.contiguous(), [logit_cut(t) for t in bounds], file_offsets=file_offsets,
+                                 mode=ops.DECODE_LOGIT).cpu().numpy()
+    labels = label_encoder.base_labels
+    if file_offsets is None:
+        return _table_to_intervals(table, conv_settings, labels)
+    return [_table_to_intervals(table[table[:, 0] == f], conv_settings, labels) for f in range(len(file_offsets) - 1)]
+
+
+def write_intervals(intervals: list[tuple[int, int, str]], audio_path: Path, output_p: Path) -> None:
+    """``output_p/raw_rttm/<stem>.rttm`` in the reference's text format (inference.py:266-283)."""
+    rttm_out = Path(output_p) / "raw_rttm"
+    rttm_out.mkdir(exist_ok=True, parents=True)
+    uri = Path(audio_path).stem
+    with (rttm_out / f"{uri}.rttm").open("w") as f:
+        f.write("".join(rttm_line(uri, s, e, lab) + "\n" for s, e, lab in intervals))
+
+
+def default_thresholds(label_encoder: MultiLabelEncoder) -> dict:
+    return {label: {"lower_bound": 0.5, "upper_bound": 1.0} for label in label_encoder._labels}
+
+
+def infer_file(audio_path, model: BaseSegmentationModel, output_p: Path, config: Config, batch_size: int,
+               device="cuda", thresholds: None | dict = None, save_logits: bool = False, window_step: int | None = None):
+    """Window, forward, threshold, decode and write one file (inference.py:286-357). Returns the intervals."""
+    if thresholds is None:
+        thresholds = default_thresholds(model.label_encoder)
+    logits_t = apply_model_on_audio(audio_path=audio_path, model=model, batch_size=batch_size,
+                                    chunk_duration_s=config.audio.chunk_duration_s, conv_settings=INFERENCE_SETTINGS,
+                                    device=device, window_step=window_step)
+    stem = Path(audio_path).stem if not isinstance(audio_path, (np.ndarray, torch.Tensor)) else "audio"
+    if save_logits:
+        logits_out_p = Path(output_p) / "logits"
+        logits_out_p.mkdir(parents=True, exist_ok=True)
+        host = logits_t.cpu()
+        torch.save({model.label_encoder.inv_transform(i): host[:, i].clone() for i in range(model.label_encoder.n_labels)},
+                   f"{logits_out_p}/{stem}-logits_dict_t.pt")
+    intervals = decode_logits(logits_t, thresholds, model.label_encoder, INFERENCE_SETTINGS)
+    if output_p is not None:
+        write_intervals(intervals=intervals, audio_path=Path(stem), output_p=output_p)
+    return intervals
+
+
+def get_list_of_files_to_process(wavs: Path, recursive: bool = False, uris: Path | None = None) -> tuple[list[Path], int]:
+    """Sorted list of ``.wav`` files under ``wavs`` (or those named in ``uris``) (inference.py:360-395)."""
+    wavs = Path(wavs)
+    if not wavs.exists():
+        raise FileNotFoundError(f"Path `{wavs=}` does not exists")
+    if uris:
+        with Path(uris).open("r") as f:
+            files = [(wavs / line.strip()).with_suffix(".wav") for line in f.readlines()]
+    elif recursive:
+        import warnings
+
+        warnings.warn("Search for .wav files is done recursively, might be slow.")
+        files = list(wavs.rglob("*.wav"))
+    else:
+        files = list(wavs.glob("*.wav"))
+    return sorted(files), len(files)
+
+
+def run_inference_on_audios(config, uris, wavs, checkpoint, output, thresholds, batch_size: int,
+                            device: Literal["gpu", "cuda"] = "cuda", recursive: bool = False, save_logits: bool = False,
+                            logger: Logger | None = None, shard: tuple[int, int] | None = None) -> list[Path]:
+    """File list -> per-file RTTM (inference.py:398-459).  ``shard=(rank, world_size)`` restricts the loop
+    to this rank's files (see ``segma_b200.distributed``); the default processes every file."""
+    wavs, checkpoint, output = Path(wavs), Path(checkpoint), Path(output)
+    device = "cuda" if device == "gpu" else device
+    if not checkpoint.exists():
+        raise ValueError(f"Path `{checkpoint=}` does not exists")
+    if thresholds:
+        if not Path(thresholds).exists():
+            raise ValueError("Path to a valid threshold dict does not exist.")
+        with Path(thresholds).open("r") as f:
+            thresholds = yaml.safe_load(f)
+    files, n_files = get_list_of_files_to_process(wavs, recursive, uris)
+    cfg: Config = load_config(config) if not isinstance(config, Config) else config
+    if "hydra" not in cfg.model.name:
+        raise ValueError("only MultiLabelEncoder is supported")
+    l_encoder = MultiLabelEncoder(labels=cfg.data.classes)
+    model = Models[cfg.model.name].load_from_checkpoint(checkpoint_path=checkpoint, label_encoder=l_encoder, config=cfg,
+                                                        train=False)
+    model.eval()
+    model.to(torch.device(device))
+    mine = files
+    if shard is not None:
+        from .distributed import assign_files
+
+        sizes = [get_audio_info(p).n_samples for p in files]
+        mine = [files[i] for i in assign_files(sizes, shard[1])[shard[0]]]
+    for i, audio_path in enumerate(mine, 1):
+        s = f"({i:>{len(str(n_files))}}/{n_files}) - running inference for file: '{audio_path.stem}'"
+        if logger:
+            logger.info(s)
+        else:
+            print(f"[log] - {s}", flush=True)
+        infer_file(audio_path=audio_path, model=model, output_p=output, config=cfg, batch_size=batch_size,
+                   device=device, thresholds=thresholds, save_logits=save_logits)
+    return mine
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser(description="segma_b200 sliding-window inference (same flags as segma.inference)")
+    parser.add_argument("--config", type=str, required=True)
+    parser.add_argument("--uris")
+    parser.add_argument("--wavs", required=True, default="data/debug/wav")
+    parser.add_argument("--checkpoint", default="models/last/best.ckpt")
+    parser.add_argument("--output", required=True)
+    parser.add_argument("--thresholds")
+    parser.add_argument("--batch_size", default=128, type=int)
+    parser.add_argument("--device", default="cuda", choices=["gpu", "cuda"])
+    args = parser.parse_args(argv)
+    run_inference_on_audios(**vars(args))
+
+
+if __name__ == "__main__":
+    main()

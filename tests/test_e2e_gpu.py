@@ -1,0 +1,118 @@
+"""End-to-end parity of the Whisper-family path on the GPU against the oracle (the reference's fp32
+arithmetic restated in oracle/segma_oracle.py and pinned against the reference itself).
+
+Stated tolerances (north_star): interval decoding bit-exact on identical logits; logits within a bf16
+tolerance of the fp32 oracle with >= 99.9 % frame-label agreement."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import segma_oracle as O
+from segma_b200 import synth
+from segma_b200.config import make_config
+from segma_b200.encoders import MultiLabelEncoder
+from segma_b200.inference import apply_model_on_audio, apply_thresholds, create_intervals, decode_logits, default_thresholds
+from segma_b200.geometry import INFERENCE_SETTINGS
+from segma_b200.models import Models
+
+pytestmark = pytest.mark.gpu
+LABELS = synth.DEFAULT_LABELS
+
+# bf16 GEMM operands with fp32 accumulation/residual/LayerNorm/LSTM: absolute logit tolerance, scaled
+# by the logit spread of the run
+LOGIT_RTOL_OF_STD = 0.05
+MIN_LABEL_AGREEMENT = 0.999
+
+
+def _report(got, ref):
+    err = (got - ref).abs()
+    std = ref.std().item()
+    agree = ((got > 0) == (ref > 0)).float().mean().item()
+    return err.max().item(), err.mean().item(), std, agree
+
+
+def _check_logits(got, ref, what):
+    mx, mean, std, agree = _report(got, ref)
+    print(f"{what}: max|err| {mx:.4g} mean|err| {mean:.4g} logit std {std:.4g} label agreement {agree:.5f}")
+    assert mx <= LOGIT_RTOL_OF_STD * max(std, 1.0), f"{what}: max logit error {mx} vs std {std}"
+    assert agree >= MIN_LABEL_AGREEMENT, f"{what}: frame-label agreement {agree}"
+
+
+@pytest.mark.parametrize("kind,dims", [("surgical_hydra", synth.WHISPER_TEST), ("hydra_whisper", synth.WHISPER_TEST)])
+def test_whisper_file_level(cuda, kind, dims):
+    sd = (synth.surgical_hydra_state_dict if kind == "surgical_hydra" else synth.hydra_whisper_state_dict)(dims, seed=3)
+    cfg = make_config(kind)
+    le = MultiLabelEncoder(list(LABELS))
+    model = Models[kind].from_state_dict(sd, le, cfg)
+    n = 63680 * 3 + 20000  # 3 full windows (batches of 2 + 1) and a 20000-sample tail
+    pcm = synth.synth_audio(n, 11)
+    got = apply_model_on_audio(pcm, model, INFERENCE_SETTINGS, "cuda", batch_size=2).cpu()
+    fwd = (lambda f: O.surgical_hydra_forward(sd, f, LABELS)) if kind == "surgical_hydra" else (lambda f: O.hydra_whisper_forward(sd, f, LABELS))
+    ref = O.apply_model_on_audio(torch.from_numpy(pcm), fwd, 4, batch_size=2, whisper=True)
+    assert got.shape == ref.shape == ((n - 400) // 320 + 1, 4)
+    _check_logits(got, ref, f"{kind} file-level")
+    # decode is bit-exact on identical logits
+    thr = default_thresholds(le)
+    mask = apply_thresholds(got.cuda(), thr)
+    assert torch.equal(mask.cpu(), O.apply_thresholds(got, [0.5] * 4))
+    iv = create_intervals(mask, INFERENCE_SETTINGS, le)
+    assert iv == O.create_intervals(mask.cpu().numpy(), LABELS)
+    assert decode_logits(got.cuda(), thr, le) == iv
+
+
+def test_whisper_forward_dropin(cuda):
+    dims = synth.WHISPER_TEST
+    sd = synth.surgical_hydra_state_dict(dims, seed=4)
+    le = MultiLabelEncoder(list(LABELS))
+    model = Models["surgical_hydra"].from_state_dict(sd, le, make_config("surgical_hydra"))
+    wav = [torch.from_numpy(synth.synth_audio(64000, s)) for s in range(3)]
+    feats = torch.cat([model.audio_preparation_hook(w) for w in wav])
+    assert feats.shape == (3, 80, 3000)
+    ref_feats = torch.stack([O.whisper_logmel(w) for w in wav])
+    assert (feats.cpu() - ref_feats).abs().max() <= 1e-4
+    out = model(feats)
+    assert out.shape == (3, 199, 1, 4)
+    _check_logits(out.cpu(), O.surgical_hydra_forward(sd, ref_feats, LABELS), "forward drop-in")
+
+
+def test_whisper_small_dims_few_windows(cuda):
+    """BASELINE config 2 model (Whisper-small dims) on a short file."""
+    dims = synth.WHISPER_SMALL
+    sd = synth.surgical_hydra_state_dict(dims, seed=0)
+    le = MultiLabelEncoder(list(LABELS))
+    model = Models["surgical_hydra"].from_state_dict(sd, le, make_config("surgical_hydra"))
+    n = 63680 * 4 + 320
+    pcm = synth.synth_audio(n, 1)
+    got = apply_model_on_audio(pcm, model, INFERENCE_SETTINGS, "cuda", batch_size=128).cpu()
+    ref = O.apply_model_on_audio(torch.from_numpy(pcm), lambda f: O.surgical_hydra_forward(sd, f, LABELS), 4,
+                                 batch_size=128, whisper=True)
+    _check_logits(got, ref, "whisper-small dims")
+
+
+def test_overlapping_windows_stitch(cuda):
+    dims = synth.WHISPER_TEST
+    sd = synth.hydra_whisper_state_dict(dims, seed=5)
+    le = MultiLabelEncoder(list(LABELS))
+    model = Models["hydra_whisper"].from_state_dict(sd, le, make_config("hydra_whisper"))
+    n = 64000 + 32000 * 3 + 5000
+    pcm = synth.synth_audio(n, 12)
+    step = 32000  # 50 % overlap, multiple of 320
+    got = apply_model_on_audio(pcm, model, INFERENCE_SETTINGS, "cuda", batch_size=3, window_step=step).cpu()
+    # composed oracle: same windows/batches, logit-domain mean
+    n_fit = (n - 64000) // step + 1
+    wins, offs = [], []
+    t = torch.from_numpy(pcm)
+    for b0 in range(0, n_fit, 3):
+        idx = list(range(b0, min(b0 + 3, n_fit)))
+        feats = torch.stack([O.whisper_logmel(t[i * step: i * step + 64000]) for i in idx])
+        out = O.hydra_whisper_forward(sd, feats, LABELS).reshape(len(idx), 199, 4)
+        wins += list(out)
+        offs += [i * step // 320 for i in idx]
+    tail = t[n_fit * step:]
+    ft = (tail.numel() - 400) // 320 + 1
+    wins.append(O.hydra_whisper_forward(sd, O.whisper_logmel(tail)[None], LABELS).reshape(199, 4)[:ft])
+    offs.append(n_fit * step // 320)
+    n_frames = max(o + w.shape[0] for o, w in zip(offs, wins))
+    ref = O.stitch_mean(wins, offs, n_frames)
+    assert got.shape == ref.shape
+    _check_logits(got, ref, "50% overlap")

@@ -48,7 +48,7 @@ SEGMA_API int segma_sm_count(void);
  * centre/reflect), power, 80 slaney mel bins, log10, per-window max-8 clamp, (x+4)/4.
  * Samples at or beyond pcm_len read as zero (a tail window is n_windows=1 with its own win_len).
  *   out_f32  [dev] (n_windows, 80, 3000) fp32, or NULL
- *   out_tm   [dev] (n_windows, 3002, 80) bf16 time-major with one zero row before and after each
+ *   out_tm   [dev] (n_windows, 3002, 80) fp16 time-major with one zero row before and after each
  *            window (the layout the conv-stem implicit GEMM reads), or NULL
  *   scratch  [dev] segma_logmel_scratch_bytes(n_windows, win_len) bytes
  */
@@ -66,7 +66,7 @@ SEGMA_API int segma_logmel_get_filters(float* mel_201x80);
  * and torchaudio's wav2vec2 Encoder (site-packages/torchaudio/models/wav2vec2/components.py).
  */
 
-/* C = epilogue(A * W^T): A bf16, W bf16 (n, k) row-major, fp32 accumulation on tcgen05 tensor cores (TMEM
+/* C = epilogue(A * W^T): A fp16, W fp16 (n, k) row-major, fp32 accumulation on tcgen05 tensor cores (TMEM
  * accumulators, TMA-fed 128B-swizzled shared-memory stages).
  * Plain GEMM (conv_taps <= 1): A is (batch, rows_per_batch, k) with element strides (a_batch_stride,
  * a_row_stride, 1).
@@ -77,12 +77,12 @@ SEGMA_API int segma_logmel_get_filters(float* mel_201x80);
  * viewed s rows at a time.
  * epilogue: v = acc + bias[n]; if (flags & GELU) v = gelu_erf(v);
  *           if (add_src) v += add_src[((b*rows_per_batch + r) % add_period) * n + col]   (fp32)
- *           out[(b*out_batch_rows + out_row_offset + r) * ldo + col] = v  (bf16, or fp32 with OUT_F32)
+ *           out[(b*out_batch_rows + out_row_offset + r) * ldo + col] = v  (fp16, or fp32 with OUT_F32)
  */
 #define SEGMA_GEMM_GELU 1
 #define SEGMA_GEMM_OUT_F32 2
 typedef struct {
-  const void* a;          /* [dev] bf16, 16-byte aligned */
+  const void* a;          /* [dev] fp16, 16-byte aligned */
   int64_t a_batch_stride; /* elements, multiple of 8 */
   int64_t a_row_stride;   /* elements, multiple of 8 */
   int batch;
@@ -91,7 +91,7 @@ typedef struct {
   int k;                  /* total reduction length (conv: conv_taps * channels) */
   int conv_taps;          /* 0 or 1: plain GEMM */
   int conv_stride;        /* 0 or 1: unit stride */
-  const void* w;          /* [dev] bf16 (n, k) row-major */
+  const void* w;          /* [dev] fp16 (n, k) row-major */
   int n;                  /* multiple of 32 */
   const float* bias;      /* [dev] (n) or NULL */
   const float* add_src;   /* [dev] fp32 (add_period, n) or NULL; may alias out (residual update in place) */
@@ -104,29 +104,29 @@ typedef struct {
   int a_col_per_ntile;    /* grouped conv: extra A column offset per N tile (0 otherwise) */
   int force_bn;           /* 0 = auto; 128, 192 or 256 = N tile width */
 } segma_gemm_args;
-SEGMA_API int segma_gemm_bf16(const segma_gemm_args* args, void* stream);
+SEGMA_API int segma_gemm_f16(const segma_gemm_args* args, void* stream);
 
 /* y = LayerNorm(x) * gamma + beta over the last dim (eps 1e-5), x fp32 (rows, d).
- *   out_bf16 [dev] (rows, d) or NULL;  out_f32 [dev] (rows, d) fp32 or NULL (may alias x)
+ *   out_f16 [dev] (rows, d) or NULL;  out_f32 [dev] (rows, d) fp32 or NULL (may alias x)
  *   mix      [dev] fp32 (rows/period, n_keep, d) or NULL: for rows r with (r % period) < n_keep,
  *            mix += w_in * x + w_out * y   (the layer-weighted sum of
  *            src/segma/models/whisper/surgical_hydra.py:82-98 restricted to the kept frames)
  *   mix_init: 1 = overwrite instead of accumulate
  */
-SEGMA_API int segma_layernorm(const float* x, const float* gamma, const float* beta, int64_t rows, int d, void* out_bf16,
+SEGMA_API int segma_layernorm(const float* x, const float* gamma, const float* beta, int64_t rows, int d, void* out_f16,
                     float* out_f32, float* mix, int period, int n_keep, float w_in, float w_out, int mix_init,
                     void* stream);
 
-/* softmax(Q K^T + bias) V per (window, head); qkv bf16 (n_windows*T, 3*d) rows = [q | k | v],
- * q pre-scaled, head_dim 64; out bf16 (n_windows*T, d).  Optional WavLM gated relative bias:
+/* softmax(Q K^T + bias) V per (window, head); qkv fp16 (n_windows*T, 3*d) rows = [q | k | v],
+ * q pre-scaled, head_dim 64; out fp16 (n_windows*T, d).  Optional WavLM gated relative bias:
  * bias[b,h,i,j] = gate[(b*H + h)*T + i] * pos_bias[(h*T + i)*T + j] (fp32), both NULL otherwise.
  * n_query: only the first n_query rows of each window are computed (<= T).
  */
 SEGMA_API int segma_attention(const void* qkv, int n_windows, int T, int n_heads, int n_query, const float* gate,
                     const float* pos_bias, void* out, void* stream);
 
-/* fp32 -> bf16 copy of a (rows, cols) matrix with row strides. */
-SEGMA_API int segma_cast_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
+/* fp32 -> fp16 copy of a (rows, cols) matrix with row strides. */
+SEGMA_API int segma_cast_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
 
 /* ---- LSTM over the window axis + per-label heads ---------------------------------------------
  * One direction-pair of one nn.LSTM layer (src/segma/models/whisper/hydra.py:48-51,81): the
@@ -134,10 +134,10 @@ SEGMA_API int segma_cast_bf16(const float* src, int64_t lds, void* dst, int64_t 
  *   pre   [dev] fp32 (n_steps, n_rows, n_dirs*4H): x W_ih^T + b_ih + b_hh, gate order i,f,g,o,
  *         forward direction first
  *   w_hh_t[dev] fp32 (n_dirs, H, 4H): W_hh transposed
- *   out   [dev] fp32 (n_steps, n_rows, n_dirs*H); out_bf16 same shape or NULL
+ *   out   [dev] fp32 (n_steps, n_rows, n_dirs*H); out_f16 same shape or NULL
  */
 SEGMA_API int segma_lstm_layer(const float* pre, const float* w_hh_t, int n_steps, int n_rows, int hidden, int n_dirs,
-                     float* out, void* out_bf16, void* stream);
+                     float* out, void* out_f16, void* stream);
 
 /* logits[(frame_offset + s*step_frames + r) * C + c] = feat[s, r, :] . w[c, :] + b[c] for r < n_keep
  * (torch.stack of the per-label Linear(F, 1) heads, surgical_hydra.py:107-109), written straight

@@ -53,10 +53,10 @@ SIGNATURES = {
     "segma_logmel": (_i, [_vp, _i64, _i, _i, _i64, _vp, _vp, _vp, _vp]),
     "segma_logmel_set_filters": (_i, [_vp]),
     "segma_logmel_get_filters": (_i, [_vp]),
-    "segma_gemm_bf16": (_i, [C.POINTER(GemmArgs), _vp]),
+    "segma_gemm_f16": (_i, [C.POINTER(GemmArgs), _vp]),
     "segma_layernorm": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp]),
     "segma_attention": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "segma_cast_bf16": (_i, [_vp, _i64, _vp, _i64, _i64, _i, _vp]),
+    "segma_cast_f16": (_i, [_vp, _i64, _vp, _i64, _i64, _i, _vp]),
     "segma_lstm_layer": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "segma_heads": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i64, _i, _vp]),
     "segma_stitch": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i64, _vp]),

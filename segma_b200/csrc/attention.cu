@@ -1,4 +1,4 @@
-// Fused multi-head self-attention softmax(Q K^T + bias) V, head_dim 64, bf16 in / fp32 softmax / bf16 out.
+// Fused multi-head self-attention softmax(Q K^T + bias) V, head_dim 64, fp16 in / fp32 softmax / fp16 out.
 //
 // Replaces torch SDPA as dispatched by WhisperAttention (site-packages/transformers/models/whisper/
 // modeling_whisper.py:338-352; T = 1500, no mask) and torchaudio SelfAttention / WavLMSelfAttention
@@ -7,7 +7,7 @@
 //
 // Flash-style single pass: a CTA owns 64 query rows of one (window, head); K/V tiles of 64 keys stream
 // through a double-buffered cp.async ring in XOR-swizzled shared memory; scores never leave registers.
-// This version uses the warp-level mma.sync tensor path (m16n8k16 bf16); the tcgen05/TMEM pipeline is the
+// This version uses the warp-level mma.sync tensor path (m16n8k16 fp16); the tcgen05/TMEM pipeline is the
 // GEMM kernel's and is the planned upgrade for this kernel.
 #include "common.cuh"
 
@@ -18,7 +18,7 @@ constexpr int kQTile = 64;     // queries per CTA (16 per warp)
 constexpr int kKTile = 64;     // keys per pipeline stage
 constexpr int kAttnThreads = 128;
 
-// 64 x 64 bf16 tile, rows of 128 B split in 8 chunks of 16 B; chunk index XOR (row & 7)
+// 64 x 64 fp16 tile, rows of 128 B split in 8 chunks of 16 B; chunk index XOR (row & 7)
 __device__ __forceinline__ uint32_t tile_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -27,24 +27,24 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// load a (rows x 64) bf16 tile from global rows [row0, row0+64) of a matrix with leading dimension ld
-__device__ __forceinline__ void load_tile_async(unsigned char* smem_tile, const __nv_bfloat16* __restrict__ g,
+// load a (rows x 64) fp16 tile from global rows [row0, row0+64) of a matrix with leading dimension ld
+__device__ __forceinline__ void load_tile_async(unsigned char* smem_tile, const __half* __restrict__ g,
                                                 long long ld, int row0, int row_limit, int tid) {
 #pragma unroll
   for (int i = 0; i < (64 * 8) / kAttnThreads; ++i) {
     const int idx = tid + i * kAttnThreads;
     const int r = idx >> 3, c = idx & 7;
     const bool ok = (row0 + r) < row_limit;
-    const __nv_bfloat16* src = g + (long long)(ok ? row0 + r : 0) * ld + c * 8;
+    const __half* src = g + (long long)(ok ? row0 + r : 0) * ld + c * 8;
     cp_async_16(smem_tile + tile_off(r, c), src, ok);
   }
 }
 
-__global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T,
+__global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __half* __restrict__ qkv, int T,
                                                                  int n_heads, int n_query,
                                                                  const float* __restrict__ gate,
                                                                  const float* __restrict__ pos_bias,
-                                                                 __nv_bfloat16* __restrict__ out) {
+                                                                 __half* __restrict__ out) {
   __shared__ __align__(128) unsigned char s_q[kQTile * 128];
   __shared__ __align__(128) unsigned char s_k[2][kKTile * 128];
   __shared__ __align__(128) unsigned char s_v[2][kKTile * 128];
@@ -55,10 +55,10 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __nv_bflo
   const int b = blockIdx.z;
   const int d = n_heads * kHd;
   const long long ld = 3ll * d;
-  const __nv_bfloat16* base = qkv + (long long)b * T * ld;
-  const __nv_bfloat16* gq = base + h * kHd;
-  const __nv_bfloat16* gk = base + d + h * kHd;
-  const __nv_bfloat16* gv = base + 2 * d + h * kHd;
+  const __half* base = qkv + (long long)b * T * ld;
+  const __half* gq = base + h * kHd;
+  const __half* gk = base + d + h * kHd;
+  const __half* gv = base + 2 * d + h * kHd;
   const int n_kt = ceil_div(T, kKTile);
 
   load_tile_async(s_q, gq, ld, q0, T, tid);
@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __nv_bflo
         const int r = nb * 8 + (lane & 7);
         const int c = kp * 4 + (lane >> 3);
         ldmatrix_x4(kf, smem_u32(s_k[st] + tile_off(r, c)));
-        mma_bf16_16816(s_acc[nb], q_frag[kp * 2], kf[0], kf[1]);
-        mma_bf16_16816(s_acc[nb], q_frag[kp * 2 + 1], kf[2], kf[3]);
+        mma_f16_16816(s_acc[nb], q_frag[kp * 2], kf[0], kf[1]);
+        mma_f16_16816(s_acc[nb], q_frag[kp * 2 + 1], kf[2], kf[3]);
       }
     }
     // ---- bias, key mask, online softmax ----
@@ -158,8 +158,8 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __nv_bflo
       const float p3 = fast_exp2(s_acc[nb][3] - m_run[1]);
       rs[0] += p0 + p1;
       rs[1] += p2 + p3;
-      p_frag[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16x2(p0, p1);
-      p_frag[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      p_frag[nb >> 1][(nb & 1) * 2 + 0] = pack_f16x2(p0, p1);
+      p_frag[nb >> 1][(nb & 1) * 2 + 1] = pack_f16x2(p2, p3);
     }
     l_run[0] += rs[0];
     l_run[1] += rs[1];
@@ -177,8 +177,8 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __nv_bflo
         const int r = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
         const int c = np * 2 + (lane >> 4);
         ldmatrix_x4_trans(vf, smem_u32(s_v[st] + tile_off(r, c)));
-        mma_bf16_16816(o_acc[np * 2], p_frag[ks], vf[0], vf[1]);
-        mma_bf16_16816(o_acc[np * 2 + 1], p_frag[ks], vf[2], vf[3]);
+        mma_f16_16816(o_acc[np * 2], p_frag[ks], vf[0], vf[1]);
+        mma_f16_16816(o_acc[np * 2 + 1], p_frag[ks], vf[2], vf[3]);
       }
     }
   }
@@ -190,15 +190,15 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __nv_bflo
     l_run[i] += __shfl_xor_sync(0xffffffffu, l_run[i], 2);
   }
   const float inv_a = 1.0f / l_run[0], inv_b = 1.0f / l_run[1];
-  __nv_bfloat16* o_base = out + (long long)b * T * d + h * kHd + (lane & 3) * 2;
+  __half* o_base = out + (long long)b * T * d + h * kHd + (lane & 3) * 2;
 #pragma unroll
   for (int nb = 0; nb < 8; ++nb) {
     if (row_a < n_query)
       *reinterpret_cast<uint32_t*>(o_base + (long long)row_a * d + nb * 8) =
-          pack_bf16x2(o_acc[nb][0] * inv_a, o_acc[nb][1] * inv_a);
+          pack_f16x2(o_acc[nb][0] * inv_a, o_acc[nb][1] * inv_a);
     if (row_b < n_query)
       *reinterpret_cast<uint32_t*>(o_base + (long long)row_b * d + nb * 8) =
-          pack_bf16x2(o_acc[nb][2] * inv_b, o_acc[nb][3] * inv_b);
+          pack_f16x2(o_acc[nb][2] * inv_b, o_acc[nb][3] * inv_b);
   }
 }
 
@@ -217,7 +217,7 @@ int segma_attention(const void* qkv, int n_windows, int T, int n_heads, int n_qu
   SEGMA_REQUIRE(n_heads <= 65535 && n_windows <= 65535, "segma_attention: grid too large");
   dim3 grid(ceil_div(n_query, kQTile), n_heads, n_windows);
   attention_kernel<<<grid, kAttnThreads, 0, (cudaStream_t)stream>>>(
-      static_cast<const __nv_bfloat16*>(qkv), T, n_heads, n_query, gate, pos_bias, static_cast<__nv_bfloat16*>(out));
+      static_cast<const __half*>(qkv), T, n_heads, n_query, gate, pos_bias, static_cast<__half*>(out));
   return launch_status("attention_kernel");
 }
 

@@ -3,7 +3,7 @@
 #pragma once
 
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -63,7 +63,7 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// exact-erf GELU through Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below the bf16
+// exact-erf GELU through Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below the fp16
 // resolution of every consumer); 2 MUFU + ~12 FMA-pipe ops instead of libdevice erff's ~30.
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
@@ -79,8 +79,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erf_v);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
@@ -147,8 +147,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
 __device__ __forceinline__ void tc5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate, issued by one thread.
-__device__ __forceinline__ void tc5_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+// D[tmem] (+)= A[smem desc] * B[smem desc], fp16 inputs, fp32 accumulate, issued by one thread.
+__device__ __forceinline__ void tc5_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -181,7 +181,7 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "memory");
 }
 
-// K-major, 128-byte-swizzled shared-memory operand descriptor (rows of 64 bf16 = 128 B, 8-row
+// K-major, 128-byte-swizzled shared-memory operand descriptor (rows of 64 fp16 = 128 B, 8-row
 // swizzle atoms of 1024 B).  Bit layout: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout_type=SWIZZLE_128B(2) [61,64).
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
@@ -193,7 +193,7 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
   return d;
 }
-// MN-major, 128-byte-swizzled operand: 64 contiguous bf16 along MN per 128-B row, K rows at a
+// MN-major, 128-byte-swizzled operand: 64 contiguous fp16 along MN per 128-B row, K rows at a
 // 128-B pitch, 8-row (K) atoms of 1024 B.  LBO = byte distance between 64-element MN chunks.
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
   uint64_t d = 0;
@@ -204,11 +204,11 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-// kind::f16 instruction descriptor: fp32 accumulate, bf16 A and B, dense.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
+// kind::f16 instruction descriptor: fp32 accumulate, fp16 A and B (format code 0), dense.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n, int a_mn_major, int b_mn_major) {
   return (1u << 4)                                   // c_format = F32
-         | (1u << 7)                                 // a_format = BF16
-         | (1u << 10)                                // b_format = BF16
+         | (0u << 7)                                 // a_format = F16
+         | (0u << 10)                                // b_format = F16
          | (static_cast<uint32_t>(a_mn_major) << 15) // a_major
          | (static_cast<uint32_t>(b_mn_major) << 16) // b_major
          | (static_cast<uint32_t>(n >> 3) << 17)     // n_dim
@@ -236,10 +236,10 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(addr));
 }
-// D(16x8 fp32) += A(16x16 bf16, row) * B(16x8 bf16, col)
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+// D(16x8 fp32) += A(16x16 fp16, row) * B(16x8 fp16, col)
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }

@@ -1,9 +1,9 @@
 // Row-wise LayerNorm (fp32 statistics) with the layer-weighted hidden-state mix folded in, and a strided
-// fp32 -> bf16 cast.  Replaces ATen LayerNorm inside WhisperEncoderLayer / torchaudio EncoderLayer
+// fp32 -> fp16 cast.  Replaces ATen LayerNorm inside WhisperEncoderLayer / torchaudio EncoderLayer
 // (site-packages/transformers/models/whisper/modeling_whisper.py:380-412, 643;
 // site-packages/torchaudio/models/wav2vec2/components.py:363-401) and torch.stack + einsum of
 // src/segma/models/whisper/surgical_hydra.py:82-98.  HBM-bound: one read of the fp32 residual row,
-// one bf16 (and/or fp32) write, 128-bit accesses, one warp per row.
+// one fp16 (and/or fp32) write, 128-bit accesses, one warp per row.
 #include <algorithm>
 
 #include "common.cuh"
@@ -15,7 +15,7 @@ constexpr int kLnWarps = 8;
 template <int VPL>  // float4 chunks per lane: d = VPL * 128
 __global__ void __launch_bounds__(kLnWarps * 32) layernorm_kernel(
     const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long long rows,
-    __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32, float* __restrict__ mix, int period,
+    __half* __restrict__ out_f16, float* __restrict__ out_f32, float* __restrict__ mix, int period,
     int n_keep, float w_in, float w_out, int mix_init) {
   constexpr int d = VPL * 128;
   const long long row = (long long)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
@@ -50,11 +50,11 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_kernel(
     y.y = (v[i].y - mean) * rstd * g.y + b.y;
     y.z = (v[i].z - mean) * rstd * g.z + b.z;
     y.w = (v[i].w - mean) * rstd * g.w + b.w;
-    if (out_bf16) {
+    if (out_f16) {
       uint2 p;
-      p.x = pack_bf16x2(y.x, y.y);
-      p.y = pack_bf16x2(y.z, y.w);
-      reinterpret_cast<uint2*>(out_bf16 + row * d)[c4] = p;
+      p.x = pack_f16x2(y.x, y.y);
+      p.y = pack_f16x2(y.z, y.w);
+      reinterpret_cast<uint2*>(out_f16 + row * d)[c4] = p;
     }
     if (out_f32) reinterpret_cast<float4*>(out_f32 + row * d)[c4] = y;
     if (do_mix) {
@@ -68,8 +68,8 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_kernel(
   }
 }
 
-__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, long long lds,
-                                                         __nv_bfloat16* __restrict__ dst, long long ldd,
+__global__ void __launch_bounds__(256) cast_f16_kernel(const float* __restrict__ src, long long lds,
+                                                         __half* __restrict__ dst, long long ldd,
                                                          long long rows, int cols) {
   const int quads = cols / 4;
   const long long total = rows * quads;
@@ -79,19 +79,19 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
     const int q = (int)(i - r * quads);
     const float4 v = __ldg(reinterpret_cast<const float4*>(src + r * lds) + q);
     uint2 p;
-    p.x = pack_bf16x2(v.x, v.y);
-    p.y = pack_bf16x2(v.z, v.w);
+    p.x = pack_f16x2(v.x, v.y);
+    p.y = pack_f16x2(v.z, v.w);
     reinterpret_cast<uint2*>(dst + r * ldd)[q] = p;
   }
 }
 
 template <int VPL>
-static int launch_ln(const float* x, const float* gamma, const float* beta, long long rows, void* out_bf16,
+static int launch_ln(const float* x, const float* gamma, const float* beta, long long rows, void* out_f16,
                      float* out_f32, float* mix, int period, int n_keep, float w_in, float w_out, int mix_init,
                      cudaStream_t st) {
   const long long blocks = ceil_div_ll(rows, kLnWarps);
   layernorm_kernel<VPL><<<(unsigned)blocks, kLnWarps * 32, 0, st>>>(
-      x, gamma, beta, rows, static_cast<__nv_bfloat16*>(out_bf16), out_f32, mix, period, n_keep, w_in, w_out,
+      x, gamma, beta, rows, static_cast<__half*>(out_f16), out_f32, mix, period, n_keep, w_in, w_out,
       mix_init);
   return launch_status("layernorm_kernel");
 }
@@ -102,7 +102,7 @@ using namespace segma;
 
 extern "C" {
 
-int segma_layernorm(const float* x, const float* gamma, const float* beta, int64_t rows, int d, void* out_bf16,
+int segma_layernorm(const float* x, const float* gamma, const float* beta, int64_t rows, int d, void* out_f16,
                     float* out_f32, float* mix, int period, int n_keep, float w_in, float w_out, int mix_init,
                     void* stream) {
   SEGMA_REQUIRE(rows >= 0 && d > 0, "segma_layernorm: bad shape");
@@ -115,7 +115,7 @@ int segma_layernorm(const float* x, const float* gamma, const float* beta, int64
   if (period <= 0) period = 1;
 #define SEGMA_LN_CASE(V)                                                                                       \
   case V:                                                                                                      \
-    return launch_ln<V>(x, gamma, beta, rows, out_bf16, out_f32, mix, period, n_keep, w_in, w_out, mix_init, st);
+    return launch_ln<V>(x, gamma, beta, rows, out_f16, out_f32, mix, period, n_keep, w_in, w_out, mix_init, st);
   switch (d / 128) {
     SEGMA_LN_CASE(1) SEGMA_LN_CASE(2) SEGMA_LN_CASE(3) SEGMA_LN_CASE(4) SEGMA_LN_CASE(5) SEGMA_LN_CASE(6)
     SEGMA_LN_CASE(7) SEGMA_LN_CASE(8) SEGMA_LN_CASE(9) SEGMA_LN_CASE(10) SEGMA_LN_CASE(11) SEGMA_LN_CASE(12)
@@ -126,15 +126,15 @@ int segma_layernorm(const float* x, const float* gamma, const float* beta, int64
   return SEGMA_ERR_UNSUPPORTED;
 }
 
-int segma_cast_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream) {
-  SEGMA_REQUIRE(rows >= 0 && cols > 0, "segma_cast_bf16: bad shape");
+int segma_cast_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream) {
+  SEGMA_REQUIRE(rows >= 0 && cols > 0, "segma_cast_f16: bad shape");
   if (rows == 0) return SEGMA_OK;
-  SEGMA_REQUIRE(src && dst, "segma_cast_bf16: NULL buffer");
-  SEGMA_REQUIRE(cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "segma_cast_bf16: cols and strides must be multiples of 4");
+  SEGMA_REQUIRE(src && dst, "segma_cast_f16: NULL buffer");
+  SEGMA_REQUIRE(cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "segma_cast_f16: cols and strides must be multiples of 4");
   const long long total = rows * (cols / 4);
   const int grid = (int)std::min<long long>(ceil_div_ll(total, 256), (long long)device_sm_count() * 16);
-  cast_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, lds, static_cast<__nv_bfloat16*>(dst), ldd, rows, cols);
-  return launch_status("cast_bf16_kernel");
+  cast_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, lds, static_cast<__half*>(dst), ldd, rows, cols);
+  return launch_status("cast_f16_kernel");
 }
 
 }  // extern "C"

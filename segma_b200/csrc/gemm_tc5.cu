@@ -1,4 +1,4 @@
-// bf16 GEMM / implicit-GEMM Conv1d on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+// fp16 GEMM / implicit-GEMM Conv1d on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
 //
 // C[M, N] = epilogue(A[M, K] * W[N, K]^T) with fp32 accumulation.  Replaces torch's dispatch of
 // nn.Linear (q/k/v/out projections, fc1/fc2; site-packages/transformers/models/whisper/modeling_whisper.py:
@@ -10,7 +10,7 @@
 //   warp 0      TMA producer: 128B-swizzled A (128 x 64) and W (BN x 64) tiles into a multi-stage ring
 //   warp 1      allocates TMEM, one elected lane issues tcgen05.mma (M=128, N=BN, K=16) per 32 bytes of K
 //   warps 2-5   epilogue: tcgen05.ld of the fp32 accumulator (double-buffered in TMEM so the next tile's
-//               MMAs overlap), + bias, exact-erf GELU, + fp32 residual / position table, bf16 or fp32 store
+//               MMAs overlap), + bias, exact-erf GELU, + fp32 residual / position table, fp16 or fp32 store
 // A strided Conv1d is the same loop with the K axis split into taps: tap j of a stride-s convolution reads
 // the activation map (rows merged s at a time) at column block (j % s) * C and row offset j / s, so no
 // im2col buffer is ever written.
@@ -22,7 +22,7 @@
 namespace segma {
 
 constexpr int kBM = 128;
-constexpr int kBK = 64;  // 128 bytes of bf16: one swizzle row
+constexpr int kBK = 64;  // 128 bytes of fp16: one swizzle row
 constexpr int kGemmThreads = 192;
 
 struct GemmKernelArgs {
@@ -124,7 +124,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_f16(kBM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -143,7 +143,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t da = umma_desc_k_sw128(a_addr + k * 32);
             const uint64_t db = umma_desc_k_sw128(b_addr + k * 32);
-            tc5_mma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc5_mma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           tc5_commit(empty_bar + stage);  // frees the smem stage once these MMAs retire
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -206,14 +206,14 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           } else {
-            uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + nc);
+            uint4* o4 = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + out_row * p.ldo + nc);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               uint4 q;
-              q.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);
-              q.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-              q.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-              q.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+              q.x = pack_f16x2(v[8 * i], v[8 * i + 1]);
+              q.y = pack_f16x2(v[8 * i + 2], v[8 * i + 3]);
+              q.z = pack_f16x2(v[8 * i + 4], v[8 * i + 5]);
+              q.w = pack_f16x2(v[8 * i + 6], v[8 * i + 7]);
               o4[i] = q;
             }
           }
@@ -251,8 +251,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 tensor map with a (64 x box_rows [x 1]) box and 128B swizzle
-int make_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+// fp16 tensor map with a (64 x box_rows [x 1]) box and 128B swizzle
+int make_f16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                   int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
@@ -271,7 +271,7 @@ int make_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* 
   }
   box[0] = kBK;
   box[1] = box_rows;
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, box, estr,
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -295,7 +295,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, GemmKernelA
   ka.n_tiles = ceil_div(ka.n, BN);
   const long long tiles = (long long)ka.batch * ka.tiles_per_batch * ka.n_tiles;
   if (tiles > 0x7fffffffll) {
-    set_last_error("segma_gemm_bf16: too many tiles");
+    set_last_error("segma_gemm_f16: too many tiles");
     return SEGMA_ERR_INVALID_ARGUMENT;
   }
   const int grid = (int)std::min<long long>(tiles, device_sm_count());
@@ -309,28 +309,28 @@ using namespace segma;
 
 extern "C" {
 
-int segma_gemm_bf16(const segma_gemm_args* a, void* stream) {
-  SEGMA_REQUIRE(a != nullptr, "segma_gemm_bf16: NULL args");
-  SEGMA_REQUIRE(a->batch >= 0 && a->rows_per_batch >= 0, "segma_gemm_bf16: negative shape");
+int segma_gemm_f16(const segma_gemm_args* a, void* stream) {
+  SEGMA_REQUIRE(a != nullptr, "segma_gemm_f16: NULL args");
+  SEGMA_REQUIRE(a->batch >= 0 && a->rows_per_batch >= 0, "segma_gemm_f16: negative shape");
   if (a->batch == 0 || a->rows_per_batch == 0) return SEGMA_OK;
-  SEGMA_REQUIRE(a->a && a->w && a->out, "segma_gemm_bf16: NULL buffer");
-  SEGMA_REQUIRE(a->n > 0 && a->n % 32 == 0, "segma_gemm_bf16: n=%d must be a positive multiple of 32", a->n);
+  SEGMA_REQUIRE(a->a && a->w && a->out, "segma_gemm_f16: NULL buffer");
+  SEGMA_REQUIRE(a->n > 0 && a->n % 32 == 0, "segma_gemm_f16: n=%d must be a positive multiple of 32", a->n);
   SEGMA_REQUIRE(a->a_row_stride % 8 == 0 && a->a_batch_stride % 8 == 0,
-                "segma_gemm_bf16: A strides must be multiples of 8 elements (16 bytes)");
+                "segma_gemm_f16: A strides must be multiples of 8 elements (16 bytes)");
   SEGMA_REQUIRE((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0,
-                "segma_gemm_bf16: A and W must be 16-byte aligned");
+                "segma_gemm_f16: A and W must be 16-byte aligned");
   SEGMA_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && a->ldo % 8 == 0,
-                "segma_gemm_bf16: out must be 16-byte aligned with ldo a multiple of 8");
+                "segma_gemm_f16: out must be 16-byte aligned with ldo a multiple of 8");
   const int taps = a->conv_taps > 0 ? a->conv_taps : 1;
   const int s = a->conv_stride > 0 ? a->conv_stride : 1;
-  SEGMA_REQUIRE(a->k > 0 && a->k % taps == 0, "segma_gemm_bf16: k=%d must be a positive multiple of conv_taps=%d",
+  SEGMA_REQUIRE(a->k > 0 && a->k % taps == 0, "segma_gemm_f16: k=%d must be a positive multiple of conv_taps=%d",
                 a->k, taps);
   const int c = a->k / taps;  // channels per tap
-  SEGMA_REQUIRE(c % 8 == 0, "segma_gemm_bf16: channels per tap (%d) must be a multiple of 8", c);
+  SEGMA_REQUIRE(c % 8 == 0, "segma_gemm_f16: channels per tap (%d) must be a multiple of 8", c);
   SEGMA_REQUIRE(taps == 1 || s == 1 || c % kBK == 0,
-                "segma_gemm_bf16: strided conv needs channels per tap (%d) to be a multiple of 64", c);
-  SEGMA_REQUIRE(a->a_row_stride >= (int64_t)c, "segma_gemm_bf16: a_row_stride smaller than the row");
-  if (a->add_src) SEGMA_REQUIRE(a->add_period > 0, "segma_gemm_bf16: add_period must be positive");
+                "segma_gemm_f16: strided conv needs channels per tap (%d) to be a multiple of 64", c);
+  SEGMA_REQUIRE(a->a_row_stride >= (int64_t)c, "segma_gemm_f16: a_row_stride smaller than the row");
+  if (a->add_src) SEGMA_REQUIRE(a->add_period > 0, "segma_gemm_f16: add_period must be positive");
 
   GemmKernelArgs ka{};
   ka.batch = a->batch;
@@ -354,26 +354,26 @@ int segma_gemm_bf16(const segma_gemm_args* a, void* stream) {
 
   // A map: stride-s convolutions view s consecutive input rows as one map row of s*c channels
   const int in_rows = a->a_rows_per_batch > 0 ? a->a_rows_per_batch : a->rows_per_batch;
-  SEGMA_REQUIRE(in_rows % s == 0, "segma_gemm_bf16: a_rows_per_batch=%d must be a multiple of conv_stride=%d", in_rows, s);
+  SEGMA_REQUIRE(in_rows % s == 0, "segma_gemm_f16: a_rows_per_batch=%d must be a multiple of conv_stride=%d", in_rows, s);
   CUtensorMap ma, mw;
   {
     uint64_t dims[3] = {(uint64_t)s * c, (uint64_t)(in_rows / s), (uint64_t)a->batch};
     uint64_t strides[3] = {1, (uint64_t)a->a_row_stride * s, (uint64_t)a->a_batch_stride};
     if (a->batch == 1 && strides[2] == 0) strides[2] = strides[1] * dims[1];
-    int rc = make_bf16_map(&ma, a->a, 3, dims, strides, kBM);
+    int rc = make_f16_map(&ma, a->a, 3, dims, strides, kBM);
     if (rc != SEGMA_OK) return rc;
   }
   int bn = 256;
   if (a->n % 256 != 0 && a->n < 512) bn = 128;
   if (a->n % 256 != 0 && a->n % 128 != 0 && a->n % 192 == 0) bn = 192;
   if (a->force_bn) {
-    SEGMA_REQUIRE(a->force_bn == 128 || a->force_bn == 192 || a->force_bn == 256, "segma_gemm_bf16: bad force_bn");
+    SEGMA_REQUIRE(a->force_bn == 128 || a->force_bn == 192 || a->force_bn == 256, "segma_gemm_f16: bad force_bn");
     bn = a->force_bn;
   }
   {
     uint64_t dims[2] = {(uint64_t)a->k, (uint64_t)a->n};
     uint64_t strides[2] = {1, (uint64_t)a->k};
-    int rc = make_bf16_map(&mw, a->w, 2, dims, strides, bn);
+    int rc = make_f16_map(&mw, a->w, 2, dims, strides, bn);
     if (rc != SEGMA_OK) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;

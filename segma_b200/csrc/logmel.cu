@@ -11,7 +11,7 @@
 // frames), runs a packed real FFT (200-point complex Stockham, radix 8*5*5, in shared memory/registers),
 // applies the sparse mel filters and the log, and reduces the window maximum with one atomic per
 // block.  Kernel B applies the window-global clamp, scales, and streams out the 3000-frame rows
-// (constant beyond the last frame that touches audio), optionally also as the bf16 time-major tile
+// (constant beyond the last frame that touches audio), optionally also as the fp16 time-major tile
 // the conv-stem GEMM consumes.
 #include <cmath>
 #include <cstring>
@@ -360,12 +360,12 @@ __global__ void __launch_bounds__(256) logmel_finish_f32_kernel(const float* __r
   }
 }
 
-// bf16 time-major (3002, 80) per window: row 0 and row 3001 are the conv padding (zeros)
+// fp16 time-major (3002, 80) per window: row 0 and row 3001 are the conv padding (zeros)
 constexpr int kTmTile = 32;
 __global__ void __launch_bounds__(256) logmel_finish_tm_kernel(const float* __restrict__ logspec,
                                                                 const uint32_t* __restrict__ win_max,
                                                                 long long pcm_len, int win_len, long long step,
-                                                                int nvp, __nv_bfloat16* __restrict__ out) {
+                                                                int nvp, __half* __restrict__ out) {
   __shared__ float tile[kMels][kTmTile + 1];
   const int win = blockIdx.y;
   const int n_valid = window_n_valid(pcm_len, win, step, win_len);
@@ -374,11 +374,11 @@ __global__ void __launch_bounds__(256) logmel_finish_tm_kernel(const float* __re
   if (n_valid < kFramesOut) gmax = fmaxf(gmax, -10.f);
   const float floor_v = gmax - 8.0f;
   const float fill = (fmaxf(-10.f, floor_v) + 4.0f) / 4.0f;
-  __nv_bfloat16* o = out + (long long)win * (kFramesOut + 2) * kMels;
+  __half* o = out + (long long)win * (kFramesOut + 2) * kMels;
   const int t0 = blockIdx.x * kTmTile;
   if (blockIdx.x == 0 && threadIdx.x < kMels) {
-    o[threadIdx.x] = __float2bfloat16(0.f);
-    o[(long long)(kFramesOut + 1) * kMels + threadIdx.x] = __float2bfloat16(0.f);
+    o[threadIdx.x] = __float2half(0.f);
+    o[(long long)(kFramesOut + 1) * kMels + threadIdx.x] = __float2half(0.f);
   }
   if (t0 < n_valid) {
     for (int id = threadIdx.x; id < kMels * kTmTile; id += blockDim.x) {
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(256) logmel_finish_tm_kernel(const float* __re
     if (t >= kFramesOut) continue;
     float a = fill, b = fill;
     if (t0 < n_valid) { a = tile[m][f]; b = tile[m + 1][f]; }
-    *reinterpret_cast<uint32_t*>(o + (long long)(t + 1) * kMels + m) = pack_bf16x2(a, b);
+    *reinterpret_cast<uint32_t*>(o + (long long)(t + 1) * kMels + m) = pack_f16x2(a, b);
   }
 }
 
@@ -471,7 +471,7 @@ int segma_logmel(const float* pcm, int64_t pcm_len, int n_windows, int win_len, 
   if (out_tm) {
     dim3 grid_c(ceil_div(kFramesOut, kTmTile), n_windows);
     logmel_finish_tm_kernel<<<grid_c, 256, 0, st>>>(logspec, win_max, pcm_len, win_len, step, nvp,
-                                                    static_cast<__nv_bfloat16*>(out_tm));
+                                                    static_cast<__half*>(out_tm));
     rc = launch_status("logmel_finish_tm_kernel");
     if (rc != SEGMA_OK) return rc;
   }

@@ -18,7 +18,7 @@ template <int H>
 __global__ void __launch_bounds__(4 * H) lstm_layer_kernel(const float* __restrict__ pre,
                                                             const float* __restrict__ w_hh_t, int n_steps,
                                                             int n_rows, int n_dirs, float* __restrict__ out,
-                                                            __nv_bfloat16* __restrict__ out_bf16) {
+                                                            __half* __restrict__ out_f16) {
   constexpr int R = kLstmRows;
   constexpr int G = 4 * H;
   constexpr int kItems = (R * H) / G;  // pointwise items per thread
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(4 * H) lstm_layer_kernel(const float* __restri
       if (row < n_rows) {
         const long long o = ((long long)s * n_rows + row) * (n_dirs * H) + dir * H + u;
         out[o] = h;
-        if (out_bf16) out_bf16[o] = __float2bfloat16(h);
+        if (out_f16) out_f16[o] = __float2half(h);
       }
     }
     __syncthreads();
@@ -100,13 +100,13 @@ using namespace segma;
 extern "C" {
 
 int segma_lstm_layer(const float* pre, const float* w_hh_t, int n_steps, int n_rows, int hidden, int n_dirs,
-                     float* out, void* out_bf16, void* stream) {
+                     float* out, void* out_f16, void* stream) {
   SEGMA_REQUIRE(n_steps >= 0 && n_rows >= 0 && (n_dirs == 1 || n_dirs == 2), "segma_lstm_layer: bad shape");
   if (n_steps == 0 || n_rows == 0) return SEGMA_OK;
   SEGMA_REQUIRE(pre && w_hh_t && out, "segma_lstm_layer: NULL buffer");
   dim3 grid(ceil_div(n_rows, kLstmRows), n_dirs);
   cudaStream_t st = (cudaStream_t)stream;
-  __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out_bf16);
+  __half* ob = static_cast<__half*>(out_f16);
   switch (hidden) {
     case 64: lstm_layer_kernel<64><<<grid, 256, 0, st>>>(pre, w_hh_t, n_steps, n_rows, n_dirs, out, ob); break;
     case 128: lstm_layer_kernel<128><<<grid, 512, 0, st>>>(pre, w_hh_t, n_steps, n_rows, n_dirs, out, ob); break;

@@ -6,7 +6,7 @@ windowing and the log-mel hook in front of them (inference.py:148-152, hydra.py:
 PCM resident on the device and writes frame logits straight onto the file timeline.  Every arithmetic
 step is a libsegma_b200 kernel; torch only owns the buffers and the stream.
 
-Weights are packed once from the reference ``state_dict``: bf16 GEMM operands
+Weights are packed once from the reference ``state_dict``: fp16 GEMM operands
 (q/k/v fused, the query scale 64**-0.5 folded into W_q/b_q -- exact, it is a power of two --, conv
 kernels re-laid tap-major), fp32 biases / LayerNorm / LSTM recurrence / heads.
 """
@@ -23,8 +23,8 @@ N_CTX = 1500
 MEL_FRAMES = 3000
 
 
-def _bf16(t: torch.Tensor, device) -> torch.Tensor:
-    return t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+def _f16(t: torch.Tensor, device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.float16).contiguous()
 
 
 def _f32(t: torch.Tensor, device) -> torch.Tensor:
@@ -33,7 +33,7 @@ def _f32(t: torch.Tensor, device) -> torch.Tensor:
 
 @dataclass
 class _LstmLayer:
-    w_ih: torch.Tensor  # (n_dirs*4H, in) bf16
+    w_ih: torch.Tensor  # (n_dirs*4H, in) fp16
     bias: torch.Tensor  # (n_dirs*4H) fp32 = b_ih + b_hh
     w_hh_t: torch.Tensor  # (n_dirs, H, 4H) fp32
 
@@ -49,7 +49,7 @@ class LstmHeads:
             w_ih = torch.cat([sd[f"{prefix}weight_ih_l{layer}{s}"] for s in sufs], dim=0)
             bias = torch.cat([sd[f"{prefix}bias_ih_l{layer}{s}"] + sd[f"{prefix}bias_hh_l{layer}{s}"] for s in sufs])
             w_hh_t = torch.stack([sd[f"{prefix}weight_hh_l{layer}{s}"].T.contiguous() for s in sufs])
-            self.layers.append(_LstmLayer(_bf16(w_ih, device), _f32(bias, device), _f32(w_hh_t, device)))
+            self.layers.append(_LstmLayer(_f16(w_ih, device), _f32(bias, device), _f32(w_hh_t, device)))
             layer += 1
         self.hidden = self.layers[0].w_hh_t.shape[1] if self.layers else 0
         self.n_dirs = self.layers[0].w_hh_t.shape[0] if self.layers else 0
@@ -57,15 +57,15 @@ class LstmHeads:
         self.head_b = _f32(torch.cat([sd[f"task_heads.linear_head_{lab}.bias"] for lab in labels], dim=0), device)
         self.n_labels = len(labels)
 
-    def run(self, feat_f32: torch.Tensor, feat_bf16: torch.Tensor, n_steps: int, n_rows: int, logits: torch.Tensor,
+    def run(self, feat_f32: torch.Tensor, feat_f16: torch.Tensor, n_steps: int, n_rows: int, logits: torch.Tensor,
             frame_offset: int, step_frames: int, n_keep: int) -> None:
-        """feat_* (n_steps*n_rows, F): LSTM input (bf16 copy for the tensor-core projection)."""
-        cur_f32, cur_bf16 = feat_f32, feat_bf16
+        """feat_* (n_steps*n_rows, F): LSTM input (fp16 copy for the tensor-core projection)."""
+        cur_f32, cur_f16 = feat_f32, feat_f16
         for lay in self.layers:
-            pre = ops.linear(cur_bf16, lay.w_ih, lay.bias, out_f32=True)
-            out_bf16 = torch.empty((n_steps, n_rows, self.n_dirs * self.hidden), dtype=torch.bfloat16, device=pre.device)
-            cur_f32 = ops.lstm_layer(pre.view(n_steps, n_rows, -1), lay.w_hh_t, self.hidden, out_bf16=out_bf16)
-            cur_bf16 = out_bf16.view(n_steps * n_rows, -1)
+            pre = ops.linear(cur_f16, lay.w_ih, lay.bias, out_f32=True)
+            out_f16 = torch.empty((n_steps, n_rows, self.n_dirs * self.hidden), dtype=torch.float16, device=pre.device)
+            cur_f32 = ops.lstm_layer(pre.view(n_steps, n_rows, -1), lay.w_hh_t, self.hidden, out_f16=out_f16)
+            cur_f16 = out_f16.view(n_steps * n_rows, -1)
         ops.heads(cur_f32.view(n_steps, n_rows, -1), self.head_w, self.head_b, logits, frame_offset, step_frames, n_keep)
 
 
@@ -85,9 +85,9 @@ class WhisperEngine:
         self.n_mels = sd[p + "conv1.weight"].shape[1]
         assert self.n_mels == 80 and d % 128 == 0, "Whisper encoder dims must be 80 mel bins and d_model % 128 == 0"
         # conv stem, tap-major K
-        self.conv1_w = _bf16(sd[p + "conv1.weight"].permute(0, 2, 1).reshape(d, -1), dev)
+        self.conv1_w = _f16(sd[p + "conv1.weight"].permute(0, 2, 1).reshape(d, -1), dev)
         self.conv1_b = _f32(sd[p + "conv1.bias"], dev)
-        self.conv2_w = _bf16(sd[p + "conv2.weight"].permute(0, 2, 1).reshape(d, -1), dev)
+        self.conv2_w = _f16(sd[p + "conv2.weight"].permute(0, 2, 1).reshape(d, -1), dev)
         self.conv2_b = _f32(sd[p + "conv2.bias"], dev)
         self.pos = _f32(sd[p + "embed_positions.weight"], dev)
         assert self.pos.shape == (N_CTX, d)
@@ -101,12 +101,12 @@ class WhisperEngine:
             wv, bv = sd[lp + "self_attn.v_proj.weight"], sd[lp + "self_attn.v_proj.bias"]
             self.layers.append(dict(
                 ln1_g=_f32(sd[lp + "self_attn_layer_norm.weight"], dev), ln1_b=_f32(sd[lp + "self_attn_layer_norm.bias"], dev),
-                wqkv=_bf16(torch.cat([wq, wk, wv], dim=0), dev),
+                wqkv=_f16(torch.cat([wq, wk, wv], dim=0), dev),
                 bqkv=_f32(torch.cat([bq, torch.zeros_like(bq), bv]), dev),
-                wo=_bf16(sd[lp + "self_attn.out_proj.weight"], dev), bo=_f32(sd[lp + "self_attn.out_proj.bias"], dev),
+                wo=_f16(sd[lp + "self_attn.out_proj.weight"], dev), bo=_f32(sd[lp + "self_attn.out_proj.bias"], dev),
                 ln2_g=_f32(sd[lp + "final_layer_norm.weight"], dev), ln2_b=_f32(sd[lp + "final_layer_norm.bias"], dev),
-                w1=_bf16(sd[lp + "fc1.weight"], dev), b1=_f32(sd[lp + "fc1.bias"], dev),
-                w2=_bf16(sd[lp + "fc2.weight"], dev), b2=_f32(sd[lp + "fc2.bias"], dev),
+                w1=_f16(sd[lp + "fc1.weight"], dev), b1=_f32(sd[lp + "fc1.bias"], dev),
+                w2=_f16(sd[lp + "fc2.weight"], dev), b2=_f32(sd[lp + "fc2.bias"], dev),
             ))
             i += 1
         self.n_layers = i
@@ -137,22 +137,22 @@ class WhisperEngine:
         dev, d = self.device, self.d
         M = n * N_CTX
         ws = {}
-        ws["mel_tm"] = torch.zeros((n, MEL_FRAMES + 2, 80), dtype=torch.bfloat16, device=dev)
-        ws["c1"] = torch.zeros((n, MEL_FRAMES + 2, d), dtype=torch.bfloat16, device=dev)  # pad rows stay zero
+        ws["mel_tm"] = torch.zeros((n, MEL_FRAMES + 2, 80), dtype=torch.float16, device=dev)
+        ws["c1"] = torch.zeros((n, MEL_FRAMES + 2, d), dtype=torch.float16, device=dev)  # pad rows stay zero
         ws["x"] = torch.empty((M, d), dtype=torch.float32, device=dev)
-        ws["xn"] = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
-        ws["qkv"] = torch.empty((M, 3 * d), dtype=torch.bfloat16, device=dev)
-        ws["att"] = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
-        ws["h1"] = torch.empty((M, self.ffn), dtype=torch.bfloat16, device=dev)
+        ws["xn"] = torch.empty((M, d), dtype=torch.float16, device=dev)
+        ws["qkv"] = torch.empty((M, 3 * d), dtype=torch.float16, device=dev)
+        ws["att"] = torch.empty((M, d), dtype=torch.float16, device=dev)
+        ws["h1"] = torch.empty((M, self.ffn), dtype=torch.float16, device=dev)
         ws["mix"] = torch.empty((n, self.n_keep, d), dtype=torch.float32, device=dev)
-        ws["mix_bf16"] = torch.empty((n * self.n_keep, d), dtype=torch.bfloat16, device=dev)
+        ws["mix_f16"] = torch.empty((n * self.n_keep, d), dtype=torch.float16, device=dev)
         ws["mel_scratch"] = torch.empty(max(ops.logmel_scratch_bytes(n, 64_000 * 2), 1), dtype=torch.uint8, device=dev)
         self._ws = ws
         self._cap = n
 
     # ---- stages ------------------------------------------------------------------------------------
     def encode_tm(self, mel_tm: torch.Tensor, n: int) -> None:
-        """(n, 3002, 80) bf16 padded time-major log-mel -> ws['mix'] (n, n_keep, d) fp32 (+ bf16 copy)."""
+        """(n, 3002, 80) fp16 padded time-major log-mel -> ws['mix'] (n, n_keep, d) fp32 (+ fp16 copy)."""
         ws, d, T = self._ws, self.d, N_CTX
         M = n * T
         x, xn, qkv, att, h1, mix = ws["x"][:M], ws["xn"][:M], ws["qkv"][:M], ws["att"][:M], ws["h1"][:M], ws["mix"][:n]
@@ -164,20 +164,20 @@ class WhisperEngine:
         for li, L in enumerate(self.layers):
             w_in = self.mix_w[li - 1] if li > 0 else 0.0
             if w_in != 0.0:
-                ops.layernorm(x, L["ln1_g"], L["ln1_b"], out_bf16=xn, mix=mix, period=T, n_keep=self.n_keep, w_in=w_in,
+                ops.layernorm(x, L["ln1_g"], L["ln1_b"], out_f16=xn, mix=mix, period=T, n_keep=self.n_keep, w_in=w_in,
                               mix_init=not mixed)
                 mixed = True
             else:
-                ops.layernorm(x, L["ln1_g"], L["ln1_b"], out_bf16=xn)
+                ops.layernorm(x, L["ln1_g"], L["ln1_b"], out_f16=xn)
             ops.linear(xn, L["wqkv"], L["bqkv"], out=qkv)
             ops.attention(qkv, n, T, self.n_heads, out=att)
             ops.linear(att, L["wo"], L["bo"], add_src=x, out=x)
-            ops.layernorm(x, L["ln2_g"], L["ln2_b"], out_bf16=xn)
+            ops.layernorm(x, L["ln2_g"], L["ln2_b"], out_f16=xn)
             ops.linear(xn, L["w1"], L["b1"], gelu=True, out=h1)
             ops.linear(h1, L["w2"], L["b2"], add_src=x, out=x)
         ops.layernorm(x, self.lnf_g, self.lnf_b, mix=mix, period=T, n_keep=self.n_keep, w_in=0.0,
                       w_out=self.mix_w[-1], mix_init=not mixed)
-        ops.cast_bf16(mix.view(n * self.n_keep, d), ws["mix_bf16"][: n * self.n_keep])
+        ops.cast_f16(mix.view(n * self.n_keep, d), ws["mix_f16"][: n * self.n_keep])
 
     def forward_pcm(self, pcm: torch.Tensor, start: int, n: int, win_len: int, step: int, logits: torch.Tensor,
                     frame_offset: int, step_frames: int, n_keep: int | None = None) -> None:
@@ -192,7 +192,7 @@ class WhisperEngine:
         ops.logmel_into(view, n, win_len, step, ws["mel_tm"], ws["mel_scratch"])
         self.encode_tm(ws["mel_tm"], n)
         keep = self.n_keep if n_keep is None else n_keep
-        self.tail.run(ws["mix"][:n].view(n * self.n_keep, self.d), ws["mix_bf16"][: n * self.n_keep], n, self.n_keep,
+        self.tail.run(ws["mix"][:n].view(n * self.n_keep, self.d), ws["mix_f16"][: n * self.n_keep], n, self.n_keep,
                       logits, frame_offset, step_frames, keep)
 
     def forward_features(self, feats: torch.Tensor) -> torch.Tensor:
@@ -201,9 +201,9 @@ class WhisperEngine:
         self._reserve(n)
         ws = self._ws
         tm = ws["mel_tm"][:n]
-        tm[:, 1:-1] = feats.to(self.device).transpose(1, 2).to(torch.bfloat16)  # layout change only
+        tm[:, 1:-1] = feats.to(self.device).transpose(1, 2).to(torch.float16)  # layout change only
         self.encode_tm(ws["mel_tm"], n)
         logits = torch.empty((n * self.n_keep, len(self.labels)), dtype=torch.float32, device=self.device)
-        self.tail.run(ws["mix"][:n].view(n * self.n_keep, self.d), ws["mix_bf16"][: n * self.n_keep], n, self.n_keep,
+        self.tail.run(ws["mix"][:n].view(n * self.n_keep, self.d), ws["mix_f16"][: n * self.n_keep], n, self.n_keep,
                       logits, 0, self.n_keep, self.n_keep)
         return logits.view(n, self.n_keep, 1, len(self.labels))

@@ -46,12 +46,12 @@ def device_check() -> None:
 def logmel(pcm: torch.Tensor, n_windows: int, win_len: int, step: int, out_f32: bool = True, out_tm: bool = False,
            pcm_offset: int = 0):
     """Windows ``pcm[pcm_offset + i*step : ... + win_len]`` -> Whisper log-mel.
-    Returns ``(f32 (n,80,3000) | None, bf16 time-major (n,3002,80) | None)``."""
+    Returns ``(f32 (n,80,3000) | None, fp16 time-major (n,3002,80) | None)``."""
     lib = _lib()
     _dev(pcm, torch.float32, "pcm")
     assert pcm.dim() == 1 and pcm.is_contiguous()
     f32 = torch.empty((n_windows, 80, 3000), dtype=torch.float32, device=pcm.device) if out_f32 else None
-    tm = torch.empty((n_windows, 3002, 80), dtype=torch.bfloat16, device=pcm.device) if out_tm else None
+    tm = torch.empty((n_windows, 3002, 80), dtype=torch.float16, device=pcm.device) if out_tm else None
     nbytes = lib.segma_logmel_scratch_bytes(n_windows, win_len)
     scratch = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=pcm.device)
     view = pcm[pcm_offset:]
@@ -96,24 +96,24 @@ def gemm_raw(a_ptr, a_batch_stride, a_row_stride, batch, rows_per_batch, k, w, n
     args = GemmArgs(
         a=a_ptr, a_batch_stride=a_batch_stride, a_row_stride=a_row_stride, batch=batch,
         rows_per_batch=rows_per_batch, a_rows_per_batch=a_rows_per_batch, k=k, conv_taps=conv_taps,
-        conv_stride=conv_stride, w=_dev(w, torch.bfloat16, "w"), n=n, bias=_ptr(bias, torch.float32, "bias"),
+        conv_stride=conv_stride, w=_dev(w, torch.float16, "w"), n=n, bias=_ptr(bias, torch.float32, "bias"),
         add_src=add_src_ptr, add_period=add_period, out=out_ptr,
         out_batch_rows=rows_per_batch if out_batch_rows is None else out_batch_rows,
         out_row_offset=out_row_offset, ldo=ldo, flags=flags, a_col_per_ntile=a_col_per_ntile, force_bn=force_bn,
     )
-    check(_lib().segma_gemm_bf16(C.byref(args), _stream()), "segma_gemm_bf16")
+    check(_lib().segma_gemm_f16(C.byref(args), _stream()), "segma_gemm_f16")
 
 
 def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, gelu=False, add_src=None, add_period=None, out=None,
            out_f32=False, force_bn=0) -> torch.Tensor:
-    """out = epilogue(a @ w.T); a (M, K) bf16, w (N, K) bf16."""
-    _dev(a, torch.bfloat16, "a")
+    """out = epilogue(a @ w.T); a (M, K) fp16, w (N, K) fp16."""
+    _dev(a, torch.float16, "a")
     assert a.dim() == 2 and a.stride(1) == 1 and w.is_contiguous()
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K
     if out is None:
-        out = torch.empty((M, N), dtype=torch.float32 if out_f32 else torch.bfloat16, device=a.device)
+        out = torch.empty((M, N), dtype=torch.float32 if out_f32 else torch.float16, device=a.device)
     out_f32 = out.dtype == torch.float32
     flags = (GEMM_GELU if gelu else 0) | (GEMM_OUT_F32 if out_f32 else 0)
     gemm_raw(a.data_ptr(), 0, a.stride(0), 1, M, K, w, N, out.data_ptr(), out.stride(0), bias=bias,
@@ -125,16 +125,16 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, gelu=False, add_src=N
 
 def conv1d_tm(x_tm: torch.Tensor, w_tap_major: torch.Tensor, bias, taps: int, stride: int, out_rows: int, *,
               gelu=True, add_src=None, add_period=0, out=None, out_batch_rows=None, out_row_offset=0, out_f32=False):
-    """Implicit-GEMM Conv1d on a padded time-major activation x_tm (B, rows_in, C) bf16;
-    w_tap_major (N, taps*C) bf16.  Output (B, out_batch_rows, N) rows [out_row_offset, +out_rows)."""
+    """Implicit-GEMM Conv1d on a padded time-major activation x_tm (B, rows_in, C) fp16;
+    w_tap_major (N, taps*C) fp16.  Output (B, out_batch_rows, N) rows [out_row_offset, +out_rows)."""
     B, rows_in, Cc = x_tm.shape
     assert x_tm.is_contiguous()
     N = w_tap_major.shape[0]
     obr = out_rows if out_batch_rows is None else out_batch_rows
     if out is None:
-        out = torch.zeros((B, obr, N), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x_tm.device)
+        out = torch.zeros((B, obr, N), dtype=torch.float32 if out_f32 else torch.float16, device=x_tm.device)
     flags = (GEMM_GELU if gelu else 0) | (GEMM_OUT_F32 if out.dtype == torch.float32 else 0)
-    gemm_raw(_dev(x_tm, torch.bfloat16, "x_tm"), rows_in * Cc, Cc, B, out_rows, taps * Cc, w_tap_major, N,
+    gemm_raw(_dev(x_tm, torch.float16, "x_tm"), rows_in * Cc, Cc, B, out_rows, taps * Cc, w_tap_major, N,
              out.data_ptr(), N, bias=bias,
              add_src_ptr=None if add_src is None else _dev(add_src, torch.float32, "add_src"), add_period=add_period,
              out_batch_rows=obr, out_row_offset=out_row_offset, flags=flags, conv_taps=taps, conv_stride=stride,
@@ -143,25 +143,25 @@ def conv1d_tm(x_tm: torch.Tensor, w_tap_major: torch.Tensor, bias, taps: int, st
 
 
 # ---- layernorm / cast / attention ----------------------------------------------------------------
-def layernorm(x: torch.Tensor, gamma, beta, *, out_bf16=None, out_f32=None, mix=None, period=1, n_keep=0, w_in=0.0,
+def layernorm(x: torch.Tensor, gamma, beta, *, out_f16=None, out_f32=None, mix=None, period=1, n_keep=0, w_in=0.0,
               w_out=0.0, mix_init=False) -> None:
     rows, d = x.shape
     assert x.is_contiguous()
     check(
         _lib().segma_layernorm(_dev(x, torch.float32, "x"), _dev(gamma, torch.float32, "gamma"),
-                               _dev(beta, torch.float32, "beta"), rows, d, _ptr(out_bf16, torch.bfloat16, "out_bf16"),
+                               _dev(beta, torch.float32, "beta"), rows, d, _ptr(out_f16, torch.float16, "out_f16"),
                                _ptr(out_f32, torch.float32, "out_f32"), _ptr(mix, torch.float32, "mix"), period,
                                n_keep, float(w_in), float(w_out), int(mix_init), _stream()),
         "segma_layernorm",
     )
 
 
-def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
+def cast_f16(src: torch.Tensor, dst: torch.Tensor) -> None:
     rows, cols = src.shape
     check(
-        _lib().segma_cast_bf16(_dev(src, torch.float32, "src"), src.stride(0), _dev(dst, torch.bfloat16, "dst"),
+        _lib().segma_cast_f16(_dev(src, torch.float32, "src"), src.stride(0), _dev(dst, torch.float16, "dst"),
                                dst.stride(0), rows, cols, _stream()),
-        "segma_cast_bf16",
+        "segma_cast_f16",
     )
 
 
@@ -169,18 +169,18 @@ def attention(qkv: torch.Tensor, n_windows: int, T: int, n_heads: int, *, n_quer
               out=None) -> torch.Tensor:
     assert qkv.is_contiguous() and qkv.shape == (n_windows * T, 3 * n_heads * 64)
     if out is None:
-        out = torch.zeros((n_windows * T, n_heads * 64), dtype=torch.bfloat16, device=qkv.device)
+        out = torch.zeros((n_windows * T, n_heads * 64), dtype=torch.float16, device=qkv.device)
     check(
-        _lib().segma_attention(_dev(qkv, torch.bfloat16, "qkv"), n_windows, T, n_heads, T if n_query is None else n_query,
+        _lib().segma_attention(_dev(qkv, torch.float16, "qkv"), n_windows, T, n_heads, T if n_query is None else n_query,
                                _ptr(gate, torch.float32, "gate"), _ptr(pos_bias, torch.float32, "pos_bias"),
-                               _dev(out, torch.bfloat16, "out"), _stream()),
+                               _dev(out, torch.float16, "out"), _stream()),
         "segma_attention",
     )
     return out
 
 
 # ---- LSTM / heads ------------------------------------------------------------------------------
-def lstm_layer(pre: torch.Tensor, w_hh_t: torch.Tensor, hidden: int, *, out=None, out_bf16=None) -> torch.Tensor:
+def lstm_layer(pre: torch.Tensor, w_hh_t: torch.Tensor, hidden: int, *, out=None, out_f16=None) -> torch.Tensor:
     n_steps, n_rows, g = pre.shape
     n_dirs = g // (4 * hidden)
     assert pre.is_contiguous() and w_hh_t.is_contiguous() and w_hh_t.shape == (n_dirs, hidden, 4 * hidden)
@@ -189,7 +189,7 @@ def lstm_layer(pre: torch.Tensor, w_hh_t: torch.Tensor, hidden: int, *, out=None
     check(
         _lib().segma_lstm_layer(_dev(pre, torch.float32, "pre"), _dev(w_hh_t, torch.float32, "w_hh_t"), n_steps, n_rows,
                                 hidden, n_dirs, _dev(out, torch.float32, "out"),
-                                _ptr(out_bf16, torch.bfloat16, "out_bf16"), _stream()),
+                                _ptr(out_f16, torch.float16, "out_f16"), _stream()),
         "segma_lstm_layer",
     )
     return out

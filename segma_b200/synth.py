@@ -5,7 +5,7 @@ There is no network for datasets or checkpoints, so every measurement and parity
     own synthetic-data recipe (/root/reference/scripts/generate_data.py:41-65,89-155), seeded per file;
   * weights: one fp32 ``state_dict`` with the reference's key names, each tensor drawn
     from its own CPU generator seeded by ``crc32(name) ^ seed`` so that the reference model, the oracle
-    and the packed bf16 build all load identical values regardless of construction order.
+    and the packed fp16 build all load identical values regardless of construction order.
 Scales are chosen so activations stay O(1) through the stack and logits spread over a few units,
 as in a trained model; they are not the default ``nn.Module`` inits.
 """

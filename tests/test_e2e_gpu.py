@@ -1,7 +1,7 @@
 """End-to-end parity of the Whisper-family path on the GPU against the oracle (the reference's fp32
 arithmetic restated in oracle/segma_oracle.py and pinned against the reference itself).
 
-Stated tolerances (north_star): interval decoding bit-exact on identical logits; logits within a bf16
+Stated tolerances (north_star): interval decoding bit-exact on identical logits; logits within (a fraction of) a bf16
 tolerance of the fp32 oracle with >= 99.9 % frame-label agreement."""
 import numpy as np
 import pytest
@@ -18,9 +18,10 @@ from segma_b200.models import Models
 pytestmark = pytest.mark.gpu
 LABELS = synth.DEFAULT_LABELS
 
-# bf16 GEMM operands with fp32 accumulation/residual/LayerNorm/LSTM: absolute logit tolerance, scaled
-# by the logit spread of the run
-LOGIT_RTOL_OF_STD = 0.05
+# fp16 tensor-core operands (11-bit mantissa: 8x tighter than the bf16 tolerance north_star allows) with
+# fp32 accumulation / residual stream / LayerNorm / softmax / LSTM state: max |logit error| as a
+# fraction of the logit spread of the run
+LOGIT_RTOL_OF_STD = 0.01
 MIN_LABEL_AGREEMENT = 0.999
 
 

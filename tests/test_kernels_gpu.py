@@ -29,23 +29,23 @@ def _close(got, ref, rtol, atol, what=""):
 @pytest.mark.parametrize("M,K,N", [(128, 64, 128), (300, 768, 768), (1500, 768, 2304), (257, 3072, 768), (199, 256, 1024),
                                    (1000, 128, 384), (130, 512, 192)])
 def test_gemm_plain(cuda, M, K, N):
-    a = _rand((M, K), 1).to(cuda, torch.bfloat16)
-    w = _rand((N, K), 2, K**-0.5).to(cuda, torch.bfloat16)
+    a = _rand((M, K), 1).to(cuda, torch.float16)
+    w = _rand((N, K), 2, K**-0.5).to(cuda, torch.float16)
     bias = _rand((N,), 3).to(cuda)
     out = ops.linear(a, w, bias)
     ref = a.float() @ w.float().T + bias
-    # bf16 output rounding: 2^-8 relative
-    _close(out, ref, 1e-2, 1e-2, f"gemm {M}x{K}x{N}")
+    # fp16 operands and output: 2^-11 relative rounding
+    _close(out, ref, 2e-3, 2e-3, f"gemm {M}x{K}x{N}")
 
 
 def test_gemm_epilogues(cuda):
     M, K, N = 700, 256, 512
-    a = _rand((M, K), 4).to(cuda, torch.bfloat16)
-    w = _rand((N, K), 5, K**-0.5).to(cuda, torch.bfloat16)
+    a = _rand((M, K), 4).to(cuda, torch.float16)
+    w = _rand((N, K), 5, K**-0.5).to(cuda, torch.float16)
     bias = _rand((N,), 6).to(cuda)
     ref = a.float() @ w.float().T + bias
     out = ops.linear(a, w, bias, gelu=True)
-    _close(out, F.gelu(ref), 1e-2, 1e-2, "gelu epilogue")
+    _close(out, F.gelu(ref), 2e-3, 2e-3, "gelu epilogue")
     out32 = ops.linear(a, w, bias, out_f32=True)
     _close(out32, ref, 1e-4, 1e-4, "fp32 out")
     gelu32 = ops.linear(a, w, bias, gelu=True, out_f32=True)
@@ -72,14 +72,14 @@ def test_gemm_conv(cuda, C, N, taps, stride, T_in, pad):
     x = _rand((B, C, T_in), 9)
     wt = _rand((N, C, taps), 10, (C * taps) ** -0.5)
     bias = _rand((N,), 11)
-    xb, wb = x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float()
+    xb, wb = x.to(torch.float16).float(), wt.to(torch.float16).float()
     ref = F.gelu(F.conv1d(xb, wb, bias, stride=stride, padding=pad)).transpose(1, 2)  # (B, T_out, N)
     T_out = ref.shape[1]
     rows_in = T_in + 2 * pad
     rows_in += (-rows_in) % stride
-    x_tm = torch.zeros((B, rows_in, C), dtype=torch.bfloat16)
-    x_tm[:, pad:pad + T_in] = x.transpose(1, 2).to(torch.bfloat16)
-    w_tm = wt.permute(0, 2, 1).reshape(N, taps * C).contiguous().to(torch.bfloat16)
+    x_tm = torch.zeros((B, rows_in, C), dtype=torch.float16)
+    x_tm[:, pad:pad + T_in] = x.transpose(1, 2).to(torch.float16)
+    w_tm = wt.permute(0, 2, 1).reshape(N, taps * C).contiguous().to(torch.float16)
     out = ops.conv1d_tm(x_tm.to(cuda), w_tm.to(cuda), bias.to(cuda), taps, stride, T_out, gelu=True, out_f32=True)
     _close(out, ref, 2e-3, 2e-3, f"conv C={C} N={N} k={taps} s={stride}")
 
@@ -92,41 +92,41 @@ def test_layernorm(cuda, d):
     g = (1 + 0.1 * _rand((d,), 13)).to(cuda)
     b = (0.1 * _rand((d,), 14)).to(cuda)
     ref = F.layer_norm(x, (d,), g, b, 1e-5)
-    ob = torch.empty((rows, d), dtype=torch.bfloat16, device=cuda)
+    ob = torch.empty((rows, d), dtype=torch.float16, device=cuda)
     of = torch.empty((rows, d), dtype=torch.float32, device=cuda)
     mix = torch.zeros((rows // period, keep, d), device=cuda)
-    ops.layernorm(x, g, b, out_bf16=ob, out_f32=of, mix=mix, period=period, n_keep=keep, w_in=0.25, w_out=0.0, mix_init=True)
+    ops.layernorm(x, g, b, out_f16=ob, out_f32=of, mix=mix, period=period, n_keep=keep, w_in=0.25, w_out=0.0, mix_init=True)
     ops.layernorm(x, g, b, mix=mix, period=period, n_keep=keep, w_in=0.0, w_out=0.5)
     _close(of, ref, 1e-5, 1e-5, "layernorm fp32")
-    _close(ob, ref, 8e-3, 8e-3, "layernorm bf16")
+    _close(ob, ref, 1e-3, 1e-3, "layernorm fp16")
     want = 0.25 * x.view(-1, period, d)[:, :keep] + 0.5 * ref.view(-1, period, d)[:, :keep]
     _close(mix, want, 1e-5, 1e-5, "layer mix")
 
 
-def test_cast_bf16(cuda):
+def test_cast_f16(cuda):
     x = _rand((77, 256), 15).to(cuda)
-    dst = torch.empty((77, 256), dtype=torch.bfloat16, device=cuda)
-    ops.cast_bf16(x, dst)
-    assert torch.equal(dst, x.to(torch.bfloat16))
+    dst = torch.empty((77, 256), dtype=torch.float16, device=cuda)
+    ops.cast_f16(x, dst)
+    assert torch.equal(dst, x.to(torch.float16))
 
 
 # ---- attention -----------------------------------------------------------------------------------------
 @pytest.mark.parametrize("T,H,B,nq", [(199, 2, 3, 199), (1500, 2, 2, 1500), (1500, 12, 1, 199), (64, 1, 1, 64), (65, 3, 2, 65)])
 def test_attention(cuda, T, H, B, nq):
     d = H * 64
-    qkv = _rand((B * T, 3 * d), 16).to(torch.bfloat16)
+    qkv = _rand((B * T, 3 * d), 16).to(torch.float16)
     qkv[:, :d] *= 0.35
     out = ops.attention(qkv.to(cuda), B, T, H, n_query=nq)
     q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
     ref = (torch.softmax(q @ k.transpose(-1, -2), -1) @ v).permute(0, 2, 1, 3).reshape(B, T, d)
     got = out.view(B, T, d)[:, :nq]
-    _close(got, ref[:, :nq], 2e-2, 2e-2, f"attention T={T}")
+    _close(got, ref[:, :nq], 3e-3, 3e-3, f"attention T={T}")
 
 
 def test_attention_wavlm_bias(cuda):
     T, H, B = 199, 2, 2
     d = H * 64
-    qkv = _rand((B * T, 3 * d), 17).to(torch.bfloat16)
+    qkv = _rand((B * T, 3 * d), 17).to(torch.float16)
     qkv[:, :d] *= 0.35
     gate = (1.0 + 0.3 * _rand((B, H, T), 18)).contiguous()
     pos = _rand((H, T, T), 19).contiguous()
@@ -134,7 +134,7 @@ def test_attention_wavlm_bias(cuda):
     q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
     s = q @ k.transpose(-1, -2) + gate[..., None] * pos[None]
     ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * T, d)
-    _close(out, ref, 2e-2, 2e-2, "attention + gated bias")
+    _close(out, ref, 3e-3, 3e-3, "attention + gated bias")
 
 
 # ---- LSTM + heads -----------------------------------------------------------------------------------------
@@ -187,7 +187,7 @@ def test_logmel_windows(cuda):
     for i in range(4):
         ref = O.whisper_logmel(pcm[i * 63680: i * 63680 + 64000])
         _logmel_close(f32[i], ref, f"window {i}")
-        assert torch.equal(tm[i, 1:3001].float().cpu(), f32[i].T.to(torch.bfloat16).float().cpu())
+        assert torch.equal(tm[i, 1:3001].float().cpu(), f32[i].T.to(torch.float16).float().cpu())
         assert (tm[i, 0] == 0).all() and (tm[i, 3001] == 0).all()
 
 

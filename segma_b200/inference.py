@@ -81,6 +81,8 @@ def apply_model_on_audio(
     step = chunky.step if window_step is None else int(window_step)
     if isinstance(audio_path, torch.Tensor) and audio_path.is_cuda:
         pcm = audio_path.reshape(-1).to(torch.float32).contiguous()
+    elif isinstance(audio_path, torch.Tensor) and audio_path.dtype == torch.float32 and audio_path.is_pinned():
+        pcm = audio_path.reshape(-1).to(dev, non_blocking=True)  # already staged in pinned host memory
     else:
         pcm = prepare_audio(audio_path, model, dev, 0, None)
     n_samples = pcm.numel()

@@ -22,6 +22,22 @@ def _lib():
     return _native.load()
 
 
+class _Stats:
+    """Launch accounting (bench.py's ``gpu_launches``) and optional CUDA-event timing of the GEMM launches."""
+
+    def __init__(self):
+        self.launches = 0
+        self.profile_gemm = False
+        self.gemm_events: list[tuple[torch.cuda.Event, torch.cuda.Event, float]] = []
+
+    def reset(self):
+        self.launches = 0
+        self.gemm_events = []
+
+
+stats = _Stats()
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -61,6 +77,7 @@ def logmel(pcm: torch.Tensor, n_windows: int, win_len: int, step: int, out_f32: 
                          scratch.data_ptr(), _stream()),
         "segma_logmel",
     )
+    stats.launches += 3
     return f32, tm
 
 
@@ -71,6 +88,7 @@ def logmel_into(pcm_view: torch.Tensor, n_windows: int, win_len: int, step: int,
                             scratch.data_ptr(), _stream()),
         "segma_logmel",
     )
+    stats.launches += 3
 
 
 def logmel_scratch_bytes(n_windows: int, win_len: int) -> int:
@@ -101,7 +119,15 @@ def gemm_raw(a_ptr, a_batch_stride, a_row_stride, batch, rows_per_batch, k, w, n
         out_batch_rows=rows_per_batch if out_batch_rows is None else out_batch_rows,
         out_row_offset=out_row_offset, ldo=ldo, flags=flags, a_col_per_ntile=a_col_per_ntile, force_bn=force_bn,
     )
-    check(_lib().segma_gemm_f16(C.byref(args), _stream()), "segma_gemm_f16")
+    if stats.profile_gemm:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_lib().segma_gemm_f16(C.byref(args), _stream()), "segma_gemm_f16")
+        e1.record()
+        stats.gemm_events.append((e0, e1, 2.0 * batch * rows_per_batch * n * k))
+    else:
+        check(_lib().segma_gemm_f16(C.byref(args), _stream()), "segma_gemm_f16")
+    stats.launches += 1
 
 
 def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, gelu=False, add_src=None, add_period=None, out=None,
@@ -154,6 +180,7 @@ def layernorm(x: torch.Tensor, gamma, beta, *, out_f16=None, out_f32=None, mix=N
                                n_keep, float(w_in), float(w_out), int(mix_init), _stream()),
         "segma_layernorm",
     )
+    stats.launches += 1
 
 
 def cast_f16(src: torch.Tensor, dst: torch.Tensor) -> None:
@@ -163,6 +190,7 @@ def cast_f16(src: torch.Tensor, dst: torch.Tensor) -> None:
                                dst.stride(0), rows, cols, _stream()),
         "segma_cast_f16",
     )
+    stats.launches += 1
 
 
 def attention(qkv: torch.Tensor, n_windows: int, T: int, n_heads: int, *, n_query=None, gate=None, pos_bias=None,
@@ -176,6 +204,7 @@ def attention(qkv: torch.Tensor, n_windows: int, T: int, n_heads: int, *, n_quer
                                _dev(out, torch.float16, "out"), _stream()),
         "segma_attention",
     )
+    stats.launches += 1
     return out
 
 
@@ -192,6 +221,7 @@ def lstm_layer(pre: torch.Tensor, w_hh_t: torch.Tensor, hidden: int, *, out=None
                                 _ptr(out_f16, torch.float16, "out_f16"), _stream()),
         "segma_lstm_layer",
     )
+    stats.launches += 1
     return out
 
 
@@ -205,6 +235,7 @@ def heads(feat: torch.Tensor, w: torch.Tensor, b: torch.Tensor, logits: torch.Te
                            _dev(logits, torch.float32, "logits"), frame_offset, step_frames, _stream()),
         "segma_heads",
     )
+    stats.launches += 1
 
 
 # ---- stitch / decode -----------------------------------------------------------------------------
@@ -218,6 +249,7 @@ def stitch(window_logits: torch.Tensor, n_windows: int, frames_per_window: int, 
                             step_frames, tail_frames, C_, out.data_ptr(), n_frames, _stream()),
         "segma_stitch",
     )
+    stats.launches += 1
     return out
 
 
@@ -230,6 +262,7 @@ def threshold_mask(logits: torch.Tensor, thresholds, mode: int = DECODE_SIGMOID)
         _lib().segma_threshold_mask(_dev(logits, torch.float32, "logits"), n, C_, thr, mode, mask.data_ptr(), _stream()),
         "segma_threshold_mask",
     )
+    stats.launches += 1
     return mask.bool()
 
 
@@ -256,6 +289,7 @@ def decode_intervals(logits: torch.Tensor, thresholds, *, file_offsets=None, mod
                                        table.data_ptr(), cap, count.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
             "segma_decode_intervals",
         )
+        stats.launches += 3
         total = int(count.item())
         if total <= cap:
             return table[:total]

@@ -222,14 +222,14 @@ def run_gpu(args):
 
     # roofline of the dominant kernel: a separately timed pass with an event pair around every GEMM launch
     ops.stats.reset()
-    ops.stats.profile_gemm = True
+    ops.stats.profile = True
     barrier()
     step_resident()
     torch.cuda.synchronize()
-    ops.stats.profile_gemm = False
-    g_ms = sum(a.elapsed_time(b) for a, b, _ in ops.stats.gemm_events)
-    g_flops = sum(f for _, _, f in ops.stats.gemm_events)
-    n_gemm = len(ops.stats.gemm_events)
+    ops.stats.profile = False
+    breakdown = ops.stats.breakdown()
+    gemms = [v for k, v in breakdown.items() if k.startswith("segma_gemm_f16")]
+    g_ms, g_flops, n_gemm = sum(v["ms"] for v in gemms), sum(v["work"] for v in gemms), sum(v["calls"] for v in gemms)
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -265,6 +265,8 @@ def run_gpu(args):
                      "share_of_step": (g_ms / 1e3) / (dev_s / args.steps), "peak_source": peak_src},
         "cpu_baseline": cpu,
         "clocks": clocks.summary(),
+        "breakdown_ms_per_step": {k: [round(v["ms"], 3), round(v["work"] / max(v["ms"], 1e-9) / 1e9, 1)]
+                                  for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

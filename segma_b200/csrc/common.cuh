@@ -65,18 +65,28 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // exact-erf GELU through Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below the fp16
 // resolution of every consumer); 2 MUFU + ~12 FMA-pipe ops instead of libdevice erff's ~30.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
   p *= t;
-  const float e = exp2f(-1.4426950408889634f * z * z);
-  const float erf_abs = fmaf(-p, e, 1.0f);
-  const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
+  const float e = ex2_approx(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-p, e, 1.0f);        // erf(|x| / sqrt 2)
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), erf_abs, hx);            // 0.5 x (1 + sign(x) erf_abs)
 }
 
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {

@@ -24,6 +24,7 @@ namespace segma {
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 128 bytes of fp16: one swizzle row
 constexpr int kGemmThreads = 192;
+constexpr int kEpiPitch = 36;  // floats per staged accumulator row (32 + 4 pad: conflict-free 128-bit access)
 
 struct GemmKernelArgs {
   int batch, rows_per_batch, tiles_per_batch;
@@ -49,7 +50,8 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = BN == 128 ? 256 : 512;
   static constexpr int kAccStride = BN == 192 ? 256 : BN;  // column offset between the two accumulators
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                    4 * 32 * kEpiPitch * 4 /*epilogue transpose tiles*/;
 };
 
 template <int BN>
@@ -153,9 +155,14 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else {
     // ===================== epilogue warps =====================
+    // TMEM hands each lane one accumulator row; a 32 x 32 chunk is transposed through a padded
+    // shared-memory tile so that global loads/stores run along rows (8 lanes x 16 B per row).
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const bool out_f32 = (p.flags & SEGMA_GEMM_OUT_F32) != 0;
     const bool do_gelu = (p.flags & SEGMA_GEMM_GELU) != 0;
+    float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256) + (warp - 2) * (32 * kEpiPitch);
+    const int sub_r = lane >> 3;   // row within a group of 4
+    const int c4 = lane & 7;       // float4 column within the 32-column chunk
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -163,11 +170,11 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       const int b = m_tile / p.tiles_per_batch;
-      const int r = (m_tile - b * p.tiles_per_batch) * kBM + quad * 32 + lane;
+      const int r_base = (m_tile - b * p.tiles_per_batch) * kBM + quad * 32;  // first row of this warp
       const int n0 = n_tile * BN;
-      const bool row_ok = r < p.rows_per_batch;
-      const long long out_row = (long long)b * p.out_batch_rows + p.out_row_offset + r;
-      const long long src_row = p.add_src ? ((long long)b * p.rows_per_batch + r) % p.add_period : 0;
+      const long long out_row0 = (long long)b * p.out_batch_rows + p.out_row_offset + r_base;
+      long long src_base = 0;
+      if (p.add_src) src_base = ((long long)b * p.rows_per_batch + r_base) % p.add_period;
       mbar_wait(tmem_full + as, aphase);
       tc5_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::kAccStride;
@@ -175,49 +182,50 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       for (int chunk = 0; chunk < BN / 32; ++chunk) {
         const int nc = n0 + chunk * 32;
         if (nc >= p.n) break;  // warp-uniform
+        // issue the residual / position-table loads first so their latency hides behind the TMEM read
+        float4 src4[8];
+        if (p.add_src) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int rr = g * 4 + sub_r;
+            long long sr = src_base + rr;
+            while (sr >= p.add_period) sr -= p.add_period;
+            const bool ok = r_base + rr < p.rows_per_batch;
+            src4[g] = ok ? *(reinterpret_cast<const float4*>(p.add_src + sr * p.n + nc) + c4)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + c4);
         uint32_t acc[32];
         tmem_ld_32x32(t_addr + chunk * 32, acc);
         tmem_ld_wait();
-        if (row_ok) {
-          float v[32];
+        float4* my_row = reinterpret_cast<float4*>(stg + lane * kEpiPitch);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-          if (p.bias) {
+        for (int j = 0; j < 8; ++j)
+          my_row[j] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                                  __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+        __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nc + i));
-              v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
-            }
-          }
-          if (do_gelu) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-          }
-          if (p.add_src) {
-            const float4* s4 = reinterpret_cast<const float4*>(p.add_src + src_row * p.n + nc);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 sv = s4[i];
-              v[4 * i] += sv.x; v[4 * i + 1] += sv.y; v[4 * i + 2] += sv.z; v[4 * i + 3] += sv.w;
-            }
-          }
-          if (out_f32) {
-            float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_row * p.ldo + nc);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else {
-            uint4* o4 = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + out_row * p.ldo + nc);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 q;
-              q.x = pack_f16x2(v[8 * i], v[8 * i + 1]);
-              q.y = pack_f16x2(v[8 * i + 2], v[8 * i + 3]);
-              q.z = pack_f16x2(v[8 * i + 4], v[8 * i + 5]);
-              q.w = pack_f16x2(v[8 * i + 6], v[8 * i + 7]);
-              o4[i] = q;
+        for (int g = 0; g < 8; ++g) {
+          const int rr = g * 4 + sub_r;
+          float4 v = *reinterpret_cast<const float4*>(stg + rr * kEpiPitch + c4 * 4);
+          v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+          if (do_gelu) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+          if (p.add_src) { v.x += src4[g].x; v.y += src4[g].y; v.z += src4[g].z; v.w += src4[g].w; }
+          if (r_base + rr < p.rows_per_batch) {
+            const long long o = (out_row0 + rr) * p.ldo + nc;
+            if (out_f32) {
+              reinterpret_cast<float4*>(static_cast<float*>(p.out) + o)[c4] = v;
+            } else {
+              uint2 q;
+              q.x = pack_f16x2(v.x, v.y);
+              q.y = pack_f16x2(v.z, v.w);
+              reinterpret_cast<uint2*>(static_cast<__half*>(p.out) + o)[c4] = q;
             }
           }
         }
+        __syncwarp();
       }
       tc5_fence_before();
       __syncwarp();

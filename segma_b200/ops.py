@@ -23,19 +23,42 @@ def _lib():
 
 
 class _Stats:
-    """Launch accounting (bench.py's ``gpu_launches``) and optional CUDA-event timing of the GEMM launches."""
+    """Launch accounting (bench.py's ``gpu_launches``) and optional CUDA-event timing of every C-ABI call."""
 
     def __init__(self):
         self.launches = 0
-        self.profile_gemm = False
-        self.gemm_events: list[tuple[torch.cuda.Event, torch.cuda.Event, float]] = []
+        self.profile = False
+        self.events: list[tuple[str, torch.cuda.Event, torch.cuda.Event, float]] = []
 
     def reset(self):
         self.launches = 0
-        self.gemm_events = []
+        self.events = []
+
+    def breakdown(self) -> dict:
+        """name -> {"ms": total, "calls": n, "work": summed flops/bytes}; call after a synchronize."""
+        out: dict[str, dict] = {}
+        for name, e0, e1, work in self.events:
+            d = out.setdefault(name, {"ms": 0.0, "calls": 0, "work": 0.0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["calls"] += 1
+            d["work"] += work
+        return out
 
 
 stats = _Stats()
+
+
+def _call(name: str, n_launches: int, fn, *args, work: float = 0.0) -> None:
+    if stats.profile:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        stats.events.append((name, e0, e1, work))
+    else:
+        rc = fn(*args)
+    check(rc, name.split("[")[0])
+    stats.launches += n_launches
 
 
 def _stream() -> int:
@@ -71,24 +94,16 @@ def logmel(pcm: torch.Tensor, n_windows: int, win_len: int, step: int, out_f32: 
     nbytes = lib.segma_logmel_scratch_bytes(n_windows, win_len)
     scratch = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=pcm.device)
     view = pcm[pcm_offset:]
-    check(
-        lib.segma_logmel(view.data_ptr(), view.numel(), n_windows, win_len, step,
+    _call("segma_logmel", 3, _lib().segma_logmel, view.data_ptr(), view.numel(), n_windows, win_len, step,
                          None if f32 is None else f32.data_ptr(), None if tm is None else tm.data_ptr(),
-                         scratch.data_ptr(), _stream()),
-        "segma_logmel",
-    )
-    stats.launches += 3
+                         scratch.data_ptr(), _stream())
     return f32, tm
 
 
 def logmel_into(pcm_view: torch.Tensor, n_windows: int, win_len: int, step: int, tm: torch.Tensor,
                 scratch: torch.Tensor) -> None:
-    check(
-        _lib().segma_logmel(pcm_view.data_ptr(), pcm_view.numel(), n_windows, win_len, step, None, tm.data_ptr(),
-                            scratch.data_ptr(), _stream()),
-        "segma_logmel",
-    )
-    stats.launches += 3
+    _call("segma_logmel", 3, _lib().segma_logmel, pcm_view.data_ptr(), pcm_view.numel(), n_windows, win_len, step, None, tm.data_ptr(),
+                            scratch.data_ptr(), _stream())
 
 
 def logmel_scratch_bytes(n_windows: int, win_len: int) -> int:
@@ -119,15 +134,11 @@ def gemm_raw(a_ptr, a_batch_stride, a_row_stride, batch, rows_per_batch, k, w, n
         out_batch_rows=rows_per_batch if out_batch_rows is None else out_batch_rows,
         out_row_offset=out_row_offset, ldo=ldo, flags=flags, a_col_per_ntile=a_col_per_ntile, force_bn=force_bn,
     )
-    if stats.profile_gemm:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        check(_lib().segma_gemm_f16(C.byref(args), _stream()), "segma_gemm_f16")
-        e1.record()
-        stats.gemm_events.append((e0, e1, 2.0 * batch * rows_per_batch * n * k))
-    else:
-        check(_lib().segma_gemm_f16(C.byref(args), _stream()), "segma_gemm_f16")
-    stats.launches += 1
+    name = "segma_gemm_f16"
+    if stats.profile:
+        name += f"[n{n} k{k}{' conv' if conv_taps > 1 else ''}{' gelu' if flags & GEMM_GELU else ''}" \
+                f"{' +src' if add_src_ptr else ''}{' f32' if flags & GEMM_OUT_F32 else ''}]"
+    _call(name, 1, _lib().segma_gemm_f16, C.byref(args), _stream(), work=2.0 * batch * rows_per_batch * n * k)
 
 
 def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, gelu=False, add_src=None, add_period=None, out=None,
@@ -173,24 +184,16 @@ def layernorm(x: torch.Tensor, gamma, beta, *, out_f16=None, out_f32=None, mix=N
               w_out=0.0, mix_init=False) -> None:
     rows, d = x.shape
     assert x.is_contiguous()
-    check(
-        _lib().segma_layernorm(_dev(x, torch.float32, "x"), _dev(gamma, torch.float32, "gamma"),
+    _call("segma_layernorm", 1, _lib().segma_layernorm, _dev(x, torch.float32, "x"), _dev(gamma, torch.float32, "gamma"),
                                _dev(beta, torch.float32, "beta"), rows, d, _ptr(out_f16, torch.float16, "out_f16"),
                                _ptr(out_f32, torch.float32, "out_f32"), _ptr(mix, torch.float32, "mix"), period,
-                               n_keep, float(w_in), float(w_out), int(mix_init), _stream()),
-        "segma_layernorm",
-    )
-    stats.launches += 1
+                               n_keep, float(w_in), float(w_out), int(mix_init), _stream())
 
 
 def cast_f16(src: torch.Tensor, dst: torch.Tensor) -> None:
     rows, cols = src.shape
-    check(
-        _lib().segma_cast_f16(_dev(src, torch.float32, "src"), src.stride(0), _dev(dst, torch.float16, "dst"),
-                               dst.stride(0), rows, cols, _stream()),
-        "segma_cast_f16",
-    )
-    stats.launches += 1
+    _call("segma_cast_f16", 1, _lib().segma_cast_f16, _dev(src, torch.float32, "src"), src.stride(0), _dev(dst, torch.float16, "dst"),
+                               dst.stride(0), rows, cols, _stream())
 
 
 def attention(qkv: torch.Tensor, n_windows: int, T: int, n_heads: int, *, n_query=None, gate=None, pos_bias=None,
@@ -198,13 +201,9 @@ def attention(qkv: torch.Tensor, n_windows: int, T: int, n_heads: int, *, n_quer
     assert qkv.is_contiguous() and qkv.shape == (n_windows * T, 3 * n_heads * 64)
     if out is None:
         out = torch.zeros((n_windows * T, n_heads * 64), dtype=torch.float16, device=qkv.device)
-    check(
-        _lib().segma_attention(_dev(qkv, torch.float16, "qkv"), n_windows, T, n_heads, T if n_query is None else n_query,
+    _call("segma_attention", 1, _lib().segma_attention, _dev(qkv, torch.float16, "qkv"), n_windows, T, n_heads, T if n_query is None else n_query,
                                _ptr(gate, torch.float32, "gate"), _ptr(pos_bias, torch.float32, "pos_bias"),
-                               _dev(out, torch.float16, "out"), _stream()),
-        "segma_attention",
-    )
-    stats.launches += 1
+                               _dev(out, torch.float16, "out"), _stream())
     return out
 
 
@@ -215,13 +214,9 @@ def lstm_layer(pre: torch.Tensor, w_hh_t: torch.Tensor, hidden: int, *, out=None
     assert pre.is_contiguous() and w_hh_t.is_contiguous() and w_hh_t.shape == (n_dirs, hidden, 4 * hidden)
     if out is None:
         out = torch.empty((n_steps, n_rows, n_dirs * hidden), dtype=torch.float32, device=pre.device)
-    check(
-        _lib().segma_lstm_layer(_dev(pre, torch.float32, "pre"), _dev(w_hh_t, torch.float32, "w_hh_t"), n_steps, n_rows,
+    _call("segma_lstm_layer", 1, _lib().segma_lstm_layer, _dev(pre, torch.float32, "pre"), _dev(w_hh_t, torch.float32, "w_hh_t"), n_steps, n_rows,
                                 hidden, n_dirs, _dev(out, torch.float32, "out"),
-                                _ptr(out_f16, torch.float16, "out_f16"), _stream()),
-        "segma_lstm_layer",
-    )
-    stats.launches += 1
+                                _ptr(out_f16, torch.float16, "out_f16"), _stream())
     return out
 
 
@@ -229,13 +224,9 @@ def heads(feat: torch.Tensor, w: torch.Tensor, b: torch.Tensor, logits: torch.Te
           step_frames: int, n_keep: int) -> None:
     n_steps, n_rows, n_feat = feat.shape
     assert feat.is_contiguous() and w.is_contiguous() and logits.is_contiguous()
-    check(
-        _lib().segma_heads(_dev(feat, torch.float32, "feat"), n_steps, n_rows, n_feat, n_keep,
+    _call("segma_heads", 1, _lib().segma_heads, _dev(feat, torch.float32, "feat"), n_steps, n_rows, n_feat, n_keep,
                            _dev(w, torch.float32, "w"), _dev(b, torch.float32, "b"), w.shape[0],
-                           _dev(logits, torch.float32, "logits"), frame_offset, step_frames, _stream()),
-        "segma_heads",
-    )
-    stats.launches += 1
+                           _dev(logits, torch.float32, "logits"), frame_offset, step_frames, _stream())
 
 
 # ---- stitch / decode -----------------------------------------------------------------------------
@@ -244,12 +235,8 @@ def stitch(window_logits: torch.Tensor, n_windows: int, frames_per_window: int, 
     C_ = window_logits.shape[-1]
     assert window_logits.is_contiguous()
     out = torch.empty((n_frames, C_), dtype=torch.float32, device=window_logits.device)
-    check(
-        _lib().segma_stitch(_dev(window_logits, torch.float32, "window_logits"), n_windows, frames_per_window,
-                            step_frames, tail_frames, C_, out.data_ptr(), n_frames, _stream()),
-        "segma_stitch",
-    )
-    stats.launches += 1
+    _call("segma_stitch", 1, _lib().segma_stitch, _dev(window_logits, torch.float32, "window_logits"), n_windows, frames_per_window,
+                            step_frames, tail_frames, C_, out.data_ptr(), n_frames, _stream())
     return out
 
 
@@ -258,11 +245,7 @@ def threshold_mask(logits: torch.Tensor, thresholds, mode: int = DECODE_SIGMOID)
     assert logits.is_contiguous()
     thr = (C.c_float * C_)(*[float(t) for t in thresholds])
     mask = torch.empty((n, C_), dtype=torch.uint8, device=logits.device)
-    check(
-        _lib().segma_threshold_mask(_dev(logits, torch.float32, "logits"), n, C_, thr, mode, mask.data_ptr(), _stream()),
-        "segma_threshold_mask",
-    )
-    stats.launches += 1
+    _call("segma_threshold_mask", 1, _lib().segma_threshold_mask, _dev(logits, torch.float32, "logits"), n, C_, thr, mode, mask.data_ptr(), _stream())
     return mask.bool()
 
 

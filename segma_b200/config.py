@@ -229,6 +229,9 @@ def load_config(config_path, cli_extra_args: list[str] = ()) -> Config:
     with Path(config_path).open("r") as f:
         tree = yaml.safe_load(f)
     model = tree["model"]
+    for extra in cli_extra_args:  # a model.name override selects which sub-config file is read
+        if extra.split("=", 1)[0] == "model.name":
+            _apply_override(tree, extra)
     if "config" not in model:
         side = Path(f"src/segma/config/{model['name']}.yml")
         if side.exists():

@@ -70,7 +70,7 @@ def _read_frames(path: Path, lay: _WavLayout, start: int, count: int) -> np.ndar
         f.seek(lay.data_offset + start * lay.n_channels * bps)
         raw = f.read(count * lay.n_channels * bps)
     if lay.fmt == 3 and lay.bits == 32:
-        x = np.frombuffer(raw, dtype="<f4").astype(np.float32, copy=False)
+        x = np.frombuffer(raw, dtype="<f4").astype(np.float32)
     elif lay.fmt == 3 and lay.bits == 64:
         x = np.frombuffer(raw, dtype="<f8").astype(np.float32)
     elif lay.fmt == 1 and lay.bits == 16:

@@ -1,0 +1,68 @@
+"""Multi-rank host logic on CPU: file assignment and the final interval-table all-gather over gloo
+(world_size 2), the N > 1 path of SURVEY.md section 8e."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from segma_b200.distributed import all_gather_tables, assign_files, gather_file_tables
+
+
+def test_assign_files_is_balanced_and_complete():
+    sizes = [100, 90, 80, 10, 10, 10, 5, 5, 1, 0]
+    parts = assign_files(sizes, 3)
+    assert sorted(i for p in parts for i in p) == list(range(len(sizes)))
+    loads = [sum(sizes[i] for i in p) for p in parts]
+    assert max(loads) - min(loads) <= max(sizes)
+    assert assign_files(sizes, 3) == parts  # deterministic
+    assert assign_files([5], 4) == [[0], [], [], []]
+    thousand = assign_files([57_600_000] * 1000, 8)
+    assert [len(p) for p in thousand] == [125] * 8
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    files = assign_files([300, 200, 100, 50, 10], world)[rank]
+    rows = []
+    for f in files:
+        n = f + 1 + rank  # different, non-empty counts per file
+        rows += [(f, k % 4, 320 * k, 320 * (k + 1)) for k in range(n)]
+    table = torch.tensor(rows, dtype=torch.int32).reshape(-1, 4)
+    if rank == 1:
+        empty = all_gather_tables(torch.zeros((0, 4), dtype=torch.int32))
+        assert empty.shape[1] == 4
+    else:
+        all_gather_tables(torch.zeros((0, 4), dtype=torch.int32))
+    full = gather_file_tables(table)
+    np.save(os.path.join(out_dir, f"r{rank}.npy"), full.numpy())
+    dist.destroy_process_group()
+
+
+def test_interval_table_all_gather_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "r0.npy"), np.load(tmp_path / "r1.npy")
+    assert np.array_equal(a, b)
+    assert list(a[:, 0]) == sorted(a[:, 0])  # ordered by global file index
+    assert set(a[:, 0]) == {0, 1, 2, 3, 4}
+    # every file's rows stay in their rank-local (label, time) order
+    for f in range(5):
+        rows = a[a[:, 0] == f]
+        assert list(rows[:, 2]) == [320 * k for k in range(len(rows))]
+
+
+def test_single_process_gather_is_identity():
+    t = torch.arange(12, dtype=torch.int32).reshape(3, 4)
+    assert torch.equal(all_gather_tables(t), t)

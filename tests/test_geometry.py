@@ -1,0 +1,97 @@
+"""Frame/sample geometry: the reference's own ConvolutionSettings known-answer tests
+(/root/reference/tests/test_ConvolutionSettings.py:4-28), the golden values produced by the reference's
+class, and the window/batch plan against the oracle's restatement of inference.py:129-206."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import segma_oracle as O
+from segma_b200.geometry import INFERENCE_SETTINGS, Chunkyfier, ConvolutionSettings, conv_frames, plan_windows
+
+GOLDEN = Path(__file__).parent / "golden"
+
+
+def test_rf_start_i():
+    assert ConvolutionSettings((3, 2), (3, 1), (1, 0)).rf_start_i(0) == -1
+    assert ConvolutionSettings((2,), (1,), (0,)).rf_start_i(0) == 0
+
+
+def test_rf_end_i():
+    assert ConvolutionSettings((3, 2), (3, 1), (1, 0)).rf_end_i(0) == 4
+    assert ConvolutionSettings((2,), (1,), (0,)).rf_end_i(0) == 1
+
+
+def test_rf_size():
+    assert ConvolutionSettings((3, 2), (3, 1), (1, 0)).rf_size == 6
+    assert ConvolutionSettings((2,), (1,), (0,)).rf_size == 2
+
+
+def test_mismatched_settings_raise():
+    with pytest.raises(ValueError):
+        ConvolutionSettings((3, 2), (3,), (1, 0))
+
+
+def test_golden_receptive_fields():
+    g = np.load(GOLDEN / "geometry.npz")
+    for row in g["rf"]:
+        L = int(row[0])
+        ks, ss, ps = tuple(row[1:1 + L]), tuple(row[1 + L:1 + 2 * L]), tuple(row[1 + 2 * L:1 + 3 * L])
+        u, start, end, size, step = (int(v) for v in row[1 + 3 * L:6 + 3 * L])
+        cs = ConvolutionSettings(tuple(int(k) for k in ks), tuple(int(s) for s in ss), tuple(int(p) for p in ps))
+        assert (cs.rf_start_i(u), cs.rf_end_i(u), cs.rf_size, cs.rf_step) == (start, end, size, step)
+        assert O.rf_start(u, ks, ss, ps) == start and O.rf_end(u, ks, ss, ps) == end and O.rf_size(ks, ss) == size
+    whisper = ConvolutionSettings((400, 3, 3), (160, 1, 2), (200, 1, 1))
+    for chunk, strict_n, loose_n in g["n_windows"]:
+        assert INFERENCE_SETTINGS.n_windows(int(chunk), True) == strict_n
+        assert whisper.n_windows(int(chunk), False) == loose_n
+
+
+def test_chunkyfier_matches_reference_constants():
+    c = Chunkyfier(128, 64000, INFERENCE_SETTINGS)
+    assert (c.n_windows, c.missing_n_frames, c.step) == (199, 320, 63680)
+    assert c.chunk_start_i(3) == 3 * 63680 and c.chunk_end_i(3) == 3 * 63680 + 64000
+    assert c.batch_start_i(2) == 2 * 128 * 63680
+    assert c.batch_end_i_coverage(0) == 128 * 63680
+    assert c.get_n_fitting_chunks(64000) == 1 and c.get_n_fitting_chunks(63999) == 0
+    assert c.get_n_fitting_chunks(57_600_000) == 904
+
+
+@pytest.mark.parametrize("n", [0, 399, 400, 50_000, 64_000, 64_319, 127_460, 127_680, 193_234, 960_000, 2_880_000, 57_600_000])
+@pytest.mark.parametrize("bs", [1, 2, 128])
+def test_plan_equals_oracle_batches(n, bs):
+    plan = plan_windows(n, 64000, bs)
+    mine = [(b.start_sample, b.n_windows, b.win_len) for b in plan.batches]
+    assert mine == O.file_batches(n, 64000, bs)
+    assert plan.n_frames == conv_frames(n)  # contiguous 20 ms grid: (n-400)//320+1
+    assert sum(b.n_windows * b.frames_per_window for b in plan.batches) == plan.n_frames
+
+
+def test_one_hour_file_counts():
+    plan = plan_windows(57_600_000)
+    assert plan.n_windows == 905 and plan.n_frames == 179_999
+    assert [b.n_windows for b in plan.batches] == [128] * 7 + [8, 1]
+    assert plan.batches[-1].is_tail and plan.batches[-1].win_len == 33_280 and plan.batches[-1].frames_per_window == 103
+
+
+@pytest.mark.parametrize("win_s,overlap", [(2, 0.5), (3, 0.75), (4, 0.9), (6, 0.5), (8, 0.75)])
+def test_overlapping_plans_cover_every_frame(win_s, overlap):
+    win = win_s * 16000
+    F = conv_frames(win)
+    step = max(320, int(win * (1 - overlap)) // 320 * 320)
+    n = 1_000_000
+    plan = plan_windows(n, win, 16, step, F)
+    cover = np.zeros(plan.n_frames, dtype=int)
+    for b in plan.batches:
+        for i in range(b.n_windows):
+            off = (b.first_window + i) * plan.step_frames
+            cover[off: off + b.frames_per_window] += 1
+    assert cover.min() >= 1
+    assert plan.n_frames <= conv_frames(n)
+
+
+def test_bad_steps_rejected():
+    with pytest.raises(ValueError):
+        plan_windows(100_000, 64000, 4, step=1000)
+    with pytest.raises(ValueError):
+        plan_windows(100_000, 64000, 4, step=64000 + 320)

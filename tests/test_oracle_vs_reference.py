@@ -1,0 +1,92 @@
+"""Where the read-only reference checkout is mounted (this container, not the GPU box), run the
+reference's own code next to the oracle on fresh inputs.  Skipped elsewhere; the committed golden
+fixtures (tests/test_oracle_golden.py) carry the same pin to the GPU box."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shim, segma_oracle as O
+from segma_b200 import synth
+from segma_b200.encoders import MultiLabelEncoder as MyEncoder
+from segma_b200.geometry import Chunkyfier as MyChunkyfier, ConvolutionSettings as MyCS
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference is not mounted")
+LABELS = synth.DEFAULT_LABELS
+
+
+@pytest.fixture(scope="module")
+def ref():
+    ref_shim.install()
+    import segma.inference as inf
+    from segma.models.base import ConvolutionSettings
+    from segma.utils.encoders import MultiLabelEncoder
+
+    return dict(inf=inf, CS=ConvolutionSettings, LE=MultiLabelEncoder)
+
+
+def test_convolution_settings_agree(ref):
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        L = int(rng.integers(1, 6))
+        ks = tuple(int(v) for v in rng.integers(1, 12, L))
+        ss = tuple(int(v) for v in rng.integers(1, 5, L))
+        ps = tuple(int(v) for v in rng.integers(0, 4, L))
+        a, b = ref["CS"](ks, ss, ps), MyCS(ks, ss, ps)
+        for u in (0, 1, 5, 100):
+            assert a.rf_start_i(u) == b.rf_start_i(u) and a.rf_end_i(u) == b.rf_end_i(u)
+            assert a.rf_center_i(u) == b.rf_center_i(u)
+        assert a.rf_size == b.rf_size and a.rf_step == b.rf_step
+        for chunk in (32000, 64000, 112000):
+            assert a.n_windows(chunk, True) == b.n_windows(chunk, True)
+            assert a.n_windows(chunk, False) == b.n_windows(chunk, False)
+
+
+def test_chunkyfier_agrees(ref):
+    cs_r, cs_m = ref["CS"]((320,), (320,), (0,)), MyCS((320,), (320,), (0,))
+    a, b = ref["inf"].Chunkyfier(128, 64000, cs_r), MyChunkyfier(128, 64000, cs_m)
+    for i in (0, 1, 7):
+        for fn in ("chunk_start_i", "chunk_end_i", "chunk_end_i_coverage", "batch_start_i", "batch_end_i", "batch_end_i_coverage"):
+            assert getattr(a, fn)(i) == getattr(b, fn)(i)
+    for n in (64000, 100_000, 127_680, 57_600_000):
+        assert a.get_n_fitting_chunks(n) == b.get_n_fitting_chunks(n)
+
+
+def test_label_encoder_agrees(ref):
+    a, b = ref["LE"](list(LABELS)), MyEncoder(list(LABELS))
+    assert a.labels == b.labels and a.base_labels == b.base_labels and a.n_labels == b.n_labels
+    assert [a.inv_transform(i) for i in range(4)] == [b.inv_transform(i) for i in range(4)]
+    assert np.array_equal(a.one_hot(("KCHI", "FEM")), b.one_hot(("KCHI", "FEM")))
+
+
+def test_thresholds_and_intervals_agree_on_random_logits(ref):
+    inf = ref["inf"]
+    le, cs = ref["LE"](list(LABELS)), ref["CS"]((320,), (320,), (0,))
+    g = torch.Generator().manual_seed(1)
+    logits = torch.randn((20_000, 4), generator=g)
+    for t in (0.5, 0.31, 0.77):
+        thr = {lab: {"lower_bound": t, "upper_bound": 1.0} for lab in LABELS}
+        mask = inf.apply_thresholds(logits, thr, "cpu")
+        assert torch.equal(mask, O.apply_thresholds(logits, [t] * 4))
+        assert inf.create_intervals(mask, cs, le) == O.create_intervals(mask.numpy(), LABELS)
+
+
+def test_hubert_file_level_through_reference_driver(ref):
+    from segma.config.base import SurgicalHydraLightHuBERTConfig
+    from segma.models import Models
+
+    le = ref["LE"](list(LABELS))
+    sub = SurgicalHydraLightHuBERTConfig(wav_encoder="none", encoder_layers=[], reduction="weighted", classifier=256, freeze_encoder=True)
+    m = Models["surgical_hubert_hydra"](le, ref_shim.make_config("surgical_hubert_hydra", sub), train=False).eval()
+    sd = synth.hubert_hydra_state_dict(synth.HUBERT_BASE, seed=9)
+    torch.nn.Module.load_state_dict(m, sd, strict=True)
+    n = 64000 + 63680 + 5000
+    pcm = synth.synth_audio(n, 21)
+    audio = ref_shim.InMemoryAudio()
+    audio.add("/mem/b.wav", pcm)
+    inf = audio.patch()
+    want = inf.apply_model_on_audio(Path("/mem/b.wav"), m, ref["CS"]((320,), (320,), (0,)), "cpu", batch_size=128)
+    got = O.apply_model_on_audio(torch.from_numpy(pcm), lambda w: O.hubert_hydra_forward(sd, w, LABELS), 4, batch_size=128)
+    assert got.shape == want.shape == ((n - 400) // 320 + 1, 4)
+    assert (got - want).abs().max() <= 1e-4 * max(1.0, want.abs().max().item())

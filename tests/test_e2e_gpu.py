@@ -117,3 +117,43 @@ def test_overlapping_windows_stitch(cuda):
     ref = O.stitch_mean(wins, offs, n_frames)
     assert got.shape == ref.shape
     _check_logits(got, ref, "50% overlap")
+
+
+# ---- against the fixtures the reference itself produced (tests/golden/models.npz) ---------------------------
+from pathlib import Path  # noqa: E402
+
+GOLDEN = Path(__file__).parent / "golden"
+
+
+@pytest.mark.parametrize("key,kind,seed,extra", [
+    ("surgical_hydra_logits", "surgical_hydra", 3, {}),
+    ("surgical_hydra_avg_l2_logits", "surgical_hydra", 8, {"encoder_layers": [2], "reduction": "average"}),
+    ("hydra_whisper_logits", "hydra_whisper", 7, {}),
+])
+def test_whisper_family_vs_reference_golden(cuda, key, kind, seed, extra):
+    g = np.load(GOLDEN / "models.npz")
+    n, audio_seed, bs = (int(v) for v in g["meta"])
+    if kind == "surgical_hydra":
+        sd = synth.surgical_hydra_state_dict(synth.WHISPER_TEST, n_mixed_layers=1 if extra else None, seed=seed)
+    else:
+        sd = synth.hydra_whisper_state_dict(synth.WHISPER_TEST, seed=seed)
+    le = MultiLabelEncoder(list(LABELS))
+    model = Models[kind].from_state_dict(sd, le, make_config(kind, extra))
+    got = apply_model_on_audio(synth.synth_audio(n, audio_seed), model, INFERENCE_SETTINGS, "cuda", batch_size=bs).cpu()
+    _check_logits(got, torch.from_numpy(g[key]), f"{key} vs reference golden")
+
+
+def test_decode_vs_reference_golden(cuda):
+    g = np.load(GOLDEN / "models.npz")
+    logits = torch.from_numpy(g["hubert_logits"]).cuda()
+    le = MultiLabelEncoder(list(LABELS))
+    for tname, t in (("t50", 0.5), ("t30", 0.3), ("t70", 0.7)):
+        thr = {lab: {"lower_bound": t, "upper_bound": 1.0} for lab in LABELS}
+        assert np.array_equal(apply_thresholds(logits, thr).cpu().numpy(), g[f"hubert_mask_{tname}"])
+        iv = decode_logits(logits, thr, le)
+        want = [(int(s), int(e), LABELS[int(c)]) for c, s, e in g[f"hubert_intervals_{tname}"]]
+        assert iv == want
+    gi = np.load(GOLDEN / "intervals.npz")
+    for k in sorted(k[5:] for k in gi.files if k.startswith("mask_")):
+        iv = create_intervals(torch.from_numpy(gi[f"mask_{k}"]), INFERENCE_SETTINGS, le)
+        assert iv == [(int(s), int(e), LABELS[int(c)]) for c, s, e in gi[f"iv_{k}"]], k

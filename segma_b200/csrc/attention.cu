@@ -9,6 +9,8 @@
 // through a double-buffered cp.async ring in XOR-swizzled shared memory; scores never leave registers.
 // This version uses the warp-level mma.sync tensor path (m16n8k16 fp16); the tcgen05/TMEM pipeline is the
 // GEMM kernel's and is the planned upgrade for this kernel.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace segma {
@@ -202,6 +204,9 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __half* _
   }
 }
 
+int launch_attention_tc5(const void* qkv, int n_windows, int T, int n_heads, int n_query, void* out,
+                         cudaStream_t st);
+
 }  // namespace segma
 
 using namespace segma;
@@ -215,6 +220,11 @@ int segma_attention(const void* qkv, int n_windows, int T, int n_heads, int n_qu
   SEGMA_REQUIRE(qkv && out, "segma_attention: NULL buffer");
   SEGMA_REQUIRE((gate == nullptr) == (pos_bias == nullptr), "segma_attention: gate and pos_bias go together");
   SEGMA_REQUIRE(n_heads <= 65535 && n_windows <= 65535, "segma_attention: grid too large");
+  // tcgen05 path for plain attention; the gated-bias (WavLM) variant and SEGMA_ATTN_LEGACY=1 use the
+  // warp-level mma.sync kernel below
+  static const bool legacy = getenv("SEGMA_ATTN_LEGACY") != nullptr;
+  if (pos_bias == nullptr && !legacy && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
+    return launch_attention_tc5(qkv, n_windows, T, n_heads, n_query, out, (cudaStream_t)stream);
   dim3 grid(ceil_div(n_query, kQTile), n_heads, n_windows);
   attention_kernel<<<grid, kAttnThreads, 0, (cudaStream_t)stream>>>(
       static_cast<const __half*>(qkv), T, n_heads, n_query, gate, pos_bias, static_cast<__half*>(out));

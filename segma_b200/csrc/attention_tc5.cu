@@ -1,0 +1,259 @@
+// Fused multi-head self-attention on tcgen05 tensor cores: softmax(Q K^T) V, head_dim 64, fp16 operands,
+// fp32 scores / softmax statistics / output accumulation in TMEM.
+//
+// Replaces torch SDPA as dispatched by WhisperAttention (site-packages/transformers/models/whisper/
+// modeling_whisper.py:338-352; 1500 positions, no mask) and torchaudio SelfAttention
+// (site-packages/torchaudio/models/wav2vec2/components.py:305-307; 199 positions).
+//
+// One CTA owns 128 query rows of one (window, head); two CTAs are resident per SM so that one CTA's
+// softmax (MUFU-bound) overlaps the other's MMAs.  Per 128-key tile:
+//   warp 0      TMA: Q once, then K and V tiles (128 x 64, 128B swizzle) into a 2-stage ring, straight from the
+//               fused QKV activation through one 3-D tensor map (column block selects q / k / v and the head)
+//   warp 1      one lane issues  O += P_{j-1} V_{j-1}  (M128 N64, V as an MN-major B operand) and
+//               S = Q K_j^T (M128 N128) back to back, then one tcgen05.commit
+//   warps 2-5   one thread per query row: tcgen05.ld of its S row, running max with lazy rescale of O/l
+//               (only when the max grows by more than 2^8), exp2, P -> fp16 into the swizzled A-operand tile
+// Scores, probabilities and the output accumulator never touch HBM.
+#include "common.cuh"
+
+namespace segma {
+
+constexpr int kAtQ = 128;     // queries per CTA
+constexpr int kAtK = 128;     // keys per tile
+constexpr int kAtD = 64;      // head dim
+constexpr int kAtThreads = 192;
+constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 fp16
+constexpr int kAtSmem = 1024 + kTileBytes /*Q*/ + 2 * 2 * kTileBytes /*K,V ring*/ + 2 * kTileBytes /*P*/ + 256;
+constexpr uint32_t kTmemColsAttn = 256;  // S: 128 columns, O: 64 columns
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+__global__ void __launch_bounds__(kAtThreads, 2)
+attention_tc5_kernel(const __grid_constant__ CUtensorMap map_qkv, int T, int n_heads, int n_query,
+                     __half* __restrict__ out) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + ((1024 - (raw_addr & 1023)) & 1023);
+  unsigned char* s_q = smem;
+  unsigned char* s_kv = smem + kTileBytes;                 // stage s: K at s*2*tile, V at s*2*tile + tile
+  unsigned char* s_p = smem + kTileBytes + 4 * kTileBytes;  // two 64-key k-blocks of 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * kTileBytes);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* mma_done = bars + 5;
+  uint64_t* p_ready = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  const int q0 = blockIdx.x * kAtQ;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int d = n_heads * kAtD;
+  const int n_kt = ceil_div(T, kAtK);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_qkv);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(kv_full + i, 1);
+      mbar_init(kv_empty + i, 1);
+    }
+    mbar_init(mma_done, 1);
+    mbar_init(p_ready, 4);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemColsAttn);
+    tmem_relinquish();
+  }
+  tc5_fence_before();
+  __syncthreads();
+  tc5_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;
+  const uint32_t tmem_o = tmem_base + kAtK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kTileBytes);
+      tma_load_3d(s_q, &map_qkv, q_full, h * kAtD, q0, b);
+      for (int j = 0; j < n_kt; ++j) {
+        const int st = j & 1;
+        mbar_wait(kv_empty + st, ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(kv_full + st, 2 * kTileBytes);
+        tma_load_3d(s_kv + st * 2 * kTileBytes, &map_qkv, kv_full + st, d + h * kAtD, j * kAtK, b);
+        tma_load_3d(s_kv + st * 2 * kTileBytes + kTileBytes, &map_qkv, kv_full + st, 2 * d + h * kAtD, j * kAtK, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(kAtQ, kAtK, 0, 0);  // S = Q K^T, both K-major
+      constexpr uint32_t idesc_o = umma_idesc_f16(kAtQ, kAtD, 0, 1);  // O += P V, V is MN-major
+      const uint32_t q_addr = smem_u32(s_q);
+      const uint32_t p_addr = smem_u32(s_p);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j <= n_kt; ++j) {
+        if (j < n_kt) mbar_wait(kv_full + (j & 1), (j >> 1) & 1);
+        if (j > 0) {
+          mbar_wait(p_ready, (j - 1) & 1);
+          tc5_fence_after();
+          const uint32_t v_addr = smem_u32(s_kv + ((j - 1) & 1) * 2 * kTileBytes + kTileBytes);
+#pragma unroll
+          for (int ks = 0; ks < kAtK / 16; ++ks) {
+            const uint64_t da = umma_desc_k_sw128(p_addr + (ks >> 2) * kTileBytes + (ks & 3) * 32);
+            const uint64_t db = umma_desc_mn_sw128(v_addr + ks * 2048, kTileBytes);
+            tc5_mma_f16(tmem_o, da, db, idesc_o, (j > 1 || ks > 0) ? 1u : 0u);
+          }
+          tc5_commit(kv_empty + ((j - 1) & 1));
+        }
+        if (j < n_kt) {
+          tc5_fence_after();
+          const uint32_t k_addr = smem_u32(s_kv + (j & 1) * 2 * kTileBytes);
+#pragma unroll
+          for (int ks = 0; ks < kAtD / 16; ++ks) {
+            const uint64_t da = umma_desc_k_sw128(q_addr + ks * 32);
+            const uint64_t db = umma_desc_k_sw128(k_addr + ks * 32);
+            tc5_mma_f16(tmem_s, da, db, idesc_s, ks > 0 ? 1u : 0u);
+          }
+        }
+        tc5_commit(mma_done);
+      }
+    }
+  } else {
+    // ===================== softmax / correction / epilogue: one thread per query row =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;           // row inside the tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const float kLog2e = 1.4426950408889634f;
+    float m_run = -INFINITY;  // running max, log2 units
+    float l_run = 0.f;
+    unsigned char* p_row = s_p + row * 128;
+    const int sw = row & 7;
+    for (int j = 0; j < n_kt; ++j) {
+      mbar_wait(mma_done, j & 1);
+      tc5_fence_after();
+      const int key0 = j * kAtK;
+      // pass 1: tile max of this row
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32];
+        tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
+        tmem_ld_wait();
+        if (key0 + c * 32 + 32 <= T) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (key0 + c * 32 + i < T) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        }
+      }
+      const float t = mx * kLog2e;
+      // tcgen05.ld/st are warp-collective: the rescale decision is taken per warp, each lane with its own factor
+      if (__any_sync(0xffffffffu, t > m_run + kRescaleThreshold)) {
+        const float m_new = fmaxf(m_run, t);
+        const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_new);
+        l_run *= alpha;
+        m_run = m_new;
+        if (j > 0) {  // O holds contributions of earlier tiles: rescale it in place
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t ov[32];
+            tmem_ld_32x32(tmem_o + lane_addr + c * 32, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st_32x32(tmem_o + lane_addr + c * 32, ov);
+          }
+          tmem_st_wait();
+        }
+      }
+      // pass 2: probabilities -> fp16 A-operand tile (K-major, 128B swizzle: 16-byte chunk index ^ (row & 7))
+      float psum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32];
+        tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float p = ex2_approx(fmaf(__uint_as_float(sv[i]), kLog2e, -m_run));
+          if (key0 + c * 32 + i >= T) p = 0.f;
+          pv[i] = p;
+          psum += p;
+        }
+        unsigned char* blk = p_row + (c >> 1) * kTileBytes;  // 64-key k-block
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 pk;
+          pk.x = pack_f16x2(pv[8 * q], pv[8 * q + 1]);
+          pk.y = pack_f16x2(pv[8 * q + 2], pv[8 * q + 3]);
+          pk.z = pack_f16x2(pv[8 * q + 4], pv[8 * q + 5]);
+          pk.w = pack_f16x2(pv[8 * q + 6], pv[8 * q + 7]);
+          const int chunk = (c & 1) * 4 + q;
+          *reinterpret_cast<uint4*>(blk + ((chunk ^ sw) << 4)) = pk;
+        }
+      }
+      l_run += psum;
+      fence_proxy_async_smem();
+      tc5_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+    }
+    // epilogue: wait for the last P V, normalise, store
+    mbar_wait(mma_done, n_kt & 1);
+    tc5_fence_after();
+    const int q_row = q0 + row;
+    const float inv_l = 1.0f / l_run;
+    __half* o_ptr = out + ((long long)b * T + q_row) * d + h * kAtD;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t ov[32];
+      tmem_ld_32x32(tmem_o + lane_addr + c * 32, ov);
+      tmem_ld_wait();
+      if (q_row < n_query) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 pk;
+          pk.x = pack_f16x2(__uint_as_float(ov[8 * q]) * inv_l, __uint_as_float(ov[8 * q + 1]) * inv_l);
+          pk.y = pack_f16x2(__uint_as_float(ov[8 * q + 2]) * inv_l, __uint_as_float(ov[8 * q + 3]) * inv_l);
+          pk.z = pack_f16x2(__uint_as_float(ov[8 * q + 4]) * inv_l, __uint_as_float(ov[8 * q + 5]) * inv_l);
+          pk.w = pack_f16x2(__uint_as_float(ov[8 * q + 6]) * inv_l, __uint_as_float(ov[8 * q + 7]) * inv_l);
+          reinterpret_cast<uint4*>(o_ptr + c * 32)[q] = pk;
+        }
+      }
+    }
+  }
+
+  tc5_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc5_fence_after();
+    tmem_dealloc(tmem_base, kTmemColsAttn);
+  }
+}
+
+int make_f16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                 int box_rows);
+
+int launch_attention_tc5(const void* qkv, int n_windows, int T, int n_heads, int n_query, void* out,
+                         cudaStream_t st) {
+  const int d = n_heads * kAtD;
+  CUtensorMap map;
+  uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)T, (uint64_t)n_windows};
+  uint64_t strides[3] = {1, (uint64_t)3 * d, (uint64_t)3 * d * T};
+  int rc = make_f16_map(&map, qkv, 3, dims, strides, kAtK);
+  if (rc != SEGMA_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(n_query, kAtQ), n_heads, n_windows);
+  attention_tc5_kernel<<<grid, kAtThreads, kAtSmem, st>>>(map, T, n_heads, n_query, static_cast<__half*>(out));
+  return launch_status("attention_tc5_kernel");
+}
+
+}  // namespace segma

@@ -278,7 +278,7 @@ int make_f16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* d
     if (i > 0) gstr[i - 1] = strides_elems[i] * 2;
   }
   box[0] = kBK;
-  box[1] = box_rows;
+  box[1] = box_rows;  // (64 x box_rows) tile; higher dims have a box of 1
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -76,7 +76,8 @@ SEGMA_API int segma_logmel_get_filters(float* mel_201x80);
  * No im2col buffer is written: tap j is a TMA box at column (j % s) * c, row t + j / s of the activation
  * viewed s rows at a time.
  * epilogue: v = acc + bias[n]; if (flags & GELU) v = gelu_erf(v);
- *           if (add_src) v += add_src[((b*rows_per_batch + r) % add_period) * n + col]   (fp32)
+ *           if (add_src) v += add_src[(b*add_batch_rows + r) * n + col]   (fp32; add_batch_rows = 0: one
+ *                        (rows_per_batch, n) table shared by every batch, e.g. position embeddings)
  *           out[(b*out_batch_rows + out_row_offset + r) * ldo + col] = v  (fp16, or fp32 with OUT_F32)
  */
 #define SEGMA_GEMM_GELU 1
@@ -94,8 +95,8 @@ typedef struct {
   const void* w;          /* [dev] fp16 (n, k) row-major */
   int n;                  /* multiple of 32 */
   const float* bias;      /* [dev] (n) or NULL */
-  const float* add_src;   /* [dev] fp32 (add_period, n) or NULL; may alias out (residual update in place) */
-  int64_t add_period;
+  const float* add_src;   /* [dev] fp32 rows of n, or NULL; may alias out (residual update in place) */
+  int64_t add_batch_rows; /* rows between consecutive batches in add_src */
   void* out;              /* [dev] 16-byte aligned */
   int64_t out_batch_rows;
   int64_t out_row_offset;
@@ -112,10 +113,12 @@ SEGMA_API int segma_gemm_f16(const segma_gemm_args* args, void* stream);
  *            mix += w_in * x + w_out * y   (the layer-weighted sum of
  *            src/segma/models/whisper/surgical_hydra.py:82-98 restricted to the kept frames)
  *   mix_init: 1 = overwrite instead of accumulate
+ *   only_kept: 1 = normalise only the rows with (r % period) < n_keep (the frames the heads read); the
+ *              other rows of the outputs are left untouched
  */
 SEGMA_API int segma_layernorm(const float* x, const float* gamma, const float* beta, int64_t rows, int d, void* out_f16,
                     float* out_f32, float* mix, int period, int n_keep, float w_in, float w_out, int mix_init,
-                    void* stream);
+                    int only_kept, void* stream);
 
 /* softmax(Q K^T + bias) V per (window, head); qkv fp16 (n_windows*T, 3*d) rows = [q | k | v],
  * q pre-scaled, head_dim 64; out fp16 (n_windows*T, d).  Optional WavLM gated relative bias:

@@ -30,7 +30,7 @@ class GemmArgs(C.Structure):
         ("n", C.c_int),
         ("bias", C.c_void_p),
         ("add_src", C.c_void_p),
-        ("add_period", C.c_int64),
+        ("add_batch_rows", C.c_int64),
         ("out", C.c_void_p),
         ("out_batch_rows", C.c_int64),
         ("out_row_offset", C.c_int64),
@@ -54,7 +54,7 @@ SIGNATURES = {
     "segma_logmel_set_filters": (_i, [_vp]),
     "segma_logmel_get_filters": (_i, [_vp]),
     "segma_gemm_f16": (_i, [C.POINTER(GemmArgs), _vp]),
-    "segma_layernorm": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp]),
+    "segma_layernorm": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _f, _f, _i, _i, _vp]),
     "segma_attention": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "segma_cast_f16": (_i, [_vp, _i64, _vp, _i64, _i64, _i, _vp]),
     "segma_lstm_layer": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),

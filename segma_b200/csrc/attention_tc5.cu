@@ -23,16 +23,18 @@ constexpr int kAtK = 128;     // keys per tile
 constexpr int kAtD = 64;      // head dim
 constexpr int kAtThreads = 192;
 constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 fp16
-constexpr int kAtSmem = 1024 + kTileBytes /*Q*/ + 2 * 2 * kTileBytes /*K,V ring*/ + 2 * kTileBytes /*P*/ + 256;
+// exactly 7 tiles + barriers: 114 816 B, so that two CTAs fit the 227 KB of an SM (no alignment slack: the
+// dynamic shared-memory window of a kernel without static shared memory starts 1024-byte aligned; checked at run time)
+constexpr int kAtSmem = kTileBytes /*Q*/ + 2 * 2 * kTileBytes /*K,V ring*/ + 2 * kTileBytes /*P*/ + 128;
 constexpr uint32_t kTmemColsAttn = 256;  // S: 128 columns, O: 64 columns
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 __global__ void __launch_bounds__(kAtThreads, 2)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap map_qkv, int T, int n_heads, int n_query,
                      __half* __restrict__ out) {
-  extern __shared__ unsigned char smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  unsigned char* smem = smem_raw + ((1024 - (raw_addr & 1023)) & 1023);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // 128B-swizzled operand tiles need 1024-byte alignment
+  unsigned char* smem = smem_raw;
   unsigned char* s_q = smem;
   unsigned char* s_kv = smem + kTileBytes;                 // stage s: K at s*2*tile, V at s*2*tile + tile
   unsigned char* s_p = smem + kTileBytes + 4 * kTileBytes;  // two 64-key k-blocks of 16 KB

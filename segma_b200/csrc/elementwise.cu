@@ -16,10 +16,15 @@ template <int VPL>  // float4 chunks per lane: d = VPL * 128
 __global__ void __launch_bounds__(kLnWarps * 32) layernorm_kernel(
     const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long long rows,
     __half* __restrict__ out_f16, float* __restrict__ out_f32, float* __restrict__ mix, int period,
-    int n_keep, float w_in, float w_out, int mix_init) {
+    int n_keep, float w_in, float w_out, int mix_init, int only_kept) {
   constexpr int d = VPL * 128;
-  const long long row = (long long)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  long long row = (long long)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (only_kept) {  // enumerate kept rows only: row = window * period + frame, frame < n_keep
+    if (row >= (rows / period) * n_keep) return;
+    row = (row / n_keep) * period + row % n_keep;
+  } else if (row >= rows) {
+    return;
+  }
   const int lane = lane_id();
   const float4* xr = reinterpret_cast<const float4*>(x + row * d);
   float4 v[VPL];
@@ -88,11 +93,11 @@ __global__ void __launch_bounds__(256) cast_f16_kernel(const float* __restrict__
 template <int VPL>
 static int launch_ln(const float* x, const float* gamma, const float* beta, long long rows, void* out_f16,
                      float* out_f32, float* mix, int period, int n_keep, float w_in, float w_out, int mix_init,
-                     cudaStream_t st) {
-  const long long blocks = ceil_div_ll(rows, kLnWarps);
+                     int only_kept, cudaStream_t st) {
+  const long long blocks = ceil_div_ll(only_kept ? (rows / period) * n_keep : rows, kLnWarps);
   layernorm_kernel<VPL><<<(unsigned)blocks, kLnWarps * 32, 0, st>>>(
       x, gamma, beta, rows, static_cast<__half*>(out_f16), out_f32, mix, period, n_keep, w_in, w_out,
-      mix_init);
+      mix_init, only_kept);
   return launch_status("layernorm_kernel");
 }
 
@@ -104,18 +109,19 @@ extern "C" {
 
 int segma_layernorm(const float* x, const float* gamma, const float* beta, int64_t rows, int d, void* out_f16,
                     float* out_f32, float* mix, int period, int n_keep, float w_in, float w_out, int mix_init,
-                    void* stream) {
+                    int only_kept, void* stream) {
   SEGMA_REQUIRE(rows >= 0 && d > 0, "segma_layernorm: bad shape");
   if (rows == 0) return SEGMA_OK;
   SEGMA_REQUIRE(x && gamma && beta, "segma_layernorm: NULL input");
   SEGMA_REQUIRE(d % 128 == 0 && d <= 2048, "segma_layernorm: d=%d must be a multiple of 128 and <= 2048", d);
-  SEGMA_REQUIRE(mix == nullptr || (period > 0 && n_keep > 0 && n_keep <= period), "segma_layernorm: bad mix geometry");
+  SEGMA_REQUIRE((mix == nullptr && !only_kept) || (period > 0 && n_keep > 0 && n_keep <= period && rows % period == 0),
+                "segma_layernorm: bad period / n_keep geometry");
   SEGMA_REQUIRE(rows < (1ll << 31) * kLnWarps, "segma_layernorm: too many rows");
   cudaStream_t st = (cudaStream_t)stream;
   if (period <= 0) period = 1;
 #define SEGMA_LN_CASE(V)                                                                                       \
   case V:                                                                                                      \
-    return launch_ln<V>(x, gamma, beta, rows, out_f16, out_f32, mix, period, n_keep, w_in, w_out, mix_init, st);
+    return launch_ln<V>(x, gamma, beta, rows, out_f16, out_f32, mix, period, n_keep, w_in, w_out, mix_init, only_kept, st);
   switch (d / 128) {
     SEGMA_LN_CASE(1) SEGMA_LN_CASE(2) SEGMA_LN_CASE(3) SEGMA_LN_CASE(4) SEGMA_LN_CASE(5) SEGMA_LN_CASE(6)
     SEGMA_LN_CASE(7) SEGMA_LN_CASE(8) SEGMA_LN_CASE(9) SEGMA_LN_CASE(10) SEGMA_LN_CASE(11) SEGMA_LN_CASE(12)

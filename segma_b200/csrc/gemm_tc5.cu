@@ -36,7 +36,7 @@ struct GemmKernelArgs {
   int a_ntile_off;   // extra A column offset per N tile (grouped convolution), else 0
   const float* bias;
   const float* add_src;
-  long long add_period;
+  long long add_batch_rows;
   void* out;
   long long out_batch_rows, out_row_offset, ldo;
   int flags;
@@ -174,7 +174,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int n0 = n_tile * BN;
       const long long out_row0 = (long long)b * p.out_batch_rows + p.out_row_offset + r_base;
       long long src_base = 0;
-      if (p.add_src) src_base = ((long long)b * p.rows_per_batch + r_base) % p.add_period;
+      if (p.add_src) src_base = (long long)b * p.add_batch_rows + r_base;
       mbar_wait(tmem_full + as, aphase);
       tc5_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::kAccStride;
@@ -188,8 +188,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const int rr = g * 4 + sub_r;
-            long long sr = src_base + rr;
-            while (sr >= p.add_period) sr -= p.add_period;
+            const long long sr = src_base + rr;
             const bool ok = r_base + rr < p.rows_per_batch;
             src4[g] = ok ? *(reinterpret_cast<const float4*>(p.add_src + sr * p.n + nc) + c4)
                          : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -338,7 +337,7 @@ int segma_gemm_f16(const segma_gemm_args* a, void* stream) {
   SEGMA_REQUIRE(taps == 1 || s == 1 || c % kBK == 0,
                 "segma_gemm_f16: strided conv needs channels per tap (%d) to be a multiple of 64", c);
   SEGMA_REQUIRE(a->a_row_stride >= (int64_t)c, "segma_gemm_f16: a_row_stride smaller than the row");
-  if (a->add_src) SEGMA_REQUIRE(a->add_period > 0, "segma_gemm_f16: add_period must be positive");
+  if (a->add_src) SEGMA_REQUIRE(a->add_batch_rows >= 0, "segma_gemm_f16: add_batch_rows must be non-negative");
 
   GemmKernelArgs ka{};
   ka.batch = a->batch;
@@ -353,7 +352,7 @@ int segma_gemm_f16(const segma_gemm_args* a, void* stream) {
   ka.a_ntile_off = a->a_col_per_ntile;
   ka.bias = a->bias;
   ka.add_src = a->add_src;
-  ka.add_period = a->add_period;
+  ka.add_batch_rows = a->add_batch_rows;
   ka.out = a->out;
   ka.out_batch_rows = a->out_batch_rows;
   ka.out_row_offset = a->out_row_offset;

@@ -158,25 +158,35 @@ class WhisperEngine:
         x, xn, qkv, att, h1, mix = ws["x"][:M], ws["xn"][:M], ws["qkv"][:M], ws["att"][:M], ws["h1"][:M], ws["mix"][:n]
         ops.conv1d_tm(mel_tm[:n], self.conv1_w, self.conv1_b, 3, 1, MEL_FRAMES, gelu=True, out=ws["c1"][:n],
                       out_batch_rows=MEL_FRAMES + 2, out_row_offset=1)
-        ops.conv1d_tm(ws["c1"][:n], self.conv2_w, self.conv2_b, 3, 2, T, gelu=True, add_src=self.pos, add_period=T,
+        ops.conv1d_tm(ws["c1"][:n], self.conv2_w, self.conv2_b, 3, 2, T, gelu=True, add_src=self.pos, add_batch_rows=0,
                       out=x.view(n, T, d))
         mixed = False
+        keep = self.n_keep
         for li, L in enumerate(self.layers):
             w_in = self.mix_w[li - 1] if li > 0 else 0.0
             if w_in != 0.0:
-                ops.layernorm(x, L["ln1_g"], L["ln1_b"], out_f16=xn, mix=mix, period=T, n_keep=self.n_keep, w_in=w_in,
+                ops.layernorm(x, L["ln1_g"], L["ln1_b"], out_f16=xn, mix=mix, period=T, n_keep=keep, w_in=w_in,
                               mix_init=not mixed)
                 mixed = True
             else:
                 ops.layernorm(x, L["ln1_g"], L["ln1_b"], out_f16=xn)
             ops.linear(xn, L["wqkv"], L["bqkv"], out=qkv)
-            ops.attention(qkv, n, T, self.n_heads, out=att)
-            ops.linear(att, L["wo"], L["bo"], add_src=x, out=x)
-            ops.layernorm(x, L["ln2_g"], L["ln2_b"], out_f16=xn)
-            ops.linear(xn, L["w1"], L["b1"], gelu=True, out=h1)
-            ops.linear(h1, L["w2"], L["b2"], add_src=x, out=x)
-        ops.layernorm(x, self.lnf_g, self.lnf_b, mix=mix, period=T, n_keep=self.n_keep, w_in=0.0,
-                      w_out=self.mix_w[-1], mix_init=not mixed)
+            if li < self.n_layers - 1 or keep >= T:
+                ops.attention(qkv, n, T, self.n_heads, out=att)
+                ops.linear(att, L["wo"], L["bo"], add_src=x, out=x)
+                ops.layernorm(x, L["ln2_g"], L["ln2_b"], out_f16=xn)
+                ops.linear(xn, L["w1"], L["b1"], gelu=True, out=h1)
+                ops.linear(h1, L["w2"], L["b2"], add_src=x, out=x)
+            else:
+                # last layer: nothing downstream reads positions >= n_keep, so only those query rows are
+                # attended, projected and fed through the MLP (keys / values still span all T positions)
+                ops.attention(qkv, n, T, self.n_heads, n_query=keep, out=att)
+                ops.linear_rows(att, n, T, keep, L["wo"], L["bo"], x, add_src=x)
+                ops.layernorm(x, L["ln2_g"], L["ln2_b"], out_f16=xn, period=T, n_keep=keep, only_kept=True)
+                ops.linear_rows(xn, n, T, keep, L["w1"], L["b1"], h1, gelu=True)
+                ops.linear_rows(h1, n, T, keep, L["w2"], L["b2"], x, add_src=x)
+        ops.layernorm(x, self.lnf_g, self.lnf_b, mix=mix, period=T, n_keep=keep, w_in=0.0,
+                      w_out=self.mix_w[-1], mix_init=not mixed, only_kept=True)
         ops.cast_f16(mix.view(n * self.n_keep, d), ws["mix_f16"][: n * self.n_keep])
 
     def forward_pcm(self, pcm: torch.Tensor, start: int, n: int, win_len: int, step: int, logits: torch.Tensor,

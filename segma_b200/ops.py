@@ -124,13 +124,13 @@ def set_mel_filters(mel: np.ndarray) -> None:
 
 # ---- GEMM / conv ---------------------------------------------------------------------------------
 def gemm_raw(a_ptr, a_batch_stride, a_row_stride, batch, rows_per_batch, k, w, n, out_ptr, ldo, *, bias=None,
-             add_src_ptr=None, add_period=0, out_batch_rows=None, out_row_offset=0, flags=0, conv_taps=0,
+             add_src_ptr=None, add_batch_rows=0, out_batch_rows=None, out_row_offset=0, flags=0, conv_taps=0,
              conv_stride=0, a_rows_per_batch=0, a_col_per_ntile=0, force_bn=0) -> None:
     args = GemmArgs(
         a=a_ptr, a_batch_stride=a_batch_stride, a_row_stride=a_row_stride, batch=batch,
         rows_per_batch=rows_per_batch, a_rows_per_batch=a_rows_per_batch, k=k, conv_taps=conv_taps,
         conv_stride=conv_stride, w=_dev(w, torch.float16, "w"), n=n, bias=_ptr(bias, torch.float32, "bias"),
-        add_src=add_src_ptr, add_period=add_period, out=out_ptr,
+        add_src=add_src_ptr, add_batch_rows=add_batch_rows, out=out_ptr,
         out_batch_rows=rows_per_batch if out_batch_rows is None else out_batch_rows,
         out_row_offset=out_row_offset, ldo=ldo, flags=flags, a_col_per_ntile=a_col_per_ntile, force_bn=force_bn,
     )
@@ -141,8 +141,8 @@ def gemm_raw(a_ptr, a_batch_stride, a_row_stride, batch, rows_per_batch, k, w, n
     _call(name, 1, _lib().segma_gemm_f16, C.byref(args), _stream(), work=2.0 * batch * rows_per_batch * n * k)
 
 
-def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, gelu=False, add_src=None, add_period=None, out=None,
-           out_f32=False, force_bn=0) -> torch.Tensor:
+def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, gelu=False, add_src=None, out=None, out_f32=False,
+           force_bn=0) -> torch.Tensor:
     """out = epilogue(a @ w.T); a (M, K) fp16, w (N, K) fp16."""
     _dev(a, torch.float16, "a")
     assert a.dim() == 2 and a.stride(1) == 1 and w.is_contiguous()
@@ -154,14 +154,24 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, gelu=False, add_src=N
     out_f32 = out.dtype == torch.float32
     flags = (GEMM_GELU if gelu else 0) | (GEMM_OUT_F32 if out_f32 else 0)
     gemm_raw(a.data_ptr(), 0, a.stride(0), 1, M, K, w, N, out.data_ptr(), out.stride(0), bias=bias,
-             add_src_ptr=None if add_src is None else _dev(add_src, torch.float32, "add_src"),
-             add_period=(M if add_period is None else add_period) if add_src is not None else 0, flags=flags,
+             add_src_ptr=None if add_src is None else _dev(add_src, torch.float32, "add_src"), flags=flags,
              force_bn=force_bn)
     return out
 
 
+def linear_rows(a: torch.Tensor, n_batch: int, batch_rows: int, keep: int, w: torch.Tensor, bias, out: torch.Tensor, *,
+                gelu=False, add_src=None) -> None:
+    """``linear`` on the first ``keep`` rows of every ``batch_rows``-row block of a (n_batch*batch_rows, K);
+    out / add_src use the same row blocking (rows >= keep of each block are left untouched)."""
+    K, N = a.shape[1], w.shape[0]
+    flags = (GEMM_GELU if gelu else 0) | (GEMM_OUT_F32 if out.dtype == torch.float32 else 0)
+    gemm_raw(_dev(a, torch.float16, "a"), batch_rows * a.stride(0), a.stride(0), n_batch, keep, K, w, N, out.data_ptr(),
+             out.stride(0), bias=bias, add_src_ptr=None if add_src is None else _dev(add_src, torch.float32, "add_src"),
+             add_batch_rows=batch_rows, out_batch_rows=batch_rows, flags=flags)
+
+
 def conv1d_tm(x_tm: torch.Tensor, w_tap_major: torch.Tensor, bias, taps: int, stride: int, out_rows: int, *,
-              gelu=True, add_src=None, add_period=0, out=None, out_batch_rows=None, out_row_offset=0, out_f32=False):
+              gelu=True, add_src=None, add_batch_rows=0, out=None, out_batch_rows=None, out_row_offset=0, out_f32=False):
     """Implicit-GEMM Conv1d on a padded time-major activation x_tm (B, rows_in, C) fp16;
     w_tap_major (N, taps*C) fp16.  Output (B, out_batch_rows, N) rows [out_row_offset, +out_rows)."""
     B, rows_in, Cc = x_tm.shape
@@ -173,7 +183,7 @@ def conv1d_tm(x_tm: torch.Tensor, w_tap_major: torch.Tensor, bias, taps: int, st
     flags = (GEMM_GELU if gelu else 0) | (GEMM_OUT_F32 if out.dtype == torch.float32 else 0)
     gemm_raw(_dev(x_tm, torch.float16, "x_tm"), rows_in * Cc, Cc, B, out_rows, taps * Cc, w_tap_major, N,
              out.data_ptr(), N, bias=bias,
-             add_src_ptr=None if add_src is None else _dev(add_src, torch.float32, "add_src"), add_period=add_period,
+             add_src_ptr=None if add_src is None else _dev(add_src, torch.float32, "add_src"), add_batch_rows=add_batch_rows,
              out_batch_rows=obr, out_row_offset=out_row_offset, flags=flags, conv_taps=taps, conv_stride=stride,
              a_rows_per_batch=rows_in)
     return out
@@ -181,13 +191,13 @@ def conv1d_tm(x_tm: torch.Tensor, w_tap_major: torch.Tensor, bias, taps: int, st
 
 # ---- layernorm / cast / attention ----------------------------------------------------------------
 def layernorm(x: torch.Tensor, gamma, beta, *, out_f16=None, out_f32=None, mix=None, period=1, n_keep=0, w_in=0.0,
-              w_out=0.0, mix_init=False) -> None:
+              w_out=0.0, mix_init=False, only_kept=False) -> None:
     rows, d = x.shape
     assert x.is_contiguous()
     _call("segma_layernorm", 1, _lib().segma_layernorm, _dev(x, torch.float32, "x"), _dev(gamma, torch.float32, "gamma"),
                                _dev(beta, torch.float32, "beta"), rows, d, _ptr(out_f16, torch.float16, "out_f16"),
                                _ptr(out_f32, torch.float32, "out_f32"), _ptr(mix, torch.float32, "mix"), period,
-                               n_keep, float(w_in), float(w_out), int(mix_init), _stream())
+                               n_keep, float(w_in), float(w_out), int(mix_init), int(only_kept), _stream())
 
 
 def cast_f16(src: torch.Tensor, dst: torch.Tensor) -> None:

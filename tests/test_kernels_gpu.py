@@ -55,11 +55,21 @@ def test_gemm_epilogues(cuda):
     want = x + ref
     ops.linear(a, w, bias, add_src=x, out=x)
     _close(x, want, 1e-4, 1e-4, "residual in place")
-    # periodic table (position embedding) added after GELU
+    # one table shared by every batch (position embedding), added after GELU; rows blocked 7 x 100
     pos = _rand((100, N), 8).to(cuda)
-    out = ops.linear(a, w, bias, gelu=True, add_src=pos, add_period=100, out_f32=True)
+    out = torch.empty((M, N), device=cuda)
+    flags = ops.GEMM_GELU | ops.GEMM_OUT_F32
+    ops.gemm_raw(a.data_ptr(), 100 * K, K, 7, 100, K, w, N, out.data_ptr(), N, bias=bias, add_src_ptr=pos.data_ptr(),
+                 add_batch_rows=0, flags=flags)
     idx = torch.arange(M, device=cuda) % 100
-    _close(out, F.gelu(ref) + pos[idx], 1e-4, 1e-4, "gelu + periodic add")
+    _close(out, F.gelu(ref) + pos[idx], 1e-4, 1e-4, "gelu + shared table")
+    # first 60 rows of every 100-row block only (last-layer row pruning), residual in place
+    x2 = _rand((M, N), 9).to(cuda)
+    want2 = x2.clone()
+    sel = (torch.arange(M, device=cuda) % 100) < 60
+    want2[sel] = (x2 + ref)[sel]
+    ops.linear_rows(a, 7, 100, 60, w, bias, x2, add_src=x2)
+    _close(x2, want2, 1e-4, 1e-4, "row-pruned residual")
     # no bias
     out = ops.linear(a, w, None, out_f32=True)
     _close(out, a.float() @ w.float().T, 1e-4, 1e-4, "no bias")
@@ -101,6 +111,12 @@ def test_layernorm(cuda, d):
     _close(ob, ref, 1e-3, 1e-3, "layernorm fp16")
     want = 0.25 * x.view(-1, period, d)[:, :keep] + 0.5 * ref.view(-1, period, d)[:, :keep]
     _close(mix, want, 1e-5, 1e-5, "layer mix")
+    # only the kept rows
+    ok = torch.full((rows, d), 7.0, dtype=torch.float16, device=cuda)
+    ops.layernorm(x, g, b, out_f16=ok, period=period, n_keep=keep, only_kept=True)
+    okv = ok.view(-1, period, d)
+    _close(okv[:, :keep], ref.view(-1, period, d)[:, :keep], 1e-3, 1e-3, "only_kept rows")
+    assert (okv[:, keep:] == 7.0).all()
 
 
 def test_cast_f16(cuda):

@@ -60,6 +60,22 @@ SEGMA_API int segma_logmel_set_filters(const float* mel_201x80);
 /* Copy the active dense (201, 80) filterbank to [host] memory. */
 SEGMA_API int segma_logmel_get_filters(float* mel_201x80);
 
+/* ---- wav2vec2 / HuBERT / WavLM waveform front end, layer 0 ------------------------------------
+ * Conv1d(1, C, k=10, s=5, no bias) -> GroupNorm(C groups: per (window, channel) over time, eps 1e-5, biased
+ * variance) -> exact GELU (site-packages/torchaudio/models/wav2vec2/components.py:77-99), fused with the
+ * windowing of src/segma/inference.py:148-152.  out: fp16 time-major (n_windows, out_rows, C), rows at or
+ * beyond the (win_len-10)/5+1 conv outputs are written as zeros; scale_shift: (n_windows, C, 2) fp32 scratch.
+ */
+SEGMA_API int segma_w2v2_layer0(const float* pcm, int64_t pcm_len, int n_windows, int win_len, int64_t step, const float* w,
+                      const float* gamma, const float* beta, int channels, void* scale_shift, void* out,
+                      int out_rows, void* stream);
+
+/* WavLM gate on the relative-position bias (site-packages/torchaudio/models/wav2vec2/wavlm_attention.py:185-193):
+ * x fp32 (rows = n_windows*T, n_heads*64) layer input; gate_w (8, 64), gate_b (8), gate_const (n_heads);
+ * gate[(b*n_heads + h)*T + i] = ga*(gb*const_h - 1) + 2 -- the per-row factor segma_attention applies to pos_bias. */
+SEGMA_API int segma_wavlm_gate(const float* x, int64_t rows, int T, int n_heads, const float* gate_w, const float* gate_b,
+                     const float* gate_const, float* gate, void* stream);
+
 /* ---- dense encoder building blocks ----------------------------------------------------------
  * Replace torch's dispatch of nn.Linear / nn.Conv1d / LayerNorm / SDPA inside
  * WhisperEncoder.forward (site-packages/transformers/models/whisper/modeling_whisper.py:593-647)
@@ -103,6 +119,7 @@ typedef struct {
   int64_t ldo;            /* elements, multiple of 8 */
   int flags;
   int a_col_per_ntile;    /* grouped conv: extra A column offset per N tile (0 otherwise) */
+  int a_cols;             /* columns of an activation row (0 = channels per tap); > channels for grouped conv */
   int force_bn;           /* 0 = auto; 128, 192 or 256 = N tile width */
 } segma_gemm_args;
 SEGMA_API int segma_gemm_f16(const segma_gemm_args* args, void* stream);

@@ -37,6 +37,7 @@ class GemmArgs(C.Structure):
         ("ldo", C.c_int64),
         ("flags", C.c_int),
         ("a_col_per_ntile", C.c_int),
+        ("a_cols", C.c_int),
         ("force_bn", C.c_int),
     ]
 
@@ -53,6 +54,8 @@ SIGNATURES = {
     "segma_logmel": (_i, [_vp, _i64, _i, _i, _i64, _vp, _vp, _vp, _vp]),
     "segma_logmel_set_filters": (_i, [_vp]),
     "segma_logmel_get_filters": (_i, [_vp]),
+    "segma_w2v2_layer0": (_i, [_vp, _i64, _i, _i, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "segma_wavlm_gate": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "segma_gemm_f16": (_i, [C.POINTER(GemmArgs), _vp]),
     "segma_layernorm": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _f, _f, _i, _i, _vp]),
     "segma_attention": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

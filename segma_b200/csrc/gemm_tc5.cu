@@ -336,7 +336,7 @@ int segma_gemm_f16(const segma_gemm_args* a, void* stream) {
   SEGMA_REQUIRE(c % 8 == 0, "segma_gemm_f16: channels per tap (%d) must be a multiple of 8", c);
   SEGMA_REQUIRE(taps == 1 || s == 1 || c % kBK == 0,
                 "segma_gemm_f16: strided conv needs channels per tap (%d) to be a multiple of 64", c);
-  SEGMA_REQUIRE(a->a_row_stride >= (int64_t)c, "segma_gemm_f16: a_row_stride smaller than the row");
+  SEGMA_REQUIRE(a->a_row_stride >= (int64_t)(a->a_cols > 0 ? a->a_cols : c), "segma_gemm_f16: a_row_stride smaller than the row");
   if (a->add_src) SEGMA_REQUIRE(a->add_batch_rows >= 0, "segma_gemm_f16: add_batch_rows must be non-negative");
 
   GemmKernelArgs ka{};
@@ -347,7 +347,7 @@ int segma_gemm_f16(const segma_gemm_args* a, void* stream) {
   ka.taps = taps;
   ka.kb_per_tap = ceil_div(c, kBK);
   ka.conv_stride = s;
-  ka.a_tap_elems = c;
+  ka.a_tap_elems = a->a_cols > 0 ? a->a_cols : c;
   ka.w_tap_elems = c;
   ka.a_ntile_off = a->a_col_per_ntile;
   ka.bias = a->bias;
@@ -364,7 +364,8 @@ int segma_gemm_f16(const segma_gemm_args* a, void* stream) {
   SEGMA_REQUIRE(in_rows % s == 0, "segma_gemm_f16: a_rows_per_batch=%d must be a multiple of conv_stride=%d", in_rows, s);
   CUtensorMap ma, mw;
   {
-    uint64_t dims[3] = {(uint64_t)s * c, (uint64_t)(in_rows / s), (uint64_t)a->batch};
+    const int row_cols = a->a_cols > 0 ? a->a_cols : c;
+    uint64_t dims[3] = {(uint64_t)s * row_cols, (uint64_t)(in_rows / s), (uint64_t)a->batch};
     uint64_t strides[3] = {1, (uint64_t)a->a_row_stride * s, (uint64_t)a->a_batch_stride};
     if (a->batch == 1 && strides[2] == 0) strides[2] = strides[1] * dims[1];
     int rc = make_f16_map(&ma, a->a, 3, dims, strides, kBM);

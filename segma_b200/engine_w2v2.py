@@ -1,0 +1,221 @@
+"""Device-side execution of ``SurgicalHydraHubert.forward`` for wav2vec2 / HuBERT / WavLM encoders.
+
+Follows /root/reference/src/segma/models/hubert/surgical_hydra.py:87-101 through torchaudio's module tree
+(site-packages/torchaudio/models/wav2vec2/components.py: FeatureExtractor 117-143, FeatureProjection 171-183,
+ConvolutionalPositionalEmbedding 194-234, Transformer._preprocess 421-428, EncoderLayer 363-401, SelfAttention
+263-310; wavlm_attention.py 166-211), fused with the windowing of inference.py:148-152: raw PCM on the
+device in, frame logits on the file timeline out.  All arithmetic is libsegma_b200 kernels:
+layer 0 (conv + GroupNorm + GELU) in one kernel pair, layers 1-6 and the grouped positional convolution as
+implicit GEMMs on the tcgen05 kernel, post-LN transformer layers, per-label heads.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+
+HEAD_DIM = 64
+CONV_KERNELS = (10, 3, 3, 3, 3, 2, 2)
+CONV_STRIDES = (5, 2, 2, 2, 2, 2, 2)
+
+
+def _f16(t, device):
+    return t.detach().to(device=device, dtype=torch.float16).contiguous()
+
+
+def _f32(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def conv_lengths(n_samples: int) -> list[int]:
+    out, t = [], n_samples
+    for k, s in zip(CONV_KERNELS, CONV_STRIDES):
+        t = (t - k) // s + 1 if t >= k else 0
+        out.append(t)
+    return out
+
+
+def _even(v: int) -> int:
+    return v + (v & 1)
+
+
+def wavlm_position_bias(rel_attn_embed: torch.Tensor, T: int, num_buckets: int, max_distance: int = 800) -> torch.Tensor:
+    """(n_heads, T, T) bucketed relative-position bias table (wavlm_attention.py:85-139); a weight-derived
+    constant, built once per sequence length on the host."""
+    ctx = torch.arange(T)[:, None]
+    mem = torch.arange(T)[None, :]
+    rel = mem - ctx
+    nb = num_buckets // 2
+    buckets = (rel > 0).to(torch.long) * nb
+    rel = rel.abs()
+    max_exact = nb // 2
+    large = max_exact + (torch.log(rel.float() / max_exact) / math.log(max_distance / max_exact) * (nb - max_exact)).to(torch.long)
+    large = torch.min(large, torch.full_like(large, nb - 1))
+    buckets = buckets + torch.where(rel < max_exact, rel, large)
+    return torch.nn.functional.embedding(buckets, rel_attn_embed.detach().float().cpu()).permute(2, 0, 1).contiguous()
+
+
+class W2V2Engine:
+    def __init__(self, sd: dict, labels, device="cuda", prefix: str = "wav2vec2."):
+        ops.device_check()
+        dev = self.device = torch.device(device)
+        self.labels = tuple(labels)
+        fe = prefix + "feature_extractor."
+        w0 = sd[fe + "conv_layers.0.conv.weight"]
+        self.C = C = w0.shape[0]
+        assert C % 128 == 0, "conv feature dimension must be a multiple of 128"
+        self.conv0_w = _f32(w0.reshape(C, CONV_KERNELS[0]), dev)
+        self.gn_g = _f32(sd[fe + "conv_layers.0.layer_norm.weight"], dev)
+        self.gn_b = _f32(sd[fe + "conv_layers.0.layer_norm.bias"], dev)
+        self.conv_w = [_f16(sd[f"{fe}conv_layers.{i}.conv.weight"].permute(0, 2, 1).reshape(C, -1), dev) for i in range(1, 7)]
+        enc = prefix + "encoder."
+        self.proj_ln_g = _f32(sd[enc + "feature_projection.layer_norm.weight"], dev)
+        self.proj_ln_b = _f32(sd[enc + "feature_projection.layer_norm.bias"], dev)
+        self.proj_w = _f16(sd[enc + "feature_projection.projection.weight"], dev)
+        self.proj_b = _f32(sd[enc + "feature_projection.projection.bias"], dev)
+        self.d = d = self.proj_w.shape[0]
+        self.n_heads = d // HEAD_DIM
+        assert d % 128 == 0
+        t = enc + "transformer."
+        # positional convolution: fold weight-norm, then lay the grouped kernel out for N tiles of whole groups
+        g = sd[t + "pos_conv_embed.conv.parametrizations.weight.original0"].float()
+        v = sd[t + "pos_conv_embed.conv.parametrizations.weight.original1"].float()
+        w = v * (g / v.norm(dim=(0, 1), keepdim=True))  # (d, cg, K)
+        cg, K = w.shape[1], w.shape[2]
+        self.pos_k = K
+        self.pos_pad = K // 2
+        bn = next((b for b in (192, 256, 128) if d % b == 0 and b % cg == 0), None)
+        assert bn is not None, f"no N tile fits positional-conv groups of {cg} channels in d={d}"
+        self.pos_bn = bn
+        wg = torch.zeros((d, K, bn), dtype=torch.float32)
+        for co in range(d):
+            gl = (co % bn) // cg  # group index inside the N tile
+            wg[co, :, gl * cg:(gl + 1) * cg] = w[co].T
+        self.pos_w = _f16(wg.reshape(d, K * bn), dev)
+        self.pos_b = _f32(sd[t + "pos_conv_embed.conv.bias"], dev)
+        self.ln0_g = _f32(sd[t + "layer_norm.weight"], dev)
+        self.ln0_b = _f32(sd[t + "layer_norm.bias"], dev)
+        self.wavlm = (t + "layers.0.attention.attention.in_proj_weight") in sd
+        scale = HEAD_DIM**-0.5
+        self.layers = []
+        i = 0
+        while f"{t}layers.{i}.feed_forward.intermediate_dense.weight" in sd:
+            lp = f"{t}layers.{i}."
+            if self.wavlm:
+                wi, bi = sd[lp + "attention.attention.in_proj_weight"].clone().float(), sd[lp + "attention.attention.in_proj_bias"].clone().float()
+                wi[:d] *= scale
+                bi[:d] *= scale
+                wo, bo = sd[lp + "attention.attention.out_proj.weight"], sd[lp + "attention.attention.out_proj.bias"]
+                extra = dict(gate_w=_f32(sd[lp + "attention.gru_rel_pos_linear.weight"], dev),
+                             gate_b=_f32(sd[lp + "attention.gru_rel_pos_linear.bias"], dev),
+                             gate_c=_f32(sd[lp + "attention.gru_rel_pos_const"].reshape(-1), dev))
+            else:
+                wi = torch.cat([sd[lp + "attention.q_proj.weight"] * scale, sd[lp + "attention.k_proj.weight"], sd[lp + "attention.v_proj.weight"]])
+                bi = torch.cat([sd[lp + "attention.q_proj.bias"] * scale, sd[lp + "attention.k_proj.bias"], sd[lp + "attention.v_proj.bias"]])
+                wo, bo = sd[lp + "attention.out_proj.weight"], sd[lp + "attention.out_proj.bias"]
+                extra = {}
+            self.layers.append(dict(
+                wqkv=_f16(wi, dev), bqkv=_f32(bi, dev), wo=_f16(wo, dev), bo=_f32(bo, dev),
+                ln1_g=_f32(sd[lp + "layer_norm.weight"], dev), ln1_b=_f32(sd[lp + "layer_norm.bias"], dev),
+                w1=_f16(sd[lp + "feed_forward.intermediate_dense.weight"], dev), b1=_f32(sd[lp + "feed_forward.intermediate_dense.bias"], dev),
+                w2=_f16(sd[lp + "feed_forward.output_dense.weight"], dev), b2=_f32(sd[lp + "feed_forward.output_dense.bias"], dev),
+                ln2_g=_f32(sd[lp + "final_layer_norm.weight"], dev), ln2_b=_f32(sd[lp + "final_layer_norm.bias"], dev), **extra))
+            i += 1
+        self.ffn = self.layers[0]["w1"].shape[0]
+        if self.wavlm:
+            self.rel_embed = sd[t + "layers.0.attention.rel_attn_embed.weight"]
+            self._pos_bias: dict[int, torch.Tensor] = {}
+        self.head_w = _f32(torch.cat([sd[f"task_heads.linear_head_{lab}.weight"] for lab in labels], dim=0), dev)
+        self.head_b = _f32(torch.cat([sd[f"task_heads.linear_head_{lab}.bias"] for lab in labels], dim=0), dev)
+        self._ws: dict[tuple[int, int], dict] = {}
+
+    def _pos_bias_for(self, T: int) -> torch.Tensor:
+        if T not in self._pos_bias:
+            self._pos_bias[T] = wavlm_position_bias(self.rel_embed, T, self.rel_embed.shape[0]).to(self.device)
+        return self._pos_bias[T]
+
+    def _workspace(self, n: int, win_len: int) -> dict:
+        key = (n, win_len)
+        if key in self._ws:
+            return self._ws[key]
+        if len(self._ws) > 4:  # full batch, remainder, tail (+ slack); drop the rest
+            self._ws.clear()
+        dev, C, d = self.device, self.C, self.d
+        lens = conv_lengths(win_len)
+        T = lens[-1]
+        ws = {"lens": lens, "T": T}
+        ws["ss"] = torch.empty((n, C, 2), dtype=torch.float32, device=dev)
+        ws["act"] = [torch.zeros((n, _even(t), C), dtype=torch.float16, device=dev) for t in lens[:-1]]
+        ws["feat"] = torch.empty((n * T, C), dtype=torch.float32, device=dev)
+        ws["feat_f16"] = torch.empty((n * T, C), dtype=torch.float16, device=dev)
+        rows_p = (T + self.pos_k + 7) // 8 * 8
+        ws["xp"] = torch.zeros((n, rows_p, d), dtype=torch.float16, device=dev)
+        ws["x0"] = torch.empty((n * T, d), dtype=torch.float32, device=dev)
+        ws["tmp"] = torch.empty((n * T, d), dtype=torch.float32, device=dev)
+        ws["x"] = torch.empty((n * T, d), dtype=torch.float32, device=dev)
+        ws["x_f16"] = torch.empty((n * T, d), dtype=torch.float16, device=dev)
+        ws["qkv"] = torch.empty((n * T, 3 * d), dtype=torch.float16, device=dev)
+        ws["att"] = torch.empty((n * T, d), dtype=torch.float16, device=dev)
+        ws["h1"] = torch.empty((n * T, self.ffn), dtype=torch.float16, device=dev)
+        if self.wavlm:
+            ws["gate"] = torch.empty((n, self.n_heads, T), dtype=torch.float32, device=dev)
+        self._ws[key] = ws
+        return ws
+
+    def forward_pcm(self, pcm: torch.Tensor, start: int, n: int, win_len: int, step: int, logits: torch.Tensor,
+                    frame_offset: int, step_frames: int, n_keep: int | None = None) -> None:
+        """Windows ``pcm[start + i*step : +win_len]``, i < n -> ``logits[frame_offset + i*step_frames + r]``, r < n_keep."""
+        ws = self._workspace(n, win_len)
+        lens, T, C, d = ws["lens"], ws["T"], self.C, self.d
+        if T <= 0:
+            return
+        view = pcm[start:]
+        act = ws["act"]
+        ops.w2v2_layer0(view, n, win_len, step, self.conv0_w, self.gn_g, self.gn_b, ws["ss"], act[0])
+        for i in range(1, 7):
+            src = act[i - 1]
+            if i < 6:
+                ops.conv1d_tm(src, self.conv_w[i - 1], None, CONV_KERNELS[i], CONV_STRIDES[i], lens[i], gelu=True,
+                              out=act[i], out_batch_rows=act[i].shape[1])
+            else:
+                ops.conv1d_tm(src, self.conv_w[i - 1], None, CONV_KERNELS[i], CONV_STRIDES[i], T, gelu=True,
+                              out=ws["feat"].view(n, T, C))
+        # feature projection, positional convolution, pre-encoder LayerNorm
+        ops.layernorm(ws["feat"], self.proj_ln_g, self.proj_ln_b, out_f16=ws["feat_f16"])
+        ops.linear(ws["feat_f16"], self.proj_w, self.proj_b, out=ws["x0"])
+        xp = ws["xp"]
+        ops.gemm_raw(ws["feat_f16"].data_ptr(), T * C, C, n, T, C, self.proj_w, d, xp.data_ptr(), d, bias=self.proj_b,
+                     out_batch_rows=xp.shape[1], out_row_offset=self.pos_pad)
+        bn = self.pos_bn
+        ops.gemm_raw(xp.data_ptr(), xp.shape[1] * d, d, n, T, self.pos_k * bn, self.pos_w, d, ws["tmp"].data_ptr(), d,
+                     bias=self.pos_b, add_src_ptr=ws["x0"].data_ptr(), add_batch_rows=T, out_batch_rows=T,
+                     flags=ops.GEMM_GELU | ops.GEMM_OUT_F32, conv_taps=self.pos_k, conv_stride=1,
+                     a_rows_per_batch=xp.shape[1], a_col_per_ntile=bn, a_cols=d, force_bn=bn)
+        x, xh, tmp = ws["x"], ws["x_f16"], ws["tmp"]
+        ops.layernorm(tmp, self.ln0_g, self.ln0_b, out_f16=xh, out_f32=x)
+        pos_bias = self._pos_bias_for(T) if self.wavlm else None
+        for L in self.layers:
+            ops.linear(xh, L["wqkv"], L["bqkv"], out=ws["qkv"])
+            if self.wavlm:
+                ops.wavlm_gate(x, T, self.n_heads, L["gate_w"], L["gate_b"], L["gate_c"], ws["gate"])
+                ops.attention(ws["qkv"], n, T, self.n_heads, gate=ws["gate"], pos_bias=pos_bias, out=ws["att"])
+            else:
+                ops.attention(ws["qkv"], n, T, self.n_heads, out=ws["att"])
+            ops.linear(ws["att"], L["wo"], L["bo"], add_src=x, out=tmp)
+            ops.layernorm(tmp, L["ln1_g"], L["ln1_b"], out_f16=xh, out_f32=x)
+            ops.linear(xh, L["w1"], L["b1"], gelu=True, out=ws["h1"])
+            ops.linear(ws["h1"], L["w2"], L["b2"], add_src=x, out=tmp)
+            ops.layernorm(tmp, L["ln2_g"], L["ln2_b"], out_f16=xh, out_f32=x)
+        keep = T if n_keep is None else min(n_keep, T)
+        ops.heads(x.view(n, T, d), self.head_w, self.head_b, logits, frame_offset, step_frames, keep)
+
+    def forward_waveforms(self, wav: torch.Tensor) -> torch.Tensor:
+        """Drop-in ``model.forward``: (B, n_samples) fp32 -> (B, T, 1, C) fp32 logits."""
+        wav = wav.to(self.device, torch.float32).contiguous()
+        B, L = wav.shape
+        T = conv_lengths(L)[-1]
+        logits = torch.empty((B * T, len(self.labels)), dtype=torch.float32, device=self.device)
+        self.forward_pcm(wav.reshape(-1), 0, B, L, L, logits, 0, T, T)
+        return logits.view(B, T, 1, len(self.labels))

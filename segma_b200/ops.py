@@ -125,14 +125,14 @@ def set_mel_filters(mel: np.ndarray) -> None:
 # ---- GEMM / conv ---------------------------------------------------------------------------------
 def gemm_raw(a_ptr, a_batch_stride, a_row_stride, batch, rows_per_batch, k, w, n, out_ptr, ldo, *, bias=None,
              add_src_ptr=None, add_batch_rows=0, out_batch_rows=None, out_row_offset=0, flags=0, conv_taps=0,
-             conv_stride=0, a_rows_per_batch=0, a_col_per_ntile=0, force_bn=0) -> None:
+             conv_stride=0, a_rows_per_batch=0, a_col_per_ntile=0, a_cols=0, force_bn=0) -> None:
     args = GemmArgs(
         a=a_ptr, a_batch_stride=a_batch_stride, a_row_stride=a_row_stride, batch=batch,
         rows_per_batch=rows_per_batch, a_rows_per_batch=a_rows_per_batch, k=k, conv_taps=conv_taps,
         conv_stride=conv_stride, w=_dev(w, torch.float16, "w"), n=n, bias=_ptr(bias, torch.float32, "bias"),
         add_src=add_src_ptr, add_batch_rows=add_batch_rows, out=out_ptr,
         out_batch_rows=rows_per_batch if out_batch_rows is None else out_batch_rows,
-        out_row_offset=out_row_offset, ldo=ldo, flags=flags, a_col_per_ntile=a_col_per_ntile, force_bn=force_bn,
+        out_row_offset=out_row_offset, ldo=ldo, flags=flags, a_col_per_ntile=a_col_per_ntile, a_cols=a_cols, force_bn=force_bn,
     )
     name = "segma_gemm_f16"
     if stats.profile:
@@ -287,3 +287,21 @@ def decode_intervals(logits: torch.Tensor, thresholds, *, file_offsets=None, mod
         if total <= cap:
             return table[:total]
         cap = total
+
+
+# ---- wav2vec2 / WavLM ------------------------------------------------------------------------------
+def w2v2_layer0(pcm_view: torch.Tensor, n_windows: int, win_len: int, step: int, w: torch.Tensor, gamma, beta,
+                scale_shift: torch.Tensor, out: torch.Tensor) -> None:
+    """out (n_windows, out_rows, C) fp16 = gelu(GroupNorm(conv_k10_s5(window)))."""
+    C_ = w.shape[0]
+    assert out.is_contiguous() and out.shape[0] >= n_windows and out.shape[2] == C_
+    _call("segma_w2v2_layer0", 2, _lib().segma_w2v2_layer0, _dev(pcm_view, torch.float32, "pcm"), pcm_view.numel(),
+          n_windows, win_len, step, _dev(w, torch.float32, "w"), _dev(gamma, torch.float32, "gamma"),
+          _dev(beta, torch.float32, "beta"), C_, scale_shift.data_ptr(), _dev(out, torch.float16, "out"), out.shape[1],
+          _stream())
+
+
+def wavlm_gate(x: torch.Tensor, T: int, n_heads: int, gate_w, gate_b, gate_const, gate: torch.Tensor) -> None:
+    _call("segma_wavlm_gate", 1, _lib().segma_wavlm_gate, _dev(x, torch.float32, "x"), x.shape[0], T, n_heads,
+          _dev(gate_w, torch.float32, "gate_w"), _dev(gate_b, torch.float32, "gate_b"),
+          _dev(gate_const, torch.float32, "gate_const"), _dev(gate, torch.float32, "gate"), _stream())

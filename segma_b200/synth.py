@@ -164,8 +164,8 @@ class W2V2Dims:
 
 HUBERT_BASE = W2V2Dims()
 WAVLM_BASE = W2V2Dims(wavlm=True)
-W2V2_TEST = W2V2Dims(d_model=128, n_layers=2, ffn=256, conv_dim=64, pos_kernel=16, pos_groups=4)
-WAVLM_TEST = W2V2Dims(d_model=128, n_layers=2, ffn=256, conv_dim=64, pos_kernel=16, pos_groups=4, wavlm=True)
+W2V2_TEST = W2V2Dims(d_model=128, n_layers=2, ffn=256, conv_dim=128, pos_kernel=16, pos_groups=4)
+WAVLM_TEST = W2V2Dims(d_model=128, n_layers=2, ffn=256, conv_dim=128, pos_kernel=16, pos_groups=4, wavlm=True)
 
 W2V2_KERNELS = (10, 3, 3, 3, 3, 2, 2)
 

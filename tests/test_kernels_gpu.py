@@ -283,3 +283,69 @@ def test_decode_logit_cut_mode(cuda):
     ref = O.apply_thresholds(logits, thr)
     got = ops.threshold_mask(logits.to(cuda), cuts, mode=ops.DECODE_LOGIT)
     assert torch.equal(got.cpu(), ref)
+
+
+# ---- wav2vec2 front end / WavLM gate / grouped positional conv -----------------------------------------------
+@pytest.mark.parametrize("L,C", [(64000, 128), (33280, 512), (400, 128)])
+def test_w2v2_layer0(cuda, L, C):
+    n_win, step = 3, 1000
+    pcm = torch.from_numpy(synth.synth_audio(L + (n_win - 1) * step, 31))
+    w = _rand((C, 1, 10), 32, 0.5)
+    g, b = 1 + 0.1 * _rand((C,), 33), 0.1 * _rand((C,), 34)
+    T0 = (L - 10) // 5 + 1
+    rows = T0 + (T0 & 1)
+    out = torch.full((n_win, rows, C), 7.0, dtype=torch.float16, device=cuda)
+    ss = torch.empty((n_win, C, 2), device=cuda)
+    ops.w2v2_layer0(pcm.to(cuda), n_win, L, step, w.reshape(C, 10).contiguous().to(cuda), g.to(cuda), b.to(cuda), ss, out)
+    wins = torch.stack([pcm[i * step: i * step + L] for i in range(n_win)])
+    y = F.conv1d(wins.unsqueeze(1), w, None, stride=5)
+    ref = F.gelu(F.group_norm(y, C, g, b, 1e-5)).transpose(1, 2)
+    _close(out[:, :T0], ref, 2e-3, 2e-3, "layer 0")
+    assert (out[:, T0:] == 0).all()
+
+
+def test_w2v2_layer0_silence(cuda):
+    """All-zero audio (the reference's io fixture): GroupNorm variance 0 -> output gelu(beta)."""
+    C, L = 128, 64000
+    w = _rand((C, 10), 35, 0.5).to(cuda)
+    g, b = (1 + 0.1 * _rand((C,), 36)).to(cuda), (0.3 * _rand((C,), 37)).to(cuda)
+    out = torch.empty((1, 12800, C), dtype=torch.float16, device=cuda)
+    ops.w2v2_layer0(torch.zeros(L, device=cuda), 1, L, L, w, g, b, torch.empty((1, C, 2), device=cuda), out)
+    _close(out[0, :12799], F.gelu(b).expand(12799, C), 1e-3, 1e-3, "silent layer 0")
+
+
+def test_wavlm_gate(cuda):
+    B, T, H = 2, 199, 2
+    x = _rand((B * T, H * 64), 38).to(cuda)
+    gw, gb, gc = _rand((8, 64), 39, 0.2).to(cuda), _rand((8,), 40, 0.2).to(cuda), (1 + 0.2 * _rand((H,), 41)).to(cuda)
+    gate = torch.empty((B, H, T), device=cuda)
+    ops.wavlm_gate(x, T, H, gw, gb, gc, gate)
+    xh = x.view(B, T, H, 64).permute(0, 2, 1, 3)
+    gab = torch.sigmoid((xh @ gw.T + gb).view(B, H, T, 2, 4).sum(-1))
+    ref = gab[..., 0] * (gab[..., 1] * gc.view(1, H, 1) - 1.0) + 2.0
+    _close(gate, ref, 1e-5, 1e-5, "wavlm gate")
+
+
+@pytest.mark.parametrize("dims", [synth.W2V2_TEST, synth.HUBERT_BASE])
+def test_grouped_positional_conv(cuda, dims):
+    """The grouped pos-conv + GELU + residual through the engine's packed weights vs F.conv1d."""
+    from segma_b200.engine_w2v2 import W2V2Engine
+
+    sd = synth.hubert_hydra_state_dict(dims, seed=12)
+    eng = W2V2Engine(sd, synth.DEFAULT_LABELS, device=cuda)
+    n, T, d = 2, 199, dims.d_model
+    x0 = _rand((n, T, d), 42).to(torch.float16)
+    rows_p = (T + eng.pos_k + 7) // 8 * 8
+    xp = torch.zeros((n, rows_p, d), dtype=torch.float16, device=cuda)
+    xp[:, eng.pos_pad: eng.pos_pad + T] = x0.to(cuda)
+    x0f = x0.float().to(cuda).reshape(n * T, d).contiguous()
+    out = torch.empty((n * T, d), device=cuda)
+    bn = eng.pos_bn
+    ops.gemm_raw(xp.data_ptr(), rows_p * d, d, n, T, eng.pos_k * bn, eng.pos_w, d, out.data_ptr(), d, bias=eng.pos_b,
+                 add_src_ptr=x0f.data_ptr(), add_batch_rows=T, out_batch_rows=T, flags=ops.GEMM_GELU | ops.GEMM_OUT_F32,
+                 conv_taps=eng.pos_k, conv_stride=1, a_rows_per_batch=rows_p, a_col_per_ntile=bn, a_cols=d, force_bn=bn)
+    w = O._pos_conv_weight(sd, "wav2vec2.encoder.transformer.").to(torch.float16).float()
+    pc = F.conv1d(x0.float().transpose(1, 2), w, sd["wav2vec2.encoder.transformer.pos_conv_embed.conv.bias"],
+                  padding=eng.pos_k // 2, groups=dims.pos_groups)[..., :-1]
+    ref = x0.float() + F.gelu(pc.transpose(1, 2))
+    _close(out.view(n, T, d), ref, 3e-3, 3e-3, "positional conv")

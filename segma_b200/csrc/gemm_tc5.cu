@@ -9,7 +9,7 @@
 // Structure (persistent, warp-specialised, one CTA per SM):
 //   warp 0      TMA producer: 128B-swizzled A (128 x 64) and W (BN x 64) tiles into a multi-stage ring
 //   warp 1      allocates TMEM, one elected lane issues tcgen05.mma (M=128, N=BN, K=16) per 32 bytes of K
-//   warps 2-5   epilogue: tcgen05.ld of the fp32 accumulator (double-buffered in TMEM so the next tile's
+//   warps 2-9   epilogue: tcgen05.ld of the fp32 accumulator (double-buffered in TMEM so the next tile's
 //               MMAs overlap), + bias, exact-erf GELU, + fp32 residual / position table, fp16 or fp32 store
 // A strided Conv1d is the same loop with the K axis split into taps: tap j of a stride-s convolution reads
 // the activation map (rows merged s at a time) at column block (j % s) * C and row offset j / s, so no
@@ -23,8 +23,10 @@ namespace segma {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 128 bytes of fp16: one swizzle row
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;       // two warps per TMEM lane quadrant, alternating 32-column chunks
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kEpiPitch = 36;  // floats per staged accumulator row (32 + 4 pad: conflict-free 128-bit access)
+constexpr int kEpiRows = 16;   // rows staged per round (half a warp's accumulator rows)
 
 struct GemmKernelArgs {
   int batch, rows_per_batch, tiles_per_batch;
@@ -51,7 +53,7 @@ struct GemmCfg {
   static constexpr int kTmemCols = BN == 128 ? 256 : 512;
   static constexpr int kAccStride = BN == 192 ? 256 : BN;  // column offset between the two accumulators
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                    4 * 32 * kEpiPitch * 4 /*epilogue transpose tiles*/;
+                                    kEpiWarps * kEpiRows * kEpiPitch * 4 /*epilogue transpose tiles*/;
 };
 
 template <int BN>
@@ -85,7 +87,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
-      mbar_init(tmem_empty + i, 4);
+      mbar_init(tmem_empty + i, kEpiWarps);
     }
     mbar_fence_init();
   }
@@ -157,10 +159,11 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // ===================== epilogue warps =====================
     // TMEM hands each lane one accumulator row; a 32 x 32 chunk is transposed through a padded
     // shared-memory tile so that global loads/stores run along rows (8 lanes x 16 B per row).
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;   // which of the two warps of the quadrant: even or odd chunks
     const bool out_f32 = (p.flags & SEGMA_GEMM_OUT_F32) != 0;
     const bool do_gelu = (p.flags & SEGMA_GEMM_GELU) != 0;
-    float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256) + (warp - 2) * (32 * kEpiPitch);
+    float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256) + (warp - 2) * (kEpiRows * kEpiPitch);
     const int sub_r = lane >> 3;   // row within a group of 4
     const int c4 = lane & 7;       // float4 column within the 32-column chunk
     int it = 0;
@@ -179,7 +182,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       tc5_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::kAccStride;
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      for (int chunk = half; chunk < BN / 32; chunk += 2) {
         const int nc = n0 + chunk * 32;
         if (nc >= p.n) break;  // warp-uniform
         // issue the residual / position-table loads first so their latency hides behind the TMEM read
@@ -199,32 +202,39 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         uint32_t acc[32];
         tmem_ld_32x32(t_addr + chunk * 32, acc);
         tmem_ld_wait();
-        float4* my_row = reinterpret_cast<float4*>(stg + lane * kEpiPitch);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          my_row[j] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
-                                  __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
-        __syncwarp();
+        for (int round = 0; round < 2; ++round) {
+          // lanes [16*round, 16*round+16) stage their accumulator rows, then the whole warp stores them row-wise
+          if ((lane >> 4) == round) {
+            float4* my_row = reinterpret_cast<float4*>(stg + (lane & 15) * kEpiPitch);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int rr = g * 4 + sub_r;
-          float4 v = *reinterpret_cast<const float4*>(stg + rr * kEpiPitch + c4 * 4);
-          v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-          if (do_gelu) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
-          if (p.add_src) { v.x += src4[g].x; v.y += src4[g].y; v.z += src4[g].z; v.w += src4[g].w; }
-          if (r_base + rr < p.rows_per_batch) {
-            const long long o = (out_row0 + rr) * p.ldo + nc;
-            if (out_f32) {
-              reinterpret_cast<float4*>(static_cast<float*>(p.out) + o)[c4] = v;
-            } else {
-              uint2 q;
-              q.x = pack_f16x2(v.x, v.y);
-              q.y = pack_f16x2(v.z, v.w);
-              reinterpret_cast<uint2*>(static_cast<__half*>(p.out) + o)[c4] = q;
+            for (int j = 0; j < 8; ++j)
+              my_row[j] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                                      __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+          }
+          __syncwarp();
+#pragma unroll
+          for (int gi = 0; gi < 4; ++gi) {
+            const int g = round * 4 + gi;
+            const int rr = g * 4 + sub_r;
+            float4 v = *reinterpret_cast<const float4*>(stg + (gi * 4 + sub_r) * kEpiPitch + c4 * 4);
+            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+            if (do_gelu) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+            if (p.add_src) { v.x += src4[g].x; v.y += src4[g].y; v.z += src4[g].z; v.w += src4[g].w; }
+            if (r_base + rr < p.rows_per_batch) {
+              const long long o = (out_row0 + rr) * p.ldo + nc;
+              if (out_f32) {
+                reinterpret_cast<float4*>(static_cast<float*>(p.out) + o)[c4] = v;
+              } else {
+                uint2 q;
+                q.x = pack_f16x2(v.x, v.y);
+                q.y = pack_f16x2(v.z, v.w);
+                reinterpret_cast<uint2*>(static_cast<__half*>(p.out) + o)[c4] = q;
+              }
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
       tc5_fence_before();
       __syncwarp();

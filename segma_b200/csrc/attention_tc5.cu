@@ -5,40 +5,42 @@
 // modeling_whisper.py:338-352; 1500 positions, no mask) and torchaudio SelfAttention
 // (site-packages/torchaudio/models/wav2vec2/components.py:305-307; 199 positions).
 //
-// One CTA owns 128 query rows of one (window, head); two CTAs are resident per SM so that one CTA's
-// softmax (MUFU-bound) overlaps the other's MMAs.  Per 128-key tile:
-//   warp 0      TMA: Q once, then K and V tiles (128 x 64, 128B swizzle) into a 2-stage ring, straight from the
-//               fused QKV activation through one 3-D tensor map (column block selects q / k / v and the head)
-//   warp 1      one lane issues  O += P_{j-1} V_{j-1}  (M128 N64, V as an MN-major B operand) and
-//               S = Q K_j^T (M128 N128) back to back, then one tcgen05.commit
-//   warps 2-5   one thread per query row: tcgen05.ld of its S row, running max with lazy rescale of O/l
-//               (only when the max grows by more than 2^8), exp2, P -> fp16 into the swizzled A-operand tile
+// One CTA owns 128 query rows of one (window, head) and walks the keys in tiles of 64; three CTAs are
+// resident per SM (64 KB of shared memory, 128 TMEM columns each) so that one CTA's softmax (MUFU-bound)
+// overlaps the others' MMAs and barrier hand-offs.  Per key tile:
+//   warp 0      TMA: Q once, then K and V tiles (64 x 64, 128B swizzle) into a 2-stage ring, straight from the
+//               fused QKV activation through 3-D tensor maps (column block selects q / k / v and the head)
+//   warp 1      one lane issues  O += P_{j-1} V_{j-1}  (M128 N64 K64, V as an MN-major B operand) and
+//               S = Q K_j^T (M128 N64 K64) back to back, then one tcgen05.commit
+//   warps 2-5   one thread per query row: a single tcgen05.ld of its 64 scores, exp2 against the running
+//               reference max (the tile is redone, and O/l rescaled, only when a score exceeds it by more than
+//               2^8), P -> fp16 into the swizzled A-operand tile
 // Scores, probabilities and the output accumulator never touch HBM.
 #include "common.cuh"
 
 namespace segma {
 
 constexpr int kAtQ = 128;     // queries per CTA
-constexpr int kAtK = 128;     // keys per tile
+constexpr int kAtK = 64;      // keys per tile
 constexpr int kAtD = 64;      // head dim
 constexpr int kAtThreads = 192;
-constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 fp16
-// exactly 7 tiles + barriers: 114 816 B, so that two CTAs fit the 227 KB of an SM (no alignment slack: the
-// dynamic shared-memory window of a kernel without static shared memory starts 1024-byte aligned; checked at run time)
-constexpr int kAtSmem = kTileBytes /*Q*/ + 2 * 2 * kTileBytes /*K,V ring*/ + 2 * kTileBytes /*P*/ + 128;
-constexpr uint32_t kTmemColsAttn = 256;  // S: 128 columns, O: 64 columns
+constexpr int kQBytes = kAtQ * 128;   // 128 rows x 64 fp16
+constexpr int kKVBytes = kAtK * 128;  // 64 rows x 64 fp16
+// Q + 2 x (K, V) + P + barriers = 65 664 B: three CTAs per SM.  No alignment slack: the dynamic shared-memory
+// window of a kernel without static shared memory starts 1024-byte aligned (checked at run time).
+constexpr int kAtSmem = kQBytes + 4 * kKVBytes + kQBytes + 128;
+constexpr uint32_t kTmemColsAttn = 128;    // S: columns [0, 64), O: columns [64, 128)
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
-__global__ void __launch_bounds__(kAtThreads, 2)
-attention_tc5_kernel(const __grid_constant__ CUtensorMap map_qkv, int T, int n_heads, int n_query,
-                     __half* __restrict__ out) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // 128B-swizzled operand tiles need 1024-byte alignment
-  unsigned char* smem = smem_raw;
+__global__ void __launch_bounds__(kAtThreads, 3)
+attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, int T,
+                     int n_heads, int n_query, __half* __restrict__ out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzled operand tiles need 1024-byte alignment
   unsigned char* s_q = smem;
-  unsigned char* s_kv = smem + kTileBytes;                 // stage s: K at s*2*tile, V at s*2*tile + tile
-  unsigned char* s_p = smem + kTileBytes + 4 * kTileBytes;  // two 64-key k-blocks of 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * kTileBytes);
+  unsigned char* s_kv = smem + kQBytes;                // stage s: K at s*2*kKVBytes, V right after it
+  unsigned char* s_p = smem + kQBytes + 4 * kKVBytes;  // 128 rows x 64 keys
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + kQBytes);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;   // [2]
   uint64_t* kv_empty = bars + 3;  // [2]
@@ -54,7 +56,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_qkv, int T, int n_h
   const int n_kt = ceil_div(T, kAtK);
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_kv);
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(kv_full + i, 1);
@@ -77,14 +80,14 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_qkv, int T, int n_h
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kTileBytes);
-      tma_load_3d(s_q, &map_qkv, q_full, h * kAtD, q0, b);
+      mbar_arrive_expect_tx(q_full, kQBytes);
+      tma_load_3d(s_q, &map_q, q_full, h * kAtD, q0, b);
       for (int j = 0; j < n_kt; ++j) {
         const int st = j & 1;
         mbar_wait(kv_empty + st, ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(kv_full + st, 2 * kTileBytes);
-        tma_load_3d(s_kv + st * 2 * kTileBytes, &map_qkv, kv_full + st, d + h * kAtD, j * kAtK, b);
-        tma_load_3d(s_kv + st * 2 * kTileBytes + kTileBytes, &map_qkv, kv_full + st, 2 * d + h * kAtD, j * kAtK, b);
+        mbar_arrive_expect_tx(kv_full + st, 2 * kKVBytes);
+        tma_load_3d(s_kv + st * 2 * kKVBytes, &map_kv, kv_full + st, d + h * kAtD, j * kAtK, b);
+        tma_load_3d(s_kv + st * 2 * kKVBytes + kKVBytes, &map_kv, kv_full + st, 2 * d + h * kAtD, j * kAtK, b);
       }
     }
   } else if (warp == 1) {
@@ -99,18 +102,18 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_qkv, int T, int n_h
         if (j > 0) {
           mbar_wait(p_ready, (j - 1) & 1);
           tc5_fence_after();
-          const uint32_t v_addr = smem_u32(s_kv + ((j - 1) & 1) * 2 * kTileBytes + kTileBytes);
+          const uint32_t v_addr = smem_u32(s_kv + ((j - 1) & 1) * 2 * kKVBytes + kKVBytes);
 #pragma unroll
           for (int ks = 0; ks < kAtK / 16; ++ks) {
-            const uint64_t da = umma_desc_k_sw128(p_addr + (ks >> 2) * kTileBytes + (ks & 3) * 32);
-            const uint64_t db = umma_desc_mn_sw128(v_addr + ks * 2048, kTileBytes);
+            const uint64_t da = umma_desc_k_sw128(p_addr + ks * 32);
+            const uint64_t db = umma_desc_mn_sw128(v_addr + ks * 2048, kKVBytes);
             tc5_mma_f16(tmem_o, da, db, idesc_o, (j > 1 || ks > 0) ? 1u : 0u);
           }
           tc5_commit(kv_empty + ((j - 1) & 1));
         }
         if (j < n_kt) {
           tc5_fence_after();
-          const uint32_t k_addr = smem_u32(s_kv + (j & 1) * 2 * kTileBytes);
+          const uint32_t k_addr = smem_u32(s_kv + (j & 1) * 2 * kKVBytes);
 #pragma unroll
           for (int ks = 0; ks < kAtD / 16; ++ks) {
             const uint64_t da = umma_desc_k_sw128(q_addr + ks * 32);
@@ -127,38 +130,63 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_qkv, int T, int n_h
     const int row = quad * 32 + lane;           // row inside the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const float kLog2e = 1.4426950408889634f;
-    float m_run = -INFINITY;  // running max, log2 units
+    float m_run = 0.f;  // reference max, log2 units (set from the first tile)
     float l_run = 0.f;
     unsigned char* p_row = s_p + row * 128;
     const int sw = row & 7;
     for (int j = 0; j < n_kt; ++j) {
       mbar_wait(mma_done, j & 1);
       tc5_fence_after();
-      const int key0 = j * kAtK;
-      // pass 1: tile max of this row
-      float mx = -INFINITY;
+      const int n_valid = min(kAtK, T - j * kAtK);  // keys of this tile that exist
+      if (j == 0) {  // the first tile fixes the reference max
+        float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32];
-        tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
-        tmem_ld_wait();
-        if (key0 + c * 32 + 32 <= T) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
-        } else {
+        for (int c = 0; c < 2; ++c) {
+          uint32_t sv[32];
+          tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
+          tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (key0 + c * 32 + i < T) mx = fmaxf(mx, __uint_as_float(sv[i]));
+            if (c * 32 + i < n_valid) mx = fmaxf(mx, __uint_as_float(sv[i]));
         }
+        m_run = mx * kLog2e;
       }
-      const float t = mx * kLog2e;
-      // tcgen05.ld/st are warp-collective: the rescale decision is taken per warp, each lane with its own factor
-      if (__any_sync(0xffffffffu, t > m_run + kRescaleThreshold)) {
-        const float m_new = fmaxf(m_run, t);
-        const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_new);
+      float psum;
+      while (true) {
+        float ymax = -INFINITY;
+        psum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t sv[32];
+          tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float pv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int i = c * 32 + q * 8 + e;
+              float y = fmaf(__uint_as_float(sv[q * 8 + e]), kLog2e, -m_run);
+              if (i >= n_valid) y = -INFINITY;
+              ymax = fmaxf(ymax, y);
+              pv[e] = ex2_approx(y);
+              psum += pv[e];
+            }
+            uint4 pk;
+            pk.x = pack_f16x2(pv[0], pv[1]);
+            pk.y = pack_f16x2(pv[2], pv[3]);
+            pk.z = pack_f16x2(pv[4], pv[5]);
+            pk.w = pack_f16x2(pv[6], pv[7]);
+            *reinterpret_cast<uint4*>(p_row + (((c * 4 + q) ^ sw) << 4)) = pk;  // K-major, 128B swizzle
+          }
+        }
+        // tcgen05.ld/st are warp-collective: the rescale decision is taken per warp, each lane with its own factor
+        if (!__any_sync(0xffffffffu, ymax > kRescaleThreshold)) break;
+        const float grow = fmaxf(ymax, 0.f);
+        const float alpha = ex2_approx(-grow);
+        m_run += grow;
         l_run *= alpha;
-        m_run = m_new;
-        if (j > 0) {  // O holds contributions of earlier tiles: rescale it in place
+        if (j > 0) {  // O holds contributions of earlier tiles: rescale it in place, then redo this tile
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
             uint32_t ov[32];
@@ -169,33 +197,6 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_qkv, int T, int n_h
             tmem_st_32x32(tmem_o + lane_addr + c * 32, ov);
           }
           tmem_st_wait();
-        }
-      }
-      // pass 2: probabilities -> fp16 A-operand tile (K-major, 128B swizzle: 16-byte chunk index ^ (row & 7))
-      float psum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32];
-        tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
-        tmem_ld_wait();
-        float pv[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float p = ex2_approx(fmaf(__uint_as_float(sv[i]), kLog2e, -m_run));
-          if (key0 + c * 32 + i >= T) p = 0.f;
-          pv[i] = p;
-          psum += p;
-        }
-        unsigned char* blk = p_row + (c >> 1) * kTileBytes;  // 64-key k-block
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 pk;
-          pk.x = pack_f16x2(pv[8 * q], pv[8 * q + 1]);
-          pk.y = pack_f16x2(pv[8 * q + 2], pv[8 * q + 3]);
-          pk.z = pack_f16x2(pv[8 * q + 4], pv[8 * q + 5]);
-          pk.w = pack_f16x2(pv[8 * q + 6], pv[8 * q + 7]);
-          const int chunk = (c & 1) * 4 + q;
-          *reinterpret_cast<uint4*>(blk + ((chunk ^ sw) << 4)) = pk;
         }
       }
       l_run += psum;
@@ -243,10 +244,12 @@ int make_f16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* d
 int launch_attention_tc5(const void* qkv, int n_windows, int T, int n_heads, int n_query, void* out,
                          cudaStream_t st) {
   const int d = n_heads * kAtD;
-  CUtensorMap map;
+  CUtensorMap map_q, map_kv;
   uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)T, (uint64_t)n_windows};
   uint64_t strides[3] = {1, (uint64_t)3 * d, (uint64_t)3 * d * T};
-  int rc = make_f16_map(&map, qkv, 3, dims, strides, kAtK);
+  int rc = make_f16_map(&map_q, qkv, 3, dims, strides, kAtQ);
+  if (rc != SEGMA_OK) return rc;
+  rc = make_f16_map(&map_kv, qkv, 3, dims, strides, kAtK);
   if (rc != SEGMA_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
@@ -254,7 +257,7 @@ int launch_attention_tc5(const void* qkv, int n_windows, int T, int n_heads, int
     attr_set = true;
   }
   dim3 grid(ceil_div(n_query, kAtQ), n_heads, n_windows);
-  attention_tc5_kernel<<<grid, kAtThreads, kAtSmem, st>>>(map, T, n_heads, n_query, static_cast<__half*>(out));
+  attention_tc5_kernel<<<grid, kAtThreads, kAtSmem, st>>>(map_q, map_kv, T, n_heads, n_query, static_cast<__half*>(out));
   return launch_status("attention_tc5_kernel");
 }
 

@@ -153,35 +153,71 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       }
       float psum;
       while (true) {
-        float ymax = -INFINITY;
+        // running max of the fp16 probabilities (packed pairs): > 2^8 (or inf) means a score exceeded the
+        // reference max by more than the threshold
+        __half2 pmax2 = __floats2half2_rn(0.f, 0.f);
         psum = 0.f;
+        if (n_valid == kAtK) {  // full tile (block-uniform): no key masking
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t sv[32];
+            tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * e]), kLog2e, -m_run));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * e + 1]), kLog2e, -m_run));
+                psum += p0 + p1;
+                const __half2 h2 = __floats2half2_rn(p0, p1);
+                pmax2 = __hmax2(pmax2, h2);
+                pk[e] = *reinterpret_cast<const uint32_t*>(&h2);
+              }
+              *reinterpret_cast<uint4*>(p_row + (((c * 4 + q) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t sv[32];
+            tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = c * 32 + q * 8 + 2 * e;
+                float p0 = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * e]), kLog2e, -m_run));
+                float p1 = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * e + 1]), kLog2e, -m_run));
+                if (i >= n_valid) p0 = 0.f;
+                if (i + 1 >= n_valid) p1 = 0.f;
+                psum += p0 + p1;
+                const __half2 h2 = __floats2half2_rn(p0, p1);
+                pmax2 = __hmax2(pmax2, h2);
+                pk[e] = *reinterpret_cast<const uint32_t*>(&h2);
+              }
+              *reinterpret_cast<uint4*>(p_row + (((c * 4 + q) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+        const float pmax = fmaxf(__low2float(pmax2), __high2float(pmax2));
+        // tcgen05.ld/st are warp-collective: the rescale decision is taken per warp, each lane with its own factor
+        if (!__any_sync(0xffffffffu, pmax > 256.0f)) break;   // 256 = 2^kRescaleThreshold
+        // how far this row's scores exceed the reference (log2 units): log2 of its largest probability,
+        // recomputed exactly from the scores since the fp16 probability may have overflowed
+        float ymax = -INFINITY;
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           uint32_t sv[32];
           tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
           tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float pv[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int i = c * 32 + q * 8 + e;
-              float y = fmaf(__uint_as_float(sv[q * 8 + e]), kLog2e, -m_run);
-              if (i >= n_valid) y = -INFINITY;
-              ymax = fmaxf(ymax, y);
-              pv[e] = ex2_approx(y);
-              psum += pv[e];
-            }
-            uint4 pk;
-            pk.x = pack_f16x2(pv[0], pv[1]);
-            pk.y = pack_f16x2(pv[2], pv[3]);
-            pk.z = pack_f16x2(pv[4], pv[5]);
-            pk.w = pack_f16x2(pv[6], pv[7]);
-            *reinterpret_cast<uint4*>(p_row + (((c * 4 + q) ^ sw) << 4)) = pk;  // K-major, 128B swizzle
-          }
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < n_valid) ymax = fmaxf(ymax, fmaf(__uint_as_float(sv[i]), kLog2e, -m_run));
         }
-        // tcgen05.ld/st are warp-collective: the rescale decision is taken per warp, each lane with its own factor
-        if (!__any_sync(0xffffffffu, ymax > kRescaleThreshold)) break;
         const float grow = fmaxf(ymax, 0.f);
         const float alpha = ex2_approx(-grow);
         m_run += grow;

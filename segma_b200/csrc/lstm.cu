@@ -74,6 +74,70 @@ __global__ void __launch_bounds__(4 * H) lstm_layer_kernel(const float* __restri
   }
 }
 
+// Same recurrence with W_hh resident in shared memory as fp16 (H <= 128: 128 KB), R = 3 frames per CTA so
+// that 2 x ceil(199 / 3) = 134 CTAs cover the 148 SMs in one wave.  Per step a thread owns one gate column:
+// 128 (LDS.16 + cvt + R FMAs), then the pointwise cell update; the fetch of W_hh no longer depends on L2
+// latency, which bounded the kernel above at ~11 us per step.  The rounding of W_hh to fp16 matches the
+// precision of W_ih (an fp16 tensor-core operand); h, c and the gate pre-activations stay fp32.
+constexpr int kLstmRowsSmem = 3;
+
+template <int H>
+__global__ void __launch_bounds__(4 * H) lstm_layer_smem_kernel(const float* __restrict__ pre,
+                                                                 const float* __restrict__ w_hh_t, int n_steps,
+                                                                 int n_rows, int n_dirs, float* __restrict__ out,
+                                                                 __half* __restrict__ out_f16) {
+  constexpr int R = kLstmRowsSmem;
+  constexpr int G = 4 * H;
+  extern __shared__ __align__(16) unsigned char lstm_smem[];
+  __half* s_w = reinterpret_cast<__half*>(lstm_smem);                 // [H][G]
+  float* s_h = reinterpret_cast<float*>(lstm_smem + sizeof(__half) * H * G);  // [H][4] (R padded to 4)
+  float* s_g = s_h + H * 4;                                          // [R][G]
+  const int dir = blockIdx.y;
+  const int r0 = blockIdx.x * R;
+  const int j = threadIdx.x;
+  for (int k = 0; k < H; ++k) s_w[k * G + j] = __float2half(__ldg(w_hh_t + ((long long)dir * H + k) * G + j));
+  for (int i = j; i < H * 4; i += G) s_h[i] = 0.f;
+  float c_state = 0.f;
+  __syncthreads();
+  const int pr = j / H, pu = j - pr * H;  // pointwise item of this thread (valid if pr < R)
+  for (int step = 0; step < n_steps; ++step) {
+    const int s = dir == 0 ? step : n_steps - 1 - step;
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = r0 + r;
+      acc[r] = row < n_rows ? __ldg(pre + ((long long)s * n_rows + row) * (n_dirs * G) + dir * G + j) : 0.f;
+    }
+#pragma unroll 16
+    for (int k = 0; k < H; ++k) {
+      const float wk = __half2float(s_w[k * G + j]);
+      const float4 hv = *reinterpret_cast<const float4*>(s_h + k * 4);
+      acc[0] = fmaf(wk, hv.x, acc[0]);
+      acc[1] = fmaf(wk, hv.y, acc[1]);
+      acc[2] = fmaf(wk, hv.z, acc[2]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) s_g[r * G + j] = acc[r];
+    __syncthreads();
+    if (pr < R) {
+      const float ig = sigmoid_acc(s_g[pr * G + pu]);
+      const float fg = sigmoid_acc(s_g[pr * G + H + pu]);
+      const float gg = tanhf(s_g[pr * G + 2 * H + pu]);
+      const float og = sigmoid_acc(s_g[pr * G + 3 * H + pu]);
+      c_state = fmaf(fg, c_state, ig * gg);
+      const float h = og * tanhf(c_state);
+      s_h[pu * 4 + pr] = h;
+      const int row = r0 + pr;
+      if (row < n_rows) {
+        const long long o = ((long long)s * n_rows + row) * (n_dirs * H) + dir * H + pu;
+        out[o] = h;
+        if (out_f16) out_f16[o] = __float2half(h);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // one warp per (step, frame) row: C dot products of length n_feat
 __global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ feat, int n_steps, int n_rows,
                                                      int n_feat, int n_keep, const float* __restrict__ w,
@@ -107,9 +171,23 @@ int segma_lstm_layer(const float* pre, const float* w_hh_t, int n_steps, int n_r
   dim3 grid(ceil_div(n_rows, kLstmRows), n_dirs);
   cudaStream_t st = (cudaStream_t)stream;
   __half* ob = static_cast<__half*>(out_f16);
+  dim3 grid_s(ceil_div(n_rows, kLstmRowsSmem), n_dirs);
   switch (hidden) {
-    case 64: lstm_layer_kernel<64><<<grid, 256, 0, st>>>(pre, w_hh_t, n_steps, n_rows, n_dirs, out, ob); break;
-    case 128: lstm_layer_kernel<128><<<grid, 512, 0, st>>>(pre, w_hh_t, n_steps, n_rows, n_dirs, out, ob); break;
+    case 64: {
+      constexpr int kSmem = 64 * 256 * 2 + 64 * 4 * 4 + kLstmRowsSmem * 256 * 4;
+      lstm_layer_smem_kernel<64><<<grid_s, 256, kSmem, st>>>(pre, w_hh_t, n_steps, n_rows, n_dirs, out, ob);
+      break;
+    }
+    case 128: {
+      constexpr int kSmem = 128 * 512 * 2 + 128 * 4 * 4 + kLstmRowsSmem * 512 * 4;
+      static bool attr_set = false;
+      if (!attr_set) {
+        SEGMA_CUDA_OK(cudaFuncSetAttribute(lstm_layer_smem_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        attr_set = true;
+      }
+      lstm_layer_smem_kernel<128><<<grid_s, 512, kSmem, st>>>(pre, w_hh_t, n_steps, n_rows, n_dirs, out, ob);
+      break;
+    }
     case 256: lstm_layer_kernel<256><<<grid, 1024, 0, st>>>(pre, w_hh_t, n_steps, n_rows, n_dirs, out, ob); break;
     default:
       set_last_error("segma_lstm_layer: hidden size %d not supported (64, 128, 256)", hidden);

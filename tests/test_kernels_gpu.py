@@ -169,7 +169,8 @@ def test_lstm_layer(cuda, H, dirs):
         whh.append(w_hh.T.contiguous())
     pre = torch.cat(pres, dim=-1).contiguous().to(cuda)
     out = ops.lstm_layer(pre, torch.stack(whh).contiguous().to(cuda), H)
-    _close(out, ref, 1e-4, 1e-5, "lstm layer")
+    # W_hh is held in shared memory as fp16 (2^-11 relative rounding, like W_ih); state and gates are fp32
+    _close(out, ref, 1e-3, 3e-4, "lstm layer")
 
 
 def test_heads(cuda):

@@ -203,3 +203,69 @@ def test_w2v2_silent_file(cuda):
     ref = O.apply_model_on_audio(torch.from_numpy(pcm), lambda w: O.hubert_hydra_forward(sd, w, LABELS), 4, batch_size=4)
     assert torch.isfinite(got).all()
     assert (got - ref).abs().max() <= 0.01 * max(1.0, ref.abs().max().item())
+
+
+# ---- BASELINE config 5: window length / overlap / threshold sweep -------------------------------------------------
+def _composed_oracle(pcm, forward, win, step, batch_size, whisper, frames_per_window):
+    """Same windows and batch boundaries as the product, logit-domain mean over covering windows."""
+    t = torch.from_numpy(pcm)
+    n = t.numel()
+    n_fit = (n - win) // step + 1 if n >= win else 0
+    wins, offs = [], []
+    for b0 in range(0, n_fit, batch_size):
+        idx = list(range(b0, min(b0 + batch_size, n_fit)))
+        chunk = [t[i * step: i * step + win] for i in idx]
+        x = torch.stack([O.whisper_logmel(w) for w in chunk]) if whisper else torch.stack(chunk)
+        out = forward(x).reshape(len(idx), -1, len(LABELS))[:, :frames_per_window]
+        wins += list(out)
+        offs += [i * step // 320 for i in idx]
+    tail = t[n_fit * step:]
+    if tail.numel() >= 400:
+        ft = min((tail.numel() - 400) // 320 + 1, frames_per_window)
+        x = O.whisper_logmel(tail)[None] if whisper else tail[None]
+        wins.append(forward(x).reshape(-1, len(LABELS))[:ft])
+        offs.append(n_fit * step // 320)
+    n_frames = max(o + w.shape[0] for o, w in zip(offs, wins))
+    return O.stitch_mean(wins, offs, n_frames)
+
+
+@pytest.mark.parametrize("win_s,overlap", [(2, 0.5), (3, 0.75), (4, 0.9), (6, 0.5), (8, 0.75)])
+def test_sweep_waveform_model(cuda, win_s, overlap):
+    sd = synth.hubert_hydra_state_dict(synth.W2V2_TEST, seed=5)
+    le = MultiLabelEncoder(list(LABELS))
+    cfg = make_config("surgical_hubert_hydra", chunk_duration_s=float(win_s))
+    model = Models["surgical_hubert_hydra"].from_state_dict(sd, le, cfg)
+    win = win_s * 16000
+    step = max(320, int(win * (1 - overlap)) // 320 * 320)
+    F_ = (win - 400) // 320 + 1
+    n = win + step * 5 + 4000
+    pcm = synth.synth_audio(n, 40 + win_s)
+    got = apply_model_on_audio(pcm, model, INFERENCE_SETTINGS, "cuda", batch_size=4, chunk_duration_s=float(win_s),
+                               window_step=step)
+    ref = _composed_oracle(pcm, lambda w: O.hubert_hydra_forward(sd, w, LABELS), win, step, 4, False, F_)
+    assert got.shape == ref.shape
+    _check_logits(got.cpu(), ref, f"sweep {win_s}s overlap {overlap}", min_agreement=0.998)
+    for t in (0.3, 0.5, 0.7):  # decoding of the product's own logits is bit-exact at every threshold
+        thr = {lab: {"lower_bound": t, "upper_bound": 1.0} for lab in LABELS}
+        mask = O.apply_thresholds(got.cpu(), [t] * 4)
+        assert decode_logits(got, thr, le) == O.create_intervals(mask.numpy(), LABELS)
+
+
+@pytest.mark.parametrize("win_s", [2, 6])
+def test_sweep_whisper_window_length(cuda, win_s):
+    """Whisper-family windows other than 4 s keep conv_settings.n_windows(chunk, strict=False) frames."""
+    sd = synth.hydra_whisper_state_dict(synth.WHISPER_TEST, seed=7)
+    le = MultiLabelEncoder(list(LABELS))
+    cfg = make_config("hydra_whisper", chunk_duration_s=float(win_s))
+    model = Models["hydra_whisper"].from_state_dict(sd, le, cfg)
+    win = win_s * 16000
+    F_ = win // 321
+    assert model.n_keep == F_
+    step = F_ * 320  # windows tile the frame grid
+    n = win + step * 2 + 3000
+    pcm = synth.synth_audio(n, 50 + win_s)
+    got = apply_model_on_audio(pcm, model, INFERENCE_SETTINGS, "cuda", batch_size=2, chunk_duration_s=float(win_s),
+                               window_step=step)
+    ref = _composed_oracle(pcm, lambda f: O.hydra_whisper_forward(sd, f, LABELS, n_keep=F_), win, step, 2, True, F_)
+    assert got.shape == ref.shape
+    _check_logits(got.cpu(), ref, f"whisper {win_s}s windows")

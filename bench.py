@@ -240,6 +240,51 @@ def run_gpu(args):
     achieved_tf = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     total_flops_per_step = 905 * 344.7e9 * (n_samples / HOUR_SAMPLES)
 
+    # secondary HBM-bound kernels, timed alone (burst peak): log-mel front end on one 128-window batch and
+    # threshold + run-length decode on a >= 100 h batch of logits
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    def time_kernel(fn, iters=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e-3
+
+    side = {}
+    if rank == 0 and not args.no_side_kernels:
+        n_w = 1024  # 1024 windows: 262 MB in + 983 MB out, larger than L2
+        span = STEP_SAMPLES * (n_w - 1) + WIN
+        pcm_side = dev_pcm[:span] if dev_pcm.numel() >= span else torch.randn(span, device=dev) * 0.1
+        out_f32 = torch.empty((n_w, 80, 3000), dtype=torch.float32, device=dev)
+        scratch = torch.empty(ops.logmel_scratch_bytes(n_w, WIN), dtype=torch.uint8, device=dev)
+        lib = ops._lib()
+        st = torch.cuda.current_stream().cuda_stream
+        t_mel = time_kernel(lambda: lib.segma_logmel(pcm_side.data_ptr(), pcm_side.numel(), n_w, WIN, STEP_SAMPLES,
+                                                     out_f32.data_ptr(), None, scratch.data_ptr(), st))
+        mel_bytes = n_w * (4 * WIN + 4 * 80 * 3000)
+        side["logmel"] = {"bound": "hbm", "achieved": mel_bytes / t_mel / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                          "frac": mel_bytes / t_mel / 1e9 / hbm_peak, "us_per_window": t_mel / n_w * 1e6,
+                          "algorithmic_bytes_per_window": 4 * WIN + 4 * 80 * 3000}
+        del out_f32, scratch
+        n_fr = 180_000 * 200  # 200 h of frames: 576 MB of logits
+        big = torch.randn((n_fr, len(LABELS)), device=dev)
+        offs = [i * 180_000 for i in range(201)]
+        tbl = ops.decode_intervals(big, cuts, file_offsets=offs, mode=ops.DECODE_LOGIT)
+        n_iv = int(tbl.shape[0])
+        t_dec = time_kernel(lambda: ops.decode_intervals(big, cuts, file_offsets=offs, mode=ops.DECODE_LOGIT,
+                                                         capacity=n_iv), iters=5)
+        dec_bytes = 4 * len(LABELS) * n_fr + 16 * n_iv
+        side["decode"] = {"bound": "hbm", "achieved": dec_bytes / t_dec / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                          "frac": dec_bytes / t_dec / 1e9 / hbm_peak, "hours_of_logits": 200, "intervals": n_iv,
+                          "note": "includes the count read-back and table allocation of the Python wrapper"}
+        del big, tbl
+
     if rank != 0:
         return
     value = world * (audio_s / 3600.0) * args.steps / dev_s
@@ -264,6 +309,7 @@ def run_gpu(args):
                      "traffic": None, "launches": n_gemm, "avg_launch_ms": g_ms / max(n_gemm, 1),
                      "share_of_step": (g_ms / 1e3) / (dev_s / args.steps), "peak_source": peak_src},
         "cpu_baseline": cpu,
+        "side_kernels": side,
         "clocks": clocks.summary(),
         "breakdown_ms_per_step": {k: [round(v["ms"], 3), round(v["work"] / max(v["ms"], 1e-9) / 1e9, 1)]
                                   for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])},
@@ -282,6 +328,7 @@ def main():
     ap.add_argument("--hours", type=float, default=1.0, help="audio hours per GPU per step")
     ap.add_argument("--ref-windows", type=int, default=16, help="windows per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-kernels", action="store_true", help="skip the log-mel / decode roofline measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

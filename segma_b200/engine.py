@@ -127,12 +127,15 @@ class WhisperEngine:
         else:
             raise ValueError(f"unknown Whisper-family model kind '{kind}'")
         self.tail = LstmHeads(sd, labels, dev)
-        self._cap = 0
+        self._slots: dict[int, tuple[int, dict]] = {}  # workspace slot -> (capacity in windows, buffers)
         self._ws: dict[str, torch.Tensor] = {}
 
     # ---- workspace -------------------------------------------------------------------------------
-    def _reserve(self, n: int) -> None:
-        if n <= self._cap:
+    def _reserve(self, n: int, slot: int = 0) -> None:
+        """Make ``self._ws`` the buffers of ``slot`` (one slot per concurrently running batch), grown to n windows."""
+        cap, ws = self._slots.get(slot, (0, {}))
+        if n <= cap:
+            self._ws = ws
             return
         dev, d = self.device, self.d
         M = n * N_CTX
@@ -147,8 +150,8 @@ class WhisperEngine:
         ws["mix"] = torch.empty((n, self.n_keep, d), dtype=torch.float32, device=dev)
         ws["mix_f16"] = torch.empty((n * self.n_keep, d), dtype=torch.float16, device=dev)
         ws["mel_scratch"] = torch.empty(max(ops.logmel_scratch_bytes(n, 64_000 * 2), 1), dtype=torch.uint8, device=dev)
+        self._slots[slot] = (n, ws)
         self._ws = ws
-        self._cap = n
 
     # ---- stages ------------------------------------------------------------------------------------
     def encode_tm(self, mel_tm: torch.Tensor, n: int) -> None:
@@ -190,10 +193,11 @@ class WhisperEngine:
         ops.cast_f16(mix.view(n * self.n_keep, d), ws["mix_f16"][: n * self.n_keep])
 
     def forward_pcm(self, pcm: torch.Tensor, start: int, n: int, win_len: int, step: int, logits: torch.Tensor,
-                    frame_offset: int, step_frames: int, n_keep: int | None = None) -> None:
+                    frame_offset: int, step_frames: int, n_keep: int | None = None, slot: int = 0) -> None:
         """Windows ``pcm[start + i*step : +win_len]``, i < n, of a device-resident 1-D fp32 signal ->
-        ``logits[(frame_offset + i*step_frames + r), :]`` for r < n_keep."""
-        self._reserve(n)
+        ``logits[(frame_offset + i*step_frames + r), :]`` for r < n_keep.  ``slot`` selects the workspace
+        (batches running concurrently on different streams use different slots)."""
+        self._reserve(n, slot)
         ws = self._ws
         need = ops.logmel_scratch_bytes(n, win_len)
         if ws["mel_scratch"].numel() < need:

@@ -136,11 +136,11 @@ class W2V2Engine:
             self._pos_bias[T] = wavlm_position_bias(self.rel_embed, T, self.rel_embed.shape[0]).to(self.device)
         return self._pos_bias[T]
 
-    def _workspace(self, n: int, win_len: int) -> dict:
-        key = (n, win_len)
+    def _workspace(self, n: int, win_len: int, slot: int = 0) -> dict:
+        key = (n, win_len, slot)
         if key in self._ws:
             return self._ws[key]
-        if len(self._ws) > 4:  # full batch, remainder, tail (+ slack); drop the rest
+        if len(self._ws) > 8:  # (full batch, remainder, tail) x 2 slots (+ slack); drop the rest
             self._ws.clear()
         dev, C, d = self.device, self.C, self.d
         lens = conv_lengths(win_len)
@@ -165,9 +165,9 @@ class W2V2Engine:
         return ws
 
     def forward_pcm(self, pcm: torch.Tensor, start: int, n: int, win_len: int, step: int, logits: torch.Tensor,
-                    frame_offset: int, step_frames: int, n_keep: int | None = None) -> None:
+                    frame_offset: int, step_frames: int, n_keep: int | None = None, slot: int = 0) -> None:
         """Windows ``pcm[start + i*step : +win_len]``, i < n -> ``logits[frame_offset + i*step_frames + r]``, r < n_keep."""
-        ws = self._workspace(n, win_len)
+        ws = self._workspace(n, win_len, slot)
         lens, T, C, d = ws["lens"], ws["T"], self.C, self.d
         if T <= 0:
             return

@@ -260,6 +260,170 @@ __global__ void __launch_bounds__(kDecodeBlock) decode_write_kernel(
   }
 }
 
+// ---- fast path for C <= 8 labels: 4 frames per thread, one activity byte per frame ---------------------------
+// Pass 1 streams the logits once (4 x 128-bit loads per thread for C = 4), keeps one byte of activity bits
+// per frame for pass 3, and counts run starts / ends per label with byte-packed warp reductions (a warp
+// holds at most 128 boundaries per label, so four labels share one 32-bit word).
+constexpr int kFastThreads = 256;
+constexpr int kFastFrames = 4;                             // consecutive frames per thread
+constexpr int kFastBlock = kFastThreads * kFastFrames;     // 1024 frames per block (== kDecodeBlock)
+
+__device__ __forceinline__ uint32_t packed_warp_sum(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ uint32_t packed_warp_excl_scan(uint32_t v, int lane) {
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += t;
+  }
+  return x - v;
+}
+// bit c of every frame byte -> count of set bits among the 4 frames, packed one byte per label (labels lo..lo+3)
+__device__ __forceinline__ uint32_t packed_counts(uint32_t flags4, int lo) {
+  uint32_t out = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) out |= static_cast<uint32_t>(__popc(flags4 & (0x01010101u << (lo + c)))) << (8 * c);
+  return out;
+}
+
+// activity bytes of this thread's 4 frames plus the neighbouring frames on either side
+struct FrameBits {
+  uint32_t cur;   // byte i = frame i of the thread
+  uint32_t prev;  // byte i = frame i-1
+  uint32_t next;  // byte i = frame i+1
+};
+
+__device__ __forceinline__ FrameBits neighbour_bits(uint32_t cur, uint32_t halo_prev, uint32_t halo_next, int lane,
+                                                    const uint32_t* s_edge_lo, const uint32_t* s_edge_hi, int warp,
+                                                    int n_warps) {
+  // byte 3 of the previous thread / byte 0 of the next thread, across warps through shared memory
+  uint32_t left = __shfl_up_sync(0xffffffffu, cur >> 24, 1);
+  uint32_t right = __shfl_down_sync(0xffffffffu, cur & 0xffu, 1);
+  if (lane == 0) left = warp == 0 ? halo_prev : s_edge_hi[warp - 1];
+  if (lane == 31) right = warp == n_warps - 1 ? halo_next : s_edge_lo[warp + 1];
+  FrameBits fb;
+  fb.cur = cur;
+  fb.prev = (cur << 8) | (left & 0xffu);
+  fb.next = (cur >> 8) | ((right & 0xffu) << 24);
+  return fb;
+}
+
+template <bool kWrite>
+__global__ void __launch_bounds__(kFastThreads) decode_fast_kernel(
+    const float* __restrict__ logits, const long long* __restrict__ file_offsets,
+    const int* __restrict__ block_offsets, int n_files, DecodeParams p, uint8_t* __restrict__ bits,
+    int* __restrict__ start_counts, int* __restrict__ end_counts, int32_t* __restrict__ table, long long capacity) {
+  __shared__ uint32_t s_edge_lo[kFastThreads / 32], s_edge_hi[kFastThreads / 32];
+  __shared__ uint32_t s_warp[4][kFastThreads / 32];  // [starts lo, starts hi, ends lo, ends hi][warp]
+  __shared__ int s_base[2][8];
+  const int file = find_file(block_offsets, n_files, blockIdx.x);
+  const int local_block = blockIdx.x - block_offsets[file];
+  const int nblk_file = block_offsets[file + 1] - block_offsets[file];
+  const long long f_begin = file_offsets[file], f_end = file_offsets[file + 1];
+  const long long frame0 = f_begin + (long long)local_block * kFastBlock + threadIdx.x * kFastFrames;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  constexpr int n_warps = kFastThreads / 32;
+
+  uint32_t cur = 0;
+  if (kWrite) {
+    if (frame0 + kFastFrames <= f_end && ((reinterpret_cast<uintptr_t>(bits + frame0) & 3) == 0)) {
+      cur = *reinterpret_cast<const uint32_t*>(bits + frame0);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kFastFrames; ++i)
+        if (frame0 + i < f_end) cur |= static_cast<uint32_t>(bits[frame0 + i]) << (8 * i);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kFastFrames; ++i)
+      if (frame0 + i < f_end) cur |= frame_bits(logits, frame0 + i, p) << (8 * i);
+    if (frame0 + kFastFrames <= f_end && ((reinterpret_cast<uintptr_t>(bits + frame0) & 3) == 0)) {
+      *reinterpret_cast<uint32_t*>(bits + frame0) = cur;
+    } else {
+#pragma unroll
+      for (int i = 0; i < kFastFrames; ++i)
+        if (frame0 + i < f_end) bits[frame0 + i] = static_cast<uint8_t>(cur >> (8 * i));
+    }
+  }
+  // block halos: the frame before the block and the frame after it (inside the same file)
+  uint32_t halo_prev = 0, halo_next = 0;
+  if (threadIdx.x == 0) {
+    const long long pf = frame0 - 1;
+    if (pf >= f_begin) halo_prev = kWrite ? bits[pf] : frame_bits(logits, pf, p);
+  }
+  if (threadIdx.x == kFastThreads - 1) {
+    const long long nf = f_begin + (long long)(local_block + 1) * kFastBlock;
+    if (nf < f_end) halo_next = kWrite ? bits[nf] : frame_bits(logits, nf, p);
+  }
+  if (lane == 0) s_edge_lo[warp] = cur & 0xffu;
+  if (lane == 31) s_edge_hi[warp] = cur >> 24;
+  __syncthreads();
+  const FrameBits fb = neighbour_bits(cur, halo_prev, halo_next, lane, s_edge_lo, s_edge_hi, warp, n_warps);
+  const uint32_t starts = fb.cur & ~fb.prev, ends = fb.cur & ~fb.next;
+  const uint32_t cs_lo = packed_counts(starts, 0), ce_lo = packed_counts(ends, 0);
+  const uint32_t cs_hi = p.C > 4 ? packed_counts(starts, 4) : 0u, ce_hi = p.C > 4 ? packed_counts(ends, 4) : 0u;
+
+  if (!kWrite) {
+    const uint32_t ws_lo = packed_warp_sum(cs_lo), we_lo = packed_warp_sum(ce_lo);
+    const uint32_t ws_hi = p.C > 4 ? packed_warp_sum(cs_hi) : 0u, we_hi = p.C > 4 ? packed_warp_sum(ce_hi) : 0u;
+    if (lane == 0) { s_warp[0][warp] = ws_lo; s_warp[1][warp] = ws_hi; s_warp[2][warp] = we_lo; s_warp[3][warp] = we_hi; }
+    __syncthreads();
+    if (threadIdx.x < 2 * p.C) {
+      const int which = threadIdx.x / p.C, c = threadIdx.x - which * p.C;  // 0 = starts, 1 = ends
+      int total = 0;
+      for (int w = 0; w < n_warps; ++w) total += (s_warp[which * 2 + (c >> 2)][w] >> (8 * (c & 3))) & 0xff;
+      const long long idx = (long long)p.C * block_offsets[file] + (long long)c * nblk_file + local_block;
+      (which == 0 ? start_counts : end_counts)[idx] = total;
+    }
+    return;
+  }
+
+  // ---- write pass: rank of this thread's first boundary of each label inside the block ----
+  const uint32_t xs_lo = packed_warp_excl_scan(cs_lo, lane), xe_lo = packed_warp_excl_scan(ce_lo, lane);
+  const uint32_t xs_hi = p.C > 4 ? packed_warp_excl_scan(cs_hi, lane) : 0u, xe_hi = p.C > 4 ? packed_warp_excl_scan(ce_hi, lane) : 0u;
+  if (lane == 31) {
+    s_warp[0][warp] = xs_lo + cs_lo; s_warp[1][warp] = xs_hi + cs_hi;
+    s_warp[2][warp] = xe_lo + ce_lo; s_warp[3][warp] = xe_hi + ce_hi;
+  }
+  if (threadIdx.x < 2 * p.C) {
+    const int which = threadIdx.x / p.C, c = threadIdx.x - which * p.C;
+    const long long idx = (long long)p.C * block_offsets[file] + (long long)c * nblk_file + local_block;
+    s_base[which][c] = (which == 0 ? start_counts : end_counts)[idx];  // exclusive-scanned by pass 2
+  }
+  __syncthreads();
+  const int rel0 = static_cast<int>(frame0 - f_begin);
+  for (int c = 0; c < p.C; ++c) {
+    const int word = c >> 2, sh = 8 * (c & 3);
+    int rs = ((word ? xs_hi : xs_lo) >> sh) & 0xff, re = ((word ? xe_hi : xe_lo) >> sh) & 0xff;
+    for (int w = 0; w < warp; ++w) {
+      rs += (s_warp[word][w] >> sh) & 0xff;
+      re += (s_warp[2 + word][w] >> sh) & 0xff;
+    }
+    long long row_s = (long long)s_base[0][c] + rs, row_e = (long long)s_base[1][c] + re;
+    const uint32_t m = 0x01010101u << c;
+    uint32_t sb = starts & m, eb = ends & m;
+#pragma unroll
+    for (int i = 0; i < kFastFrames; ++i) {
+      if (sb & (0xffu << (8 * i))) {
+        if (row_s < capacity) {
+          table[row_s * 4 + 0] = file;
+          table[row_s * 4 + 1] = c;
+          table[row_s * 4 + 2] = (rel0 + i) * SEGMA_FRAME_SAMPLES;
+        }
+        ++row_s;
+      }
+      if (eb & (0xffu << (8 * i))) {
+        if (row_e < capacity) table[row_e * 4 + 3] = (rel0 + i + 1) * SEGMA_FRAME_SAMPLES;
+        ++row_e;
+      }
+    }
+  }
+}
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct DecodeLayout {
@@ -365,15 +529,27 @@ int segma_decode_intervals(const float* logits, const int64_t* file_offsets, int
   SEGMA_CUDA_OK(cudaMemcpyAsync(d_file, file_offsets, sizeof(int64_t) * (n_files + 1), cudaMemcpyHostToDevice, st));
   SEGMA_CUDA_OK(cudaMemcpyAsync(d_block, block_offsets.data(), sizeof(int) * (n_files + 1), cudaMemcpyHostToDevice, st));
   // pageable-source async copies are staged before returning, so block_offsets may go out of scope
-  decode_count_kernel<<<total_blocks, kDecodeBlock, 0, st>>>(logits, d_file, d_block, n_files, p, bits, starts, ends);
-  rc = launch_status("decode_count_kernel");
+  const bool fast = n_labels <= 8;  // one activity byte per frame, 4 frames per thread
+  static_assert(kFastBlock == kDecodeBlock, "both paths tile files in blocks of 1024 frames");
+  if (fast) {
+    decode_fast_kernel<false><<<total_blocks, kFastThreads, 0, st>>>(
+        logits, d_file, d_block, n_files, p, reinterpret_cast<uint8_t*>(bits), starts, ends, table, capacity);
+  } else {
+    decode_count_kernel<<<total_blocks, kDecodeBlock, 0, st>>>(logits, d_file, d_block, n_files, p, bits, starts, ends);
+  }
+  rc = launch_status("decode count pass");
   if (rc != SEGMA_OK) return rc;
   decode_scan_kernel<<<1, kScanThreads, 0, st>>>(starts, ends, (long long)total_blocks * n_labels, count);
   rc = launch_status("decode_scan_kernel");
   if (rc != SEGMA_OK) return rc;
-  decode_write_kernel<<<total_blocks, kDecodeBlock, 0, st>>>(bits, d_file, d_block, n_files, n_labels, starts, ends,
-                                                             table, capacity);
-  return launch_status("decode_write_kernel");
+  if (fast) {
+    decode_fast_kernel<true><<<total_blocks, kFastThreads, 0, st>>>(
+        logits, d_file, d_block, n_files, p, reinterpret_cast<uint8_t*>(bits), starts, ends, table, capacity);
+  } else {
+    decode_write_kernel<<<total_blocks, kDecodeBlock, 0, st>>>(bits, d_file, d_block, n_files, n_labels, starts, ends,
+                                                               table, capacity);
+  }
+  return launch_status("decode write pass");
 }
 
 }  // extern "C"

@@ -7,7 +7,7 @@
 // -> max(., window_max - 8) -> (. + 4) / 4, padded with the constant value to 3000 frames.
 //
 // HBM-bound: per window 256 KB of PCM in, 960 KB of features out.  Kernel A stages the overlapping
-// samples of 32 consecutive frames once in shared memory (128-bit loads; each sample is used by 2.5
+// samples of 16 consecutive frames once in shared memory (128-bit loads; each sample is used by 2.5
 // frames), runs a packed real FFT (200-point complex Stockham, radix 8*5*5, in shared memory/registers),
 // applies the sparse mel filters and the log, and reduces the window maximum with one atomic per
 // block.  Kernel B applies the window-global clamp, scales, and streams out the 3000-frame rows
@@ -29,7 +29,7 @@ constexpr int kBins = 201;
 constexpr int kMels = SEGMA_MEL_BINS;
 constexpr int kFramesOut = SEGMA_MEL_FRAMES;
 constexpr int kPadSamples = 480000;  // 30 s
-constexpr int kGroup = 32;           // frames per block
+constexpr int kGroup = 16;           // frames per work item (4 CTAs of 160 threads per SM; 8 or 32 frames are slower)
 constexpr int kThreadsA = 160;
 constexpr int kMaxTaps = 32;         // max contiguous FFT bins per mel filter
 constexpr int kStage = (kGroup - 1) * kHop + kNfft;  // 5360 staged samples per group
@@ -183,143 +183,187 @@ __device__ __forceinline__ float sample_at(const float* __restrict__ w, long lon
 }
 
 // ---- kernel A: log10 mel power of the frames that touch audio + window max ---------------------------
-__global__ void __launch_bounds__(kThreadsA) logmel_power_kernel(const float* __restrict__ pcm, long long pcm_len,
-                                                                 int win_len, long long step, int n_valid_max,
-                                                                 int nvp, float* __restrict__ logspec,
+// Persistent CTAs walk (window, 32-frame group) work items; the Hann window, both twiddle tables and the
+// compacted mel filters live in shared memory for the lifetime of the CTA.
+constexpr int kMelTapsSmem = 16;  // the slaney bank has at most 14 taps per filter; wider banks read global
+
+struct __align__(16) SmemTables {
+  float hann[kNfft];
+  float2 tw200[kHalf];
+  float2 tw400[kBins + 1];
+  float mel_w[kMels][kMelTapsSmem];
+  short mel_k0[kMels];
+  short mel_len[kMels];
+};
+
+__global__ void __launch_bounds__(kThreadsA, 4) logmel_power_kernel(const float* __restrict__ pcm, long long pcm_len,
+                                                                 int win_len, long long step, int n_windows,
+                                                                 int groups_per_window, int nvp,
+                                                                 float* __restrict__ logspec,
                                                                  uint32_t* __restrict__ win_max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* Z = reinterpret_cast<float2*>(smem_raw);                              // [kGroup][kHalf]
-  float* stage = reinterpret_cast<float*>(smem_raw + sizeof(float2) * kGroup * kHalf);  // samples, later power
+  float2* Z = reinterpret_cast<float2*>(smem_raw);                                       // [kGroup][kHalf]
+  float* stage = reinterpret_cast<float*>(smem_raw + sizeof(float2) * kGroup * kHalf);   // samples, later power
+  SmemTables& tab = *reinterpret_cast<SmemTables*>(smem_raw + sizeof(float2) * kGroup * kHalf +
+                                                   sizeof(float) * (kGroup * kBins > kStage ? kGroup * kBins : kStage));
   __shared__ float s_red[kThreadsA / 32];
-
-  const int win = blockIdx.y;
-  const int t0 = blockIdx.x * kGroup;
-  const long long w_off = (long long)win * step;
-  long long avail = pcm_len - w_off;
-  if (avail > win_len) avail = win_len;
-  if (avail < 0) avail = 0;
-  // frames >= n_valid see only zeros
-  int n_valid = (int)((avail + 200 + kHop - 1) / kHop);
-  if (avail == 0) n_valid = 0;
-  if (n_valid > kFramesOut) n_valid = kFramesOut;
-  if (t0 >= n_valid) return;  // whole group is silent padding (uniform per block)
-  const float* w = pcm + w_off;
   const int tid = threadIdx.x;
 
-  // 1. stage samples [160*t0 - 200, +5360) with 128-bit loads where possible
-  {
-    const long long s0 = (long long)kHop * t0 - 200;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
-    for (int q = tid; q < kStage / 4; q += kThreadsA) {
-      const long long n = s0 + 4 * q;
-      float4 v;
-      if (aligned && n >= 0 && n + 3 < avail) {
-        v = __ldg(reinterpret_cast<const float4*>(w + n));
-      } else {
-        v.x = sample_at(w, n, avail);
-        v.y = sample_at(w, n + 1, avail);
-        v.z = sample_at(w, n + 2, avail);
-        v.w = sample_at(w, n + 3, avail);
-      }
-      reinterpret_cast<float4*>(stage)[q] = v;
-    }
+  for (int i = tid; i < kNfft; i += kThreadsA) tab.hann[i] = g_tab.hann[i];
+  for (int i = tid; i < kHalf; i += kThreadsA) tab.tw200[i] = g_tab.tw200[i];
+  for (int i = tid; i < kBins; i += kThreadsA) tab.tw400[i] = g_tab.tw400[i];
+  bool wide_bank = false;
+  for (int m = tid; m < kMels; m += kThreadsA) {
+    tab.mel_k0[m] = static_cast<short>(g_tab.mel_k0[m]);
+    tab.mel_len[m] = static_cast<short>(g_tab.mel_len[m]);
+    for (int i = 0; i < kMelTapsSmem; ++i) tab.mel_w[m][i] = g_tab.mel_w[m][i];
   }
+  for (int m = 0; m < kMels; ++m) wide_bank |= g_tab.mel_len[m] > kMelTapsSmem;  // uniform across the grid
   __syncthreads();
 
-  // 2. FFT stage 1 (radix 8, Ns = 1): z[n] = (x[2n] h[2n], x[2n+1] h[2n+1]); butterfly j takes n = j + 25 t
-  {
-#pragma unroll 1
-    for (int it = 0; it < (kGroup * 25) / kThreadsA; ++it) {
-      const int id = tid + it * kThreadsA;
-      const int f = id / 25, j = id - f * 25;
-      float2 v[8];
-      const float* s = stage + f * kHop;
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int n = j + 25 * t;
-        const float2 x = *reinterpret_cast<const float2*>(s + 2 * n);
-        v[t] = make_float2(x.x * g_tab.hann[2 * n], x.y * g_tab.hann[2 * n + 1]);
-      }
-      dft8(v);
-      float2* z = Z + f * kHalf + j * 8;  // expand(j, 1, 8) = 8 j
-#pragma unroll
-      for (int t = 0; t < 8; ++t) z[t] = v[t];
-    }
-  }
-  __syncthreads();
+  const int n_items = n_windows * groups_per_window;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int win = item / groups_per_window;
+    const int t0 = (item - win * groups_per_window) * kGroup;
+    const long long w_off = (long long)win * step;
+    long long avail = pcm_len - w_off;
+    if (avail > win_len) avail = win_len;
+    if (avail < 0) avail = 0;
+    int n_valid = (int)((avail + 200 + kHop - 1) / kHop);  // frames >= n_valid see only zeros
+    if (avail == 0) n_valid = 0;
+    if (n_valid > kFramesOut) n_valid = kFramesOut;
+    if (t0 >= n_valid) continue;  // whole group is silent padding (uniform per block)
+    const float* w = pcm + w_off;
 
-  // 3. FFT stages 2 and 3 (radix 5; Ns = 8 then 40), in place: read all, barrier, write all
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    const int Ns = pass == 0 ? 8 : 40;
-    constexpr int kIter = (kGroup * 40) / kThreadsA;  // 8 butterflies per thread
-    float2 v[kIter][5];
-#pragma unroll
-    for (int it = 0; it < kIter; ++it) {
-      const int id = tid + it * kThreadsA;
-      const int f = id / 40, j = id - f * 40;
-      const int k = j % Ns;
-      const float2* z = Z + f * kHalf;
-      v[it][0] = z[j];
-#pragma unroll
-      for (int t = 1; t < 5; ++t) {
-        // twiddle exp(-2 pi i t k / (5 Ns)) = tw200[t * k * (200 / (5 Ns))]
-        const int tw = t * k * (kHalf / (5 * Ns));
-        v[it][t] = cmul(z[j + 40 * t], g_tab.tw200[tw]);
+    // 1. stage samples [160*t0 - 200, +5360) with 128-bit loads where possible
+    {
+      const long long s0 = (long long)kHop * t0 - 200;
+      const bool aligned = ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
+      for (int q = tid; q < kStage / 4; q += kThreadsA) {
+        const long long n = s0 + 4 * q;
+        float4 v;
+        if (aligned && n >= 0 && n + 3 < avail) {
+          v = __ldg(reinterpret_cast<const float4*>(w + n));
+        } else {
+          v.x = sample_at(w, n, avail);
+          v.y = sample_at(w, n + 1, avail);
+          v.z = sample_at(w, n + 2, avail);
+          v.w = sample_at(w, n + 3, avail);
+        }
+        reinterpret_cast<float4*>(stage)[q] = v;
       }
     }
     __syncthreads();
+
+    // 2. FFT stage 1 (radix 8, Ns = 1): z[n] = (x[2n] h[2n], x[2n+1] h[2n+1]); butterfly j takes n = j + 25 t
+    {
+      int f = tid / 25, j = tid - f * 25;  // id = tid + it*160 -> (f, j) advanced incrementally
+#pragma unroll 1
+      for (int it = 0; it < (kGroup * 25 + kThreadsA - 1) / kThreadsA; ++it) {
+        if (f >= kGroup) break;
+        float2 v[8];
+        const float* sp = stage + f * kHop;
 #pragma unroll
-    for (int it = 0; it < kIter; ++it) {
-      const int id = tid + it * kThreadsA;
-      const int f = id / 40, j = id - f * 40;
-      const int k = j % Ns;
-      dft5(v[it]);
-      float2* z = Z + f * kHalf + (j / Ns) * Ns * 5 + k;
+        for (int t = 0; t < 8; ++t) {
+          const int n = j + 25 * t;
+          const float2 x = *reinterpret_cast<const float2*>(sp + 2 * n);
+          const float2 h = *reinterpret_cast<const float2*>(tab.hann + 2 * n);
+          v[t] = make_float2(x.x * h.x, x.y * h.y);
+        }
+        dft8(v);
+        float2* z = Z + f * kHalf + j * 8;  // expand(j, 1, 8) = 8 j
 #pragma unroll
-      for (int t = 0; t < 5; ++t) z[t * Ns] = v[it][t];
+        for (int t = 0; t < 8; ++t) z[t] = v[t];
+        j += kThreadsA % 25;   // 160 = 6 * 25 + 10
+        f += kThreadsA / 25;
+        if (j >= 25) { j -= 25; ++f; }
+      }
     }
     __syncthreads();
-  }
 
-  // 4. unpack the real FFT and take the power: P[f][k], k = 0..200 (stage buffer is reused)
-  float* P = stage;
-  for (int id = tid; id < kGroup * kBins; id += kThreadsA) {
-    const int f = id / kBins, k = id - f * kBins;
-    const float2* z = Z + f * kHalf;
-    const float2 a = z[k == kHalf ? 0 : k];
-    const float2 bq = z[(kHalf - k) % kHalf];
-    const float2 b = make_float2(bq.x, -bq.y);                       // conj(Z[200-k])
-    const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
-    const float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
-    const float2 o = mul_neg_i(d);                                   // (Zk - conj(Z[N-k])) / (2i)
-    const float2 x = cadd(e, cmul(g_tab.tw400[k], o));
-    P[f * kBins + k] = fmaf(x.x, x.x, x.y * x.y);
-  }
-  __syncthreads();
-
-  // 5. sparse mel filters + log10; frame index fastest so global stores coalesce along time
-  float local_max = -INFINITY;
-  for (int id = tid; id < kGroup * kMels; id += kThreadsA) {
-    const int m = id / kGroup, f = id - m * kGroup;
-    const int t = t0 + f;
-    if (t < n_valid) {
-      const float* p = P + f * kBins + g_tab.mel_k0[m];
-      const int len = g_tab.mel_len[m];
-      float acc = 0.f;
-      for (int i = 0; i < len; ++i) acc = fmaf(g_tab.mel_w[m][i], p[i], acc);
-      const float v = log10f(fmaxf(acc, 1e-10f));
-      logspec[((long long)win * kMels + m) * nvp + t] = v;
-      local_max = fmaxf(local_max, v);
+    // 3. FFT stages 2 and 3 (radix 5; Ns = 8 then 40), in place: read all, barrier, write all.
+    //    id = tid + it*160 and 160 = 4 * 40, so j = tid % 40 is fixed per thread and f = tid/40 + 4*it.
+    {
+      const int j = tid % 40, fb = tid / 40;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        const int Ns = pass == 0 ? 8 : 40;
+        const int k = pass == 0 ? (j & 7) : j;
+        const int tw_step = k * (kHalf / (5 * Ns));  // twiddle exp(-2 pi i t k / (5 Ns)) = tw200[t * tw_step]
+        const float2 w1 = tab.tw200[tw_step], w2 = tab.tw200[2 * tw_step], w3 = tab.tw200[3 * tw_step],
+                     w4 = tab.tw200[4 * tw_step];
+        const int out0 = (j / Ns) * Ns * 5 + k;
+        constexpr int kIter = (kGroup * 40) / kThreadsA;  // 8 butterflies per thread
+        float2 v[kIter][5];
+#pragma unroll
+        for (int it = 0; it < kIter; ++it) {
+          const float2* z = Z + (fb + 4 * it) * kHalf + j;
+          v[it][0] = z[0];
+          v[it][1] = cmul(z[40], w1);
+          v[it][2] = cmul(z[80], w2);
+          v[it][3] = cmul(z[120], w3);
+          v[it][4] = cmul(z[160], w4);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < kIter; ++it) {
+          dft5(v[it]);
+          float2* z = Z + (fb + 4 * it) * kHalf + out0;
+#pragma unroll
+          for (int t = 0; t < 5; ++t) z[t * Ns] = v[it][t];
+        }
+        __syncthreads();
+      }
     }
-  }
-  local_max = warp_max(local_max);
-  if (lane_id() == 0) s_red[tid >> 5] = local_max;
-  __syncthreads();
-  if (tid == 0) {
-    float m = s_red[0];
-    for (int i = 1; i < kThreadsA / 32; ++i) m = fmaxf(m, s_red[i]);
-    atomicMax(win_max + win, float_order_key(m));
+
+    // 4. unpack the real FFT and take the power: P[f][k], k = 0..200 (stage buffer is reused)
+    float* P = stage;
+    {
+      int f = 0, k = tid;  // id = tid + it*160 -> (f, k) advanced incrementally (160 < 201)
+      for (int id = tid; id < kGroup * kBins; id += kThreadsA) {
+        const float2* z = Z + f * kHalf;
+        const float2 a = z[k == kHalf ? 0 : k];
+        const float2 bq = z[k == 0 ? 0 : kHalf - k];
+        const float2 b = make_float2(bq.x, -bq.y);                       // conj(Z[200-k])
+        const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
+        const float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
+        const float2 o = mul_neg_i(d);                                   // (Zk - conj(Z[N-k])) / (2i)
+        const float2 x = cadd(e, cmul(tab.tw400[k], o));
+        P[f * kBins + k] = fmaf(x.x, x.x, x.y * x.y);
+        k += kThreadsA;
+        if (k >= kBins) { k -= kBins; ++f; }
+      }
+    }
+    __syncthreads();
+
+    // 5. sparse mel filters + log10; frame index fastest so global stores coalesce along time
+    float local_max = -INFINITY;
+    for (int id = tid; id < kGroup * kMels; id += kThreadsA) {
+      const int m = id / kGroup, f = id - m * kGroup;
+      const int t = t0 + f;
+      if (t < n_valid) {
+        const float* pp = P + f * kBins + tab.mel_k0[m];
+        const int len = tab.mel_len[m];
+        float acc = 0.f;
+        if (!wide_bank) {
+          for (int i = 0; i < len; ++i) acc = fmaf(tab.mel_w[m][i], pp[i], acc);
+        } else {
+          for (int i = 0; i < len; ++i) acc = fmaf(g_tab.mel_w[m][i], pp[i], acc);
+        }
+        const float v = 0.30102999566398120f * __log2f(fmaxf(acc, 1e-10f));  // log10
+        logspec[((long long)win * kMels + m) * nvp + t] = v;
+        local_max = fmaxf(local_max, v);
+      }
+    }
+    local_max = warp_max(local_max);
+    if (lane_id() == 0) s_red[tid >> 5] = local_max;
+    __syncthreads();
+    if (tid == 0) {
+      float m = s_red[0];
+      for (int i = 1; i < kThreadsA / 32; ++i) m = fmaxf(m, s_red[i]);
+      atomicMax(win_max + win, float_order_key(m));
+    }
+    // the next item's staging writes `stage`, which every thread has finished reading (barrier above)
   }
 }
 
@@ -451,15 +495,16 @@ int segma_logmel(const float* pcm, int64_t pcm_len, int n_windows, int win_len, 
   uint32_t* win_max = static_cast<uint32_t*>(scratch);
   float* logspec = reinterpret_cast<float*>(static_cast<char*>(scratch) + head);
   SEGMA_CUDA_OK(cudaMemsetAsync(win_max, 0, (size_t)n_windows * sizeof(uint32_t), st));
-  const size_t smem = sizeof(float2) * kGroup * kHalf + sizeof(float) * std::max(kStage, kGroup * kBins);
+  const size_t smem = sizeof(float2) * kGroup * kHalf + sizeof(float) * std::max(kStage, kGroup * kBins) + sizeof(SmemTables);
   static bool attr_set = false;
   if (!attr_set) {
     SEGMA_CUDA_OK(cudaFuncSetAttribute(logmel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  dim3 grid_a(nvp / kGroup, n_windows);
-  logmel_power_kernel<<<grid_a, kThreadsA, smem, st>>>(pcm, pcm_len, win_len, step, max_valid_frames(win_len), nvp,
-                                                       logspec, win_max);
+  const int groups = nvp / kGroup;
+  const int grid_a = std::min(n_windows * groups, 4 * device_sm_count());
+  logmel_power_kernel<<<grid_a, kThreadsA, smem, st>>>(pcm, pcm_len, win_len, step, n_windows, groups, nvp, logspec,
+                                                       win_max);
   rc = launch_status("logmel_power_kernel");
   if (rc != SEGMA_OK) return rc;
   if (out_f32) {

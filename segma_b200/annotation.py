@@ -43,9 +43,6 @@ class AudioAnnotation:
 
 def rttm_line(uri: str, start_sample: int, end_sample: int, label: str) -> str:
     """One RTTM line for the sample interval ``[start_sample, end_sample)`` (inference.py:275-283)."""
-    return AudioAnnotation(
-        uid=uri,
-        start_time_s=float(frames_to_seconds(start_sample)),
-        duration_s=float(frames_to_seconds(end_sample - start_sample)),
-        label=str(label),
-    ).to_rttm()
+    # same text as AudioAnnotation(...).to_rttm(), without building the dataclass per interval
+    return (f"SPEAKER {uri} <NA> {round(start_sample / SAMPLE_RATE, PRECISION)} "
+            f"{round((end_sample - start_sample) / SAMPLE_RATE, PRECISION)} <NA> <NA> {label} <NA> <NA>")

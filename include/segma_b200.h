@@ -39,6 +39,16 @@ SEGMA_API int segma_version(void);
 SEGMA_API int segma_device_check(void);
 SEGMA_API int segma_sm_count(void);
 
+/* ---- audio staging ---------------------------------------------------------------------------
+ * Widening of native-width PCM to the float32 samples the reference's decoder hands to the model
+ * (src/segma/utils/io.py:30-47, torchcodec: int16 / 2^15, int32 / 2^31), on the device, so a file crosses
+ * PCIe in its stored width.  src [dev], dst [dev] (n) fp32.
+ */
+#define SEGMA_PCM_S16 0
+#define SEGMA_PCM_S32 1
+#define SEGMA_PCM_F32 2
+SEGMA_API int segma_pcm_to_f32(const void* src, int format, int64_t n, float* dst, void* stream);
+
 /* ---- windowing + Whisper log-mel front end --------------------------------------------------
  * Replaces `sub_audio_t.unfold(0, 64000, 63680)` (src/segma/inference.py:148-152) fused with
  * `audio_preparation_hook` -> WhisperFeatureExtractor._torch_extract_fbank_features

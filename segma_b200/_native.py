@@ -50,6 +50,7 @@ SIGNATURES = {
     "segma_version": (_i, []),
     "segma_device_check": (_i, []),
     "segma_sm_count": (_i, []),
+    "segma_pcm_to_f32": (_i, [_vp, _i, _i64, _vp, _vp]),
     "segma_logmel_scratch_bytes": (_sz, [_i, _i]),
     "segma_logmel": (_i, [_vp, _i64, _i, _i, _i64, _vp, _vp, _vp, _vp]),
     "segma_logmel_set_filters": (_i, [_vp]),

@@ -90,6 +90,15 @@ __global__ void __launch_bounds__(256) cast_f16_kernel(const float* __restrict__
   }
 }
 
+// integer PCM -> float32 in [-1, 1) exactly as the host decode does (x / 2^15, x / 2^31): the file's samples
+// cross PCIe in their native width and are widened on the device
+template <typename T>
+__global__ void __launch_bounds__(256) pcm_to_f32_kernel(const T* __restrict__ src, long long n, float scale,
+                                                          float* __restrict__ dst) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = static_cast<float>(src[i]) * scale;
+}
+
 template <int VPL>
 static int launch_ln(const float* x, const float* gamma, const float* beta, long long rows, void* out_f16,
                      float* out_f32, float* mix, int period, int n_keep, float w_in, float w_out, int mix_init,
@@ -130,6 +139,28 @@ int segma_layernorm(const float* x, const float* gamma, const float* beta, int64
 #undef SEGMA_LN_CASE
   set_last_error("segma_layernorm: unsupported d=%d", d);
   return SEGMA_ERR_UNSUPPORTED;
+}
+
+int segma_pcm_to_f32(const void* src, int format, int64_t n, float* dst, void* stream) {
+  SEGMA_REQUIRE(n >= 0, "segma_pcm_to_f32: negative length");
+  if (n == 0) return SEGMA_OK;
+  SEGMA_REQUIRE(src && dst, "segma_pcm_to_f32: NULL buffer");
+  const int grid = (int)std::min<long long>(ceil_div_ll(n, 256), (long long)device_sm_count() * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (format) {
+    case SEGMA_PCM_S16:
+      pcm_to_f32_kernel<short><<<grid, 256, 0, st>>>(static_cast<const short*>(src), n, 1.0f / 32768.0f, dst);
+      break;
+    case SEGMA_PCM_S32:
+      pcm_to_f32_kernel<int><<<grid, 256, 0, st>>>(static_cast<const int*>(src), n, 1.0f / 2147483648.0f, dst);
+      break;
+    case SEGMA_PCM_F32:
+      return check_cuda(cudaMemcpyAsync(dst, src, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st), "pcm copy");
+    default:
+      set_last_error("segma_pcm_to_f32: unknown sample format %d", format);
+      return SEGMA_ERR_INVALID_ARGUMENT;
+  }
+  return launch_status("pcm_to_f32_kernel");
 }
 
 int segma_cast_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream) {

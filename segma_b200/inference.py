@@ -28,7 +28,7 @@ from .annotation import rttm_line
 from .config import Config, load_config
 from .encoders import MultiLabelEncoder
 from .geometry import FRAME_SAMPLES, INFERENCE_SETTINGS, Chunkyfier, ConvolutionSettings, conv_frames, plan_windows
-from .io import get_audio_info, get_samples_in_range
+from .io import get_audio_info, get_samples_in_range, stage_to_device
 from .models import BaseSegmentationModel, Models
 from .thresholds import logit_cut
 
@@ -98,7 +98,7 @@ def apply_model_on_audio(
     elif isinstance(audio_path, torch.Tensor) and audio_path.dtype == torch.float32 and audio_path.is_pinned():
         pcm = audio_path.reshape(-1).to(dev, non_blocking=True)  # already staged in pinned host memory
     else:
-        pcm = prepare_audio(audio_path, model, dev, 0, None)
+        pcm = stage_to_device(audio_path, dev)  # native-width PCM over PCIe, widened on the device
     n_samples = pcm.numel()
     engine = model._require_engine()
     frames_per_window = model.n_keep if model.family == "whisper" else conv_frames(chunk_f)

@@ -136,3 +136,49 @@ def write_wav(path, pcm: np.ndarray, sample_rate: int = 16_000, subtype: str = "
     with open(path, "wb") as f:
         f.write(hdr)
         f.write(data)
+
+
+# ---- device staging ------------------------------------------------------------------
+_STAGE_CHUNK = 32 << 20  # bytes per pinned staging buffer
+
+
+def stage_to_device(audio_p, device) -> torch.Tensor:
+    """Whole file -> 1-D float32 tensor on ``device``.  Mono PCM16 / PCM32 / float32 WAV data is read straight
+    from the file into two alternating pinned buffers, copied in its stored width and widened by
+    ``segma_pcm_to_f32`` on the device; anything else goes through the host decoder."""
+    from . import ops
+
+    arr = _as_array(audio_p)
+    if arr is None:
+        lay = _parse_wav(Path(audio_p))
+        fmt = {(1, 16): (ops.PCM_S16, np.dtype("<i2"), torch.int16), (1, 32): (ops.PCM_S32, np.dtype("<i4"), torch.int32),
+               (3, 32): (ops.PCM_F32, np.dtype("<f4"), torch.float32)}.get((lay.fmt, lay.bits))
+        if fmt is not None and lay.n_channels == 1:
+            code, np_dt, t_dt = fmt
+            n = lay.n_frames
+            raw = torch.empty(n, dtype=t_dt, device=device)
+            per = max(1, _STAGE_CHUNK // np_dt.itemsize)
+            bufs = [torch.empty(min(per, max(n, 1)), dtype=t_dt).pin_memory() for _ in range(2)]
+            events = [None, None]
+            with open(audio_p, "rb") as f:
+                f.seek(lay.data_offset)
+                done, i = 0, 0
+                while done < n:
+                    cnt = min(per, n - done)
+                    if events[i & 1] is not None:
+                        events[i & 1].synchronize()  # the previous copy out of this buffer has finished
+                    view = bufs[i & 1][:cnt].numpy()
+                    got = f.readinto(memoryview(view).cast("B"))
+                    if got != cnt * np_dt.itemsize:
+                        raise ValueError(f"{audio_p}: truncated data chunk")
+                    raw[done:done + cnt].copy_(bufs[i & 1][:cnt], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    events[i & 1] = ev
+                    done += cnt
+                    i += 1
+            return ops.pcm_to_f32(raw, code) if code != ops.PCM_F32 else raw
+    t = get_samples_in_range(audio_p, 0, -1)
+    if t.shape[0] != 1:
+        raise ValueError(f"only mono audio is supported, got {t.shape[0]} channels")
+    return t.reshape(-1).pin_memory().to(device, non_blocking=True)

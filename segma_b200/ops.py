@@ -305,3 +305,17 @@ def wavlm_gate(x: torch.Tensor, T: int, n_heads: int, gate_w, gate_b, gate_const
     _call("segma_wavlm_gate", 1, _lib().segma_wavlm_gate, _dev(x, torch.float32, "x"), x.shape[0], T, n_heads,
           _dev(gate_w, torch.float32, "gate_w"), _dev(gate_b, torch.float32, "gate_b"),
           _dev(gate_const, torch.float32, "gate_const"), _dev(gate, torch.float32, "gate"), _stream())
+
+
+# ---- audio staging -----------------------------------------------------------------------------------
+PCM_S16, PCM_S32, PCM_F32 = 0, 1, 2
+
+
+def pcm_to_f32(raw: torch.Tensor, fmt: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Device tensor of native-width samples (int16 / int32 / float32) -> float32 in [-1, 1)."""
+    want = {PCM_S16: torch.int16, PCM_S32: torch.int32, PCM_F32: torch.float32}[fmt]
+    if out is None:
+        out = torch.empty(raw.numel(), dtype=torch.float32, device=raw.device)
+    _call("segma_pcm_to_f32", 1, _lib().segma_pcm_to_f32, _dev(raw, want, "raw"), fmt, raw.numel(),
+          _dev(out, torch.float32, "out"), _stream())
+    return out

@@ -269,3 +269,45 @@ def test_sweep_whisper_window_length(cuda, win_s):
     ref = _composed_oracle(pcm, lambda f: O.hydra_whisper_forward(sd, f, LABELS, n_keep=F_), win, step, 2, True, F_)
     assert got.shape == ref.shape
     _check_logits(got.cpu(), ref, f"whisper {win_s}s windows")
+
+
+# ---- audio decode + staging; f2: RTTM / logits artefacts -----------------------------------------
+@pytest.mark.parametrize("subtype", ["int16", "float32"])
+def test_wav_staging_matches_host_decode(cuda, tmp_path, subtype):
+    from segma_b200.io import get_all_samples, stage_to_device, write_wav
+
+    pcm = synth.synth_audio(100_003, 9)
+    p = tmp_path / "a.wav"
+    write_wav(p, pcm, subtype=subtype)
+    dev = stage_to_device(p, "cuda")
+    assert torch.equal(dev.cpu(), get_all_samples(p)[0])  # bit-identical to the host decoder
+
+
+def test_infer_file_on_wav_writes_reference_artefacts(cuda, tmp_path):
+    from segma_b200.inference import infer_file
+    from segma_b200.io import write_wav
+
+    sd = synth.hubert_hydra_state_dict(synth.W2V2_TEST, seed=5)
+    le = MultiLabelEncoder(list(LABELS))
+    cfg = make_config("surgical_hubert_hydra")
+    model = Models["surgical_hubert_hydra"].from_state_dict(sd, le, cfg)
+    pcm = synth.synth_audio(64000 + 63680 + 7000, 13)
+    wav = tmp_path / "rec_01.wav"
+    write_wav(wav, pcm, subtype="int16")
+    intervals = infer_file(wav, model, tmp_path / "out", cfg, batch_size=2, device="cuda", save_logits=True)
+    # logits artefact in the format scripts/tune.py:95-113 reads: {label: (n_frames,) fp32}
+    blob = torch.load(tmp_path / "out" / "logits" / "rec_01-logits_dict_t.pt")
+    assert list(blob) == list(LABELS)
+    logits = torch.stack([blob[lab] for lab in LABELS], dim=1)
+    assert logits.shape == ((pcm.size - 400) // 320 + 1, 4) and logits.dtype == torch.float32
+    # RTTM text is the reference's format and decodes the saved logits bit-exactly
+    want = O.create_intervals(O.apply_thresholds(logits, [0.5] * 4).numpy(), LABELS)
+    assert intervals == want
+    lines = (tmp_path / "out" / "raw_rttm" / "rec_01.rttm").read_text().splitlines()
+    assert len(lines) == len(want)
+    for line, (s, e, lab) in zip(lines, want):
+        assert line == f"SPEAKER rec_01 <NA> {round(s / 16000, 8)} {round((e - s) / 16000, 8)} <NA> <NA> {lab} <NA> <NA>"
+    # the int16 file was decoded exactly like the host path would
+    pcm16 = np.clip(np.round(pcm * 32768.0), -32768, 32767).astype(np.int16).astype(np.float32) / 32768.0
+    ref = O.apply_model_on_audio(torch.from_numpy(pcm16), lambda w: O.hubert_hydra_forward(sd, w, LABELS), 4, batch_size=2)
+    _check_logits(logits, ref, "infer_file on int16 wav", min_agreement=0.998)

@@ -205,6 +205,15 @@ SEGMA_API int segma_decode_intervals(const float* logits, const int64_t* file_of
 SEGMA_API int segma_threshold_mask(const float* logits, int64_t n_frames, int n_labels, const float* thresholds /* [host] */,
                          int mode, uint8_t* mask, void* stream);
 
+/* ---- threshold tuning (scripts/tune.py:213-256) ------------------------------------------------------
+ * One pass over (n_frames, C) logits and uint8 reference labels of the same shape: hist[c][y][b] counts the
+ * frames of label c with reference y (0/1) whose logit exceeds exactly b of the n_cuts ascending logit-domain
+ * cuts [host].  The prediction at grid point k is positive iff b > k, so TP/FP/FN of every threshold follow by
+ * suffix sums.  hist [dev] (C, 2, n_cuts + 1) uint64, zeroed by the call.  n_cuts <= 128.
+ */
+SEGMA_API int segma_threshold_histogram(const float* logits, const uint8_t* truth, int64_t n_frames, int n_labels,
+                              const float* cuts, int n_cuts, unsigned long long* hist, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

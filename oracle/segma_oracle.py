@@ -423,3 +423,36 @@ def interval_table(mask, n_labels: int) -> np.ndarray:
     """``create_intervals`` as an int32 ``(n, 3)`` table ``(label_idx, start_sample, end_sample)``."""
     iv = create_intervals(mask, list(range(n_labels)))
     return np.array([(c, s, e) for s, e, c in iv], dtype=np.int64).reshape(-1, 3)
+
+
+# ----------------------------------------------------------------------------------------
+# threshold tuning (scripts/tune.py)
+# ----------------------------------------------------------------------------------------
+def f1_per_label(y_true: torch.Tensor, y_pred: torch.Tensor) -> np.ndarray:
+    """``sklearn.metrics.f1_score(average=None, zero_division=1.0)`` on multilabel indicator matrices:
+    2TP / (2TP + FP + FN) per column, 1.0 where the denominator is zero (scripts/tune.py:228-236)."""
+    t = np.asarray(y_true) != 0
+    p = np.asarray(y_pred) != 0
+    tp = (t & p).sum(0).astype(np.float64)
+    fp = (~t & p).sum(0).astype(np.float64)
+    fn = (t & ~p).sum(0).astype(np.float64)
+    den = 2 * tp + fp + fn
+    return np.where(den > 0, 2 * tp / np.maximum(den, 1), 1.0)
+
+
+def tune_multilabel(y_true: torch.Tensor, logits: torch.Tensor, thresholds: torch.Tensor, labels, n_steps: int) -> dict:
+    """``tune_multilabel`` (scripts/tune.py:213-256): one F1 pass per grid threshold, best = first maximum."""
+    scores = {lab: [] for lab in labels}
+    for thresh in thresholds:
+        f1 = f1_per_label(y_true, logits.sigmoid() > thresh)
+        for i, lab in enumerate(labels):
+            scores[lab].append((thresh, f1[i]))
+    digits = int(math.log10(n_steps))
+    out = {}
+    for lab in labels:
+        best_t, best_s = None, -1.0
+        for t, s in scores[lab]:
+            if s > best_s:
+                best_t, best_s = t, s
+        out[lab] = {"lower_bound": round(float(best_t), digits), "upper_bound": 1.0}
+    return out

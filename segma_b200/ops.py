@@ -319,3 +319,16 @@ def pcm_to_f32(raw: torch.Tensor, fmt: int, out: torch.Tensor | None = None) -> 
     _call("segma_pcm_to_f32", 1, _lib().segma_pcm_to_f32, _dev(raw, want, "raw"), fmt, raw.numel(),
           _dev(out, torch.float32, "out"), _stream())
     return out
+
+
+# ---- threshold tuning -------------------------------------------------------------------------------
+def threshold_histogram(logits: torch.Tensor, truth: torch.Tensor, cuts) -> torch.Tensor:
+    """(n, C) logits + (n, C) uint8 reference labels -> int64 (C, 2, K+1) histogram of "cuts exceeded"."""
+    n, C_ = logits.shape
+    assert logits.is_contiguous() and truth.is_contiguous() and truth.shape == logits.shape
+    K = len(cuts)
+    arr = (C.c_float * K)(*[float(c) for c in cuts])
+    hist = torch.empty((C_, 2, K + 1), dtype=torch.int64, device=logits.device)
+    _call("segma_threshold_histogram", 1, _lib().segma_threshold_histogram, _dev(logits, torch.float32, "logits"),
+          _dev(truth, torch.uint8, "truth"), n, C_, arr, K, hist.data_ptr(), _stream())
+    return hist

@@ -201,6 +201,24 @@ SEGMA_API size_t segma_decode_workspace_bytes(int64_t n_frames, int n_files, int
 SEGMA_API int segma_decode_intervals(const float* logits, const int64_t* file_offsets /* [host] n_files+1 */, int n_files,
                            int n_labels, const float* thresholds /* [host] n_labels */, int mode, int32_t* table,
                            int64_t capacity, int32_t* count, void* workspace, size_t workspace_bytes, void* stream);
+/* Extension (default off in the Python API): onset / offset hysteresis with the `upper_bound` that the reference
+ * stores next to `lower_bound` but never reads (src/segma/inference.py:308-312).  A label turns on when its logit
+ * exceeds onset_cuts[c], off when it is at or below offset_cuts[c], and otherwise keeps its state (off at the start
+ * of every file).  Cuts are logit-domain [host]; onset >= offset; n_labels <= 8.  Same table / count / workspace
+ * contract as segma_decode_intervals; with onset == offset the result is identical to it. */
+SEGMA_API int segma_decode_intervals_hysteresis(const float* logits, const int64_t* file_offsets, int n_files, int n_labels,
+                                      const float* offset_cuts, const float* onset_cuts, int32_t* table,
+                                      int64_t capacity, int32_t* count, void* workspace, size_t workspace_bytes,
+                                      void* stream);
+
+/* Extension: interval-table post-processing on the device.  Rows of the same (file, label) separated by at most
+ * max_gap_samples are merged (0 merges adjacent / overlapping rows, the semantics of the reference's unused
+ * Intervals struct, src/segma/structs/interval.py:19-34), then rows shorter than min_duration_samples are dropped.
+ * table [dev] (n, 4) sorted as segma_decode_intervals emits it; scratch, out [dev] (n, 4) / (capacity, 4);
+ * counts [dev] int32[2] = {merged rows, rows written to out}. */
+SEGMA_API int segma_postprocess_intervals(const int32_t* table, int64_t n, int max_gap_samples, int min_duration_samples,
+                                int32_t* scratch, int32_t* out, int64_t capacity, int32_t* counts, void* stream);
+
 /* The boolean mask of apply_thresholds alone: mask[f*C + c] (uint8). */
 SEGMA_API int segma_threshold_mask(const float* logits, int64_t n_frames, int n_labels, const float* thresholds /* [host] */,
                          int mode, uint8_t* mask, void* stream);

@@ -456,3 +456,35 @@ def tune_multilabel(y_true: torch.Tensor, logits: torch.Tensor, thresholds: torc
                 best_t, best_s = t, s
         out[lab] = {"lower_bound": round(float(best_t), digits), "upper_bound": 1.0}
     return out
+
+
+# ----------------------------------------------------------------------------------------
+# extensions beyond the reference: hysteresis, gap merging, minimum duration
+# ----------------------------------------------------------------------------------------
+def hysteresis_mask(logits: torch.Tensor, offset_cuts, onset_cuts) -> np.ndarray:
+    """Sequential definition: on when logit > onset cut, off when logit <= offset cut, else unchanged (off initially)."""
+    x = logits.numpy()
+    n, C = x.shape
+    out = np.zeros((n, C), dtype=bool)
+    for c in range(C):
+        state = False
+        for f in range(n):
+            if x[f, c] > onset_cuts[c]:
+                state = True
+            elif not (x[f, c] > offset_cuts[c]):
+                state = False
+            out[f, c] = state
+    return out
+
+
+def postprocess_table(table: np.ndarray, max_gap: int, min_dur: int) -> np.ndarray:
+    """Merge rows (file, label, start, end) of the same (file, label) with next.start - end <= max_gap, in order
+    (the per-label merge of src/segma/structs/interval.py:19-34 when max_gap = 0), then drop rows shorter than min_dur."""
+    out = []
+    for row in table.tolist():
+        if out and out[-1][0] == row[0] and out[-1][1] == row[1] and row[2] - out[-1][3] <= max_gap:
+            out[-1][3] = max(out[-1][3], row[3])
+        else:
+            out.append(list(row))
+    out = [r for r in out if r[3] - r[2] >= min_dur]
+    return np.array(out, dtype=np.int64).reshape(-1, 4)

@@ -66,6 +66,8 @@ SIGNATURES = {
     "segma_stitch": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i64, _vp]),
     "segma_decode_workspace_bytes": (_sz, [_i64, _i, _i]),
     "segma_decode_intervals": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "segma_decode_intervals_hysteresis": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "segma_postprocess_intervals": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i64, _vp, _vp]),
     "segma_threshold_histogram": (_i, [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp]),
     "segma_threshold_mask": (_i, [_vp, _i64, _i, _vp, _i, _vp, _vp]),
 }

@@ -312,7 +312,9 @@ __device__ __forceinline__ FrameBits neighbour_bits(uint32_t cur, uint32_t halo_
   return fb;
 }
 
-template <bool kWrite>
+// MODE 0: count pass from logits (stores the activity bytes), 1: write pass from the activity bytes,
+// 2: count pass from activity bytes produced elsewhere (hysteresis)
+template <int MODE>
 __global__ void __launch_bounds__(kFastThreads) decode_fast_kernel(
     const float* __restrict__ logits, const long long* __restrict__ file_offsets,
     const int* __restrict__ block_offsets, int n_files, DecodeParams p, uint8_t* __restrict__ bits,
@@ -328,8 +330,10 @@ __global__ void __launch_bounds__(kFastThreads) decode_fast_kernel(
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   constexpr int n_warps = kFastThreads / 32;
 
+  constexpr bool kWrite = MODE == 1;
+  constexpr bool kFromBits = MODE != 0;
   uint32_t cur = 0;
-  if (kWrite) {
+  if (kFromBits) {
     if (frame0 + kFastFrames <= f_end && ((reinterpret_cast<uintptr_t>(bits + frame0) & 3) == 0)) {
       cur = *reinterpret_cast<const uint32_t*>(bits + frame0);
     } else {
@@ -353,11 +357,11 @@ __global__ void __launch_bounds__(kFastThreads) decode_fast_kernel(
   uint32_t halo_prev = 0, halo_next = 0;
   if (threadIdx.x == 0) {
     const long long pf = frame0 - 1;
-    if (pf >= f_begin) halo_prev = kWrite ? bits[pf] : frame_bits(logits, pf, p);
+    if (pf >= f_begin) halo_prev = kFromBits ? bits[pf] : frame_bits(logits, pf, p);
   }
   if (threadIdx.x == kFastThreads - 1) {
     const long long nf = f_begin + (long long)(local_block + 1) * kFastBlock;
-    if (nf < f_end) halo_next = kWrite ? bits[nf] : frame_bits(logits, nf, p);
+    if (nf < f_end) halo_next = kFromBits ? bits[nf] : frame_bits(logits, nf, p);
   }
   if (lane == 0) s_edge_lo[warp] = cur & 0xffu;
   if (lane == 31) s_edge_hi[warp] = cur >> 24;
@@ -424,10 +428,240 @@ __global__ void __launch_bounds__(kFastThreads) decode_fast_kernel(
   }
 }
 
+// ---- hysteresis (onset / offset thresholds): an extension that uses the `upper_bound` the reference carries in
+// its threshold dict but never reads (src/segma/inference.py:308-312).  A label switches on when the logit
+// exceeds the onset cut, off when it is at or below the offset cut, and otherwise keeps its state: a scan of
+// (set, value) pairs, composed within threads, warps, blocks and -- through one tiny serial pass per file --
+// across blocks.  With onset == offset it reduces to the plain threshold rule.
+struct HystParams {
+  float hi[8], lo[8];
+  int C;
+};
+
+struct SetVal {
+  uint32_t set, val;  // per-label bits: state is forced (set) to `val`
+};
+__device__ __forceinline__ SetVal compose(SetVal earlier, SetVal later) {
+  SetVal r;
+  r.set = earlier.set | later.set;
+  r.val = (earlier.val & ~later.set) | (later.val & later.set);
+  return r;
+}
+
+__device__ __forceinline__ uint32_t frame_codes(const float* __restrict__ logits, long long frame, const HystParams& p) {
+  uint32_t hi = 0, lo = 0;
+  const float* row = logits + frame * p.C;
+  for (int c = 0; c < p.C; ++c) {
+    const float x = __ldg(row + c);
+    hi |= (x > p.hi[c]) ? (1u << c) : 0u;
+    lo |= (x > p.lo[c]) ? (1u << c) : 0u;
+  }
+  return hi | (lo << 8);
+}
+__device__ __forceinline__ SetVal code_setval(uint32_t code, uint32_t label_mask) {
+  const uint32_t hi = code & 0xffu, lo = (code >> 8) & 0xffu;
+  SetVal r;
+  r.set = (hi | ~lo) & label_mask;  // above onset -> on, at/below offset -> off
+  r.val = hi & label_mask;
+  return r;
+}
+
+// pass H1: per-frame (hi, lo) codes and the (set, val) summary of every 1024-frame block
+__global__ void __launch_bounds__(kFastThreads) hyst_codes_kernel(
+    const float* __restrict__ logits, const long long* __restrict__ file_offsets,
+    const int* __restrict__ block_offsets, int n_files, HystParams p, uint16_t* __restrict__ codes,
+    uint16_t* __restrict__ block_summary) {
+  __shared__ SetVal s_w[kFastThreads / 32];
+  const int file = find_file(block_offsets, n_files, blockIdx.x);
+  const int local_block = blockIdx.x - block_offsets[file];
+  const long long f_begin = file_offsets[file], f_end = file_offsets[file + 1];
+  const long long frame0 = f_begin + (long long)local_block * kFastBlock + threadIdx.x * kFastFrames;
+  const uint32_t label_mask = (1u << p.C) - 1u;
+  SetVal sv{0u, 0u};
+#pragma unroll
+  for (int i = 0; i < kFastFrames; ++i) {
+    if (frame0 + i < f_end) {
+      const uint32_t code = frame_codes(logits, frame0 + i, p);
+      codes[frame0 + i] = static_cast<uint16_t>(code);
+      sv = compose(sv, code_setval(code, label_mask));
+    }
+  }
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {  // inclusive scan in lane order; lane 31 ends with the warp total
+    SetVal up;
+    up.set = __shfl_up_sync(0xffffffffu, sv.set, o);
+    up.val = __shfl_up_sync(0xffffffffu, sv.val, o);
+    if (lane >= o) sv = compose(up, sv);
+  }
+  if (lane == 31) s_w[warp] = sv;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    SetVal t = s_w[0];
+    for (int w = 1; w < kFastThreads / 32; ++w) t = compose(t, s_w[w]);
+    block_summary[blockIdx.x] = static_cast<uint16_t>((t.set & 0xffu) | ((t.val & 0xffu) << 8));
+  }
+}
+
+// pass H2: state entering every block (one thread per file walks its blocks)
+__global__ void hyst_carry_kernel(const uint16_t* __restrict__ block_summary, const int* __restrict__ block_offsets,
+                                  int n_files, uint8_t* __restrict__ carry_in) {
+  const int file = blockIdx.x * blockDim.x + threadIdx.x;
+  if (file >= n_files) return;
+  uint32_t state = 0;
+  for (int b = block_offsets[file]; b < block_offsets[file + 1]; ++b) {
+    carry_in[b] = static_cast<uint8_t>(state);
+    const uint32_t s = block_summary[b] & 0xffu, v = block_summary[b] >> 8;
+    state = (state & ~s) | (v & s);
+  }
+}
+
+// pass H3: resolve the state of every frame -> the activity byte the decode passes consume
+__global__ void __launch_bounds__(kFastThreads) hyst_resolve_kernel(
+    const uint16_t* __restrict__ codes, const long long* __restrict__ file_offsets,
+    const int* __restrict__ block_offsets, int n_files, int C, const uint8_t* __restrict__ carry_in,
+    uint8_t* __restrict__ bits) {
+  __shared__ SetVal s_w[kFastThreads / 32];
+  const int file = find_file(block_offsets, n_files, blockIdx.x);
+  const int local_block = blockIdx.x - block_offsets[file];
+  const long long f_begin = file_offsets[file], f_end = file_offsets[file + 1];
+  const long long frame0 = f_begin + (long long)local_block * kFastBlock + threadIdx.x * kFastFrames;
+  const uint32_t label_mask = (1u << C) - 1u;
+  SetVal own[kFastFrames];
+  SetVal sv{0u, 0u};
+#pragma unroll
+  for (int i = 0; i < kFastFrames; ++i) {
+    own[i] = SetVal{0u, 0u};
+    if (frame0 + i < f_end) own[i] = code_setval(codes[frame0 + i], label_mask);
+    sv = compose(sv, own[i]);
+  }
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  SetVal inc = sv;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    SetVal up;
+    up.set = __shfl_up_sync(0xffffffffu, inc.set, o);
+    up.val = __shfl_up_sync(0xffffffffu, inc.val, o);
+    if (lane >= o) inc = compose(up, inc);
+  }
+  if (lane == 31) s_w[warp] = inc;
+  SetVal excl;  // composition of the lanes before this one
+  excl.set = __shfl_up_sync(0xffffffffu, inc.set, 1);
+  excl.val = __shfl_up_sync(0xffffffffu, inc.val, 1);
+  if (lane == 0) excl = SetVal{0u, 0u};
+  __syncthreads();
+  SetVal before{0u, 0u};
+  for (int w = 0; w < warp; ++w) before = compose(before, s_w[w]);
+  before = compose(before, excl);
+  uint32_t state = carry_in[blockIdx.x];
+  state = (state & ~before.set) | before.val;
+#pragma unroll
+  for (int i = 0; i < kFastFrames; ++i) {
+    state = (state & ~own[i].set) | own[i].val;
+    if (frame0 + i < f_end) bits[frame0 + i] = static_cast<uint8_t>(state);
+  }
+}
+
+// ---- interval-table post-processing: merge runs of the same (file, label) separated by at most max_gap samples
+// (max_gap = 0 merges adjacent / overlapping intervals like the reference's Intervals struct,
+// src/segma/structs/interval.py:19-34), then drop intervals shorter than min_dur samples.  Tables are small
+// (KBs to a few MB): one block, chunked scans.
+constexpr int kPostThreads = 1024;
+
+__device__ __forceinline__ int block_incl_scan(int v, int* s_warp, int lane, int warp) {
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += t;
+  }
+  if (lane == 31) s_warp[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_warp[lane], y = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, y, o);
+      if (lane >= o) y += t;
+    }
+    s_warp[lane] = y - w;
+  }
+  __syncthreads();
+  const int r = x + s_warp[warp];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(kPostThreads) merge_intervals_kernel(const int4* __restrict__ in, long long n,
+                                                                       int max_gap, int4* __restrict__ merged,
+                                                                       int* __restrict__ n_merged) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  for (long long base = 0; base < n; base += kPostThreads) {
+    const long long i = base + threadIdx.x;
+    int head = 0, last = 0;
+    int4 row = make_int4(0, 0, 0, 0);
+    if (i < n) {
+      row = in[i];
+      if (i == 0) {
+        head = 1;
+      } else {
+        const int4 pr = in[i - 1];
+        head = (pr.x != row.x || pr.y != row.y || row.z - pr.w > max_gap) ? 1 : 0;
+      }
+      if (i == n - 1) {
+        last = 1;
+      } else {
+        const int4 nx = in[i + 1];
+        last = (nx.x != row.x || nx.y != row.y || nx.z - row.w > max_gap) ? 1 : 0;
+      }
+    }
+    const int g = s_carry + block_incl_scan(head, s_warp, lane, warp) - 1;  // group index of row i
+    if (i < n) {
+      if (head) { merged[g].x = row.x; merged[g].y = row.y; merged[g].z = row.z; }
+      if (last) merged[g].w = row.w;
+    }
+    __syncthreads();
+    if (threadIdx.x == kPostThreads - 1) s_carry = g + 1;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_merged = s_carry;
+}
+
+__global__ void __launch_bounds__(kPostThreads) filter_intervals_kernel(const int4* __restrict__ merged,
+                                                                        const int* __restrict__ n_merged, int min_dur,
+                                                                        int4* __restrict__ out, long long capacity,
+                                                                        int* __restrict__ count) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const long long n = *n_merged;
+  for (long long base = 0; base < n; base += kPostThreads) {
+    const long long i = base + threadIdx.x;
+    int keep = 0;
+    int4 row = make_int4(0, 0, 0, 0);
+    if (i < n) {
+      row = merged[i];
+      keep = (row.w - row.z >= min_dur) ? 1 : 0;
+    }
+    const int pos = s_carry + block_incl_scan(keep, s_warp, lane, warp) - 1;
+    if (keep && pos < capacity) out[pos] = row;
+    __syncthreads();
+    if (threadIdx.x == kPostThreads - 1) s_carry = pos + 1;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = s_carry;
+}
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct DecodeLayout {
-  size_t bits_off, starts_off, ends_off, file_off, block_off, total;
+  size_t bits_off, starts_off, ends_off, file_off, block_off, codes_off, summary_off, carry_off, total;
   long long n_count;
 };
 
@@ -441,6 +675,9 @@ static DecodeLayout decode_layout(long long n_frames, int n_files, int C) {
   L.ends_off = off; off = align_up(off + sizeof(int) * (size_t)L.n_count, 256);
   L.file_off = off; off = align_up(off + sizeof(long long) * (size_t)(n_files + 1), 256);
   L.block_off = off; off = align_up(off + sizeof(int) * (size_t)(n_files + 1), 256);
+  L.codes_off = off; off = align_up(off + sizeof(uint16_t) * (size_t)n_frames, 256);
+  L.summary_off = off; off = align_up(off + sizeof(uint16_t) * (size_t)max_blocks, 256);
+  L.carry_off = off; off = align_up(off + (size_t)max_blocks, 256);
   L.total = off;
   return L;
 }
@@ -494,9 +731,9 @@ size_t segma_decode_workspace_bytes(int64_t n_frames, int n_files, int n_labels)
   return decode_layout(n_frames, n_files, n_labels).total;
 }
 
-int segma_decode_intervals(const float* logits, const int64_t* file_offsets, int n_files, int n_labels,
-                           const float* thresholds, int mode, int32_t* table, int64_t capacity, int32_t* count,
-                           void* workspace, size_t workspace_bytes, void* stream) {
+static int decode_impl(const float* logits, const int64_t* file_offsets, int n_files, int n_labels,
+                       const float* thresholds, const float* onset, int mode, int32_t* table, int64_t capacity,
+                       int32_t* count, void* workspace, size_t workspace_bytes, void* stream) {
   DecodeParams p;
   int rc = fill_params(p, n_labels, thresholds, mode);
   if (rc != SEGMA_OK) return rc;
@@ -531,8 +768,32 @@ int segma_decode_intervals(const float* logits, const int64_t* file_offsets, int
   // pageable-source async copies are staged before returning, so block_offsets may go out of scope
   const bool fast = n_labels <= 8;  // one activity byte per frame, 4 frames per thread
   static_assert(kFastBlock == kDecodeBlock, "both paths tile files in blocks of 1024 frames");
-  if (fast) {
-    decode_fast_kernel<false><<<total_blocks, kFastThreads, 0, st>>>(
+  if (onset) {
+    SEGMA_REQUIRE(fast && mode == SEGMA_DECODE_LOGIT, "hysteresis needs logit-domain cuts and at most 8 labels");
+    HystParams hp;
+    hp.C = n_labels;
+    for (int c = 0; c < 8; ++c) {
+      hp.hi[c] = c < n_labels ? onset[c] : 0.f;
+      hp.lo[c] = c < n_labels ? thresholds[c] : 0.f;
+      if (c < n_labels) SEGMA_REQUIRE(!(hp.hi[c] < hp.lo[c]), "hysteresis: onset cut below offset cut for label %d", c);
+    }
+    uint16_t* codes = reinterpret_cast<uint16_t*>(ws + L.codes_off);
+    uint16_t* summary = reinterpret_cast<uint16_t*>(ws + L.summary_off);
+    uint8_t* carry = reinterpret_cast<uint8_t*>(ws + L.carry_off);
+    hyst_codes_kernel<<<total_blocks, kFastThreads, 0, st>>>(logits, d_file, d_block, n_files, hp, codes, summary);
+    rc = launch_status("hyst_codes_kernel");
+    if (rc != SEGMA_OK) return rc;
+    hyst_carry_kernel<<<ceil_div(n_files, 128), 128, 0, st>>>(summary, d_block, n_files, carry);
+    rc = launch_status("hyst_carry_kernel");
+    if (rc != SEGMA_OK) return rc;
+    hyst_resolve_kernel<<<total_blocks, kFastThreads, 0, st>>>(codes, d_file, d_block, n_files, n_labels, carry,
+                                                             reinterpret_cast<uint8_t*>(bits));
+    rc = launch_status("hyst_resolve_kernel");
+    if (rc != SEGMA_OK) return rc;
+    decode_fast_kernel<2><<<total_blocks, kFastThreads, 0, st>>>(
+        logits, d_file, d_block, n_files, p, reinterpret_cast<uint8_t*>(bits), starts, ends, table, capacity);
+  } else if (fast) {
+    decode_fast_kernel<0><<<total_blocks, kFastThreads, 0, st>>>(
         logits, d_file, d_block, n_files, p, reinterpret_cast<uint8_t*>(bits), starts, ends, table, capacity);
   } else {
     decode_count_kernel<<<total_blocks, kDecodeBlock, 0, st>>>(logits, d_file, d_block, n_files, p, bits, starts, ends);
@@ -543,13 +804,46 @@ int segma_decode_intervals(const float* logits, const int64_t* file_offsets, int
   rc = launch_status("decode_scan_kernel");
   if (rc != SEGMA_OK) return rc;
   if (fast) {
-    decode_fast_kernel<true><<<total_blocks, kFastThreads, 0, st>>>(
+    decode_fast_kernel<1><<<total_blocks, kFastThreads, 0, st>>>(
         logits, d_file, d_block, n_files, p, reinterpret_cast<uint8_t*>(bits), starts, ends, table, capacity);
   } else {
     decode_write_kernel<<<total_blocks, kDecodeBlock, 0, st>>>(bits, d_file, d_block, n_files, n_labels, starts, ends,
                                                                table, capacity);
   }
   return launch_status("decode write pass");
+}
+
+int segma_decode_intervals(const float* logits, const int64_t* file_offsets, int n_files, int n_labels,
+                           const float* thresholds, int mode, int32_t* table, int64_t capacity, int32_t* count,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  return decode_impl(logits, file_offsets, n_files, n_labels, thresholds, nullptr, mode, table, capacity, count,
+                     workspace, workspace_bytes, stream);
+}
+
+int segma_decode_intervals_hysteresis(const float* logits, const int64_t* file_offsets, int n_files, int n_labels,
+                                      const float* offset_cuts, const float* onset_cuts, int32_t* table,
+                                      int64_t capacity, int32_t* count, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  SEGMA_REQUIRE(onset_cuts != nullptr, "segma_decode_intervals_hysteresis: NULL onset cuts");
+  return decode_impl(logits, file_offsets, n_files, n_labels, offset_cuts, onset_cuts, SEGMA_DECODE_LOGIT, table,
+                     capacity, count, workspace, workspace_bytes, stream);
+}
+
+int segma_postprocess_intervals(const int32_t* table, int64_t n, int max_gap_samples, int min_duration_samples,
+                                int32_t* scratch, int32_t* out, int64_t capacity, int32_t* counts, void* stream) {
+  SEGMA_REQUIRE(n >= 0 && max_gap_samples >= 0 && min_duration_samples >= 0, "segma_postprocess_intervals: bad arguments");
+  SEGMA_REQUIRE(counts, "segma_postprocess_intervals: NULL counts");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) return check_cuda(cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), st), "memset counts");
+  SEGMA_REQUIRE(table && scratch && out, "segma_postprocess_intervals: NULL buffer");
+  merge_intervals_kernel<<<1, kPostThreads, 0, st>>>(reinterpret_cast<const int4*>(table), n, max_gap_samples,
+                                                    reinterpret_cast<int4*>(scratch), counts);
+  int rc = launch_status("merge_intervals_kernel");
+  if (rc != SEGMA_OK) return rc;
+  filter_intervals_kernel<<<1, kPostThreads, 0, st>>>(reinterpret_cast<const int4*>(scratch), counts,
+                                                     min_duration_samples, reinterpret_cast<int4*>(out), capacity,
+                                                     counts + 1);
+  return launch_status("filter_intervals_kernel");
 }
 
 }  // extern "C"

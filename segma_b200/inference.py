@@ -185,14 +185,28 @@ def create_intervals(thresholded_features: torch.Tensor, conv_settings: Convolut
 
 
 def decode_logits(logits: torch.Tensor, thresholds: dict, label_encoder: MultiLabelEncoder,
-                  conv_settings: ConvolutionSettings = INFERENCE_SETTINGS, file_offsets=None):
+                  conv_settings: ConvolutionSettings = INFERENCE_SETTINGS, file_offsets=None, *,
+                  hysteresis: bool = False, max_gap_s: float = 0.0, min_duration_s: float = 0.0):
     """Fused ``apply_thresholds`` + ``create_intervals`` on device logits (one pass, no boolean tensor).
-    With ``file_offsets`` the frames of several files are decoded at once; returns one list per file."""
+    With ``file_offsets`` the frames of several files are decoded at once; returns one list per file.
+
+    Optional post-processing, all off by default (= the reference's behaviour): ``hysteresis`` uses each label's
+    ``upper_bound`` as the onset and ``lower_bound`` as the offset threshold (an ``upper_bound`` of 1.0 or more,
+    the reference's default, can never fire, so it is ignored); ``max_gap_s`` merges intervals of a label
+    separated by at most that many seconds; ``min_duration_s`` drops shorter intervals."""
     bounds = _lower_bounds(thresholds, logits.shape[-1])
     if logits.shape[0] == 0:
         return [] if file_offsets is None else [[] for _ in range(len(file_offsets) - 1)]
-    table = ops.decode_intervals(logits.contiguous(), [logit_cut(t) for t in bounds], file_offsets=file_offsets,
-                                 mode=ops.DECODE_LOGIT).cpu().numpy()
+    onset = None
+    if hysteresis:
+        ups = [float(lab.get("upper_bound", 1.0)) for lab in thresholds.values()]
+        onset = [logit_cut(u) if u < 1.0 else logit_cut(lo) for u, lo in zip(ups, bounds)]
+    dev_table = ops.decode_intervals(logits.contiguous(), [logit_cut(t) for t in bounds], file_offsets=file_offsets,
+                                     mode=ops.DECODE_LOGIT, onset=onset)
+    if max_gap_s > 0.0 or min_duration_s > 0.0:
+        dev_table = ops.postprocess_intervals(dev_table.contiguous(), int(round(max_gap_s * 16_000)),
+                                              int(round(min_duration_s * 16_000)))
+    table = dev_table.cpu().numpy()
     labels = label_encoder.base_labels
     if file_offsets is None:
         return _table_to_intervals(table, conv_settings, labels)

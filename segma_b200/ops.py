@@ -260,9 +260,10 @@ def threshold_mask(logits: torch.Tensor, thresholds, mode: int = DECODE_SIGMOID)
 
 
 def decode_intervals(logits: torch.Tensor, thresholds, *, file_offsets=None, mode: int = DECODE_SIGMOID,
-                     capacity: int | None = None) -> torch.Tensor:
+                     capacity: int | None = None, onset=None) -> torch.Tensor:
     """(n_frames, C) logits -> int32 (n_intervals, 4) table (file, label, start_sample, end_sample) on the device.
-    Reads the interval count back once (the only synchronisation); retries if ``capacity`` was too small."""
+    Reads the interval count back once (the only synchronisation); retries if ``capacity`` was too small.
+    ``onset`` (logit-domain cuts >= ``thresholds``) switches to onset / offset hysteresis."""
     lib = _lib()
     n, C_ = logits.shape
     assert logits.is_contiguous()
@@ -277,12 +278,22 @@ def decode_intervals(logits: torch.Tensor, thresholds, *, file_offsets=None, mod
     cap = max(1024, n // 16) if capacity is None else capacity
     while True:
         table = torch.empty((cap, 4), dtype=torch.int32, device=logits.device)
-        check(
-            lib.segma_decode_intervals(_dev(logits, torch.float32, "logits"), off_arr, n_files, C_, thr, mode,
-                                       table.data_ptr(), cap, count.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
-            "segma_decode_intervals",
-        )
-        stats.launches += 3
+        if onset is None:
+            check(
+                lib.segma_decode_intervals(_dev(logits, torch.float32, "logits"), off_arr, n_files, C_, thr, mode,
+                                           table.data_ptr(), cap, count.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
+                "segma_decode_intervals",
+            )
+            stats.launches += 3
+        else:
+            hi = (C.c_float * C_)(*[float(t) for t in onset])
+            check(
+                lib.segma_decode_intervals_hysteresis(_dev(logits, torch.float32, "logits"), off_arr, n_files, C_, thr,
+                                                      hi, table.data_ptr(), cap, count.data_ptr(), ws.data_ptr(),
+                                                      ws_bytes, _stream()),
+                "segma_decode_intervals_hysteresis",
+            )
+            stats.launches += 6
         total = int(count.item())
         if total <= cap:
             return table[:total]
@@ -332,3 +343,19 @@ def threshold_histogram(logits: torch.Tensor, truth: torch.Tensor, cuts) -> torc
     _call("segma_threshold_histogram", 1, _lib().segma_threshold_histogram, _dev(logits, torch.float32, "logits"),
           _dev(truth, torch.uint8, "truth"), n, C_, arr, K, hist.data_ptr(), _stream())
     return hist
+
+
+def postprocess_intervals(table: torch.Tensor, max_gap_samples: int = 0, min_duration_samples: int = 0) -> torch.Tensor:
+    """Merge rows of the same (file, label) closer than ``max_gap_samples`` and drop rows shorter than
+    ``min_duration_samples``; (n, 4) int32 device table in the decode order -> filtered table."""
+    n = table.shape[0]
+    if n == 0:
+        return table
+    assert table.is_contiguous() and table.dtype == torch.int32
+    scratch = torch.empty_like(table)
+    out = torch.empty_like(table)
+    counts = torch.zeros(2, dtype=torch.int32, device=table.device)
+    _call("segma_postprocess_intervals", 2, _lib().segma_postprocess_intervals, table.data_ptr(), n,
+          int(max_gap_samples), int(min_duration_samples), scratch.data_ptr(), out.data_ptr(), n, counts.data_ptr(),
+          _stream())
+    return out[: int(counts[1].item())]

@@ -350,3 +350,59 @@ def test_grouped_positional_conv(cuda, dims):
                   padding=eng.pos_k // 2, groups=dims.pos_groups)[..., :-1]
     ref = x0.float() + F.gelu(pc.transpose(1, 2))
     _close(out.view(n, T, d), ref, 3e-3, 3e-3, "positional conv")
+
+
+# ---- extensions: hysteresis, gap merging, minimum duration --------------------------------
+@pytest.mark.parametrize("n,C", [(1, 4), (1023, 4), (1024, 4), (5000, 3), (40_000, 8)])
+def test_hysteresis_decode(cuda, n, C):
+    g = torch.Generator().manual_seed(n)
+    logits = torch.cumsum(torch.randn((n, C), generator=g) * 0.4, dim=0)
+    logits = logits - logits.mean(0, keepdim=True)
+    lo, hi = [-0.3 + 0.05 * c for c in range(C)], [0.4 + 0.05 * c for c in range(C)]
+    mask = O.hysteresis_mask(logits, lo, hi)
+    want = O.interval_table(mask, C)
+    got = ops.decode_intervals(logits.to(cuda), lo, mode=ops.DECODE_LOGIT, onset=hi).cpu().numpy()
+    assert np.array_equal(got[:, 1:], want)
+    # onset == offset is the plain threshold rule
+    same = ops.decode_intervals(logits.to(cuda), lo, mode=ops.DECODE_LOGIT, onset=lo).cpu().numpy()
+    plain = ops.decode_intervals(logits.to(cuda), lo, mode=ops.DECODE_LOGIT).cpu().numpy()
+    assert np.array_equal(same, plain)
+
+
+def test_hysteresis_resets_at_file_boundaries(cuda):
+    logits = torch.full((3000, 2), 0.1)  # between the cuts: keeps whatever state it has
+    logits[10] = 5.0                     # file 0 switches on at frame 10 and stays on
+    offs = [0, 1500, 3000]               # file 1 never crosses the onset: stays off
+    got = ops.decode_intervals(logits.to(cuda), [0.0, 0.0], file_offsets=offs, mode=ops.DECODE_LOGIT, onset=[1.0, 1.0])
+    assert got.cpu().tolist() == [[0, 0, 3200, 480000], [0, 1, 3200, 480000]]
+
+
+def test_postprocess_intervals(cuda):
+    rng = np.random.default_rng(3)
+    rows = []
+    for f in range(3):
+        for c in range(4):
+            t = 0
+            for _ in range(int(rng.integers(0, 700))):
+                t += int(rng.integers(1, 30)) * 320
+                e = t + int(rng.integers(1, 40)) * 320
+                rows.append((f, c, t, e))
+                t = e
+    table = np.array(rows, dtype=np.int32)
+    for gap, dur in [(0, 0), (320 * 5, 0), (0, 320 * 10), (320 * 8, 320 * 20)]:
+        got = ops.postprocess_intervals(torch.from_numpy(table).to(cuda), gap, dur).cpu().numpy()
+        assert np.array_equal(got, O.postprocess_table(table, gap, dur)), (gap, dur)
+
+
+def test_merge_semantics_of_the_reference_interval_struct(cuda):
+    """Known answers of the reference's tests/test_interval.py (adjacent and overlapping intervals of one label
+    merge, different labels never do), expressed on the (file, label, start, end) table."""
+    def run(rows):
+        t = torch.tensor(sorted(rows, key=lambda r: (r[0], r[1], r[2])), dtype=torch.int32, device=cuda)
+        return [tuple(r) for r in ops.postprocess_intervals(t, 0, 0).cpu().tolist()]
+
+    assert run([(0, 0, 0, 10), (0, 0, 10, 20)]) == [(0, 0, 0, 20)]
+    assert run([(0, 1, 0, 5), (0, 1, 5, 10), (0, 1, 10, 15)]) == [(0, 1, 0, 15)]
+    assert run([(0, 0, 0, 10), (0, 0, 15, 25)]) == [(0, 0, 0, 10), (0, 0, 15, 25)]
+    assert run([(0, 0, 0, 10), (0, 1, 10, 20)]) == [(0, 0, 0, 10), (0, 1, 10, 20)]
+    assert run([(0, 0, 0, 10), (1, 0, 10, 20)]) == [(0, 0, 0, 10), (1, 0, 10, 20)]

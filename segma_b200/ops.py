@@ -279,21 +279,13 @@ def decode_intervals(logits: torch.Tensor, thresholds, *, file_offsets=None, mod
     while True:
         table = torch.empty((cap, 4), dtype=torch.int32, device=logits.device)
         if onset is None:
-            check(
-                lib.segma_decode_intervals(_dev(logits, torch.float32, "logits"), off_arr, n_files, C_, thr, mode,
-                                           table.data_ptr(), cap, count.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
-                "segma_decode_intervals",
-            )
-            stats.launches += 3
+            _call("segma_decode_intervals", 3, lib.segma_decode_intervals, _dev(logits, torch.float32, "logits"), off_arr,
+                  n_files, C_, thr, mode, table.data_ptr(), cap, count.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
         else:
             hi = (C.c_float * C_)(*[float(t) for t in onset])
-            check(
-                lib.segma_decode_intervals_hysteresis(_dev(logits, torch.float32, "logits"), off_arr, n_files, C_, thr,
-                                                      hi, table.data_ptr(), cap, count.data_ptr(), ws.data_ptr(),
-                                                      ws_bytes, _stream()),
-                "segma_decode_intervals_hysteresis",
-            )
-            stats.launches += 6
+            _call("segma_decode_intervals_hysteresis", 6, lib.segma_decode_intervals_hysteresis,
+                  _dev(logits, torch.float32, "logits"), off_arr, n_files, C_, thr, hi, table.data_ptr(), cap,
+                  count.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
         total = int(count.item())
         if total <= cap:
             return table[:total]

@@ -5,10 +5,11 @@
 // modeling_whisper.py:338-352; 1500 positions, no mask) and torchaudio SelfAttention
 // (site-packages/torchaudio/models/wav2vec2/components.py:305-307; 199 positions).
 //
-// One CTA owns 128 query rows of one (window, head) and walks the keys in tiles of 64; three CTAs are
-// resident per SM (64 KB of shared memory, 128 TMEM columns each) so that one CTA's softmax (MUFU-bound)
+// One CTA owns 128 query rows of one (window, head) and walks the keys in tiles of 64; four CTAs are
+// resident per SM (48 KB of shared memory, 128 TMEM columns each) so that one CTA's softmax (MUFU-bound)
 // overlaps the others' MMAs and barrier hand-offs.  Per key tile:
-//   warp 0      TMA: Q once, then K and V tiles (64 x 64, 128B swizzle) into a 2-stage ring, straight from the
+//   warp 0      TMA: Q once, then the K and V tiles (64 x 64, 128B swizzle; single buffers refilled as soon as the
+//               MMA that read them retires), straight from the
 //               fused QKV activation through 3-D tensor maps (column block selects q / k / v and the head)
 //   warp 1      one lane issues  O += P_{j-1} V_{j-1}  (M128 N64 K64, V as an MN-major B operand) and
 //               S = Q K_j^T (M128 N64 K64) back to back, then one tcgen05.commit
@@ -26,24 +27,30 @@ constexpr int kAtD = 64;      // head dim
 constexpr int kAtThreads = 192;
 constexpr int kQBytes = kAtQ * 128;   // 128 rows x 64 fp16
 constexpr int kKVBytes = kAtK * 128;  // 64 rows x 64 fp16
-// Q + 2 x (K, V) + P + barriers = 65 664 B: three CTAs per SM.  No alignment slack: the dynamic shared-memory
-// window of a kernel without static shared memory starts 1024-byte aligned (checked at run time).
-constexpr int kAtSmem = kQBytes + 4 * kKVBytes + kQBytes + 128;
+// Q + K + V + P + barriers = 49 280 B: four CTAs per SM (their 4 x 128 TMEM columns fill the SM's 512).  K and V
+// are single-buffered with their own barriers: K_{j+1} is fetched as soon as S_j = Q K_j^T has retired and
+// V_{j+1} as soon as O += P_j V_j has, both behind the softmax of the tile in flight.  No alignment slack: the
+// dynamic shared-memory window of a kernel without static shared memory starts 1024-byte aligned (checked).
+constexpr int kAtSmem = kQBytes + 2 * kKVBytes + kQBytes + 128;
 constexpr uint32_t kTmemColsAttn = 128;    // S: columns [0, 64), O: columns [64, 128)
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+constexpr uint32_t kWaitHintNs = 2000;     // suspend hint of the mbarrier waits (a completed phase wakes the thread)
 
-__global__ void __launch_bounds__(kAtThreads, 3)
+__global__ void __launch_bounds__(kAtThreads, 4)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, int T,
                      int n_heads, int n_query, __half* __restrict__ out) {
   extern __shared__ __align__(1024) unsigned char smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzled operand tiles need 1024-byte alignment
   unsigned char* s_q = smem;
-  unsigned char* s_kv = smem + kQBytes;                // stage s: K at s*2*kKVBytes, V right after it
-  unsigned char* s_p = smem + kQBytes + 4 * kKVBytes;  // 128 rows x 64 keys
+  unsigned char* s_k = smem + kQBytes;
+  unsigned char* s_v = smem + kQBytes + kKVBytes;
+  unsigned char* s_p = smem + kQBytes + 2 * kKVBytes;  // 128 rows x 64 keys
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + kQBytes);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* k_full = bars + 1;
+  uint64_t* v_full = bars + 2;
+  uint64_t* k_empty = bars + 3;
+  uint64_t* v_empty = bars + 4;
   uint64_t* mma_done = bars + 5;
   uint64_t* p_ready = bars + 6;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
@@ -59,10 +66,10 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_kv);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(kv_full + i, 1);
-      mbar_init(kv_empty + i, 1);
-    }
+    mbar_init(k_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(k_empty, 1);
+    mbar_init(v_empty, 1);
     mbar_init(mma_done, 1);
     mbar_init(p_ready, 4);
     mbar_fence_init();
@@ -83,11 +90,12 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       mbar_arrive_expect_tx(q_full, kQBytes);
       tma_load_3d(s_q, &map_q, q_full, h * kAtD, q0, b);
       for (int j = 0; j < n_kt; ++j) {
-        const int st = j & 1;
-        mbar_wait(kv_empty + st, ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(kv_full + st, 2 * kKVBytes);
-        tma_load_3d(s_kv + st * 2 * kKVBytes, &map_kv, kv_full + st, d + h * kAtD, j * kAtK, b);
-        tma_load_3d(s_kv + st * 2 * kKVBytes + kKVBytes, &map_kv, kv_full + st, 2 * d + h * kAtD, j * kAtK, b);
+        mbar_wait_suspend(k_empty, (j & 1) ^ 1, kWaitHintNs);
+        mbar_arrive_expect_tx(k_full, kKVBytes);
+        tma_load_3d(s_k, &map_kv, k_full, d + h * kAtD, j * kAtK, b);
+        mbar_wait_suspend(v_empty, (j & 1) ^ 1, kWaitHintNs);
+        mbar_arrive_expect_tx(v_full, kKVBytes);
+        tma_load_3d(s_v, &map_kv, v_full, 2 * d + h * kAtD, j * kAtK, b);
       }
     }
   } else if (warp == 1) {
@@ -96,30 +104,32 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       constexpr uint32_t idesc_o = umma_idesc_f16(kAtQ, kAtD, 0, 1);  // O += P V, V is MN-major
       const uint32_t q_addr = smem_u32(s_q);
       const uint32_t p_addr = smem_u32(s_p);
-      mbar_wait(q_full, 0);
+      mbar_wait_suspend(q_full, 0, kWaitHintNs);
       for (int j = 0; j <= n_kt; ++j) {
-        if (j < n_kt) mbar_wait(kv_full + (j & 1), (j >> 1) & 1);
         if (j > 0) {
-          mbar_wait(p_ready, (j - 1) & 1);
+          mbar_wait_suspend(v_full, (j - 1) & 1, kWaitHintNs);
+          mbar_wait_suspend(p_ready, (j - 1) & 1, kWaitHintNs);
           tc5_fence_after();
-          const uint32_t v_addr = smem_u32(s_kv + ((j - 1) & 1) * 2 * kKVBytes + kKVBytes);
+          const uint32_t v_addr = smem_u32(s_v);
 #pragma unroll
           for (int ks = 0; ks < kAtK / 16; ++ks) {
             const uint64_t da = umma_desc_k_sw128(p_addr + ks * 32);
             const uint64_t db = umma_desc_mn_sw128(v_addr + ks * 2048, kKVBytes);
             tc5_mma_f16(tmem_o, da, db, idesc_o, (j > 1 || ks > 0) ? 1u : 0u);
           }
-          tc5_commit(kv_empty + ((j - 1) & 1));
+          tc5_commit(v_empty);
         }
         if (j < n_kt) {
+          mbar_wait_suspend(k_full, j & 1, kWaitHintNs);
           tc5_fence_after();
-          const uint32_t k_addr = smem_u32(s_kv + (j & 1) * 2 * kKVBytes);
+          const uint32_t k_addr = smem_u32(s_k);
 #pragma unroll
           for (int ks = 0; ks < kAtD / 16; ++ks) {
             const uint64_t da = umma_desc_k_sw128(q_addr + ks * 32);
             const uint64_t db = umma_desc_k_sw128(k_addr + ks * 32);
             tc5_mma_f16(tmem_s, da, db, idesc_s, ks > 0 ? 1u : 0u);
           }
+          tc5_commit(k_empty);  // K_j is free once S_j has retired
         }
         tc5_commit(mma_done);
       }
@@ -135,7 +145,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     unsigned char* p_row = s_p + row * 128;
     const int sw = row & 7;
     for (int j = 0; j < n_kt; ++j) {
-      mbar_wait(mma_done, j & 1);
+      mbar_wait_suspend(mma_done, j & 1, kWaitHintNs);
       tc5_fence_after();
       const int n_valid = min(kAtK, T - j * kAtK);  // keys of this tile that exist
       if (j == 0) {  // the first tile fixes the reference max

@@ -39,11 +39,20 @@ LABELS = ("KCHI", "OCH", "MAL", "FEM")
 METRIC, UNIT = "audio_hours_per_sec", "audio-h/s"
 
 
-def _config(n_gpus: int, audio_s: float) -> dict:
+WORKLOADS = {
+    # name: (model kind, description, GFLOP per 4 s window)
+    "whisper": ("surgical_hydra", "whisper-small-dims surgical_hydra (12x768, LSTM 2x128 bidir, 4 heads), 80-bin log-mel", 344.7),
+    "hubert": ("surgical_hubert_hydra", "HuBERT-base-dims surgical_hubert_hydra (7-layer conv front end, 12x768, 4 heads)", 56.9),
+    "wavlm": ("surgical_hubert_hydra", "WavLM-base+-dims encoder in surgical_hubert_hydra (gated relative-position bias)", 56.9),
+}
+
+
+def _config(n_gpus: int, audio_s: float, workload: str = "whisper") -> dict:
+    kind, desc, _ = WORKLOADS[workload]
     return {
-        "workload": "whisper-small-dims surgical_hydra (12x768, LSTM 2x128 bidir, 4 heads), 80-bin log-mel, "
+        "workload": f"{desc}, "
                     f"{audio_s / 3600:.4g} h synthetic 16 kHz audio per GPU per step, 4 s windows step 63680, batch 128",
-        "model": "surgical_hydra/whisper-small-dims",
+        "model": f"{kind}/{workload}",
         "audio_seconds_per_gpu_step": audio_s,
         "window_batch": BATCH,
         "parallelism": f"files sharded over {n_gpus} GPU(s), interval all-gather" if n_gpus > 1 else "single GPU",
@@ -166,9 +175,13 @@ def run_gpu(args):
     audio_s = n_samples / 16_000
 
     le = MultiLabelEncoder(list(LABELS))
-    cfg = make_config("surgical_hydra")
-    sd = synth.surgical_hydra_state_dict(synth.WHISPER_SMALL, seed=0)
-    model = Models["surgical_hydra"].from_state_dict(sd, le, cfg).to(dev)
+    kind, _, gflop_per_window = WORKLOADS[args.workload]
+    cfg = make_config(kind)
+    if args.workload == "whisper":
+        sd = synth.surgical_hydra_state_dict(synth.WHISPER_SMALL, seed=0)
+    else:
+        sd = synth.hubert_hydra_state_dict(synth.WAVLM_BASE if args.workload == "wavlm" else synth.HUBERT_BASE, seed=0)
+    model = Models[kind].from_state_dict(sd, le, cfg).to(dev)
     thr = default_thresholds(le)
     cuts = [logit_cut(0.5)] * len(LABELS)
 
@@ -238,7 +251,7 @@ def run_gpu(args):
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     achieved_tf = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
-    total_flops_per_step = 905 * 344.7e9 * (n_samples / HOUR_SAMPLES)
+    total_flops_per_step = 905 * gflop_per_window * 1e9 * (n_samples / HOUR_SAMPLES)
 
     # secondary HBM-bound kernels, timed alone (burst peak): log-mel front end on one 128-window batch and
     # threshold + run-length decode on a >= 100 h batch of logits
@@ -305,14 +318,14 @@ def run_gpu(args):
     value = world * (audio_s / 3600.0) * args.steps / dev_s
     e2e_value = world * (audio_s / 3600.0) * args.steps / e2e_wall
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "whisper":
         r = cpu_reference_run(args.ref_windows, 1, 0)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 tensor-core operands, f32 accumulate/residual/LayerNorm/LSTM",
-        "data": "synthetic", "config": _config(world, audio_s),
+        "data": "synthetic", "config": _config(world, audio_s, args.workload),
         "realtime_factor_per_gpu": value * 3600.0 / world,
         "model_tflops_per_gpu": total_flops_per_step * args.steps / dev_s / 1e12,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host_pcm.numel() * 4,
@@ -343,6 +356,8 @@ def main():
     ap.add_argument("--hours", type=float, default=1.0, help="audio hours per GPU per step")
     ap.add_argument("--ref-windows", type=int, default=16, help="windows per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="whisper", choices=sorted(WORKLOADS),
+                    help="whisper = BASELINE config 2 (the headline); hubert / wavlm = configs 1 and 3 models, informational")
     ap.add_argument("--no-side-kernels", action="store_true", help="skip the log-mel / decode roofline measurements")
     args = ap.parse_args()
     if args.impl == "reference":

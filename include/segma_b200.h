@@ -149,11 +149,12 @@ SEGMA_API int segma_layernorm(const float* x, const float* gamma, const float* b
 
 /* softmax(Q K^T + bias) V per (window, head); qkv fp16 (n_windows*T, 3*d) rows = [q | k | v],
  * q pre-scaled, head_dim 64; out fp16 (n_windows*T, d).  Optional WavLM gated relative bias:
- * bias[b,h,i,j] = gate[(b*H + h)*T + i] * pos_bias[(h*T + i)*T + j] (fp32), both NULL otherwise.
+ * bias[b,h,i,j] = gate[(b*H + h)*T + i] * pos_bias[(h*T + i)*pos_bias_ld + j] (fp32), both NULL otherwise;
+ * a row stride pos_bias_ld that is a multiple of 4 floats lets the tcgen05 kernel read it with 128-bit loads.
  * n_query: only the first n_query rows of each window are computed (<= T).
  */
 SEGMA_API int segma_attention(const void* qkv, int n_windows, int T, int n_heads, int n_query, const float* gate,
-                    const float* pos_bias, void* out, void* stream);
+                    const float* pos_bias, int pos_bias_ld, void* out, void* stream);
 
 /* fp32 -> fp16 copy of a (rows, cols) matrix with row strides. */
 SEGMA_API int segma_cast_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);

@@ -45,7 +45,7 @@ __device__ __forceinline__ void load_tile_async(unsigned char* smem_tile, const 
 __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __half* __restrict__ qkv, int T,
                                                                  int n_heads, int n_query,
                                                                  const float* __restrict__ gate,
-                                                                 const float* __restrict__ pos_bias,
+                                                                 const float* __restrict__ pos_bias, int pb_ld,
                                                                  __half* __restrict__ out) {
   __shared__ __align__(128) unsigned char s_q[kQTile * 128];
   __shared__ __align__(128) unsigned char s_k[2][kKTile * 128];
@@ -85,8 +85,8 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __half* _
     const int ra = min(row_a, T - 1), rb = min(row_b, T - 1);
     gate_a = __ldg(gate + ((long long)b * n_heads + h) * T + ra);
     gate_b = __ldg(gate + ((long long)b * n_heads + h) * T + rb);
-    pb_a = pos_bias + ((long long)h * T + ra) * T;
-    pb_b = pos_bias + ((long long)h * T + rb) * T;
+    pb_a = pos_bias + ((long long)h * T + ra) * pb_ld;
+    pb_b = pos_bias + ((long long)h * T + rb) * pb_ld;
   }
 
   for (int kt = 0; kt < n_kt; ++kt) {
@@ -204,8 +204,8 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __half* _
   }
 }
 
-int launch_attention_tc5(const void* qkv, int n_windows, int T, int n_heads, int n_query, void* out,
-                         cudaStream_t st);
+int launch_attention_tc5(const void* qkv, int n_windows, int T, int n_heads, int n_query, const float* gate,
+                         const float* pos_bias, int pb_ld, void* out, cudaStream_t st);
 
 }  // namespace segma
 
@@ -214,20 +214,23 @@ using namespace segma;
 extern "C" {
 
 int segma_attention(const void* qkv, int n_windows, int T, int n_heads, int n_query, const float* gate,
-                    const float* pos_bias, void* out, void* stream) {
+                    const float* pos_bias, int pos_bias_ld, void* out, void* stream) {
   SEGMA_REQUIRE(n_windows >= 0 && T > 0 && n_heads > 0 && n_query >= 0 && n_query <= T, "segma_attention: bad shape");
   if (n_windows == 0 || n_query == 0) return SEGMA_OK;
   SEGMA_REQUIRE(qkv && out, "segma_attention: NULL buffer");
   SEGMA_REQUIRE((gate == nullptr) == (pos_bias == nullptr), "segma_attention: gate and pos_bias go together");
   SEGMA_REQUIRE(n_heads <= 65535 && n_windows <= 65535, "segma_attention: grid too large");
-  // tcgen05 path for plain attention; the gated-bias (WavLM) variant and SEGMA_ATTN_LEGACY=1 use the
+  SEGMA_REQUIRE(pos_bias == nullptr || pos_bias_ld >= T, "segma_attention: pos_bias_ld %d < T %d", pos_bias_ld, T);
+  // tcgen05 path; SEGMA_ATTN_LEGACY=1 (or a bias table whose rows are not 16-byte aligned) selects the
   // warp-level mma.sync kernel below
   static const bool legacy = getenv("SEGMA_ATTN_LEGACY") != nullptr;
-  if (pos_bias == nullptr && !legacy && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
-    return launch_attention_tc5(qkv, n_windows, T, n_heads, n_query, out, (cudaStream_t)stream);
+  const bool bias_ok = pos_bias == nullptr || (pos_bias_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(pos_bias) & 15) == 0);
+  if (!legacy && bias_ok && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
+    return launch_attention_tc5(qkv, n_windows, T, n_heads, n_query, gate, pos_bias, pos_bias_ld, out,
+                                (cudaStream_t)stream);
   dim3 grid(ceil_div(n_query, kQTile), n_heads, n_windows);
   attention_kernel<<<grid, kAttnThreads, 0, (cudaStream_t)stream>>>(
-      static_cast<const __half*>(qkv), T, n_heads, n_query, gate, pos_bias, static_cast<__half*>(out));
+      static_cast<const __half*>(qkv), T, n_heads, n_query, gate, pos_bias, pos_bias_ld, static_cast<__half*>(out));
   return launch_status("attention_kernel");
 }
 

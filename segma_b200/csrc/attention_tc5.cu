@@ -36,9 +36,12 @@ constexpr uint32_t kTmemColsAttn = 128;    // S: columns [0, 64), O: columns [64
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 constexpr uint32_t kWaitHintNs = 2000;     // suspend hint of the mbarrier waits (a completed phase wakes the thread)
 
+// kBias: scores get the WavLM gated relative-position term gate[b,h,i] * pos_bias[h,i,j] added before the softmax
+template <bool kBias>
 __global__ void __launch_bounds__(kAtThreads, 4)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, int T,
-                     int n_heads, int n_query, __half* __restrict__ out) {
+                     int n_heads, int n_query, const float* __restrict__ gate, const float* __restrict__ pos_bias,
+                     int pb_ld, __half* __restrict__ out) {
   extern __shared__ __align__(1024) unsigned char smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzled operand tiles need 1024-byte alignment
   unsigned char* s_q = smem;
@@ -142,6 +145,14 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const float kLog2e = 1.4426950408889634f;
     float m_run = 0.f;  // reference max, log2 units (set from the first tile)
     float l_run = 0.f;
+    // gated relative-position bias of this query row (log2 units): g2 * pb[key]
+    float g2 = 0.f;
+    const float* pb = nullptr;
+    if (kBias) {
+      const int qr = min(q0 + row, T - 1);
+      g2 = __ldg(gate + ((long long)b * n_heads + h) * T + qr) * kLog2e;
+      pb = pos_bias + ((long long)h * T + qr) * pb_ld;
+    }
     unsigned char* p_row = s_p + row * 128;
     const int sw = row & 7;
     for (int j = 0; j < n_kt; ++j) {
@@ -157,9 +168,13 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < n_valid) mx = fmaxf(mx, __uint_as_float(sv[i]));
+            if (c * 32 + i < n_valid) {
+              float y = __uint_as_float(sv[i]) * kLog2e;
+              if (kBias) y = fmaf(__ldg(pb + c * 32 + i), g2, y);
+              mx = fmaxf(mx, y);
+            }
         }
-        m_run = mx * kLog2e;
+        m_run = mx;
       }
       float psum;
       while (true) {
@@ -177,9 +192,19 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             for (int q = 0; q < 4; ++q) {
               uint32_t pk[4];
 #pragma unroll
+              float4 pb0 = make_float4(0.f, 0.f, 0.f, 0.f), pb1 = pb0;
+              if (kBias) {  // 8 consecutive keys of this row's bias (rows are padded to a multiple of 4 floats)
+                const float4* src = reinterpret_cast<const float4*>(pb + j * kAtK + c * 32 + q * 8);
+                pb0 = __ldg(src);
+                pb1 = __ldg(src + 1);
+              }
+              const float off[8] = {pb0.x, pb0.y, pb0.z, pb0.w, pb1.x, pb1.y, pb1.z, pb1.w};
+#pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * e]), kLog2e, -m_run));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * e + 1]), kLog2e, -m_run));
+                const float o0 = kBias ? fmaf(off[2 * e], g2, -m_run) : -m_run;
+                const float o1 = kBias ? fmaf(off[2 * e + 1], g2, -m_run) : -m_run;
+                const float p0 = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * e]), kLog2e, o0));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * e + 1]), kLog2e, o1));
                 psum += p0 + p1;
                 const __half2 h2 = __floats2half2_rn(p0, p1);
                 pmax2 = __hmax2(pmax2, h2);
@@ -200,8 +225,13 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int i = c * 32 + q * 8 + 2 * e;
-                float p0 = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * e]), kLog2e, -m_run));
-                float p1 = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * e + 1]), kLog2e, -m_run));
+                float o0 = -m_run, o1 = -m_run;
+                if (kBias) {
+                  if (i < n_valid) o0 = fmaf(__ldg(pb + j * kAtK + i), g2, -m_run);
+                  if (i + 1 < n_valid) o1 = fmaf(__ldg(pb + j * kAtK + i + 1), g2, -m_run);
+                }
+                float p0 = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * e]), kLog2e, o0));
+                float p1 = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * e + 1]), kLog2e, o1));
                 if (i >= n_valid) p0 = 0.f;
                 if (i + 1 >= n_valid) p1 = 0.f;
                 psum += p0 + p1;
@@ -226,7 +256,11 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < n_valid) ymax = fmaxf(ymax, fmaf(__uint_as_float(sv[i]), kLog2e, -m_run));
+            if (c * 32 + i < n_valid) {
+              float y = fmaf(__uint_as_float(sv[i]), kLog2e, -m_run);
+              if (kBias) y = fmaf(__ldg(pb + j * kAtK + c * 32 + i), g2, y);
+              ymax = fmaxf(ymax, y);
+            }
         }
         const float grow = fmaxf(ymax, 0.f);
         const float alpha = ex2_approx(-grow);
@@ -287,8 +321,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 int make_f16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                  int box_rows);
 
-int launch_attention_tc5(const void* qkv, int n_windows, int T, int n_heads, int n_query, void* out,
-                         cudaStream_t st) {
+int launch_attention_tc5(const void* qkv, int n_windows, int T, int n_heads, int n_query, const float* gate,
+                         const float* pos_bias, int pb_ld, void* out, cudaStream_t st) {
   const int d = n_heads * kAtD;
   CUtensorMap map_q, map_kv;
   uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)T, (uint64_t)n_windows};
@@ -299,11 +333,17 @@ int launch_attention_tc5(const void* qkv, int n_windows, int T, int n_heads, int
   if (rc != SEGMA_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
     attr_set = true;
   }
   dim3 grid(ceil_div(n_query, kAtQ), n_heads, n_windows);
-  attention_tc5_kernel<<<grid, kAtThreads, kAtSmem, st>>>(map_q, map_kv, T, n_heads, n_query, static_cast<__half*>(out));
+  if (pos_bias)
+    attention_tc5_kernel<true><<<grid, kAtThreads, kAtSmem, st>>>(map_q, map_kv, T, n_heads, n_query, gate, pos_bias,
+                                                                 pb_ld, static_cast<__half*>(out));
+  else
+    attention_tc5_kernel<false><<<grid, kAtThreads, kAtSmem, st>>>(map_q, map_kv, T, n_heads, n_query, nullptr, nullptr,
+                                                                  0, static_cast<__half*>(out));
   return launch_status("attention_tc5_kernel");
 }
 

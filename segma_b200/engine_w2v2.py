@@ -133,7 +133,11 @@ class W2V2Engine:
 
     def _pos_bias_for(self, T: int) -> torch.Tensor:
         if T not in self._pos_bias:
-            self._pos_bias[T] = wavlm_position_bias(self.rel_embed, T, self.rel_embed.shape[0]).to(self.device)
+            pb = wavlm_position_bias(self.rel_embed, T, self.rel_embed.shape[0])
+            ld = (T + 3) // 4 * 4  # rows padded to 16 bytes for the tcgen05 kernel's 128-bit loads
+            padded = torch.zeros((pb.shape[0], T, ld), dtype=torch.float32, device=self.device)
+            padded[:, :, :T] = pb.to(self.device)
+            self._pos_bias[T] = padded[:, :, :T]  # (H, T, T) view with row stride ld
         return self._pos_bias[T]
 
     def _workspace(self, n: int, win_len: int, slot: int = 0) -> dict:

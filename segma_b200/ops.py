@@ -211,9 +211,14 @@ def attention(qkv: torch.Tensor, n_windows: int, T: int, n_heads: int, *, n_quer
     assert qkv.is_contiguous() and qkv.shape == (n_windows * T, 3 * n_heads * 64)
     if out is None:
         out = torch.zeros((n_windows * T, n_heads * 64), dtype=torch.float16, device=qkv.device)
-    _call("segma_attention", 1, _lib().segma_attention, _dev(qkv, torch.float16, "qkv"), n_windows, T, n_heads, T if n_query is None else n_query,
-                               _ptr(gate, torch.float32, "gate"), _ptr(pos_bias, torch.float32, "pos_bias"),
-                               _dev(out, torch.float16, "out"), _stream())
+    pb_ld = 0
+    if pos_bias is not None:
+        assert pos_bias.dim() == 3 and pos_bias.shape[:2] == (n_heads, T) and pos_bias.stride(2) == 1
+        assert pos_bias.stride(0) == T * pos_bias.stride(1)
+        pb_ld = pos_bias.stride(1)
+    _call("segma_attention", 1, _lib().segma_attention, _dev(qkv, torch.float16, "qkv"), n_windows, T, n_heads,
+          T if n_query is None else n_query, _ptr(gate, torch.float32, "gate"), _ptr(pos_bias, torch.float32, "pos_bias"),
+          pb_ld, _dev(out, torch.float16, "out"), _stream())
     return out
 
 

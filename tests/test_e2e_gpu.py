@@ -177,7 +177,7 @@ def test_w2v2_family_file_level_small(cuda, dims, seed):
     wav = torch.stack([torch.from_numpy(synth.synth_audio(64000, s)) for s in range(2)])
     out = model(wav)
     assert out.shape == (2, 199, 1, 4)
-    _check_logits(out.cpu(), O.hubert_hydra_forward(sd, wav, LABELS), "w2v2 forward drop-in")
+    _check_logits(out.cpu(), O.hubert_hydra_forward(sd, wav, LABELS), "w2v2 forward drop-in", min_agreement=0.998)
 
 
 @pytest.mark.parametrize("key,dims,seed", [("hubert_logits", synth.HUBERT_BASE, 5), ("wavlm_logits", synth.WAVLM_BASE, 6)])
@@ -190,7 +190,9 @@ def test_w2v2_family_vs_reference_golden(cuda, key, dims, seed):
     le = MultiLabelEncoder(list(LABELS))
     model = Models["surgical_hubert_hydra"].from_state_dict(sd, le, make_config("surgical_hubert_hydra"))
     got = apply_model_on_audio(synth.synth_audio(n, audio_seed), model, INFERENCE_SETTINGS, "cuda", batch_size=bs).cpu()
-    _check_logits(got, torch.from_numpy(g[key]), f"{key} vs reference golden")
+    # 2 636 decisions: one flipped frame is 0.04 %.  The conv front end adds seven fp16 GEMM stages to the twelve
+    # encoder layers, so |err| ~ 1e-3 of the logit spread and the agreement sits at 99.9 % +- one or two frames.
+    _check_logits(got, torch.from_numpy(g[key]), f"{key} vs reference golden", min_agreement=0.998)
 
 
 def test_w2v2_silent_file(cuda):

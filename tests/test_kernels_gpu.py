@@ -139,14 +139,22 @@ def test_attention(cuda, T, H, B, nq):
     _close(got, ref[:, :nq], 3e-3, 3e-3, f"attention T={T}")
 
 
-def test_attention_wavlm_bias(cuda):
-    T, H, B = 199, 2, 2
+@pytest.mark.parametrize("T,padded", [(199, False), (199, True), (300, True), (64, True)])
+def test_attention_wavlm_bias(cuda, T, padded):
+    """padded=True: bias rows at a 16-byte pitch -> tcgen05 kernel; False: unpadded table -> mma.sync kernel."""
+    H, B = 2, 2
     d = H * 64
     qkv = _rand((B * T, 3 * d), 17).to(torch.float16)
     qkv[:, :d] *= 0.35
     gate = (1.0 + 0.3 * _rand((B, H, T), 18)).contiguous()
     pos = _rand((H, T, T), 19).contiguous()
-    out = ops.attention(qkv.to(cuda), B, T, H, gate=gate.to(cuda), pos_bias=pos.to(cuda))
+    pos_dev = pos.to(cuda)
+    if padded:
+        ld = (T + 3) // 4 * 4
+        buf = torch.zeros((H, T, ld), device=cuda)
+        buf[:, :, :T] = pos_dev
+        pos_dev = buf[:, :, :T]
+    out = ops.attention(qkv.to(cuda), B, T, H, gate=gate.to(cuda), pos_bias=pos_dev)
     q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
     s = q @ k.transpose(-1, -2) + gate[..., None] * pos[None]
     ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * T, d)

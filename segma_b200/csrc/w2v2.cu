@@ -142,28 +142,43 @@ __global__ void __launch_bounds__(kL0Threads) w2v2_l0_apply_kernel(
 }
 
 // gate[(b*H + h)*T + i] = ga * (gb * const_h - 1) + 2, (ga, gb) = sigmoid(sum4(Linear(64 -> 8)(x[b, i, head h])))
+// One warp per row; each lane owns whole 64-long dot products (head, output) = (pair / 8, pair % 8), the 8 x 64
+// projection lives in shared memory, and the two 4-way sums are two shuffles inside aligned groups of 8 lanes.
 __global__ void __launch_bounds__(256) wavlm_gate_kernel(const float* __restrict__ x, long long rows, int T, int H,
                                                           const float* __restrict__ gw, const float* __restrict__ gb,
                                                           const float* __restrict__ gconst, float* __restrict__ gate) {
+  __shared__ __align__(16) float s_w[8 * 64];
+  __shared__ float s_b[8];
+  for (int i = threadIdx.x; i < 8 * 64; i += blockDim.x) s_w[i] = gw[i];
+  if (threadIdx.x < 8) s_b[threadIdx.x] = gb[threadIdx.x];
+  __syncthreads();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = lane_id();
   const long long b = row / T;
   const int i = (int)(row - b * T);
   const float* xr = x + row * (long long)(H * 64);
-  for (int h = 0; h < H; ++h) {
-    const float x0 = xr[h * 64 + lane], x1 = xr[h * 64 + 32 + lane];
-    float a = 0.f, bsum = 0.f;
+  for (int pair = lane; pair < ((H * 8 + 31) / 32) * 32; pair += 32) {
+    const int h = pair >> 3, o = pair & 7;
+    float acc = 0.f;
+    if (h < H) {
+      const float4* xv = reinterpret_cast<const float4*>(xr + h * 64);
+      const float4* wv = reinterpret_cast<const float4*>(s_w + o * 64);
 #pragma unroll
-    for (int o = 0; o < 4; ++o) a += __ldg(gw + o * 64 + lane) * x0 + __ldg(gw + o * 64 + 32 + lane) * x1;
-#pragma unroll
-    for (int o = 4; o < 8; ++o) bsum += __ldg(gw + o * 64 + lane) * x0 + __ldg(gw + o * 64 + 32 + lane) * x1;
-    a = warp_sum(a);
-    bsum = warp_sum(bsum);
-    if (lane == 0) {
-      a += gb[0] + gb[1] + gb[2] + gb[3];
-      bsum += gb[4] + gb[5] + gb[6] + gb[7];
-      const float ga = 1.0f / (1.0f + expf(-a)), gbv = 1.0f / (1.0f + expf(-bsum));
+      for (int k = 0; k < 16; ++k) {
+        const float4 a = __ldg(xv + k), w4 = wv[k];
+        acc = fmaf(a.x, w4.x, acc);
+        acc = fmaf(a.y, w4.y, acc);
+        acc = fmaf(a.z, w4.z, acc);
+        acc = fmaf(a.w, w4.w, acc);
+      }
+      acc += s_b[o];
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);              // lanes o = 0 and o = 4 hold the two 4-way sums
+    const float other = __shfl_down_sync(0xffffffffu, acc, 4);
+    if (h < H && o == 0) {
+      const float ga = 1.0f / (1.0f + expf(-acc)), gbv = 1.0f / (1.0f + expf(-other));
       gate[(b * H + h) * T + i] = ga * (gbv * __ldg(gconst + h) - 1.0f) + 2.0f;
     }
   }

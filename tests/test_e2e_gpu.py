@@ -313,3 +313,42 @@ def test_infer_file_on_wav_writes_reference_artefacts(cuda, tmp_path):
     pcm16 = np.clip(np.round(pcm * 32768.0), -32768, 32767).astype(np.int16).astype(np.float32) / 32768.0
     ref = O.apply_model_on_audio(torch.from_numpy(pcm16), lambda w: O.hubert_hydra_forward(sd, w, LABELS), 4, batch_size=2)
     _check_logits(logits, ref, "infer_file on int16 wav", min_agreement=0.998)
+
+
+def test_run_inference_on_audios_cli_path(cuda, tmp_path, capsys):
+    """The whole driver as the reference's __main__ calls it: YAML config, Lightning-style checkpoint, a folder
+    of wav files, a thresholds YAML -> one RTTM per file, identical to decoding the oracle-checked logits."""
+    import yaml
+
+    from segma_b200.inference import run_inference_on_audios
+    from segma_b200.io import write_wav
+
+    sd = synth.hubert_hydra_state_dict(synth.W2V2_TEST, seed=5)
+    torch.save({"state_dict": sd, "epoch": 3}, tmp_path / "best.ckpt")
+    cfg = make_config("surgical_hubert_hydra")
+    cfg.save(tmp_path / "config.yml")
+    wavs = tmp_path / "wav"
+    wavs.mkdir()
+    lens = {"b_second": 64000 + 9000, "a_first": 3 * 63680 + 500, "c_short": 300}
+    for name, n in lens.items():
+        write_wav(wavs / f"{name}.wav", synth.synth_audio(n, len(name)), subtype="float32")
+    thr = {lab: {"lower_bound": 0.4, "upper_bound": 1.0} for lab in LABELS}
+    (tmp_path / "thr.yml").write_text(yaml.safe_dump(thr))
+    done = run_inference_on_audios(config=tmp_path / "config.yml", uris=None, wavs=wavs, checkpoint=tmp_path / "best.ckpt",
+                                   output=tmp_path / "out", thresholds=tmp_path / "thr.yml", batch_size=2, device="gpu",
+                                   save_logits=True)
+    assert [p.stem for p in done] == ["a_first", "b_second", "c_short"]  # sorted, like the reference
+    log = capsys.readouterr().out
+    assert "[log] - (1/3) - running inference for file: 'a_first'" in log
+    for name, n in lens.items():
+        rttm = (tmp_path / "out" / "raw_rttm" / f"{name}.rttm").read_text().splitlines()
+        if n < 400:
+            assert rttm == []  # shorter than one receptive field: no frames, empty RTTM
+            continue
+        blob = torch.load(tmp_path / "out" / "logits" / f"{name}-logits_dict_t.pt")
+        logits = torch.stack([blob[lab] for lab in LABELS], dim=1)
+        assert logits.shape[0] == (n - 400) // 320 + 1
+        want = O.create_intervals(O.apply_thresholds(logits, [0.4] * 4).numpy(), LABELS)
+        assert len(rttm) == len(want)
+        assert rttm[:3] == [f"SPEAKER {name} <NA> {round(s / 16000, 8)} {round((e - s) / 16000, 8)} <NA> <NA> {lab} <NA> <NA>"
+                            for s, e, lab in want[:3]]

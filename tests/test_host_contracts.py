@@ -126,3 +126,46 @@ def test_logit_cut_degenerate():
     assert logit_cut(1.0) == float("inf") and logit_cut(-0.1) == float("-inf")
     # sigmoid(x) > 0.5 is not x > 0
     assert logit_cut(0.5) > 0.0
+
+
+# ---- error behaviour of the driver entry point (inference.py:398-432), checked before any CUDA work ------------
+def _write_cfg(tmp_path, model_name="surgical_hubert_hydra"):
+    cfg = {
+        "wandb": {"offline": True, "project": "p", "name": "n"},
+        "data": {"dataset_path": "d", "classes": ["KCHI", "OCH", "MAL", "FEM"]},
+        "audio": {"chunk_duration_s": 4.0, "sample_rate": 16000, "strict_frames": False},
+        "model": {"name": model_name},
+        "train": {"lr": 0.001, "batch_size": 32, "max_epochs": 1, "validation_metric": "loss", "extra_val_metrics": [],
+                  "profiler": None, "dataloader": {"num_workers": 0}, "scheduler": {"patience": 3}},
+    }
+    p = tmp_path / "cfg.yml"
+    p.write_text(yaml.safe_dump(cfg))
+    return p
+
+
+def test_driver_errors_match_the_reference(tmp_path):
+    from segma_b200.inference import get_list_of_files_to_process, run_inference_on_audios
+
+    cfg = _write_cfg(tmp_path)
+    wavs = tmp_path / "wav"
+    wavs.mkdir()
+    ckpt = tmp_path / "best.ckpt"
+    ckpt.write_bytes(b"")
+    kw = dict(config=cfg, uris=None, output=tmp_path / "out", batch_size=2)
+    with pytest.raises(ValueError):  # missing checkpoint
+        run_inference_on_audios(wavs=wavs, checkpoint=tmp_path / "nope.ckpt", thresholds=None, **kw)
+    with pytest.raises(ValueError):  # thresholds path that does not exist
+        run_inference_on_audios(wavs=wavs, checkpoint=ckpt, thresholds=tmp_path / "nope.yml", **kw)
+    with pytest.raises(FileNotFoundError):  # wavs folder
+        run_inference_on_audios(wavs=tmp_path / "nowav", checkpoint=ckpt, thresholds=None, **kw)
+    bad = _write_cfg(tmp_path, "whisperidou")
+    with pytest.raises(ValueError):  # only the multi-label ("hydra") models are accepted
+        run_inference_on_audios(config=bad, uris=None, wavs=wavs, checkpoint=ckpt, output=tmp_path / "o", thresholds=None, batch_size=2)
+    # file listing: sorted glob, or the uris file
+    for name in ("b.wav", "a.wav", "c.txt"):
+        (wavs / name).write_bytes(b"")
+    files, n = get_list_of_files_to_process(wavs)
+    assert [f.name for f in files] == ["a.wav", "b.wav"] and n == 2
+    (tmp_path / "uris.txt").write_text("b\nzz\n")
+    files, n = get_list_of_files_to_process(wavs, uris=tmp_path / "uris.txt")
+    assert [f.name for f in files] == ["b.wav", "zz.wav"] and n == 2

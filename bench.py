@@ -52,7 +52,7 @@ def _config(n_gpus: int, audio_s: float, workload: str = "whisper") -> dict:
     return {
         "workload": f"{desc}, "
                     f"{audio_s / 3600:.4g} h synthetic 16 kHz audio per GPU per step, 4 s windows step 63680, batch 128",
-        "model": f"{kind}/{workload}",
+        "weights": "random init (segma_b200.synth, seed 0), reference state_dict layout",
         "audio_seconds_per_gpu_step": audio_s,
         "window_batch": BATCH,
         "parallelism": f"files sharded over {n_gpus} GPU(s), interval all-gather" if n_gpus > 1 else "single GPU",
@@ -324,7 +324,8 @@ def run_gpu(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 tensor-core operands, f32 accumulate/residual/LayerNorm/LSTM",
+        "dtype": "f16",
+        "dtype_detail": "f16 tensor-core operands; f32 accumulation, residual stream, LayerNorm/softmax statistics, LSTM state, logits",
         "data": "synthetic", "config": _config(world, audio_s, args.workload),
         "realtime_factor_per_gpu": value * 3600.0 / world,
         "model_tflops_per_gpu": total_flops_per_step * args.steps / dev_s / 1e12,

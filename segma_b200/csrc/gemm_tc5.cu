@@ -15,6 +15,7 @@
 // the activation map (rows merged s at a time) at column block (j % s) * C and row offset j / s, so no
 // im2col buffer is ever written.
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -44,11 +45,15 @@ struct GemmKernelArgs {
   int flags;
 };
 
-template <int BN>
+// kCta2: the tile is computed by a CTA pair (cta_group::2): M = 256 (this CTA's 128 rows plus the peer's), each CTA
+// stages only its half of the W tile, and the tensor cores of both SMs read both halves -- 2/3 of the shared-memory
+// operand traffic of the single-CTA tile, and two more pipeline stages in the same shared memory.
+template <int BN, bool kCta2 = false>
 struct GemmCfg {
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 192 ? 5 : 6);
+  static constexpr int kStages = kCta2 ? 6 : (BN == 256 ? 4 : (BN == 192 ? 5 : 6));
   static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBRows = kCta2 ? BN / 2 : BN;  // W rows staged by this CTA
+  static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = BN == 128 ? 256 : 512;
   static constexpr int kAccStride = BN == 192 ? 256 : BN;  // column offset between the two accumulators
@@ -56,11 +61,11 @@ struct GemmCfg {
                                     kEpiWarps * kEpiRows * kEpiPitch * 4 /*epilogue transpose tiles*/;
 };
 
-template <int BN>
+template <int BN, bool kCta2>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                 const GemmKernelArgs p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, kCta2>;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   unsigned char* smem = smem_raw + ((1024 - (raw_addr & 1023)) & 1023);
@@ -75,8 +80,21 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = lane_id();
-  const int num_tiles = p.batch * p.tiles_per_batch * p.n_tiles;
   const int num_kb = p.taps * p.kb_per_tap;
+  // work units: single tiles, or (kCta2) pairs of consecutive M tiles of one batch sharing an N tile
+  const int rank = kCta2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int units_per_batch = kCta2 ? (p.tiles_per_batch + 1) / 2 : p.tiles_per_batch;
+  const int num_tiles = p.batch * units_per_batch * p.n_tiles;
+  const int unit0 = kCta2 ? (blockIdx.x >> 1) : blockIdx.x;
+  const int unit_step = kCta2 ? (gridDim.x >> 1) : gridDim.x;
+  // unit -> (n_tile, batch, first row of this CTA's 128-row M tile)
+  auto locate = [&](int unit, int& n_tile, int& b, int& r0) {
+    n_tile = unit % p.n_tiles;
+    const int mu = unit / p.n_tiles;
+    b = mu / units_per_batch;
+    const int m_in_batch = mu - b * units_per_batch;
+    r0 = (kCta2 ? 2 * m_in_batch + rank : m_in_batch) * kBM;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -87,16 +105,21 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
-      mbar_init(tmem_empty + i, kEpiWarps);
+      mbar_init(tmem_empty + i, kCta2 ? 2 * kEpiWarps : kEpiWarps);  // the leader collects both CTAs' epilogues
     }
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (kCta2) {
+      tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc5_fence_before();
-  __syncthreads();
+  if (kCta2) cluster_sync_all(); else __syncthreads();  // the peer's barriers and TMEM must exist before any traffic
   tc5_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -105,21 +128,26 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
-        const int b = m_tile / p.tiles_per_batch;
-        const int r0 = (m_tile - b * p.tiles_per_batch) * kBM;
-        const int n0 = n_tile * BN;
+      for (int tile = unit0; tile < num_tiles; tile += unit_step) {
+        int n_tile, b, r0;
+        locate(tile, n_tile, b, r0);
+        const int n0 = n_tile * BN + rank * Cfg::kBRows;  // this CTA's rows of the W tile
         for (int tap = 0; tap < p.taps; ++tap) {
           const int a_col = (tap % p.conv_stride) * p.a_tap_elems + n_tile * p.a_ntile_off;
           const int a_row = r0 + tap / p.conv_stride;
           const int w_col = tap * p.w_tap_elems;
           for (int kk = 0; kk < p.kb_per_tap; ++kk) {
             mbar_wait(empty_bar + stage, phase ^ 1);
-            mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
-            tma_load_3d(smem_a + stage * Cfg::kABytes, &map_a, full_bar + stage, a_col + kk * kBK, a_row, b);
-            tma_load_2d(smem_b + stage * Cfg::kBBytes, &map_w, full_bar + stage, w_col + kk * kBK, n0);
+            if (kCta2) {
+              // both CTAs' bytes are credited to the leader's barrier, which is the one the MMA thread waits on
+              if (rank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * Cfg::kStageBytes);
+              tma_load_3d_pair(smem_a + stage * Cfg::kABytes, &map_a, full_bar + stage, a_col + kk * kBK, a_row, b);
+              tma_load_2d_pair(smem_b + stage * Cfg::kBBytes, &map_w, full_bar + stage, w_col + kk * kBK, n0);
+            } else {
+              mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
+              tma_load_3d(smem_a + stage * Cfg::kABytes, &map_a, full_bar + stage, a_col + kk * kBK, a_row, b);
+              tma_load_2d(smem_b + stage * Cfg::kBBytes, &map_w, full_bar + stage, w_col + kk * kBK, n0);
+            }
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -127,12 +155,12 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(kBM, BN, 0, 0);
+    if (lane == 0 && rank == 0) {  // in a CTA pair only the leader issues
+      constexpr uint32_t idesc = umma_idesc_f16(kCta2 ? 2 * kBM : kBM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit0; tile < num_tiles; tile += unit_step, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(tmem_empty + as, aphase ^ 1);
@@ -147,12 +175,14 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t da = umma_desc_k_sw128(a_addr + k * 32);
             const uint64_t db = umma_desc_k_sw128(b_addr + k * 32);
-            tc5_mma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (kCta2) tc5_mma_f16_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else tc5_mma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tc5_commit(empty_bar + stage);  // frees the smem stage once these MMAs retire
+          // frees the smem stage (in both CTAs of a pair) once these MMAs retire
+          if (kCta2) tc5_commit_pair(empty_bar + stage); else tc5_commit(empty_bar + stage);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        tc5_commit(tmem_full + as);  // accumulator complete
+        if (kCta2) tc5_commit_pair(tmem_full + as); else tc5_commit(tmem_full + as);  // accumulator complete
       }
     }
   } else {
@@ -167,13 +197,12 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int sub_r = lane >> 3;   // row within a group of 4
     const int c4 = lane & 7;       // float4 column within the 32-column chunk
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit0; tile < num_tiles; tile += unit_step, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
-      const int b = m_tile / p.tiles_per_batch;
-      const int r_base = (m_tile - b * p.tiles_per_batch) * kBM + quad * 32;  // first row of this warp
+      int n_tile, b, r0;
+      locate(tile, n_tile, b, r0);
+      const int r_base = r0 + quad * 32;  // first row of this warp
       const int n0 = n_tile * BN;
       const long long out_row0 = (long long)b * p.out_batch_rows + p.out_row_offset + r_base;
       long long src_base = 0;
@@ -238,15 +267,17 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
       tc5_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + as);
+      if (lane == 0) {
+        if (kCta2) mbar_arrive_leader(tmem_empty + as); else mbar_arrive(tmem_empty + as);
+      }
     }
   }
 
   tc5_fence_before();
-  __syncthreads();
+  if (kCta2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc5_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (kCta2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -300,24 +331,41 @@ int make_f16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* d
   return SEGMA_OK;
 }
 
-template <int BN>
+template <int BN, bool kCta2>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, GemmKernelArgs& ka, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, kCta2>;
   static bool attr_set = false;
   if (!attr_set) {
-    SEGMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc5_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SEGMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc5_kernel<BN, kCta2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
     attr_set = true;
   }
   ka.n_tiles = ceil_div(ka.n, BN);
-  const long long tiles = (long long)ka.batch * ka.tiles_per_batch * ka.n_tiles;
-  if (tiles > 0x7fffffffll) {
+  const int units_per_batch = kCta2 ? (ka.tiles_per_batch + 1) / 2 : ka.tiles_per_batch;
+  const long long units = (long long)ka.batch * units_per_batch * ka.n_tiles;
+  if (units > 0x7fffffffll) {
     set_last_error("segma_gemm_f16: too many tiles");
     return SEGMA_ERR_INVALID_ARGUMENT;
   }
-  const int grid = (int)std::min<long long>(tiles, device_sm_count());
-  gemm_tc5_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ma, mw, ka);
-  return launch_status("gemm_tc5_kernel");
+  if (!kCta2) {
+    const int grid = (int)std::min<long long>(units, device_sm_count());
+    gemm_tc5_kernel<BN, false><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ma, mw, ka);
+    return launch_status("gemm_tc5_kernel");
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * (unsigned)std::min<long long>(units, device_sm_count() / 2));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SEGMA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc5_kernel<BN, true>, ma, mw, ka));
+  return SEGMA_OK;
 }
 
 }  // namespace segma
@@ -382,6 +430,7 @@ int segma_gemm_f16(const segma_gemm_args* a, void* stream) {
     if (rc != SEGMA_OK) return rc;
   }
   int bn = 256;
+  bool cta2 = false;
   if (a->n % 256 != 0 && a->n < 512) bn = 128;
   if (a->n % 256 != 0 && a->n % 128 != 0 && a->n % 192 == 0) bn = 192;
   if (a->force_bn) {
@@ -391,14 +440,17 @@ int segma_gemm_f16(const segma_gemm_args* a, void* stream) {
   {
     uint64_t dims[2] = {(uint64_t)a->k, (uint64_t)a->n};
     uint64_t strides[2] = {1, (uint64_t)a->k};
-    int rc = make_f16_map(&mw, a->w, 2, dims, strides, bn);
+    // CTA pairs (cta_group::2) for the 256-wide tile when there are at least two M tiles per batch to pair up
+    static const int pair_mode = getenv("SEGMA_GEMM_2CTA") ? atoi(getenv("SEGMA_GEMM_2CTA")) : 1;
+    cta2 = pair_mode != 0 && bn == 256 && ka.tiles_per_batch >= 2;
+    int rc = make_f16_map(&mw, a->w, 2, dims, strides, cta2 ? bn / 2 : bn);
     if (rc != SEGMA_OK) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;
   switch (bn) {
-    case 128: return launch_gemm<128>(ma, mw, ka, st);
-    case 192: return launch_gemm<192>(ma, mw, ka, st);
-    default: return launch_gemm<256>(ma, mw, ka, st);
+    case 128: return launch_gemm<128, false>(ma, mw, ka, st);
+    case 192: return launch_gemm<192, false>(ma, mw, ka, st);
+    default: return cta2 ? launch_gemm<256, true>(ma, mw, ka, st) : launch_gemm<256, false>(ma, mw, ka, st);
   }
 }
 

@@ -24,8 +24,8 @@ namespace segma {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 128 bytes of fp16: one swizzle row
-constexpr int kEpiWarps = 8;       // two warps per TMEM lane quadrant, alternating 32-column chunks
-constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
+// epilogue warps: kEW / 4 per TMEM lane quadrant, interleaving 32-column chunks (8, or 16 for the ALU-heavy
+// GELU epilogue without residual, whose smaller register footprint leaves room for the extra warps)
 constexpr int kEpiPitch = 36;  // floats per staged accumulator row (32 + 4 pad: conflict-free 128-bit access)
 constexpr int kEpiRows = 16;   // rows staged per round (half a warp's accumulator rows)
 
@@ -48,9 +48,10 @@ struct GemmKernelArgs {
 // kCta2: the tile is computed by a CTA pair (cta_group::2): M = 256 (this CTA's 128 rows plus the peer's), each CTA
 // stages only its half of the W tile, and the tensor cores of both SMs read both halves -- 2/3 of the shared-memory
 // operand traffic of the single-CTA tile, and two more pipeline stages in the same shared memory.
-template <int BN, bool kCta2 = false>
+template <int BN, bool kCta2 = false, int kEW = 8>
 struct GemmCfg {
-  static constexpr int kStages = kCta2 ? 6 : (BN == 256 ? 4 : (BN == 192 ? 5 : 6));
+  static constexpr int kThreads = 64 + 32 * kEW;
+  static constexpr int kStages = kCta2 ? (kEW > 8 ? 5 : 6) : (BN == 256 ? 4 : (BN == 192 ? 5 : 6));
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBRows = kCta2 ? BN / 2 : BN;  // W rows staged by this CTA
   static constexpr int kBBytes = kBRows * kBK * 2;
@@ -58,14 +59,14 @@ struct GemmCfg {
   static constexpr int kTmemCols = BN == 128 ? 256 : 512;
   static constexpr int kAccStride = BN == 192 ? 256 : BN;  // column offset between the two accumulators
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                    kEpiWarps * kEpiRows * kEpiPitch * 4 /*epilogue transpose tiles*/;
+                                    kEW * kEpiRows * kEpiPitch * 4 /*epilogue transpose tiles*/;
 };
 
-template <int BN, bool kCta2>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, bool kCta2, int kEW, bool kAddSrc>
+__global__ void __launch_bounds__(64 + 32 * kEW, 1)
 gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                 const GemmKernelArgs p) {
-  using Cfg = GemmCfg<BN, kCta2>;
+  using Cfg = GemmCfg<BN, kCta2, kEW>;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   unsigned char* smem = smem_raw + ((1024 - (raw_addr & 1023)) & 1023);
@@ -105,7 +106,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
-      mbar_init(tmem_empty + i, kCta2 ? 2 * kEpiWarps : kEpiWarps);  // the leader collects both CTAs' epilogues
+      mbar_init(tmem_empty + i, kCta2 ? 2 * kEW : kEW);  // the leader collects both CTAs' epilogues
     }
     mbar_fence_init();
   }
@@ -190,7 +191,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // TMEM hands each lane one accumulator row; a 32 x 32 chunk is transposed through a padded
     // shared-memory tile so that global loads/stores run along rows (8 lanes x 16 B per row).
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;   // which of the two warps of the quadrant: even or odd chunks
+    const int cgrp = (warp - 2) >> 2;   // which of the quadrant's kEW/4 warps: chunks cgrp, cgrp + kEW/4, ...
     const bool out_f32 = (p.flags & SEGMA_GEMM_OUT_F32) != 0;
     const bool do_gelu = (p.flags & SEGMA_GEMM_GELU) != 0;
     float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256) + (warp - 2) * (kEpiRows * kEpiPitch);
@@ -206,17 +207,17 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int n0 = n_tile * BN;
       const long long out_row0 = (long long)b * p.out_batch_rows + p.out_row_offset + r_base;
       long long src_base = 0;
-      if (p.add_src) src_base = (long long)b * p.add_batch_rows + r_base;
+      if (kAddSrc && p.add_src) src_base = (long long)b * p.add_batch_rows + r_base;
       mbar_wait(tmem_full + as, aphase);
       tc5_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * Cfg::kAccStride;
 #pragma unroll 1
-      for (int chunk = half; chunk < BN / 32; chunk += 2) {
+      for (int chunk = cgrp; chunk < BN / 32; chunk += kEW / 4) {
         const int nc = n0 + chunk * 32;
         if (nc >= p.n) break;  // warp-uniform
         // issue the residual / position-table loads first so their latency hides behind the TMEM read
-        float4 src4[8];
-        if (p.add_src) {
+        float4 src4[kAddSrc ? 8 : 1];
+        if (kAddSrc && p.add_src) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const int rr = g * 4 + sub_r;
@@ -249,7 +250,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             float4 v = *reinterpret_cast<const float4*>(stg + (gi * 4 + sub_r) * kEpiPitch + c4 * 4);
             v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
             if (do_gelu) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
-            if (p.add_src) { v.x += src4[g].x; v.y += src4[g].y; v.z += src4[g].z; v.w += src4[g].w; }
+            if (kAddSrc && p.add_src) { v.x += src4[g].x; v.y += src4[g].y; v.z += src4[g].z; v.w += src4[g].w; }
             if (r_base + rr < p.rows_per_batch) {
               const long long o = (out_row0 + rr) * p.ldo + nc;
               if (out_f32) {
@@ -331,13 +332,13 @@ int make_f16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* d
   return SEGMA_OK;
 }
 
-template <int BN, bool kCta2>
+template <int BN, bool kCta2, int kEW, bool kAddSrc>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, GemmKernelArgs& ka, cudaStream_t st) {
-  using Cfg = GemmCfg<BN, kCta2>;
+  using Cfg = GemmCfg<BN, kCta2, kEW>;
   static bool attr_set = false;
   if (!attr_set) {
-    SEGMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc5_kernel<BN, kCta2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::kSmemBytes));
+    SEGMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc5_kernel<BN, kCta2, kEW, kAddSrc>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   ka.n_tiles = ceil_div(ka.n, BN);
@@ -349,12 +350,12 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, GemmKernelA
   }
   if (!kCta2) {
     const int grid = (int)std::min<long long>(units, device_sm_count());
-    gemm_tc5_kernel<BN, false><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ma, mw, ka);
+    gemm_tc5_kernel<BN, false, kEW, kAddSrc><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(ma, mw, ka);
     return launch_status("gemm_tc5_kernel");
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * (unsigned)std::min<long long>(units, device_sm_count() / 2));
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -364,7 +365,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, GemmKernelA
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SEGMA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc5_kernel<BN, true>, ma, mw, ka));
+  SEGMA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc5_kernel<BN, true, kEW, kAddSrc>, ma, mw, ka));
   return SEGMA_OK;
 }
 
@@ -447,10 +448,16 @@ int segma_gemm_f16(const segma_gemm_args* a, void* stream) {
     if (rc != SEGMA_OK) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  // epilogues without a residual operand need few registers: 16 epilogue warps (4 per scheduler) hide the latencies
+  // of the ALU-bound erf-GELU (fc1: 800 -> 975 TFLOP/s) and of the fp16 store path (QKV: 1130 -> 1190)
+  static const int wide_epi = getenv("SEGMA_GEMM_EPI16") ? atoi(getenv("SEGMA_GEMM_EPI16")) : 2;
+  const bool heavy = wide_epi != 0 && ((a->flags & SEGMA_GEMM_GELU) || wide_epi == 2) && a->add_src == nullptr;
   switch (bn) {
-    case 128: return launch_gemm<128, false>(ma, mw, ka, st);
-    case 192: return launch_gemm<192, false>(ma, mw, ka, st);
-    default: return cta2 ? launch_gemm<256, true>(ma, mw, ka, st) : launch_gemm<256, false>(ma, mw, ka, st);
+    case 128: return launch_gemm<128, false, 8, true>(ma, mw, ka, st);
+    case 192: return launch_gemm<192, false, 8, true>(ma, mw, ka, st);
+    default:
+      if (cta2) return heavy ? launch_gemm<256, true, 16, false>(ma, mw, ka, st) : launch_gemm<256, true, 8, true>(ma, mw, ka, st);
+      return launch_gemm<256, false, 8, true>(ma, mw, ka, st);
   }
 }
 

@@ -28,7 +28,7 @@ from .annotation import rttm_line
 from .config import Config, load_config
 from .encoders import MultiLabelEncoder
 from .geometry import FRAME_SAMPLES, INFERENCE_SETTINGS, Chunkyfier, ConvolutionSettings, conv_frames, plan_windows
-from .io import get_audio_info, get_samples_in_range, stage_to_device
+from .io import PcmSource, get_audio_info, get_samples_in_range, stage_to_device
 from .models import BaseSegmentationModel, Models
 from .thresholds import logit_cut
 
@@ -93,13 +93,10 @@ def apply_model_on_audio(
     chunk_f = int(chunk_duration_s * sample_rate)
     chunky = Chunkyfier(batch_size, chunk_f, conv_settings)  # same derived quantities as the reference
     step = chunky.step if window_step is None else int(window_step)
-    if isinstance(audio_path, torch.Tensor) and audio_path.is_cuda:
-        pcm = audio_path.reshape(-1).to(torch.float32).contiguous()
-    elif isinstance(audio_path, torch.Tensor) and audio_path.dtype == torch.float32 and audio_path.is_pinned():
-        pcm = audio_path.reshape(-1).to(dev, non_blocking=True)  # already staged in pinned host memory
-    else:
-        pcm = stage_to_device(audio_path, dev)  # native-width PCM over PCIe, widened on the device
-    n_samples = pcm.numel()
+    # native-width PCM over PCIe, widened on the device, staged batch by batch behind the compute of earlier batches
+    source = PcmSource(audio_path, dev)
+    pcm = source.dev
+    n_samples = source.n_samples
     engine = model._require_engine()
     frames_per_window = model.n_keep if model.family == "whisper" else conv_frames(chunk_f)
     plan = plan_windows(n_samples, chunk_f, batch_size, step, frames_per_window)
@@ -126,6 +123,9 @@ def apply_model_on_audio(
             st.wait_stream(main)
     target = logits if tiled else win_logits
     for i, b in enumerate(plan.batches):
+        source.ensure(b.start_sample + (b.n_windows - 1) * step + b.win_len)
+        if lanes[i % n_lanes] is not main:
+            lanes[i % n_lanes].wait_stream(main)
         with torch.cuda.stream(lanes[i % n_lanes]):
             if tiled:
                 engine.forward_pcm(pcm, b.start_sample, b.n_windows, b.win_len, step, logits, b.first_window * sf, sf,

@@ -142,43 +142,102 @@ def write_wav(path, pcm: np.ndarray, sample_rate: int = 16_000, subtype: str = "
 _STAGE_CHUNK = 32 << 20  # bytes per pinned staging buffer
 
 
-def stage_to_device(audio_p, device) -> torch.Tensor:
-    """Whole file -> 1-D float32 tensor on ``device``.  Mono PCM16 / PCM32 / float32 WAV data is read straight
-    from the file into two alternating pinned buffers, copied in its stored width and widened by
-    ``segma_pcm_to_f32`` on the device; anything else goes through the host decoder."""
-    from . import ops
+class PcmSource:
+    """A file's samples as a 1-D float32 device tensor that is filled progressively.
 
-    arr = _as_array(audio_p)
-    if arr is None:
-        lay = _parse_wav(Path(audio_p))
-        fmt = {(1, 16): (ops.PCM_S16, np.dtype("<i2"), torch.int16), (1, 32): (ops.PCM_S32, np.dtype("<i4"), torch.int32),
-               (3, 32): (ops.PCM_F32, np.dtype("<f4"), torch.float32)}.get((lay.fmt, lay.bits))
-        if fmt is not None and lay.n_channels == 1:
-            code, np_dt, t_dt = fmt
-            n = lay.n_frames
-            raw = torch.empty(n, dtype=t_dt, device=device)
-            per = max(1, _STAGE_CHUNK // np_dt.itemsize)
-            bufs = [torch.empty(min(per, max(n, 1)), dtype=t_dt).pin_memory() for _ in range(2)]
-            events = [None, None]
-            with open(audio_p, "rb") as f:
-                f.seek(lay.data_offset)
-                done, i = 0, 0
-                while done < n:
-                    cnt = min(per, n - done)
-                    if events[i & 1] is not None:
-                        events[i & 1].synchronize()  # the previous copy out of this buffer has finished
-                    view = bufs[i & 1][:cnt].numpy()
-                    got = f.readinto(memoryview(view).cast("B"))
-                    if got != cnt * np_dt.itemsize:
-                        raise ValueError(f"{audio_p}: truncated data chunk")
-                    raw[done:done + cnt].copy_(bufs[i & 1][:cnt], non_blocking=True)
+    ``ensure(n)`` makes samples ``[0, n)`` valid for kernels launched afterwards on the current stream; host
+    reads, PCIe copies (on a side stream) and the widening kernel therefore overlap the compute of earlier
+    batches instead of preceding the whole file.  Sources: a device tensor (nothing to do), a pinned or
+    pageable host array, or a mono PCM16 / PCM32 / float32 WAV file read in its stored width."""
+
+    def __init__(self, audio_p, device):
+        from . import ops
+
+        self._ops = ops
+        self.device = torch.device(device)
+        self._done = 0
+        self._file = None
+        self._host = None
+        arr = audio_p if isinstance(audio_p, torch.Tensor) else _as_array(audio_p)
+        if isinstance(arr, torch.Tensor) and arr.is_cuda:
+            self.dev = arr.reshape(-1).to(torch.float32).contiguous()
+            self.n_samples = self._done = self.dev.numel()
+            return
+        if arr is not None:
+            host = torch.as_tensor(arr).reshape(-1)
+            if host.dtype != torch.float32:
+                host = host.to(torch.float32)
+            self._host = host if host.is_pinned() else host.contiguous().pin_memory()
+            self.n_samples = host.numel()
+            self._fmt = (ops.PCM_F32, np.dtype("<f4"), torch.float32)
+        else:
+            lay = _parse_wav(Path(audio_p))
+            fmt = {(1, 16): (ops.PCM_S16, np.dtype("<i2"), torch.int16), (1, 32): (ops.PCM_S32, np.dtype("<i4"), torch.int32),
+                   (3, 32): (ops.PCM_F32, np.dtype("<f4"), torch.float32)}.get((lay.fmt, lay.bits))
+            if fmt is None or lay.n_channels != 1:  # anything else goes through the host decoder
+                t = get_samples_in_range(audio_p, 0, -1)
+                if t.shape[0] != 1:
+                    raise ValueError(f"only mono audio is supported, got {t.shape[0]} channels")
+                self._host = t.reshape(-1).contiguous().pin_memory()
+                self.n_samples = self._host.numel()
+                self._fmt = (ops.PCM_F32, np.dtype("<f4"), torch.float32)
+            else:
+                self._fmt = fmt
+                self.n_samples = lay.n_frames
+                self._file = open(audio_p, "rb")
+                self._file.seek(lay.data_offset)
+                per = max(1, _STAGE_CHUNK // fmt[1].itemsize)
+                self._bufs = [torch.empty(min(per, max(self.n_samples, 1)), dtype=fmt[2]).pin_memory() for _ in range(2)]
+                self._buf_events = [None, None]
+                self._turn = 0
+        code, _, t_dt = self._fmt
+        self.dev = torch.empty(self.n_samples, dtype=torch.float32, device=self.device)
+        self._raw = self.dev if code == ops.PCM_F32 else torch.empty(self.n_samples, dtype=t_dt, device=self.device)
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+
+    def ensure(self, upto: int) -> None:
+        upto = min(int(upto), self.n_samples)
+        if upto <= self._done:
+            return
+        ops = self._ops
+        code, np_dt, _ = self._fmt
+        main = torch.cuda.current_stream(self.device)
+        a = self._done
+        if self._host is not None:
+            with torch.cuda.stream(self._copy_stream):
+                self._raw[a:upto].copy_(self._host[a:upto], non_blocking=True)
+        else:
+            per = self._bufs[0].numel()
+            pos = a
+            while pos < upto:
+                cnt = min(per, upto - pos)
+                i = self._turn & 1
+                if self._buf_events[i] is not None:
+                    self._buf_events[i].synchronize()  # the previous copy out of this pinned buffer has finished
+                view = self._bufs[i][:cnt].numpy()
+                got = self._file.readinto(memoryview(view).cast("B"))
+                if got != cnt * np_dt.itemsize:
+                    raise ValueError("truncated WAV data chunk")
+                with torch.cuda.stream(self._copy_stream):
+                    self._raw[pos:pos + cnt].copy_(self._bufs[i][:cnt], non_blocking=True)
                     ev = torch.cuda.Event()
-                    ev.record()
-                    events[i & 1] = ev
-                    done += cnt
-                    i += 1
-            return ops.pcm_to_f32(raw, code) if code != ops.PCM_F32 else raw
-    t = get_samples_in_range(audio_p, 0, -1)
-    if t.shape[0] != 1:
-        raise ValueError(f"only mono audio is supported, got {t.shape[0]} channels")
-    return t.reshape(-1).pin_memory().to(device, non_blocking=True)
+                    ev.record(self._copy_stream)
+                self._buf_events[i] = ev
+                self._turn += 1
+                pos += cnt
+        main.wait_stream(self._copy_stream)
+        if code != ops.PCM_F32:
+            ops.pcm_to_f32(self._raw[a:upto], code, out=self.dev[a:upto])
+        self._done = upto
+        if self._done >= self.n_samples and self._file is not None:
+            self._file.close()
+            self._file = None
+
+    def all(self) -> torch.Tensor:
+        self.ensure(self.n_samples)
+        return self.dev
+
+
+def stage_to_device(audio_p, device) -> torch.Tensor:
+    """Whole file -> 1-D float32 tensor on ``device`` (see ``PcmSource``)."""
+    return PcmSource(audio_p, device).all()

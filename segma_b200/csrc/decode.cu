@@ -98,6 +98,14 @@ __device__ __forceinline__ int find_file(const int* __restrict__ block_offsets, 
   return lo;
 }
 
+// One thread per block: which file does the block belong to (computed once per call; the decode / hysteresis
+// kernels then start with a single load instead of a chain of dependent global loads)
+__global__ void block_file_kernel(const int* __restrict__ block_offsets, int n_files, int total_blocks,
+                                  int* __restrict__ block_file) {
+  const int blk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blk < total_blocks) block_file[blk] = find_file(block_offsets, n_files, blk);
+}
+
 // Pass 1: per-frame activity bits (stored for pass 3) and per-(file,label,block) counts of run
 // starts and run ends.  counts index = C*block_offsets[file] + c*nblk_file + local_block.
 __global__ void __launch_bounds__(kDecodeBlock) decode_count_kernel(
@@ -198,6 +206,123 @@ __global__ void __launch_bounds__(kScanThreads) decode_scan_kernel(int* __restri
     __syncthreads();
   }
   if (threadIdx.x == 0) *count = s_carry[0];
+}
+
+// Parallel version of pass 2 for long inputs: per-tile sums, a scan of the tile sums, per-tile scans with offsets.
+constexpr int kScanTile = kScanThreads * kScanItems;  // 8192 elements per block
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const int* __restrict__ a, const int* __restrict__ b,
+                                                                       long long n, int* __restrict__ tile_sums) {
+  __shared__ int s_a[32], s_b[32];
+  const long long t0 = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
+  int sa = 0, sb = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    const long long j = t0 + i;
+    if (j < n) { sa += a[j]; sb += b[j]; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+  }
+  if (lane_id() == 0) { s_a[threadIdx.x >> 5] = sa; s_b[threadIdx.x >> 5] = sb; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int xa = s_a[threadIdx.x], xb = s_b[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      xa += __shfl_xor_sync(0xffffffffu, xa, o);
+      xb += __shfl_xor_sync(0xffffffffu, xb, o);
+    }
+    if (threadIdx.x == 0) { tile_sums[2 * blockIdx.x] = xa; tile_sums[2 * blockIdx.x + 1] = xb; }
+  }
+}
+
+// one block: exclusive scan of the (a, b) tile sums in place; total of `a` -> *count
+__global__ void __launch_bounds__(kScanThreads) scan_tile_offsets_kernel(int* __restrict__ tile_sums, int n_tiles,
+                                                                          int* __restrict__ count) {
+  __shared__ int s_warp[2][32];
+  __shared__ int s_carry[2];
+  if (threadIdx.x == 0) s_carry[0] = s_carry[1] = 0;
+  __syncthreads();
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  for (int base = 0; base < n_tiles; base += kScanThreads) {
+    const int i = base + threadIdx.x;
+    const int va = i < n_tiles ? tile_sums[2 * i] : 0, vb = i < n_tiles ? tile_sums[2 * i + 1] : 0;
+    int ia = va, ib = vb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+      if (lane >= o) { ia += ta; ib += tb; }
+    }
+    if (lane == 31) { s_warp[0][warp] = ia; s_warp[1][warp] = ib; }
+    __syncthreads();
+    if (warp == 0) {
+      const int wa = s_warp[0][lane], wb = s_warp[1][lane];
+      int xa = wa, xb = wb;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ta = __shfl_up_sync(0xffffffffu, xa, o), tb = __shfl_up_sync(0xffffffffu, xb, o);
+        if (lane >= o) { xa += ta; xb += tb; }
+      }
+      s_warp[0][lane] = xa - wa;
+      s_warp[1][lane] = xb - wb;
+    }
+    __syncthreads();
+    const int ea = s_carry[0] + s_warp[0][warp] + ia - va, eb = s_carry[1] + s_warp[1][warp] + ib - vb;
+    if (i < n_tiles) { tile_sums[2 * i] = ea; tile_sums[2 * i + 1] = eb; }
+    __syncthreads();
+    if (threadIdx.x == kScanThreads - 1) { s_carry[0] = ea + va; s_carry[1] = eb + vb; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = s_carry[0];
+}
+
+// exclusive scan of one 8192-element tile of both arrays in place, starting from the tile's offsets
+__global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(int* __restrict__ a, int* __restrict__ b, long long n,
+                                                                   const int* __restrict__ tile_offsets) {
+  __shared__ int s_warp[2][32];
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const long long t0 = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
+  int va[kScanItems], vb[kScanItems];
+  int sa = 0, sb = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    const long long j = t0 + i;
+    va[i] = j < n ? a[j] : 0;
+    vb[i] = j < n ? b[j] : 0;
+    sa += va[i];
+    sb += vb[i];
+  }
+  int ia = sa, ib = sb;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+    if (lane >= o) { ia += ta; ib += tb; }
+  }
+  if (lane == 31) { s_warp[0][warp] = ia; s_warp[1][warp] = ib; }
+  __syncthreads();
+  if (warp == 0) {
+    const int wa = s_warp[0][lane], wb = s_warp[1][lane];
+    int xa = wa, xb = wb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int ta = __shfl_up_sync(0xffffffffu, xa, o), tb = __shfl_up_sync(0xffffffffu, xb, o);
+      if (lane >= o) { xa += ta; xb += tb; }
+    }
+    s_warp[0][lane] = xa - wa;
+    s_warp[1][lane] = xb - wb;
+  }
+  __syncthreads();
+  int ea = tile_offsets[2 * blockIdx.x] + s_warp[0][warp] + ia - sa;
+  int eb = tile_offsets[2 * blockIdx.x + 1] + s_warp[1][warp] + ib - sb;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    const long long j = t0 + i;
+    if (j < n) { a[j] = ea; b[j] = eb; }
+    ea += va[i];
+    eb += vb[i];
+  }
 }
 
 // Pass 3: recompute boundary flags from the stored bits, rank them inside the block and write the
@@ -317,18 +442,25 @@ __device__ __forceinline__ FrameBits neighbour_bits(uint32_t cur, uint32_t halo_
 template <int MODE>
 __global__ void __launch_bounds__(kFastThreads) decode_fast_kernel(
     const float* __restrict__ logits, const long long* __restrict__ file_offsets,
-    const int* __restrict__ block_offsets, int n_files, DecodeParams p, uint8_t* __restrict__ bits,
-    int* __restrict__ start_counts, int* __restrict__ end_counts, int32_t* __restrict__ table, long long capacity) {
+    const int* __restrict__ block_offsets, const int* __restrict__ block_file, DecodeParams p,
+    uint8_t* __restrict__ bits, int* __restrict__ start_counts, int* __restrict__ end_counts,
+    int32_t* __restrict__ table, long long capacity) {
   __shared__ uint32_t s_edge_lo[kFastThreads / 32], s_edge_hi[kFastThreads / 32];
   __shared__ uint32_t s_warp[4][kFastThreads / 32];  // [starts lo, starts hi, ends lo, ends hi][warp]
-  __shared__ int s_base[2][8];
-  const int file = find_file(block_offsets, n_files, blockIdx.x);
+  const int file = __ldg(block_file + blockIdx.x);
   const int local_block = blockIdx.x - block_offsets[file];
   const int nblk_file = block_offsets[file + 1] - block_offsets[file];
   const long long f_begin = file_offsets[file], f_end = file_offsets[file + 1];
   const long long frame0 = f_begin + (long long)local_block * kFastBlock + threadIdx.x * kFastFrames;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   constexpr int n_warps = kFastThreads / 32;
+  // write pass: fetch this block's scanned row offsets now, so the load overlaps the rest of the dependent chain
+  int my_base = 0;
+  if (MODE == 1 && threadIdx.x < 2 * p.C) {
+    const int which = threadIdx.x / p.C, c = threadIdx.x - which * p.C;
+    const long long idx = (long long)p.C * block_offsets[file] + (long long)c * nblk_file + local_block;
+    my_base = __ldg((which == 0 ? start_counts : end_counts) + idx);  // exclusive-scanned by pass 2
+  }
 
   constexpr bool kWrite = MODE == 1;
   constexpr bool kFromBits = MODE != 0;
@@ -393,35 +525,40 @@ __global__ void __launch_bounds__(kFastThreads) decode_fast_kernel(
     s_warp[0][warp] = xs_lo + cs_lo; s_warp[1][warp] = xs_hi + cs_hi;
     s_warp[2][warp] = xe_lo + ce_lo; s_warp[3][warp] = xe_hi + ce_hi;
   }
+  __syncthreads();
+  // s_first[which][c][w]: table row of the first start / end of label c emitted by warp w of this block
+  __shared__ int s_first[2][8][n_warps];
   if (threadIdx.x < 2 * p.C) {
     const int which = threadIdx.x / p.C, c = threadIdx.x - which * p.C;
-    const long long idx = (long long)p.C * block_offsets[file] + (long long)c * nblk_file + local_block;
-    s_base[which][c] = (which == 0 ? start_counts : end_counts)[idx];  // exclusive-scanned by pass 2
+    int run = my_base;
+    for (int w = 0; w < n_warps; ++w) {
+      s_first[which][c][w] = run;
+      run += (s_warp[2 * which + (c >> 2)][w] >> (8 * (c & 3))) & 0xff;
+    }
   }
   __syncthreads();
   const int rel0 = static_cast<int>(frame0 - f_begin);
+  const unsigned cap = capacity > 0x7fffffffll ? 0x7fffffffu : static_cast<unsigned>(capacity);
   for (int c = 0; c < p.C; ++c) {
-    const int word = c >> 2, sh = 8 * (c & 3);
-    int rs = ((word ? xs_hi : xs_lo) >> sh) & 0xff, re = ((word ? xe_hi : xe_lo) >> sh) & 0xff;
-    for (int w = 0; w < warp; ++w) {
-      rs += (s_warp[word][w] >> sh) & 0xff;
-      re += (s_warp[2 + word][w] >> sh) & 0xff;
-    }
-    long long row_s = (long long)s_base[0][c] + rs, row_e = (long long)s_base[1][c] + re;
     const uint32_t m = 0x01010101u << c;
-    uint32_t sb = starts & m, eb = ends & m;
+    const uint32_t sb = starts & m, eb = ends & m;
+    if (!(sb | eb)) continue;  // most threads hold no boundary of this label
+    const int word = c >> 2, sh = 8 * (c & 3);
+    unsigned row_s = static_cast<unsigned>(s_first[0][c][warp]) + (((word ? xs_hi : xs_lo) >> sh) & 0xff);
+    unsigned row_e = static_cast<unsigned>(s_first[1][c][warp]) + (((word ? xe_hi : xe_lo) >> sh) & 0xff);
 #pragma unroll
     for (int i = 0; i < kFastFrames; ++i) {
-      if (sb & (0xffu << (8 * i))) {
-        if (row_s < capacity) {
-          table[row_s * 4 + 0] = file;
-          table[row_s * 4 + 1] = c;
-          table[row_s * 4 + 2] = (rel0 + i) * SEGMA_FRAME_SAMPLES;
+      if ((sb >> (8 * i)) & 0xffu) {
+        if (row_s < cap) {
+          int* t = table + 4ll * row_s;
+          t[0] = file;
+          t[1] = c;
+          t[2] = (rel0 + i) * SEGMA_FRAME_SAMPLES;
         }
         ++row_s;
       }
-      if (eb & (0xffu << (8 * i))) {
-        if (row_e < capacity) table[row_e * 4 + 3] = (rel0 + i + 1) * SEGMA_FRAME_SAMPLES;
+      if ((eb >> (8 * i)) & 0xffu) {
+        if (row_e < cap) table[4ll * row_e + 3] = (rel0 + i + 1) * SEGMA_FRAME_SAMPLES;
         ++row_e;
       }
     }
@@ -469,10 +606,10 @@ __device__ __forceinline__ SetVal code_setval(uint32_t code, uint32_t label_mask
 // pass H1: per-frame (hi, lo) codes and the (set, val) summary of every 1024-frame block
 __global__ void __launch_bounds__(kFastThreads) hyst_codes_kernel(
     const float* __restrict__ logits, const long long* __restrict__ file_offsets,
-    const int* __restrict__ block_offsets, int n_files, HystParams p, uint16_t* __restrict__ codes,
-    uint16_t* __restrict__ block_summary) {
+    const int* __restrict__ block_offsets, const int* __restrict__ block_file, HystParams p,
+    uint16_t* __restrict__ codes, uint16_t* __restrict__ block_summary) {
   __shared__ SetVal s_w[kFastThreads / 32];
-  const int file = find_file(block_offsets, n_files, blockIdx.x);
+  const int file = __ldg(block_file + blockIdx.x);
   const int local_block = blockIdx.x - block_offsets[file];
   const long long f_begin = file_offsets[file], f_end = file_offsets[file + 1];
   const long long frame0 = f_begin + (long long)local_block * kFastBlock + threadIdx.x * kFastFrames;
@@ -519,10 +656,10 @@ __global__ void hyst_carry_kernel(const uint16_t* __restrict__ block_summary, co
 // pass H3: resolve the state of every frame -> the activity byte the decode passes consume
 __global__ void __launch_bounds__(kFastThreads) hyst_resolve_kernel(
     const uint16_t* __restrict__ codes, const long long* __restrict__ file_offsets,
-    const int* __restrict__ block_offsets, int n_files, int C, const uint8_t* __restrict__ carry_in,
-    uint8_t* __restrict__ bits) {
+    const int* __restrict__ block_offsets, const int* __restrict__ block_file, int C,
+    const uint8_t* __restrict__ carry_in, uint8_t* __restrict__ bits) {
   __shared__ SetVal s_w[kFastThreads / 32];
-  const int file = find_file(block_offsets, n_files, blockIdx.x);
+  const int file = __ldg(block_file + blockIdx.x);
   const int local_block = blockIdx.x - block_offsets[file];
   const long long f_begin = file_offsets[file], f_end = file_offsets[file + 1];
   const long long frame0 = f_begin + (long long)local_block * kFastBlock + threadIdx.x * kFastFrames;
@@ -661,7 +798,7 @@ __global__ void __launch_bounds__(kPostThreads) filter_intervals_kernel(const in
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct DecodeLayout {
-  size_t bits_off, starts_off, ends_off, file_off, block_off, codes_off, summary_off, carry_off, total;
+  size_t bits_off, starts_off, ends_off, file_off, block_off, codes_off, summary_off, carry_off, bfile_off, tiles_off, total;
   long long n_count;
 };
 
@@ -678,6 +815,8 @@ static DecodeLayout decode_layout(long long n_frames, int n_files, int C) {
   L.codes_off = off; off = align_up(off + sizeof(uint16_t) * (size_t)n_frames, 256);
   L.summary_off = off; off = align_up(off + sizeof(uint16_t) * (size_t)max_blocks, 256);
   L.carry_off = off; off = align_up(off + (size_t)max_blocks, 256);
+  L.bfile_off = off; off = align_up(off + sizeof(int) * (size_t)max_blocks, 256);
+  L.tiles_off = off; off = align_up(off + 2 * sizeof(int) * (size_t)(L.n_count / kScanTile + 2), 256);
   L.total = off;
   return L;
 }
@@ -765,6 +904,9 @@ static int decode_impl(const float* logits, const int64_t* file_offsets, int n_f
   static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
   SEGMA_CUDA_OK(cudaMemcpyAsync(d_file, file_offsets, sizeof(int64_t) * (n_files + 1), cudaMemcpyHostToDevice, st));
   SEGMA_CUDA_OK(cudaMemcpyAsync(d_block, block_offsets.data(), sizeof(int) * (n_files + 1), cudaMemcpyHostToDevice, st));
+  int* d_bfile = reinterpret_cast<int*>(ws + L.bfile_off);
+  int* d_tiles = reinterpret_cast<int*>(ws + L.tiles_off);
+  block_file_kernel<<<ceil_div(total_blocks, 256), 256, 0, st>>>(d_block, n_files, total_blocks, d_bfile);
   // pageable-source async copies are staged before returning, so block_offsets may go out of scope
   const bool fast = n_labels <= 8;  // one activity byte per frame, 4 frames per thread
   static_assert(kFastBlock == kDecodeBlock, "both paths tile files in blocks of 1024 frames");
@@ -780,32 +922,40 @@ static int decode_impl(const float* logits, const int64_t* file_offsets, int n_f
     uint16_t* codes = reinterpret_cast<uint16_t*>(ws + L.codes_off);
     uint16_t* summary = reinterpret_cast<uint16_t*>(ws + L.summary_off);
     uint8_t* carry = reinterpret_cast<uint8_t*>(ws + L.carry_off);
-    hyst_codes_kernel<<<total_blocks, kFastThreads, 0, st>>>(logits, d_file, d_block, n_files, hp, codes, summary);
+    hyst_codes_kernel<<<total_blocks, kFastThreads, 0, st>>>(logits, d_file, d_block, d_bfile, hp, codes, summary);
     rc = launch_status("hyst_codes_kernel");
     if (rc != SEGMA_OK) return rc;
     hyst_carry_kernel<<<ceil_div(n_files, 128), 128, 0, st>>>(summary, d_block, n_files, carry);
     rc = launch_status("hyst_carry_kernel");
     if (rc != SEGMA_OK) return rc;
-    hyst_resolve_kernel<<<total_blocks, kFastThreads, 0, st>>>(codes, d_file, d_block, n_files, n_labels, carry,
+    hyst_resolve_kernel<<<total_blocks, kFastThreads, 0, st>>>(codes, d_file, d_block, d_bfile, n_labels, carry,
                                                              reinterpret_cast<uint8_t*>(bits));
     rc = launch_status("hyst_resolve_kernel");
     if (rc != SEGMA_OK) return rc;
     decode_fast_kernel<2><<<total_blocks, kFastThreads, 0, st>>>(
-        logits, d_file, d_block, n_files, p, reinterpret_cast<uint8_t*>(bits), starts, ends, table, capacity);
+        logits, d_file, d_block, d_bfile, p, reinterpret_cast<uint8_t*>(bits), starts, ends, table, capacity);
   } else if (fast) {
     decode_fast_kernel<0><<<total_blocks, kFastThreads, 0, st>>>(
-        logits, d_file, d_block, n_files, p, reinterpret_cast<uint8_t*>(bits), starts, ends, table, capacity);
+        logits, d_file, d_block, d_bfile, p, reinterpret_cast<uint8_t*>(bits), starts, ends, table, capacity);
   } else {
     decode_count_kernel<<<total_blocks, kDecodeBlock, 0, st>>>(logits, d_file, d_block, n_files, p, bits, starts, ends);
   }
   rc = launch_status("decode count pass");
   if (rc != SEGMA_OK) return rc;
-  decode_scan_kernel<<<1, kScanThreads, 0, st>>>(starts, ends, (long long)total_blocks * n_labels, count);
-  rc = launch_status("decode_scan_kernel");
+  const long long n_counts = (long long)total_blocks * n_labels;
+  if (n_counts <= 4 * kScanTile) {
+    decode_scan_kernel<<<1, kScanThreads, 0, st>>>(starts, ends, n_counts, count);
+  } else {  // long inputs: scan in parallel
+    const int n_tiles = (int)ceil_div_ll(n_counts, kScanTile);
+    scan_tile_sums_kernel<<<n_tiles, kScanThreads, 0, st>>>(starts, ends, n_counts, d_tiles);
+    scan_tile_offsets_kernel<<<1, kScanThreads, 0, st>>>(d_tiles, n_tiles, count);
+    scan_tiles_kernel<<<n_tiles, kScanThreads, 0, st>>>(starts, ends, n_counts, d_tiles);
+  }
+  rc = launch_status("decode scan pass");
   if (rc != SEGMA_OK) return rc;
   if (fast) {
     decode_fast_kernel<1><<<total_blocks, kFastThreads, 0, st>>>(
-        logits, d_file, d_block, n_files, p, reinterpret_cast<uint8_t*>(bits), starts, ends, table, capacity);
+        logits, d_file, d_block, d_bfile, p, reinterpret_cast<uint8_t*>(bits), starts, ends, table, capacity);
   } else {
     decode_write_kernel<<<total_blocks, kDecodeBlock, 0, st>>>(bits, d_file, d_block, n_files, n_labels, starts, ends,
                                                                table, capacity);

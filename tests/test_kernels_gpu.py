@@ -414,3 +414,20 @@ def test_merge_semantics_of_the_reference_interval_struct(cuda):
     assert run([(0, 0, 0, 10), (0, 0, 15, 25)]) == [(0, 0, 0, 10), (0, 0, 15, 25)]
     assert run([(0, 0, 0, 10), (0, 1, 10, 20)]) == [(0, 0, 0, 10), (0, 1, 10, 20)]
     assert run([(0, 0, 0, 10), (1, 0, 10, 20)]) == [(0, 0, 0, 10), (1, 0, 10, 20)]
+
+
+def test_decode_long_input_parallel_scan(cuda):
+    """More than 32 768 (block, label) counters: the scan of pass 2 runs as three parallel kernels."""
+    n, C = 9_000_000, 4
+    g = torch.Generator().manual_seed(7)
+    base = torch.randn((n // 500 + 1, C), generator=g).repeat_interleave(500, dim=0)[:n]
+    logits = (base + 0.02 * torch.randn((n, C), generator=g)).contiguous()
+    offs = [0, 3_000_001, 3_000_001, 7_654_321, n]
+    cuts = [0.1, -0.2, 0.0, 0.3]
+    table = ops.decode_intervals(logits.to(cuda), cuts, file_offsets=offs, mode=ops.DECODE_LOGIT).cpu().numpy()
+    rows = []
+    for f, (a, b) in enumerate(zip(offs[:-1], offs[1:])):
+        mask = (logits[a:b] > torch.tensor(cuts)).numpy()
+        t = O.interval_table(mask, C)
+        rows.append(np.concatenate([np.full((t.shape[0], 1), f), t], axis=1))
+    assert np.array_equal(table, np.concatenate(rows))

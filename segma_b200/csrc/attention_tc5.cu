@@ -6,38 +6,107 @@
 // (site-packages/torchaudio/models/wav2vec2/components.py:305-307; 199 positions).
 //
 // One CTA owns 128 query rows of one (window, head) and walks the keys in tiles of 64; four CTAs are
-// resident per SM (48 KB of shared memory, 128 TMEM columns each) so that one CTA's softmax (MUFU-bound)
-// overlaps the others' MMAs and barrier hand-offs.  Per key tile:
-//   warp 0      TMA: Q once, then the K and V tiles (64 x 64, 128B swizzle; single buffers refilled as soon as the
-//               MMA that read them retires), straight from the
+// resident per SM (48 KB of shared memory, 128 TMEM columns each) so that one CTA's softmax overlaps the others'
+// MMAs and barrier hand-offs.  Per key tile:
+//   warp 0      TMA: Q once, then the K and V tiles (64 x 64, 128B swizzle, two buffers each), straight from the
 //               fused QKV activation through 3-D tensor maps (column block selects q / k / v and the head)
-//   warp 1      one lane issues  O += P_{j-1} V_{j-1}  (M128 N64 K64, V as an MN-major B operand) and
-//               S = Q K_j^T (M128 N64 K64) back to back, then one tcgen05.commit
-//   warps 2-5   one thread per query row: a single tcgen05.ld of its 64 scores, exp2 against the running
-//               reference max (the tile is redone, and O/l rescaled, only when a score exceeds it by more than
-//               2^8), P -> fp16 into the swizzled A-operand tile
-// Scores, probabilities and the output accumulator never touch HBM.
+//   warp 1      one lane issues  O += P_{j-1} V_{j-1}  (M128 N64 K64; P read from tensor memory, V as an MN-major
+//               shared-memory B operand) and  S = Q K_j^T (M128 N64 K64) back to back, then one tcgen05.commit
+//   warps 2-5   one thread per query row, 32 keys at a time: tcgen05.ld of the scores, exp2 against the running
+//               reference max (rescaling O, l and the half tile already written only when a score exceeds it by
+//               more than 2^8), P -> fp16 pairs stored with tcgen05.st over the score columns just consumed
+// Scores and probabilities never leave tensor memory / registers; shared memory only carries Q, K and V, which is
+// what bounds the M128 N64 MMAs (A and B operand fetch), so P as a shared-memory operand would cost a third more.
 #include "common.cuh"
 
 namespace segma {
 
 constexpr int kAtQ = 128;     // queries per CTA
-constexpr int kAtK = 64;      // keys per tile
+constexpr int kAtK = 64;      // keys per K / V tile (one TMA box)
+constexpr int kAtC = 32;      // keys per score chunk (one MMA, one softmax step)
 constexpr int kAtD = 64;      // head dim
 constexpr int kAtThreads = 192;
 constexpr int kQBytes = kAtQ * 128;   // 128 rows x 64 fp16
 constexpr int kKVBytes = kAtK * 128;  // 64 rows x 64 fp16
-// Q + K + V + P + barriers = 49 280 B: four CTAs per SM (their 4 x 128 TMEM columns fill the SM's 512).  K and V
-// are single-buffered with their own barriers: K_{j+1} is fetched as soon as S_j = Q K_j^T has retired and
-// V_{j+1} as soon as O += P_j V_j has, both behind the softmax of the tile in flight.  No alignment slack: the
-// dynamic shared-memory window of a kernel without static shared memory starts 1024-byte aligned (checked).
-constexpr int kAtSmem = kQBytes + 2 * kKVBytes + kQBytes + 128;
-constexpr uint32_t kTmemColsAttn = 128;    // S: columns [0, 64), O: columns [64, 128)
-constexpr float kRescaleThreshold = 8.0f;  // log2 units
+// Q + 2 K + 2 V + barriers = 49 280 B: four CTAs per SM (their 4 x 128 TMEM columns fill the SM's 512).  No
+// alignment slack: the dynamic shared-memory window of a kernel without static shared memory starts 1024-byte
+// aligned (checked).
+constexpr int kAtSmem = kQBytes + 4 * kKVBytes + 128;
+// TMEM: two score buffers of 32 columns (even / odd chunks) and the 64 output columns.  The probabilities of a
+// chunk (fp16 pairs, 16 columns) overwrite the start of its own score buffer.
+constexpr uint32_t kTmemColsAttn = 128;
 constexpr uint32_t kWaitHintNs = 2000;     // suspend hint of the mbarrier waits (a completed phase wakes the thread)
+constexpr float kLog2e = 1.4426950408889634f;
 
-// kBias: scores get the WavLM gated relative-position term gate[b,h,i] * pos_bias[h,i,j] added before the softmax
+// Probabilities of one 32-key chunk of a row: pk = fp16 pairs, psum += their fp32 sum, pmax2 tracks the largest.
+//   kBias      scores get the WavLM gated relative-position term g2 * pbk[key] (log2 units) added
+//   kPolyMask  bit (4 q + e) set = key pair e of the q-th group of 8 keys takes its exponentials from ex2_poly_pair
+//              (FMA pipe) instead of the MUFU
+//   kMasked    only the first nv keys exist (last tile of a row)
+template <bool kBias, uint32_t kPolyMask, bool kMasked>
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&sv)[32], float m_run, float g2, const float* pbk,
+                                              int nv, uint32_t (&pk)[16], float& psum, __half2& pmax2) {
+  const uint64_t k2 = f2_pack(kLog2e, kLog2e);
+  const uint64_t nm2 = f2_pack(-m_run, -m_run);
+  uint64_t psum2 = f2_pack(0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float off[8];
+    if (kBias) {
+      if (!kMasked) {  // rows of the bias table are padded to a multiple of 4 floats
+        const float4 a = __ldg(reinterpret_cast<const float4*>(pbk + q * 8));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(pbk + q * 8) + 1);
+        off[0] = a.x; off[1] = a.y; off[2] = a.z; off[3] = a.w;
+        off[4] = b.x; off[5] = b.y; off[6] = b.z; off[7] = b.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) off[i] = (q * 8 + i < nv) ? __ldg(pbk + q * 8 + i) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = q * 8 + 2 * e;
+      const uint64_t off2 = kBias ? f2_pack(fmaf(off[2 * e], g2, -m_run), fmaf(off[2 * e + 1], g2, -m_run)) : nm2;
+      const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), k2, off2);
+      float p0, p1;
+      if ((kPolyMask >> (4 * q + e)) & 1u) {
+        ex2_poly_pair(x2, p0, p1);
+      } else {
+        float x0, x1;
+        f2_unpack(x2, x0, x1);
+        p0 = ex2_approx(x0);
+        p1 = ex2_approx(x1);
+      }
+      if (kMasked) {
+        if (i >= nv) p0 = 0.f;
+        if (i + 1 >= nv) p1 = 0.f;
+      }
+      psum2 = f2_add(psum2, f2_pack(p0, p1));
+      const __half2 h2 = __floats2half2_rn(p0, p1);
+      pmax2 = __hmax2(pmax2, h2);
+      pk[q * 4 + e] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+  }
+  float s0, s1;
+  f2_unpack(psum2, s0, s1);
+  psum += s0 + s1;
+}
+
+// largest score of the chunk in log2 units relative to `ref`, keys >= nv ignored
 template <bool kBias>
+__device__ __forceinline__ float chunk_max(const uint32_t (&sv)[32], float ref, float g2, const float* pbk, int nv) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (i < nv) {
+      float y = fmaf(__uint_as_float(sv[i]), kLog2e, -ref);
+      if (kBias) y = fmaf(__ldg(pbk + i), g2, y);
+      mx = fmaxf(mx, y);
+    }
+  return mx;
+}
+
+template <bool kBias, uint32_t kPolyMask>
 __global__ void __launch_bounds__(kAtThreads, 4)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, int T,
                      int n_heads, int n_query, const float* __restrict__ gate, const float* __restrict__ pos_bias,
@@ -45,18 +114,19 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   extern __shared__ __align__(1024) unsigned char smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzled operand tiles need 1024-byte alignment
   unsigned char* s_q = smem;
-  unsigned char* s_k = smem + kQBytes;
-  unsigned char* s_v = smem + kQBytes + kKVBytes;
-  unsigned char* s_p = smem + kQBytes + 2 * kKVBytes;  // 128 rows x 64 keys
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + kQBytes);
+  unsigned char* s_k = smem + kQBytes;                 // two K tiles
+  unsigned char* s_v = smem + kQBytes + 2 * kKVBytes;  // two V tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kQBytes + 4 * kKVBytes);
   uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;
-  uint64_t* v_full = bars + 2;
-  uint64_t* k_empty = bars + 3;
-  uint64_t* v_empty = bars + 4;
-  uint64_t* mma_done = bars + 5;
-  uint64_t* p_ready = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* k_full = bars + 1;   // [2] K tile landed
+  uint64_t* v_full = bars + 3;   // [2]
+  uint64_t* k_empty = bars + 5;  // [2] both score chunks of the tile have retired
+  uint64_t* v_empty = bars + 7;  // [2] both P V chunks of the tile have retired
+  uint64_t* s_full = bars + 9;   // [2] scores of a chunk are in their buffer
+  uint64_t* p_ready = bars + 11; // [2] probabilities of a chunk are in their buffer (4 warps arrive)
+  uint64_t* pv_done = bars + 13; // one phase per retired P V chunk
+  uint64_t* o_final = bars + 14; // the last P V chunk has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int q0 = blockIdx.x * kAtQ;
@@ -64,17 +134,12 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   const int b = blockIdx.z;
   const int d = n_heads * kAtD;
   const int n_kt = ceil_div(T, kAtK);
+  const int n_ch = ceil_div(T, kAtC);  // chunks that hold at least one key
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_kv);
-    mbar_init(q_full, 1);
-    mbar_init(k_full, 1);
-    mbar_init(v_full, 1);
-    mbar_init(k_empty, 1);
-    mbar_init(v_empty, 1);
-    mbar_init(mma_done, 1);
-    mbar_init(p_ready, 4);
+    for (int i = 0; i < 15; ++i) mbar_init(bars + i, (i == 11 || i == 12) ? 4 : 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -85,56 +150,58 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   __syncthreads();
   tc5_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;
-  const uint32_t tmem_o = tmem_base + kAtK;
+  const uint32_t tmem_s = tmem_base;             // two score / probability buffers of 32 columns
+  const uint32_t tmem_o = tmem_base + 2 * kAtC;  // 64 output columns
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, kQBytes);
       tma_load_3d(s_q, &map_q, q_full, h * kAtD, q0, b);
       for (int j = 0; j < n_kt; ++j) {
-        mbar_wait_suspend(k_empty, (j & 1) ^ 1, kWaitHintNs);
-        mbar_arrive_expect_tx(k_full, kKVBytes);
-        tma_load_3d(s_k, &map_kv, k_full, d + h * kAtD, j * kAtK, b);
-        mbar_wait_suspend(v_empty, (j & 1) ^ 1, kWaitHintNs);
-        mbar_arrive_expect_tx(v_full, kKVBytes);
-        tma_load_3d(s_v, &map_kv, v_full, 2 * d + h * kAtD, j * kAtK, b);
+        const int s = j & 1, ph = (j >> 1) & 1;
+        mbar_wait_suspend(k_empty + s, ph ^ 1, kWaitHintNs);
+        mbar_arrive_expect_tx(k_full + s, kKVBytes);
+        tma_load_3d(s_k + s * kKVBytes, &map_kv, k_full + s, d + h * kAtD, j * kAtK, b);
+        mbar_wait_suspend(v_empty + s, ph ^ 1, kWaitHintNs);
+        mbar_arrive_expect_tx(v_full + s, kKVBytes);
+        tma_load_3d(s_v + s * kKVBytes, &map_kv, v_full + s, 2 * d + h * kAtD, j * kAtK, b);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(kAtQ, kAtK, 0, 0);  // S = Q K^T, both K-major
+      constexpr uint32_t idesc_s = umma_idesc_f16(kAtQ, kAtC, 0, 0);  // S = Q K^T, both K-major, 32 keys
       constexpr uint32_t idesc_o = umma_idesc_f16(kAtQ, kAtD, 0, 1);  // O += P V, V is MN-major
       const uint32_t q_addr = smem_u32(s_q);
-      const uint32_t p_addr = smem_u32(s_p);
+      // scores of chunk t into buffer t & 1
+      auto issue_scores = [&](int t) {
+        const int tile = t >> 1, half = t & 1, s = tile & 1;
+        if (half == 0) mbar_wait_suspend(k_full + s, (tile >> 1) & 1, kWaitHintNs);
+        tc5_fence_after();
+        const uint32_t k_addr = smem_u32(s_k + s * kKVBytes) + half * (kAtC * 128);
+#pragma unroll
+        for (int ks = 0; ks < kAtD / 16; ++ks)
+          tc5_mma_f16(tmem_s + half * kAtC, umma_desc_k_sw128(q_addr + ks * 32), umma_desc_k_sw128(k_addr + ks * 32),
+                      idesc_s, ks > 0 ? 1u : 0u);
+        if (half == 1 || t == n_ch - 1) tc5_commit(k_empty + s);  // the K tile is free once its last chunk retires
+        tc5_commit(s_full + half);
+      };
       mbar_wait_suspend(q_full, 0, kWaitHintNs);
-      for (int j = 0; j <= n_kt; ++j) {
-        if (j > 0) {
-          mbar_wait_suspend(v_full, (j - 1) & 1, kWaitHintNs);
-          mbar_wait_suspend(p_ready, (j - 1) & 1, kWaitHintNs);
-          tc5_fence_after();
-          const uint32_t v_addr = smem_u32(s_v);
+      issue_scores(0);
+      if (n_ch > 1) issue_scores(1);
+      for (int t = 0; t < n_ch; ++t) {
+        const int tile = t >> 1, half = t & 1, s = tile & 1;
+        if (half == 0) mbar_wait_suspend(v_full + s, (tile >> 1) & 1, kWaitHintNs);
+        mbar_wait_suspend(p_ready + half, (t >> 1) & 1, kWaitHintNs);
+        tc5_fence_after();
+        const uint32_t v_addr = smem_u32(s_v + s * kKVBytes) + half * (kAtC * 128);
 #pragma unroll
-          for (int ks = 0; ks < kAtK / 16; ++ks) {
-            const uint64_t da = umma_desc_k_sw128(p_addr + ks * 32);
-            const uint64_t db = umma_desc_mn_sw128(v_addr + ks * 2048, kKVBytes);
-            tc5_mma_f16(tmem_o, da, db, idesc_o, (j > 1 || ks > 0) ? 1u : 0u);
-          }
-          tc5_commit(v_empty);
-        }
-        if (j < n_kt) {
-          mbar_wait_suspend(k_full, j & 1, kWaitHintNs);
-          tc5_fence_after();
-          const uint32_t k_addr = smem_u32(s_k);
-#pragma unroll
-          for (int ks = 0; ks < kAtD / 16; ++ks) {
-            const uint64_t da = umma_desc_k_sw128(q_addr + ks * 32);
-            const uint64_t db = umma_desc_k_sw128(k_addr + ks * 32);
-            tc5_mma_f16(tmem_s, da, db, idesc_s, ks > 0 ? 1u : 0u);
-          }
-          tc5_commit(k_empty);  // K_j is free once S_j has retired
-        }
-        tc5_commit(mma_done);
+        for (int ks = 0; ks < kAtC / 16; ++ks)  // 16 keys = 8 columns of fp16 pairs
+          tc5_mma_f16_ts(tmem_o, tmem_s + half * kAtC + ks * 8, umma_desc_mn_sw128(v_addr + ks * 2048, kKVBytes),
+                         idesc_o, (t > 0 || ks > 0) ? 1u : 0u);
+        if (half == 1 || t == n_ch - 1) tc5_commit(v_empty + s);
+        tc5_commit(pv_done);
+        if (t == n_ch - 1) tc5_commit(o_final);
+        if (t + 2 < n_ch) issue_scores(t + 2);  // same buffer: ordered behind the P V that reads it
       }
     }
   } else {
@@ -142,8 +209,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const int quad = warp & 3;
     const int row = quad * 32 + lane;           // row inside the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    const float kLog2e = 1.4426950408889634f;
-    float m_run = 0.f;  // reference max, log2 units (set from the first tile)
+    float m_run = 0.f;  // reference max, log2 units (set from the first chunk)
     float l_run = 0.f;
     // gated relative-position bias of this query row (log2 units): g2 * pb[key]
     float g2 = 0.f;
@@ -153,140 +219,60 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       g2 = __ldg(gate + ((long long)b * n_heads + h) * T + qr) * kLog2e;
       pb = pos_bias + ((long long)h * T + qr) * pb_ld;
     }
-    unsigned char* p_row = s_p + row * 128;
-    const int sw = row & 7;
-    for (int j = 0; j < n_kt; ++j) {
-      mbar_wait_suspend(mma_done, j & 1, kWaitHintNs);
-      tc5_fence_after();
-      const int n_valid = min(kAtK, T - j * kAtK);  // keys of this tile that exist
-      if (j == 0) {  // the first tile fixes the reference max
-        float mx = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t sv[32];
-          tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < n_valid) {
-              float y = __uint_as_float(sv[i]) * kLog2e;
-              if (kBias) y = fmaf(__ldg(pb + c * 32 + i), g2, y);
-              mx = fmaxf(mx, y);
-            }
-        }
-        m_run = mx;
-      }
+    for (int t = 0; t < n_ch; ++t) {
+      const int half = t & 1;
+      const uint32_t buf = tmem_s + lane_addr + half * kAtC;
+      mbar_wait_suspend(s_full + half, (t >> 1) & 1, kWaitHintNs);
+      tc5_fence_after();
+      const int nv = min(kAtC, T - t * kAtC);  // keys of this chunk that exist (block-uniform)
+      const float* pbk = kBias ? pb + t * kAtC : nullptr;
+      uint32_t sv[32];
+      tmem_ld_32x32(buf, sv);
+      tmem_ld_wait();
+      if (t == 0) m_run = chunk_max<kBias>(sv, 0.f, g2, pbk, nv);  // the first chunk fixes the reference
+      uint32_t pk[16];
       float psum;
       while (true) {
         // running max of the fp16 probabilities (packed pairs): > 2^8 (or inf) means a score exceeded the
         // reference max by more than the threshold
         __half2 pmax2 = __floats2half2_rn(0.f, 0.f);
         psum = 0.f;
-        if (n_valid == kAtK) {  // full tile (block-uniform): no key masking
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t sv[32];
-            tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
-            tmem_ld_wait();
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint32_t pk[4];
-#pragma unroll
-              float4 pb0 = make_float4(0.f, 0.f, 0.f, 0.f), pb1 = pb0;
-              if (kBias) {  // 8 consecutive keys of this row's bias (rows are padded to a multiple of 4 floats)
-                const float4* src = reinterpret_cast<const float4*>(pb + j * kAtK + c * 32 + q * 8);
-                pb0 = __ldg(src);
-                pb1 = __ldg(src + 1);
-              }
-              const float off[8] = {pb0.x, pb0.y, pb0.z, pb0.w, pb1.x, pb1.y, pb1.z, pb1.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float o0 = kBias ? fmaf(off[2 * e], g2, -m_run) : -m_run;
-                const float o1 = kBias ? fmaf(off[2 * e + 1], g2, -m_run) : -m_run;
-                const float p0 = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * e]), kLog2e, o0));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * e + 1]), kLog2e, o1));
-                psum += p0 + p1;
-                const __half2 h2 = __floats2half2_rn(p0, p1);
-                pmax2 = __hmax2(pmax2, h2);
-                pk[e] = *reinterpret_cast<const uint32_t*>(&h2);
-              }
-              *reinterpret_cast<uint4*>(p_row + (((c * 4 + q) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
-          }
-        } else {
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t sv[32];
-            tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
-            tmem_ld_wait();
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint32_t pk[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int i = c * 32 + q * 8 + 2 * e;
-                float o0 = -m_run, o1 = -m_run;
-                if (kBias) {
-                  if (i < n_valid) o0 = fmaf(__ldg(pb + j * kAtK + i), g2, -m_run);
-                  if (i + 1 < n_valid) o1 = fmaf(__ldg(pb + j * kAtK + i + 1), g2, -m_run);
-                }
-                float p0 = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * e]), kLog2e, o0));
-                float p1 = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * e + 1]), kLog2e, o1));
-                if (i >= n_valid) p0 = 0.f;
-                if (i + 1 >= n_valid) p1 = 0.f;
-                psum += p0 + p1;
-                const __half2 h2 = __floats2half2_rn(p0, p1);
-                pmax2 = __hmax2(pmax2, h2);
-                pk[e] = *reinterpret_cast<const uint32_t*>(&h2);
-              }
-              *reinterpret_cast<uint4*>(p_row + (((c * 4 + q) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
-          }
-        }
+        if (nv == kAtC) softmax_chunk<kBias, kPolyMask, false>(sv, m_run, g2, pbk, kAtC, pk, psum, pmax2);
+        else softmax_chunk<kBias, 0u, true>(sv, m_run, g2, pbk, nv, pk, psum, pmax2);
         const float pmax = fmaxf(__low2float(pmax2), __high2float(pmax2));
         // tcgen05.ld/st are warp-collective: the rescale decision is taken per warp, each lane with its own factor
-        if (!__any_sync(0xffffffffu, pmax > 256.0f)) break;   // 256 = 2^kRescaleThreshold
-        // how far this row's scores exceed the reference (log2 units): log2 of its largest probability,
-        // recomputed exactly from the scores since the fp16 probability may have overflowed
-        float ymax = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t sv[32];
-          tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < n_valid) {
-              float y = fmaf(__uint_as_float(sv[i]), kLog2e, -m_run);
-              if (kBias) y = fmaf(__ldg(pb + j * kAtK + c * 32 + i), g2, y);
-              ymax = fmaxf(ymax, y);
-            }
-        }
-        const float grow = fmaxf(ymax, 0.f);
+        if (!__any_sync(0xffffffffu, pmax > 256.0f)) break;
+        // how far this row's scores exceed the reference (log2 units), exactly, from the scores still in registers
+        const float grow = fmaxf(chunk_max<kBias>(sv, m_run, g2, pbk, nv), 0.f);
         const float alpha = ex2_approx(-grow);
         m_run += grow;
         l_run *= alpha;
-        if (j > 0) {  // O holds contributions of earlier tiles: rescale it in place, then redo this tile
+        if (t > 0) {  // O holds earlier chunks: wait until the last of them has retired, rescale in place
+          // (chunk t - 2 retired before these scores did, so the barrier is in phase t - 1 or t: parity is unambiguous)
+          mbar_wait(pv_done, (t - 1) & 1);
+          tc5_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
+          for (int cc = 0; cc < 2; ++cc) {
             uint32_t ov[32];
-            tmem_ld_32x32(tmem_o + lane_addr + c * 32, ov);
+            tmem_ld_32x32(tmem_o + lane_addr + cc * 32, ov);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-            tmem_st_32x32(tmem_o + lane_addr + c * 32, ov);
+            tmem_st_32x32(tmem_o + lane_addr + cc * 32, ov);
           }
           tmem_st_wait();
         }
       }
       l_run += psum;
-      fence_proxy_async_smem();
+      tmem_st_32x16(buf, pk);  // over the score columns this thread has consumed
+      tmem_st_wait();
       tc5_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready);
+      if (lane == 0) mbar_arrive(p_ready + half);
     }
     // epilogue: wait for the last P V, normalise, store
-    mbar_wait(mma_done, n_kt & 1);
+    mbar_wait(o_final, 0);
     tc5_fence_after();
     const int q_row = q0 + row;
     const float inv_l = 1.0f / l_run;
@@ -332,18 +318,26 @@ int launch_attention_tc5(const void* qkv, int n_windows, int T, int n_heads, int
   rc = make_f16_map(&map_kv, qkv, 3, dims, strides, kAtK);
   if (rc != SEGMA_OK) return rc;
   static bool attr_set = false;
+  // SEGMA_ATTN_POLY=1 moves a quarter of the exponentials from the MUFU to the FMA pipe (ex2_poly_pair).  Measured
+  // slower on B200 (0.370 vs 0.333 ms for 32 windows): the softmax warps are latency-bound, not MUFU-bound, so the
+  // longer instruction stream costs more than the freed MUFU slots give back.  Kept as a switch for re-measurement.
+  static bool poly = false;
   if (!attr_set) {
-    SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
-    SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<false, 0x0000u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<false, 0x2222u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<true, 0u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    const char* env = getenv("SEGMA_ATTN_POLY");
+    poly = env && atoi(env) != 0;
     attr_set = true;
   }
   dim3 grid(ceil_div(n_query, kAtQ), n_heads, n_windows);
-  if (pos_bias)
-    attention_tc5_kernel<true><<<grid, kAtThreads, kAtSmem, st>>>(map_q, map_kv, T, n_heads, n_query, gate, pos_bias,
-                                                                 pb_ld, static_cast<__half*>(out));
-  else
-    attention_tc5_kernel<false><<<grid, kAtThreads, kAtSmem, st>>>(map_q, map_kv, T, n_heads, n_query, nullptr, nullptr,
-                                                                  0, static_cast<__half*>(out));
+#define SEGMA_ATTN_LAUNCH(BIAS, MASK)                                                                             \
+  attention_tc5_kernel<BIAS, MASK><<<grid, kAtThreads, kAtSmem, st>>>(map_q, map_kv, T, n_heads, n_query, gate,   \
+                                                                       pos_bias, pb_ld, static_cast<__half*>(out))
+  if (pos_bias) SEGMA_ATTN_LAUNCH(true, 0u);
+  else if (poly) SEGMA_ATTN_LAUNCH(false, 0x2222u);
+  else SEGMA_ATTN_LAUNCH(false, 0x0000u);
+#undef SEGMA_ATTN_LAUNCH
   return launch_status("attention_tc5_kernel");
 }
 

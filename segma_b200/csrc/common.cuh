@@ -75,6 +75,49 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ---- packed fp32 pairs (FFMA2 / FADD2 on sm_100: two fp32 lanes per issue slot) ----------------------
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// 2^x for a pair on the FMA pipe instead of the MUFU: round-to-nearest split x = n + f, |f| <= 0.5, a degree-4
+// minimax polynomial for 2^f (relative error 2.7e-6) and n added into the exponent field.  x is clamped to
+// [-126, 126]: the result stays a finite non-negative float, and anything above 2^16 still overflows fp16.
+__device__ __forceinline__ void ex2_poly_pair(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  f2_unpack(x2, x0, x1);
+  x0 = fminf(fmaxf(x0, -126.f), 126.f);
+  x1 = fminf(fmaxf(x1, -126.f), 126.f);
+  const uint64_t xc = f2_pack(x0, x1);
+  const uint64_t t = f2_add(xc, f2_pack(12582912.f, 12582912.f));     // 1.5 * 2^23: low mantissa bits = n
+  const uint64_t r = f2_add(t, f2_pack(-12582912.f, -12582912.f));    // n as a float
+  const uint64_t f = f2_fma(r, f2_pack(-1.f, -1.f), xc);
+  uint64_t y = f2_fma(f2_pack(0.009570102207362652f, 0.009570102207362652f), f,
+                      f2_pack(0.05591785907745361f, 0.05591785907745361f));
+  y = f2_fma(y, f, f2_pack(0.240247443318367f, 0.240247443318367f));
+  y = f2_fma(y, f, f2_pack(0.6931217908859253f, 0.6931217908859253f));
+  y = f2_fma(y, f, f2_pack(0.9999992847442627f, 0.9999992847442627f));
+  float y0, y1, t0, t1;
+  f2_unpack(y, y0, y1);
+  f2_unpack(t, t0, t1);
+  p0 = __int_as_float(__float_as_int(y0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(y1) + (__float_as_int(t1) << 23));
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
   const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
@@ -250,6 +293,19 @@ __device__ __forceinline__ void tc5_mma_f16(uint32_t tmem_d, uint64_t desc_a, ui
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand is read from tensor memory (lane = row, 32-bit column c holds the
+// K elements 2c and 2c+1 of a 16-bit type), so it never passes through shared memory
+__device__ __forceinline__ void tc5_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // all previously issued MMAs of this thread arrive on `bar` when they retire
 __device__ __forceinline__ void tc5_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -292,6 +348,24 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
         "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 // make generic-proxy shared-memory writes visible to the async proxy (TMA / tcgen05 operand reads)

@@ -154,54 +154,75 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   const uint32_t tmem_o = tmem_base + 2 * kAtC;  // 64 output columns
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, kQBytes);
       tma_load_3d(s_q, &map_q, q_full, h * kAtD, q0, b);
-      for (int j = 0; j < n_kt; ++j) {
-        const int s = j & 1, ph = (j >> 1) & 1;
-        mbar_wait_suspend(k_empty + s, ph ^ 1, kWaitHintNs);
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int j = 0; j < n_kt; ++j) {
+      const int s = j & 1, ph = (j >> 1) & 1;
+      mbar_wait_suspend(k_empty + s, ph ^ 1, kWaitHintNs);
+      if (elect_one()) {
         mbar_arrive_expect_tx(k_full + s, kKVBytes);
         tma_load_3d(s_k + s * kKVBytes, &map_kv, k_full + s, d + h * kAtD, j * kAtK, b);
-        mbar_wait_suspend(v_empty + s, ph ^ 1, kWaitHintNs);
+      }
+      __syncwarp();
+      mbar_wait_suspend(v_empty + s, ph ^ 1, kWaitHintNs);
+      if (elect_one()) {
         mbar_arrive_expect_tx(v_full + s, kKVBytes);
         tma_load_3d(s_v + s * kKVBytes, &map_kv, v_full + s, 2 * d + h * kAtD, j * kAtK, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(kAtQ, kAtC, 0, 0);  // S = Q K^T, both K-major, 32 keys
-      constexpr uint32_t idesc_o = umma_idesc_f16(kAtQ, kAtD, 0, 1);  // O += P V, V is MN-major
-      const uint32_t q_addr = smem_u32(s_q);
-      // scores of chunk t into buffer t & 1
-      auto issue_scores = [&](int t) {
-        const int tile = t >> 1, half = t & 1, s = tile & 1;
-        if (half == 0) mbar_wait_suspend(k_full + s, (tile >> 1) & 1, kWaitHintNs);
-        tc5_fence_after();
-        const uint32_t k_addr = smem_u32(s_k + s * kKVBytes) + half * (kAtC * 128);
+    // The whole warp walks the chunk loop converged (all lanes poll the barriers); one elected lane issues.
+    constexpr uint32_t idesc_s = umma_idesc_f16(kAtQ, kAtC, 0, 0);  // S = Q K^T, both K-major, 32 keys
+    constexpr uint32_t idesc_o = umma_idesc_f16(kAtQ, kAtD, 0, 1);  // O += P V, V is MN-major
+    // operand descriptors differ only in the start-address field (bytes >> 4): built once, then advanced by adds
+    const uint64_t q_desc = umma_desc_k_sw128(smem_u32(s_q));
+    const uint64_t k_desc = umma_desc_k_sw128(smem_u32(s_k));
+    const uint64_t v_desc = umma_desc_mn_sw128(smem_u32(s_v), kKVBytes);
+    // scores of chunk t into buffer t & 1; u = t mod 4 fixes the TMEM buffer and the K stage at compile time
+    auto issue_scores = [&](int t, int u) {
+      const int half = u & 1, s = (u >> 1) & 1;
+      if (half == 0) mbar_wait_suspend(k_full + s, (t >> 2) & 1, kWaitHintNs);
+      tc5_fence_after();
+      if (elect_one()) {
+        const uint64_t kd = k_desc + static_cast<uint32_t>((s * kKVBytes + half * (kAtC * 128)) >> 4);
 #pragma unroll
-        for (int ks = 0; ks < kAtD / 16; ++ks)
-          tc5_mma_f16(tmem_s + half * kAtC, umma_desc_k_sw128(q_addr + ks * 32), umma_desc_k_sw128(k_addr + ks * 32),
-                      idesc_s, ks > 0 ? 1u : 0u);
+        for (int ks = 0; ks < kAtD / 16; ++ks)  // 16 head-dim elements = 32 bytes along K
+          tc5_mma_f16(tmem_s + half * kAtC, q_desc + 2 * ks, kd + 2 * ks, idesc_s, ks > 0 ? 1u : 0u);
         if (half == 1 || t == n_ch - 1) tc5_commit(k_empty + s);  // the K tile is free once its last chunk retires
         tc5_commit(s_full + half);
-      };
-      mbar_wait_suspend(q_full, 0, kWaitHintNs);
-      issue_scores(0);
-      if (n_ch > 1) issue_scores(1);
-      for (int t = 0; t < n_ch; ++t) {
-        const int tile = t >> 1, half = t & 1, s = tile & 1;
-        if (half == 0) mbar_wait_suspend(v_full + s, (tile >> 1) & 1, kWaitHintNs);
+      }
+      __syncwarp();
+    };
+    mbar_wait_suspend(q_full, 0, kWaitHintNs);
+    issue_scores(0, 0);
+    if (n_ch > 1) issue_scores(1, 1);
+#pragma unroll 1
+    for (int t0 = 0; t0 < n_ch; t0 += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + u;
+        if (t >= n_ch) break;
+        const int half = u & 1, s = (u >> 1) & 1;
+        if (half == 0) mbar_wait_suspend(v_full + s, (t >> 2) & 1, kWaitHintNs);
         mbar_wait_suspend(p_ready + half, (t >> 1) & 1, kWaitHintNs);
         tc5_fence_after();
-        const uint32_t v_addr = smem_u32(s_v + s * kKVBytes) + half * (kAtC * 128);
+        if (elect_one()) {
+          const uint64_t vd = v_desc + static_cast<uint32_t>((s * kKVBytes + half * (kAtC * 128)) >> 4);
 #pragma unroll
-        for (int ks = 0; ks < kAtC / 16; ++ks)  // 16 keys = 8 columns of fp16 pairs
-          tc5_mma_f16_ts(tmem_o, tmem_s + half * kAtC + ks * 8, umma_desc_mn_sw128(v_addr + ks * 2048, kKVBytes),
-                         idesc_o, (t > 0 || ks > 0) ? 1u : 0u);
-        if (half == 1 || t == n_ch - 1) tc5_commit(v_empty + s);
-        tc5_commit(pv_done);
-        if (t == n_ch - 1) tc5_commit(o_final);
-        if (t + 2 < n_ch) issue_scores(t + 2);  // same buffer: ordered behind the P V that reads it
+          for (int ks = 0; ks < kAtC / 16; ++ks)  // 16 keys = 8 columns of fp16 pairs = 16 V rows of 128 bytes
+            tc5_mma_f16_ts(tmem_o, tmem_s + half * kAtC + ks * 8, vd + ks * (2048 >> 4), idesc_o,
+                           (t > 0 || ks > 0) ? 1u : 0u);
+          if (half == 1 || t == n_ch - 1) tc5_commit(v_empty + s);
+          tc5_commit(pv_done);
+          if (t == n_ch - 1) tc5_commit(o_final);
+        }
+        __syncwarp();
+        if (t + 2 < n_ch) issue_scores(t + 2, (u + 2) & 3);  // same buffer: ordered behind the P V that reads it
       }
     }
   } else {

@@ -137,6 +137,21 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// one lane of a converged warp (the same lane every time): issue point of TMA / tcgen05 instructions.  Keeping the
+// warp converged around it lets the compiler hold descriptors and barrier addresses in uniform registers; a
+// divergent `if (lane == 0)` region wraps every such instruction in an ELECT / vote loop instead.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

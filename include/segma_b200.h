@@ -156,6 +156,14 @@ SEGMA_API int segma_layernorm(const float* x, const float* gamma, const float* b
 SEGMA_API int segma_attention(const void* qkv, int n_windows, int T, int n_heads, int n_query, const float* gate,
                     const float* pos_bias, int pos_bias_ld, void* out, void* stream);
 
+/* The same attention when the position table is Toeplitz, as WavLM's bucketed relative-position bias is
+ * (site-packages/torchaudio/models/wav2vec2/wavlm_attention.py:85-139: the bucket depends on j - i only):
+ * bias[b,h,i,j] = gate[(b*H + h)*T + i] * rel_bias[h*(2T-1) + (j - i + T - 1)].  The kernel keeps the slice of the
+ * vector its 128 query rows need in shared memory instead of streaming T*T floats per head.  T <= 1024.
+ */
+SEGMA_API int segma_attention_rel(const void* qkv, int n_windows, int T, int n_heads, int n_query, const float* gate,
+                        const float* rel_bias, void* out, void* stream);
+
 /* fp32 -> fp16 copy of a (rows, cols) matrix with row strides. */
 SEGMA_API int segma_cast_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
 

@@ -60,6 +60,7 @@ SIGNATURES = {
     "segma_gemm_f16": (_i, [C.POINTER(GemmArgs), _vp]),
     "segma_layernorm": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _f, _f, _i, _i, _vp]),
     "segma_attention": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "segma_attention_rel": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "segma_cast_f16": (_i, [_vp, _i64, _vp, _i64, _i64, _i, _vp]),
     "segma_lstm_layer": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "segma_heads": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i64, _i, _vp]),

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __half* _
 }
 
 int launch_attention_tc5(const void* qkv, int n_windows, int T, int n_heads, int n_query, const float* gate,
-                         const float* pos_bias, int pb_ld, void* out, cudaStream_t st);
+                         const float* pos_bias, int pb_ld, int bias_mode, void* out, cudaStream_t st);
 
 }  // namespace segma
 
@@ -226,12 +226,22 @@ int segma_attention(const void* qkv, int n_windows, int T, int n_heads, int n_qu
   static const bool legacy = getenv("SEGMA_ATTN_LEGACY") != nullptr;
   const bool bias_ok = pos_bias == nullptr || (pos_bias_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(pos_bias) & 15) == 0);
   if (!legacy && bias_ok && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
-    return launch_attention_tc5(qkv, n_windows, T, n_heads, n_query, gate, pos_bias, pos_bias_ld, out,
+    return launch_attention_tc5(qkv, n_windows, T, n_heads, n_query, gate, pos_bias, pos_bias_ld, pos_bias ? 1 : 0, out,
                                 (cudaStream_t)stream);
   dim3 grid(ceil_div(n_query, kQTile), n_heads, n_windows);
   attention_kernel<<<grid, kAttnThreads, 0, (cudaStream_t)stream>>>(
       static_cast<const __half*>(qkv), T, n_heads, n_query, gate, pos_bias, pos_bias_ld, static_cast<__half*>(out));
   return launch_status("attention_kernel");
+}
+
+int segma_attention_rel(const void* qkv, int n_windows, int T, int n_heads, int n_query, const float* gate,
+                        const float* rel_bias, void* out, void* stream) {
+  SEGMA_REQUIRE(n_windows >= 0 && T > 0 && n_heads > 0 && n_query >= 0 && n_query <= T, "segma_attention_rel: bad shape");
+  if (n_windows == 0 || n_query == 0) return SEGMA_OK;
+  SEGMA_REQUIRE(qkv && out && gate && rel_bias, "segma_attention_rel: NULL buffer");
+  SEGMA_REQUIRE(n_heads <= 65535 && n_windows <= 65535, "segma_attention_rel: grid too large");
+  SEGMA_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0, "segma_attention_rel: qkv must be 16-byte aligned");
+  return launch_attention_tc5(qkv, n_windows, T, n_heads, n_query, gate, rel_bias, 0, 2, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -13,8 +13,7 @@
 //   warp 1      one lane issues  O += P_{j-1} V_{j-1}  (M128 N64 K64; P read from tensor memory, V as an MN-major
 //               shared-memory B operand) and  S = Q K_j^T (M128 N64 K64) back to back, then one tcgen05.commit
 //   warps 2-5   one thread per query row, 32 keys at a time: tcgen05.ld of the scores, exp2 against the running
-//               reference max (rescaling O, l and the half tile already written only when a score exceeds it by
-//               more than 2^8), P -> fp16 pairs stored with tcgen05.st over the score columns just consumed
+//               reference max (rescaling O and l only when a chunk's probabilities sum to more than 2^10), P -> fp16 pairs stored with tcgen05.st over the score columns just consumed
 // Scores and probabilities never leave tensor memory / registers; shared memory only carries Q, K and V, which is
 // what bounds the M128 N64 MMAs (A and B operand fetch), so P as a shared-memory operand would cost a third more.
 #include "common.cuh"
@@ -37,22 +36,28 @@ constexpr int kAtSmem = kQBytes + 4 * kKVBytes + 128;
 constexpr uint32_t kTmemColsAttn = 128;
 constexpr uint32_t kWaitHintNs = 2000;     // suspend hint of the mbarrier waits (a completed phase wakes the thread)
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kRescaleSum = 1024.0f;  // chunk sum of probabilities that triggers a new reference max
 
-// Probabilities of one 32-key chunk of a row: pk = fp16 pairs, psum += their fp32 sum, pmax2 tracks the largest.
-//   kBias      scores get the WavLM gated relative-position term g2 * pbk[key] (log2 units) added
+// Probabilities of one 32-key chunk of a row: pk = fp16 pairs, psum += their fp32 sum.
+//   kBias      0 = none; 1 = scores get the WavLM gated relative-position term g2 * pbk[key] (log2 units), pbk a row
+//              of the (H, T, T) table in global memory; 2 = the same with pbk pointing into the CTA's shared-memory
+//              slice of the Toeplitz vector (any alignment)
 //   kPolyMask  bit (4 q + e) set = key pair e of the q-th group of 8 keys takes its exponentials from ex2_poly_pair
 //              (FMA pipe) instead of the MUFU
 //   kMasked    only the first nv keys exist (last tile of a row)
-template <bool kBias, uint32_t kPolyMask, bool kMasked>
+template <int kBias, uint32_t kPolyMask, bool kMasked>
 __device__ __forceinline__ void softmax_chunk(const uint32_t (&sv)[32], float m_run, float g2, const float* pbk,
-                                              int nv, uint32_t (&pk)[16], float& psum, __half2& pmax2) {
+                                              int nv, uint32_t (&pk)[16], float& psum) {
   const uint64_t k2 = f2_pack(kLog2e, kLog2e);
   const uint64_t nm2 = f2_pack(-m_run, -m_run);
   uint64_t psum2 = f2_pack(0.f, 0.f);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     float off[8];
-    if (kBias) {
+    if (kBias == 2) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) off[i] = (!kMasked || q * 8 + i < nv) ? pbk[q * 8 + i] : 0.f;
+    } else if (kBias == 1) {
       if (!kMasked) {  // rows of the bias table are padded to a multiple of 4 floats
         const float4 a = __ldg(reinterpret_cast<const float4*>(pbk + q * 8));
         const float4 b = __ldg(reinterpret_cast<const float4*>(pbk + q * 8) + 1);
@@ -82,9 +87,7 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&sv)[32], float m_
         if (i + 1 >= nv) p1 = 0.f;
       }
       psum2 = f2_add(psum2, f2_pack(p0, p1));
-      const __half2 h2 = __floats2half2_rn(p0, p1);
-      pmax2 = __hmax2(pmax2, h2);
-      pk[q * 4 + e] = *reinterpret_cast<const uint32_t*>(&h2);
+      pk[q * 4 + e] = pack_f16x2(p0, p1);
     }
   }
   float s0, s1;
@@ -93,20 +96,20 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&sv)[32], float m_
 }
 
 // largest score of the chunk in log2 units relative to `ref`, keys >= nv ignored
-template <bool kBias>
+template <int kBias>
 __device__ __forceinline__ float chunk_max(const uint32_t (&sv)[32], float ref, float g2, const float* pbk, int nv) {
   float mx = -INFINITY;
 #pragma unroll
   for (int i = 0; i < 32; ++i)
     if (i < nv) {
       float y = fmaf(__uint_as_float(sv[i]), kLog2e, -ref);
-      if (kBias) y = fmaf(__ldg(pbk + i), g2, y);
+      if (kBias) y = fmaf(pbk[i], g2, y);
       mx = fmaxf(mx, y);
     }
   return mx;
 }
 
-template <bool kBias, uint32_t kPolyMask>
+template <int kBias, uint32_t kPolyMask>
 __global__ void __launch_bounds__(kAtThreads, 4)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, int T,
                      int n_heads, int n_query, const float* __restrict__ gate, const float* __restrict__ pos_bias,
@@ -127,6 +130,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint64_t* pv_done = bars + 13; // one phase per retired P V chunk
   uint64_t* o_final = bars + 14; // the last P V chunk has retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  // kBias == 2: s_rel[x] = rel[h][x + (T - 1) - (q0 + 127)], so that row r and key j read s_rel[j - r + 127]
+  float* s_rel = reinterpret_cast<float*>(smem + kAtSmem);
 
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int q0 = blockIdx.x * kAtQ;
@@ -145,6 +150,13 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   if (warp == 1) {
     tmem_alloc(tmem_slot, kTmemColsAttn);
     tmem_relinquish();
+  }
+  if (kBias == 2) {
+    const float* rel = pos_bias + (long long)blockIdx.y * (2 * T - 1);
+    for (int x = threadIdx.x; x < T + kAtQ; x += kAtThreads) {
+      const int ri = x + (T - 1) - (blockIdx.x * kAtQ + kAtQ - 1);
+      s_rel[x] = (ri >= 0 && ri < 2 * T - 1) ? __ldg(rel + ri) : 0.f;
+    }
   }
   tc5_fence_before();
   __syncthreads();
@@ -238,7 +250,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     if (kBias) {
       const int qr = min(q0 + row, T - 1);
       g2 = __ldg(gate + ((long long)b * n_heads + h) * T + qr) * kLog2e;
-      pb = pos_bias + ((long long)h * T + qr) * pb_ld;
+      pb = kBias == 2 ? s_rel + (kAtQ - 1 - row) : pos_bias + ((long long)h * T + qr) * pb_ld;
     }
 #pragma unroll 1
     for (int t = 0; t < n_ch; ++t) {
@@ -254,16 +266,14 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       if (t == 0) m_run = chunk_max<kBias>(sv, 0.f, g2, pbk, nv);  // the first chunk fixes the reference
       uint32_t pk[16];
       float psum;
-      while (true) {
-        // running max of the fp16 probabilities (packed pairs): > 2^8 (or inf) means a score exceeded the
-        // reference max by more than the threshold
-        __half2 pmax2 = __floats2half2_rn(0.f, 0.f);
+      for (int pass = 0;; ++pass) {  // at most one redo: after it every score is at or below the reference
+        // The probabilities are non-negative, so their sum bounds each of them: a chunk sum above 2^10 (or inf / NaN)
+        // is the only way a score can have exceeded the reference max by enough to threaten the fp16 range.
         psum = 0.f;
-        if (nv == kAtC) softmax_chunk<kBias, kPolyMask, false>(sv, m_run, g2, pbk, kAtC, pk, psum, pmax2);
-        else softmax_chunk<kBias, 0u, true>(sv, m_run, g2, pbk, nv, pk, psum, pmax2);
-        const float pmax = fmaxf(__low2float(pmax2), __high2float(pmax2));
+        if (nv == kAtC) softmax_chunk<kBias, kPolyMask, false>(sv, m_run, g2, pbk, kAtC, pk, psum);
+        else softmax_chunk<kBias, 0u, true>(sv, m_run, g2, pbk, nv, pk, psum);
         // tcgen05.ld/st are warp-collective: the rescale decision is taken per warp, each lane with its own factor
-        if (!__any_sync(0xffffffffu, pmax > 256.0f)) break;
+        if (pass == 1 || !__any_sync(0xffffffffu, !(psum <= kRescaleSum))) break;
         // how far this row's scores exceed the reference (log2 units), exactly, from the scores still in registers
         const float grow = fmaxf(chunk_max<kBias>(sv, m_run, g2, pbk, nv), 0.f);
         const float alpha = ex2_approx(-grow);
@@ -328,8 +338,9 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 int make_f16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                  int box_rows);
 
+// bias_mode: 0 none, 1 pos_bias = (H, T, T) table with row stride pb_ld, 2 pos_bias = (H, 2T - 1) Toeplitz vectors
 int launch_attention_tc5(const void* qkv, int n_windows, int T, int n_heads, int n_query, const float* gate,
-                         const float* pos_bias, int pb_ld, void* out, cudaStream_t st) {
+                         const float* pos_bias, int pb_ld, int bias_mode, void* out, cudaStream_t st) {
   const int d = n_heads * kAtD;
   CUtensorMap map_q, map_kv;
   uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)T, (uint64_t)n_windows};
@@ -343,21 +354,29 @@ int launch_attention_tc5(const void* qkv, int n_windows, int T, int n_heads, int
   // slower on B200 (0.370 vs 0.333 ms for 32 windows): the softmax warps are latency-bound, not MUFU-bound, so the
   // longer instruction stream costs more than the freed MUFU slots give back.  Kept as a switch for re-measurement.
   static bool poly = false;
+  constexpr int kRelMaxT = 1024;  // the Toeplitz slice (T + 128 floats) must leave room for four CTAs per SM
   if (!attr_set) {
-    SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<false, 0x0000u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
-    SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<false, 0x2222u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
-    SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<true, 0u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<0, 0x0000u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<0, 0x2222u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<1, 0u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<2, 0u>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kAtSmem + 4 * (kRelMaxT + kAtQ)));
     const char* env = getenv("SEGMA_ATTN_POLY");
     poly = env && atoi(env) != 0;
     attr_set = true;
   }
+  if (bias_mode == 2 && T > kRelMaxT) {
+    set_last_error("segma_attention_rel: T=%d exceeds %d", T, kRelMaxT);
+    return SEGMA_ERR_UNSUPPORTED;
+  }
   dim3 grid(ceil_div(n_query, kAtQ), n_heads, n_windows);
-#define SEGMA_ATTN_LAUNCH(BIAS, MASK)                                                                             \
-  attention_tc5_kernel<BIAS, MASK><<<grid, kAtThreads, kAtSmem, st>>>(map_q, map_kv, T, n_heads, n_query, gate,   \
-                                                                       pos_bias, pb_ld, static_cast<__half*>(out))
-  if (pos_bias) SEGMA_ATTN_LAUNCH(true, 0u);
-  else if (poly) SEGMA_ATTN_LAUNCH(false, 0x2222u);
-  else SEGMA_ATTN_LAUNCH(false, 0x0000u);
+#define SEGMA_ATTN_LAUNCH(BIAS, MASK, SMEM)                                                                      \
+  attention_tc5_kernel<BIAS, MASK><<<grid, kAtThreads, SMEM, st>>>(map_q, map_kv, T, n_heads, n_query, gate,     \
+                                                                    pos_bias, pb_ld, static_cast<__half*>(out))
+  if (bias_mode == 2) SEGMA_ATTN_LAUNCH(2, 0u, kAtSmem + 4 * (T + kAtQ));
+  else if (bias_mode == 1) SEGMA_ATTN_LAUNCH(1, 0u, kAtSmem);
+  else if (poly) SEGMA_ATTN_LAUNCH(0, 0x2222u, kAtSmem);
+  else SEGMA_ATTN_LAUNCH(0, 0x0000u, kAtSmem);
 #undef SEGMA_ATTN_LAUNCH
   return launch_status("attention_tc5_kernel");
 }

@@ -132,6 +132,37 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(fabsf(hx), erf_abs, hx);            // 0.5 x (1 + sign(x) erf_abs)
 }
 
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_splat(float v) { return f2_pack(v, v); }
+// gelu_erf on a pair: the same formula with the polynomial, scaling and blend on packed FFMA2 / FMUL2 (two elements
+// per issue slot); only |x|, the reciprocal and the exponential stay scalar
+__device__ __forceinline__ uint64_t gelu_erf_pair(uint64_t x2) {
+  float x0, x1;
+  f2_unpack(x2, x0, x1);
+  const uint64_t ax = f2_pack(fabsf(x0), fabsf(x1));
+  const uint64_t d = f2_fma(ax, f2_splat(0.3275911f * 0.70710678118654752440f), f2_splat(1.0f));
+  float d0, d1;
+  f2_unpack(d, d0, d1);
+  const uint64_t t = f2_pack(rcp_approx(d0), rcp_approx(d1));
+  // -(a1 t + a2 t^2 + ... + a5 t^5): negated coefficients so that erf = 1 + p e needs no packed negation
+  uint64_t p = f2_fma(f2_splat(-1.061405429f), t, f2_splat(1.453152027f));
+  p = f2_fma(p, t, f2_splat(-1.421413741f));
+  p = f2_fma(p, t, f2_splat(0.284496736f));
+  p = f2_fma(p, t, f2_splat(-0.254829592f));
+  p = f2_mul(p, t);
+  const uint64_t w = f2_mul(f2_mul(x2, x2), f2_splat(-0.5f * 1.4426950408889634f));  // -(x^2 / 2) log2 e
+  float w0, w1;
+  f2_unpack(w, w0, w1);
+  const uint64_t e = f2_pack(ex2_approx(w0), ex2_approx(w1));
+  const uint64_t erf_abs = f2_fma(p, e, f2_splat(1.0f));  // erf(|x| / sqrt 2)
+  const uint64_t hx = f2_mul(x2, f2_splat(0.5f));
+  return f2_fma(f2_mul(ax, f2_splat(0.5f)), erf_abs, hx);  // 0.5 x (1 + sign(x) erf_abs)
+}
+
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   __half2 v = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -248,8 +248,13 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int g = round * 4 + gi;
             const int rr = g * 4 + sub_r;
             float4 v = *reinterpret_cast<const float4*>(stg + (gi * 4 + sub_r) * kEpiPitch + c4 * 4);
-            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-            if (do_gelu) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+            {  // bias and GELU on packed fp32 pairs: the epilogue of a GELU GEMM is issue-bound
+              uint64_t v01 = f2_add(f2_pack(v.x, v.y), f2_pack(bias4.x, bias4.y));
+              uint64_t v23 = f2_add(f2_pack(v.z, v.w), f2_pack(bias4.z, bias4.w));
+              if (do_gelu) { v01 = gelu_erf_pair(v01); v23 = gelu_erf_pair(v23); }
+              f2_unpack(v01, v.x, v.y);
+              f2_unpack(v23, v.z, v.w);
+            }
             if (kAddSrc && p.add_src) { v.x += src4[g].x; v.y += src4[g].y; v.z += src4[g].z; v.w += src4[g].w; }
             if (r_base + rr < p.rows_per_batch) {
               const long long o = (out_row0 + rr) * p.ldo + nc;
@@ -332,6 +337,17 @@ int make_f16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* d
   return SEGMA_OK;
 }
 
+// CTAs of the persistent grid: one per SM, or fewer when SEGMA_GEMM_MAX_CTAS leaves SMs to a concurrent kernel
+static int gemm_cta_limit() {
+  static int limit = 0;
+  if (limit == 0) {
+    limit = device_sm_count();
+    const char* env = getenv("SEGMA_GEMM_MAX_CTAS");
+    if (env && atoi(env) > 0) limit = std::min(limit, atoi(env));
+  }
+  return limit;
+}
+
 template <int BN, bool kCta2, int kEW, bool kAddSrc>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, GemmKernelArgs& ka, cudaStream_t st) {
   using Cfg = GemmCfg<BN, kCta2, kEW>;
@@ -349,12 +365,12 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, GemmKernelA
     return SEGMA_ERR_INVALID_ARGUMENT;
   }
   if (!kCta2) {
-    const int grid = (int)std::min<long long>(units, device_sm_count());
+    const int grid = (int)std::min<long long>(units, gemm_cta_limit());
     gemm_tc5_kernel<BN, false, kEW, kAddSrc><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(ma, mw, ka);
     return launch_status("gemm_tc5_kernel");
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * (unsigned)std::min<long long>(units, device_sm_count() / 2));
+  cfg.gridDim = dim3(2 * (unsigned)std::min<long long>(units, gemm_cta_limit() / 2));
   cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;

@@ -143,13 +143,16 @@ __global__ void __launch_bounds__(kL0Threads) w2v2_l0_apply_kernel(
 
 // gate[(b*H + h)*T + i] = ga * (gb * const_h - 1) + 2, (ga, gb) = sigmoid(sum4(Linear(64 -> 8)(x[b, i, head h])))
 // One warp per row; each lane owns whole 64-long dot products (head, output) = (pair / 8, pair % 8), the 8 x 64
-// projection lives in shared memory, and the two 4-way sums are two shuffles inside aligned groups of 8 lanes.
+// projection lives in shared memory (rows padded to 68 floats: the 8 lanes of a quarter warp read 8 different rows
+// at the same column, which a 64-float pitch would put in the same four banks), and the two 4-way sums are two
+// shuffles inside aligned groups of 8 lanes.
 __global__ void __launch_bounds__(256) wavlm_gate_kernel(const float* __restrict__ x, long long rows, int T, int H,
                                                           const float* __restrict__ gw, const float* __restrict__ gb,
                                                           const float* __restrict__ gconst, float* __restrict__ gate) {
-  __shared__ __align__(16) float s_w[8 * 64];
+  constexpr int kPitch = 68;
+  __shared__ __align__(16) float s_w[8 * kPitch];
   __shared__ float s_b[8];
-  for (int i = threadIdx.x; i < 8 * 64; i += blockDim.x) s_w[i] = gw[i];
+  for (int i = threadIdx.x; i < 8 * 64; i += blockDim.x) s_w[(i >> 6) * kPitch + (i & 63)] = gw[i];
   if (threadIdx.x < 8) s_b[threadIdx.x] = gb[threadIdx.x];
   __syncthreads();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(256) wavlm_gate_kernel(const float* __restrict
     float acc = 0.f;
     if (h < H) {
       const float4* xv = reinterpret_cast<const float4*>(xr + h * 64);
-      const float4* wv = reinterpret_cast<const float4*>(s_w + o * 64);
+      const float4* wv = reinterpret_cast<const float4*>(s_w + o * kPitch);
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const float4 a = __ldg(xv + k), w4 = wv[k];

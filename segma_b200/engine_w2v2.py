@@ -57,6 +57,13 @@ def wavlm_position_bias(rel_attn_embed: torch.Tensor, T: int, num_buckets: int, 
     return torch.nn.functional.embedding(buckets, rel_attn_embed.detach().float().cpu()).permute(2, 0, 1).contiguous()
 
 
+def wavlm_relative_bias(rel_attn_embed: torch.Tensor, T: int, num_buckets: int, max_distance: int = 800) -> torch.Tensor:
+    """(n_heads, 2T-1) Toeplitz form of ``wavlm_position_bias``: entry ``j - i + T - 1`` is the bias of key j for
+    query i (the bucket depends on j - i only, wavlm_attention.py:107-139)."""
+    pb = wavlm_position_bias(rel_attn_embed, T, num_buckets, max_distance)
+    return torch.cat([pb[:, 1:, 0].flip(1), pb[:, 0, :]], dim=1).contiguous()  # offsets -(T-1)..-1, then 0..T-1
+
+
 class W2V2Engine:
     def __init__(self, sd: dict, labels, device="cuda", prefix: str = "wav2vec2."):
         ops.device_check()
@@ -140,6 +147,14 @@ class W2V2Engine:
             self._pos_bias[T] = padded[:, :, :T]  # (H, T, T) view with row stride ld
         return self._pos_bias[T]
 
+    REL_BIAS_MAX_T = 1024  # segma_attention_rel keeps T + 128 floats of the vector in shared memory
+
+    def _rel_bias_for(self, T: int) -> torch.Tensor:
+        key = -T
+        if key not in self._pos_bias:
+            self._pos_bias[key] = wavlm_relative_bias(self.rel_embed, T, self.rel_embed.shape[0]).to(self.device)
+        return self._pos_bias[key]
+
     def _workspace(self, n: int, win_len: int, slot: int = 0) -> dict:
         key = (n, win_len, slot)
         if key in self._ws:
@@ -199,12 +214,18 @@ class W2V2Engine:
                      a_rows_per_batch=xp.shape[1], a_col_per_ntile=bn, a_cols=d, force_bn=bn)
         x, xh, tmp = ws["x"], ws["x_f16"], ws["tmp"]
         ops.layernorm(tmp, self.ln0_g, self.ln0_b, out_f16=xh, out_f32=x)
-        pos_bias = self._pos_bias_for(T) if self.wavlm else None
+        rel_bias = pos_bias = None
+        if self.wavlm:
+            if T <= self.REL_BIAS_MAX_T:
+                rel_bias = self._rel_bias_for(T)
+            else:
+                pos_bias = self._pos_bias_for(T)
         for L in self.layers:
             ops.linear(xh, L["wqkv"], L["bqkv"], out=ws["qkv"])
             if self.wavlm:
                 ops.wavlm_gate(x, T, self.n_heads, L["gate_w"], L["gate_b"], L["gate_c"], ws["gate"])
-                ops.attention(ws["qkv"], n, T, self.n_heads, gate=ws["gate"], pos_bias=pos_bias, out=ws["att"])
+                ops.attention(ws["qkv"], n, T, self.n_heads, gate=ws["gate"], pos_bias=pos_bias, rel_bias=rel_bias,
+                              out=ws["att"])
             else:
                 ops.attention(ws["qkv"], n, T, self.n_heads, out=ws["att"])
             ops.linear(ws["att"], L["wo"], L["bo"], add_src=x, out=tmp)

@@ -207,10 +207,18 @@ def cast_f16(src: torch.Tensor, dst: torch.Tensor) -> None:
 
 
 def attention(qkv: torch.Tensor, n_windows: int, T: int, n_heads: int, *, n_query=None, gate=None, pos_bias=None,
-              out=None) -> torch.Tensor:
+              rel_bias=None, out=None) -> torch.Tensor:
+    """``pos_bias`` (H, T, T) or, for a Toeplitz table, ``rel_bias`` (H, 2T-1) with bias[i, j] = rel[j - i + T - 1]."""
     assert qkv.is_contiguous() and qkv.shape == (n_windows * T, 3 * n_heads * 64)
     if out is None:
         out = torch.zeros((n_windows * T, n_heads * 64), dtype=torch.float16, device=qkv.device)
+    if rel_bias is not None:
+        assert pos_bias is None and gate is not None
+        assert rel_bias.is_contiguous() and rel_bias.shape == (n_heads, 2 * T - 1)
+        _call("segma_attention_rel", 1, _lib().segma_attention_rel, _dev(qkv, torch.float16, "qkv"), n_windows, T, n_heads,
+              T if n_query is None else n_query, _ptr(gate, torch.float32, "gate"),
+              _ptr(rel_bias, torch.float32, "rel_bias"), _dev(out, torch.float16, "out"), _stream())
+        return out
     pb_ld = 0
     if pos_bias is not None:
         assert pos_bias.dim() == 3 and pos_bias.shape[:2] == (n_heads, T) and pos_bias.stride(2) == 1

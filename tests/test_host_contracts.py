@@ -169,3 +169,18 @@ def test_driver_errors_match_the_reference(tmp_path):
     (tmp_path / "uris.txt").write_text("b\nzz\n")
     files, n = get_list_of_files_to_process(wavs, uris=tmp_path / "uris.txt")
     assert [f.name for f in files] == ["b.wav", "zz.wav"] and n == 2
+
+
+def test_wavlm_relative_bias_is_the_toeplitz_form_of_the_table():
+    """The (H, 2T-1) vector handed to segma_attention_rel reproduces every entry of the (H, T, T) table."""
+    import torch
+
+    from segma_b200.engine_w2v2 import wavlm_position_bias, wavlm_relative_bias
+
+    emb = torch.randn(320, 12, generator=torch.Generator().manual_seed(3))
+    for T in (7, 199, 349):
+        pb = wavlm_position_bias(emb, T, 320)
+        rel = wavlm_relative_bias(emb, T, 320)
+        assert rel.shape == (12, 2 * T - 1)
+        idx = torch.arange(T)[None, :] - torch.arange(T)[:, None] + T - 1
+        assert torch.equal(rel[:, idx], pb)

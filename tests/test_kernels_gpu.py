@@ -161,6 +161,24 @@ def test_attention_wavlm_bias(cuda, T, padded):
     _close(out, ref, 3e-3, 3e-3, "attention + gated bias")
 
 
+@pytest.mark.parametrize("T", [199, 64, 300, 33])
+def test_attention_wavlm_toeplitz_bias(cuda, T):
+    """segma_attention_rel against the explicit (H, T, T) table built from the same Toeplitz vector."""
+    H, B = 3, 2
+    d = H * 64
+    qkv = _rand((B * T, 3 * d), 27).to(torch.float16)
+    qkv[:, :d] *= 0.35
+    gate = (1.0 + 0.3 * _rand((B, H, T), 28)).contiguous()
+    rel = _rand((H, 2 * T - 1), 29).contiguous()
+    idx = torch.arange(T)[None, :] - torch.arange(T)[:, None] + T - 1
+    pos = rel[:, idx]  # (H, T, T)
+    out = ops.attention(qkv.to(cuda), B, T, H, gate=gate.to(cuda), rel_bias=rel.to(cuda))
+    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) + gate[..., None] * pos[None]
+    ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * T, d)
+    _close(out, ref, 3e-3, 3e-3, "attention + Toeplitz gated bias")
+
+
 # ---- LSTM + heads -----------------------------------------------------------------------------------------
 @pytest.mark.parametrize("H,dirs", [(128, 2), (64, 1)])
 def test_lstm_layer(cuda, H, dirs):

@@ -24,7 +24,7 @@ def lib():
 
 def test_header_declares_the_expected_surface():
     names = _declared()
-    for must in ("segma_logmel", "segma_gemm_f16", "segma_attention", "segma_layernorm", "segma_lstm_layer", "segma_heads",
+    for must in ("segma_logmel", "segma_gemm_f16", "segma_attention", "segma_attention_rel", "segma_layernorm", "segma_lstm_layer", "segma_heads",
                  "segma_stitch", "segma_decode_intervals", "segma_threshold_mask", "segma_last_error"):
         assert must in names
 

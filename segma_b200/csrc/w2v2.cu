@@ -115,26 +115,21 @@ __global__ void __launch_bounds__(kL0Threads) w2v2_l0_apply_kernel(
   __half* o = out + (long long)win * out_rows * C;
   for (int c2 = threadIdx.x; c2 < C / 2; c2 += kL0Threads) {
     const int c = c2 * 2;
-    float wa[kL0K], wb[kL0K];
+    // the two channels ride in one packed fp32 pair: FFMA2 for the taps and the affine, gelu_erf_pair for the GELU
+    uint64_t w2[kL0K];
 #pragma unroll
-    for (int j = 0; j < kL0K; ++j) {
-      wa[j] = __ldg(w + c * kL0K + j);
-      wb[j] = __ldg(w + (c + 1) * kL0K + j);
-    }
+    for (int j = 0; j < kL0K; ++j) w2[j] = f2_pack(__ldg(w + c * kL0K + j), __ldg(w + (c + 1) * kL0K + j));
     const float2 ssa = scale_shift[(long long)win * C + c], ssb = scale_shift[(long long)win * C + c + 1];
+    const uint64_t sc2 = f2_pack(ssa.x, ssb.x), sh2 = f2_pack(ssa.y, ssb.y);
     for (int tt = 0; tt < kL0TimeTile; ++tt) {
       const int t = t0 + tt;
       if (t >= out_rows) break;
       float ya = 0.f, yb = 0.f;
       if (t < T0) {
+        uint64_t y2 = f2_pack(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < kL0K; ++j) {
-          const float xv = s_x[tt * kL0S + j];
-          ya = fmaf(wa[j], xv, ya);
-          yb = fmaf(wb[j], xv, yb);
-        }
-        ya = gelu_erf(fmaf(ya, ssa.x, ssa.y));
-        yb = gelu_erf(fmaf(yb, ssb.x, ssb.y));
+        for (int j = 0; j < kL0K; ++j) y2 = f2_fma(w2[j], f2_splat(s_x[tt * kL0S + j]), y2);
+        f2_unpack(gelu_erf_pair(f2_fma(y2, sc2, sh2)), ya, yb);
       }
       *reinterpret_cast<uint32_t*>(o + (long long)t * C + c) = pack_f16x2(ya, yb);  // rows >= T0 are zero padding
     }
@@ -142,10 +137,12 @@ __global__ void __launch_bounds__(kL0Threads) w2v2_l0_apply_kernel(
 }
 
 // gate[(b*H + h)*T + i] = ga * (gb * const_h - 1) + 2, (ga, gb) = sigmoid(sum4(Linear(64 -> 8)(x[b, i, head h])))
-// One warp per row; each lane owns whole 64-long dot products (head, output) = (pair / 8, pair % 8), the 8 x 64
-// projection lives in shared memory (rows padded to 68 floats: the 8 lanes of a quarter warp read 8 different rows
-// at the same column, which a 64-float pitch would put in the same four banks), and the two 4-way sums are two
-// shuffles inside aligned groups of 8 lanes.
+// One warp per row; lane = (head mod 4, output): its 64-long dot products for heads h, h + 4, h + 8, ... share one
+// projection row, read from shared memory once per 4 columns and reused for every head (rows padded to 68 floats:
+// the 8 lanes of a quarter warp read 8 different rows at the same column, which a 64-float pitch would put in the
+// same four banks).  The 8 lanes of a group read the same head slice of x (one broadcast transaction).  The two
+// 4-way sums are two shuffles inside aligned groups of 8 lanes.
+constexpr int kGateMaxPasses = 4;  // up to 16 heads
 __global__ void __launch_bounds__(256) wavlm_gate_kernel(const float* __restrict__ x, long long rows, int T, int H,
                                                           const float* __restrict__ gw, const float* __restrict__ gb,
                                                           const float* __restrict__ gconst, float* __restrict__ gate) {
@@ -158,30 +155,39 @@ __global__ void __launch_bounds__(256) wavlm_gate_kernel(const float* __restrict
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = lane_id();
+  const int o = lane & 7, h0 = lane >> 3;
   const long long b = row / T;
   const int i = (int)(row - b * T);
-  const float* xr = x + row * (long long)(H * 64);
-  for (int pair = lane; pair < ((H * 8 + 31) / 32) * 32; pair += 32) {
-    const int h = pair >> 3, o = pair & 7;
-    float acc = 0.f;
-    if (h < H) {
-      const float4* xv = reinterpret_cast<const float4*>(xr + h * 64);
-      const float4* wv = reinterpret_cast<const float4*>(s_w + o * kPitch);
+  const float4* xr = reinterpret_cast<const float4*>(x + row * (long long)(H * 64));
+  const float4* wv = reinterpret_cast<const float4*>(s_w + o * kPitch);
+  float acc[kGateMaxPasses];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float4 a = __ldg(xv + k), w4 = wv[k];
-        acc = fmaf(a.x, w4.x, acc);
-        acc = fmaf(a.y, w4.y, acc);
-        acc = fmaf(a.z, w4.z, acc);
-        acc = fmaf(a.w, w4.w, acc);
+  for (int p = 0; p < kGateMaxPasses; ++p) acc[p] = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < 16; ++k) {
+    const float4 w4 = wv[k];
+#pragma unroll
+    for (int p = 0; p < kGateMaxPasses; ++p) {
+      const int h = h0 + 4 * p;
+      if (h < H) {
+        const float4 a = __ldg(xr + h * 16 + k);
+        acc[p] = fmaf(a.x, w4.x, acc[p]);
+        acc[p] = fmaf(a.y, w4.y, acc[p]);
+        acc[p] = fmaf(a.z, w4.z, acc[p]);
+        acc[p] = fmaf(a.w, w4.w, acc[p]);
       }
-      acc += s_b[o];
     }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);              // lanes o = 0 and o = 4 hold the two 4-way sums
-    const float other = __shfl_down_sync(0xffffffffu, acc, 4);
+  }
+#pragma unroll
+  for (int p = 0; p < kGateMaxPasses; ++p) {
+    const int h = h0 + 4 * p;
+    if (4 * p >= H) break;  // warp-uniform
+    float v = acc[p] + s_b[o];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);                  // lanes o = 0 and o = 4 hold the two 4-way sums
+    const float other = __shfl_down_sync(0xffffffffu, v, 4);
     if (h < H && o == 0) {
-      const float ga = 1.0f / (1.0f + expf(-acc)), gbv = 1.0f / (1.0f + expf(-other));
+      const float ga = 1.0f / (1.0f + expf(-v)), gbv = 1.0f / (1.0f + expf(-other));
       gate[(b * H + h) * T + i] = ga * (gbv * __ldg(gconst + h) - 1.0f) + 2.0f;
     }
   }
@@ -221,6 +227,7 @@ int segma_wavlm_gate(const float* x, int64_t rows, int T, int n_heads, const flo
   SEGMA_REQUIRE(rows >= 0 && T > 0 && n_heads > 0 && rows % T == 0, "segma_wavlm_gate: bad shape");
   if (rows == 0) return SEGMA_OK;
   SEGMA_REQUIRE(x && gate_w && gate_b && gate_const && gate, "segma_wavlm_gate: NULL buffer");
+  SEGMA_REQUIRE(n_heads <= 4 * kGateMaxPasses, "segma_wavlm_gate: at most %d heads", 4 * kGateMaxPasses);
   wavlm_gate_kernel<<<(unsigned)ceil_div_ll(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, T, n_heads, gate_w,
                                                                                       gate_b, gate_const, gate);
   return launch_status("wavlm_gate_kernel");

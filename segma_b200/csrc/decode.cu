@@ -565,6 +565,227 @@ __global__ void __launch_bounds__(kFastThreads) decode_fast_kernel(
   }
 }
 
+// ---- bit-plane path for C <= 8 labels (plain thresholds): one warp per 1024-frame block -----------------------
+// Count pass: lane l reads frame 32 k + l of the block (one coalesced 128-bit load per frame row for C = 4), a ballot
+// per label turns 32 frames into one word, and lane k keeps the words of step k: after 32 steps lane k holds, for every
+// label, the activity of frames [32 k, 32 k + 32) as a bit mask.  Run starts / ends are then word operations
+// (w & ~(w << 1 | carry)), their counts population counts, and the block totals one packed warp reduction per label:
+// about half an instruction per frame, so the pass runs at the speed of the logits read.  The planes (C words per
+// lane, 128 bytes per label and block) are kept for the write pass, which never touches the logits again: it recomputes
+// the boundary masks from the planes, ranks them with one packed warp scan per label and walks the set bits.
+constexpr int kPlaneWarps = 8;      // blocks (of 1024 frames) per CTA
+constexpr int kPlaneScanTile = 2048;  // block counts per scan CTA
+constexpr int kPlaneMaxLabels = 8;
+
+struct PlaneEdges {
+  uint32_t starts, ends;
+};
+__device__ __forceinline__ PlaneEdges plane_edges(uint32_t w, uint32_t prev_bit, uint32_t next_bit, int lane) {
+  const uint32_t up = __shfl_up_sync(0xffffffffu, w, 1), dn = __shfl_down_sync(0xffffffffu, w, 1);
+  const uint32_t carry = lane == 0 ? prev_bit : up >> 31;
+  const uint32_t nxt = lane == 31 ? next_bit : dn & 1u;
+  PlaneEdges e;
+  e.starts = w & ~((w << 1) | carry);
+  e.ends = w & ~((w >> 1) | (nxt << 31));
+  return e;
+}
+
+// totals of both count arrays per tile of 2048 counts
+__global__ void __launch_bounds__(256) plane_tile_sums_kernel(const int* __restrict__ a, const int* __restrict__ b,
+                                                              long long n, int* __restrict__ tile_sums) {
+  __shared__ int s_warp[2][8];
+  const long long t0 = (long long)blockIdx.x * kPlaneScanTile + threadIdx.x * 8;
+  int sa = 0, sb = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (t0 + i < n) { sa += a[t0 + i]; sb += b[t0 + i]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+  if (lane_id() == 0) { s_warp[0][threadIdx.x >> 5] = sa; s_warp[1][threadIdx.x >> 5] = sb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int ta = 0, tb = 0;
+    for (int w = 0; w < 8; ++w) { ta += s_warp[0][w]; tb += s_warp[1][w]; }
+    tile_sums[2 * blockIdx.x] = ta;
+    tile_sums[2 * blockIdx.x + 1] = tb;
+  }
+}
+
+// Exclusive scan of both count arrays in place, one CTA per tile of 2048 counts.  Every CTA sums the totals of the tiles before it (a few hundred values even for 1000 h of audio),
+// so there is no separate offsets kernel and no inter-CTA dependency.  The last CTA writes the number of intervals.
+__global__ void __launch_bounds__(256) plane_scan_kernel(int* __restrict__ a, int* __restrict__ b, long long n,
+                                                         const int* __restrict__ tile_sums, int n_tiles,
+                                                         int* __restrict__ count) {
+  __shared__ int s_warp[2][8];
+  __shared__ int s_base[2];
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  int pa = 0, pb = 0;
+  for (int t = threadIdx.x; t < (int)blockIdx.x; t += 256) { pa += tile_sums[2 * t]; pb += tile_sums[2 * t + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { pa += __shfl_xor_sync(0xffffffffu, pa, o); pb += __shfl_xor_sync(0xffffffffu, pb, o); }
+  if (lane == 0) { s_warp[0][warp] = pa; s_warp[1][warp] = pb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int ta = 0, tb = 0;
+    for (int w = 0; w < 8; ++w) { ta += s_warp[0][w]; tb += s_warp[1][w]; }
+    s_base[0] = ta;
+    s_base[1] = tb;
+    if ((int)blockIdx.x == n_tiles - 1) *count = ta + tile_sums[2 * blockIdx.x];
+  }
+  __syncthreads();
+  // 8 consecutive counts per thread (two 128-bit accesses per array)
+  const long long t0 = (long long)blockIdx.x * kPlaneScanTile + threadIdx.x * 8;
+  int va[8], vb[8];
+  int sa = 0, sb = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    va[i] = t0 + i < n ? a[t0 + i] : 0;
+    vb[i] = t0 + i < n ? b[t0 + i] : 0;
+    sa += va[i];
+    sb += vb[i];
+  }
+  int ia = sa, ib = sb;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+    if (lane >= o) { ia += ta; ib += tb; }
+  }
+  __syncthreads();  // s_warp is reused
+  if (lane == 31) { s_warp[0][warp] = ia; s_warp[1][warp] = ib; }
+  __syncthreads();
+  int ra = s_base[0] + ia - sa, rb = s_base[1] + ib - sb;
+  for (int w = 0; w < warp; ++w) { ra += s_warp[0][w]; rb += s_warp[1][w]; }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (t0 + i < n) { a[t0 + i] = ra; b[t0 + i] = rb; }
+    ra += va[i];
+    rb += vb[i];
+  }
+}
+
+// kC: compile-time label count (4 = segma's default label set, one 128-bit load per frame), 0 = read it from p.C
+template <bool kWrite, int kC>
+__global__ void __launch_bounds__(kPlaneWarps * 32) decode_plane_kernel(
+    const float* __restrict__ logits, const long long* __restrict__ file_offsets,
+    const int* __restrict__ block_offsets, int n_files, DecodeParams p, int total_blocks,
+    uint32_t* __restrict__ planes, int* __restrict__ start_counts, int* __restrict__ end_counts,
+    int32_t* __restrict__ table, long long capacity) {
+  const int lane = lane_id();
+  const int blk = blockIdx.x * kPlaneWarps + (threadIdx.x >> 5);
+  if (blk >= total_blocks) return;  // warp-uniform
+  const int C = kC ? kC : p.C;
+  constexpr int kMaxC = kC ? kC : kPlaneMaxLabels;
+  // file of this block: last f with block_offsets[f] <= blk (empty files share their successor's offset)
+  int file = 0;
+  for (int lo = 0, hi = n_files; lo < hi;) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(block_offsets + mid + 1) <= blk) lo = mid + 1; else hi = mid;
+    file = lo;
+  }
+  const int first_blk = block_offsets[file];
+  const int local_block = blk - first_blk;
+  const int nblk_file = block_offsets[file + 1] - first_blk;
+  const long long f_begin = file_offsets[file], f_end = file_offsets[file + 1];
+  const long long base = f_begin + (long long)local_block * kDecodeBlock;
+  const long long cidx0 = (long long)C * first_blk + local_block;  // + c * nblk_file
+  uint32_t* my_planes = planes + (size_t)blk * C * 32;
+
+  uint32_t w[kMaxC];
+  uint32_t prev_bits = 0, next_bits = 0;  // bit c: label c active in the frame before / after the block
+  if (!kWrite) {
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) w[c] = 0;
+    const int n_here = (int)min((long long)kDecodeBlock, f_end - base);  // frames of this block that exist
+    if (kC == 4 && p.mode == SEGMA_DECODE_LOGIT) {  // the product's configuration: four compares and ballots per step
+      const float4* rows = reinterpret_cast<const float4*>(logits) + base;
+      const float t0 = p.thr[0], t1 = p.thr[1], t2 = p.thr[2], t3 = p.thr[3];
+#pragma unroll 1
+      for (int k0 = 0; k0 < 32; k0 += 8) {  // eight independent 128-bit loads in flight per lane, then their ballots
+        if (32 * k0 >= n_here) break;  // warp-uniform
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+          if (32 * (k0 + j) + lane < n_here) v[j] = __ldg(rows + 32 * (k0 + j) + lane);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t b0 = __ballot_sync(0xffffffffu, v[j].x > t0), b1 = __ballot_sync(0xffffffffu, v[j].y > t1);
+          const uint32_t b2 = __ballot_sync(0xffffffffu, v[j].z > t2), b3 = __ballot_sync(0xffffffffu, v[j].w > t3);
+          if (lane == k0 + j) { w[0] = b0; w[1] = b1; w[2] = b2; w[3] = b3; }
+        }
+      }
+    } else {
+#pragma unroll 4
+      for (int k = 0; k < 32; ++k) {
+        if (32 * k >= n_here) break;  // warp-uniform
+        const uint32_t bits = 32 * k + lane < n_here ? frame_bits(logits, base + 32 * k + lane, p) : 0u;
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c) {
+          if (c < C) {
+            const uint32_t word = __ballot_sync(0xffffffffu, (bits >> c) & 1u);
+            if (lane == k) w[c] = word;
+          }
+        }
+      }
+    }
+    if (base - 1 >= f_begin) prev_bits = frame_bits(logits, base - 1, p);            // same address in every lane
+    if (base + kDecodeBlock < f_end) next_bits = frame_bits(logits, base + kDecodeBlock, p);
+  } else {
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) {
+      w[c] = 0;
+      if (c < C) {
+        w[c] = my_planes[c * 32 + lane];
+        // neighbouring blocks of the same file: last bit of the previous one, first bit of the next one
+        if (local_block > 0) prev_bits |= (__ldg(my_planes - C * 32 + c * 32 + 31) >> 31) << c;
+        if (local_block + 1 < nblk_file) next_bits |= (__ldg(my_planes + C * 32 + c * 32) & 1u) << c;
+      }
+    }
+  }
+
+  const int rel0 = local_block * kDecodeBlock + 32 * lane;
+  const unsigned cap = capacity > 0x7fffffffll ? 0x7fffffffu : static_cast<unsigned>(capacity);
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c) {
+    if (c >= C) break;
+    const PlaneEdges e = plane_edges(w[c], (prev_bits >> c) & 1u, (next_bits >> c) & 1u, lane);
+    // starts in the low half, ends in the high half: a block holds at most 512 of each
+    const uint32_t cnt = static_cast<uint32_t>(__popc(e.starts)) | (static_cast<uint32_t>(__popc(e.ends)) << 16);
+    if (!kWrite) {
+      my_planes[c * 32 + lane] = w[c];
+      uint32_t tot = cnt;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      if (lane == 0) {
+        const long long idx = cidx0 + (long long)c * nblk_file;
+        const int ns = static_cast<int>(tot & 0xffffu), ne = static_cast<int>(tot >> 16);
+        start_counts[idx] = ns;
+        end_counts[idx] = ne;
+      }
+    } else {
+      uint32_t x = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += t;
+      }
+      x -= cnt;  // exclusive
+      unsigned row_s = static_cast<unsigned>(__ldg(start_counts + cidx0 + (long long)c * nblk_file)) + (x & 0xffffu);
+      unsigned row_e = static_cast<unsigned>(__ldg(end_counts + cidx0 + (long long)c * nblk_file)) + (x >> 16);
+      for (uint32_t ms = e.starts, me = e.ends; ms | me; ms &= ms - 1, me &= me - 1, ++row_s, ++row_e) {
+        if (ms && row_s < cap) {
+          int* t = table + 4ll * row_s;
+          t[0] = file;
+          t[1] = c;
+          t[2] = (rel0 + __ffs(ms) - 1) * SEGMA_FRAME_SAMPLES;
+        }
+        if (me && row_e < cap) table[4ll * row_e + 3] = (rel0 + __ffs(me)) * SEGMA_FRAME_SAMPLES;
+      }
+    }
+  }
+}
+
 // ---- hysteresis (onset / offset thresholds): an extension that uses the `upper_bound` the reference carries in
 // its threshold dict but never reads (src/segma/inference.py:308-312).  A label switches on when the logit
 // exceeds the onset cut, off when it is at or below the offset cut, and otherwise keeps its state: a scan of
@@ -807,7 +1028,8 @@ static DecodeLayout decode_layout(long long n_frames, int n_files, int C) {
   const long long max_blocks = ceil_div_ll(n_frames, kDecodeBlock) + n_files;
   L.n_count = max_blocks * C;
   size_t off = 0;
-  L.bits_off = off; off = align_up(off + sizeof(uint32_t) * (size_t)n_frames, 256);
+  // one word per frame (generic path), one byte per frame (byte path) or C x 128 bytes per block (bit planes)
+  L.bits_off = off; off = align_up(off + std::max(sizeof(uint32_t) * (size_t)n_frames, (size_t)max_blocks * C * 128), 256);
   L.starts_off = off; off = align_up(off + sizeof(int) * (size_t)L.n_count, 256);
   L.ends_off = off; off = align_up(off + sizeof(int) * (size_t)L.n_count, 256);
   L.file_off = off; off = align_up(off + sizeof(long long) * (size_t)(n_files + 1), 256);
@@ -816,7 +1038,7 @@ static DecodeLayout decode_layout(long long n_frames, int n_files, int C) {
   L.summary_off = off; off = align_up(off + sizeof(uint16_t) * (size_t)max_blocks, 256);
   L.carry_off = off; off = align_up(off + (size_t)max_blocks, 256);
   L.bfile_off = off; off = align_up(off + sizeof(int) * (size_t)max_blocks, 256);
-  L.tiles_off = off; off = align_up(off + 2 * sizeof(int) * (size_t)(L.n_count / kScanTile + 2), 256);
+  L.tiles_off = off; off = align_up(off + 2 * sizeof(int) * (size_t)(L.n_count / 2048 + 2), 256);
   L.total = off;
   return L;
 }
@@ -906,9 +1128,12 @@ static int decode_impl(const float* logits, const int64_t* file_offsets, int n_f
   SEGMA_CUDA_OK(cudaMemcpyAsync(d_block, block_offsets.data(), sizeof(int) * (n_files + 1), cudaMemcpyHostToDevice, st));
   int* d_bfile = reinterpret_cast<int*>(ws + L.bfile_off);
   int* d_tiles = reinterpret_cast<int*>(ws + L.tiles_off);
-  block_file_kernel<<<ceil_div(total_blocks, 256), 256, 0, st>>>(d_block, n_files, total_blocks, d_bfile);
   // pageable-source async copies are staged before returning, so block_offsets may go out of scope
-  const bool fast = n_labels <= 8;  // one activity byte per frame, 4 frames per thread
+  const bool fast = n_labels <= 8;  // bit planes (plain thresholds) or one activity byte per frame (hysteresis)
+  const long long n_counts = (long long)total_blocks * n_labels;
+  // plain thresholds on long inputs: two-kernel scan over tiles of 2048 block counts
+  const int plane_tiles = (fast && !onset && n_counts > 4 * kScanTile) ? (int)ceil_div_ll(n_counts, kPlaneScanTile) : 0;
+  if (!fast || onset) block_file_kernel<<<ceil_div(total_blocks, 256), 256, 0, st>>>(d_block, n_files, total_blocks, d_bfile);
   static_assert(kFastBlock == kDecodeBlock, "both paths tile files in blocks of 1024 frames");
   if (onset) {
     SEGMA_REQUIRE(fast && mode == SEGMA_DECODE_LOGIT, "hysteresis needs logit-domain cuts and at most 8 labels");
@@ -935,15 +1160,21 @@ static int decode_impl(const float* logits, const int64_t* file_offsets, int n_f
     decode_fast_kernel<2><<<total_blocks, kFastThreads, 0, st>>>(
         logits, d_file, d_block, d_bfile, p, reinterpret_cast<uint8_t*>(bits), starts, ends, table, capacity);
   } else if (fast) {
-    decode_fast_kernel<0><<<total_blocks, kFastThreads, 0, st>>>(
-        logits, d_file, d_block, d_bfile, p, reinterpret_cast<uint8_t*>(bits), starts, ends, table, capacity);
+    if (n_labels == 4)
+      decode_plane_kernel<false, 4><<<ceil_div(total_blocks, kPlaneWarps), kPlaneWarps * 32, 0, st>>>(
+          logits, d_file, d_block, n_files, p, total_blocks, bits, starts, ends, table, capacity);
+    else
+      decode_plane_kernel<false, 0><<<ceil_div(total_blocks, kPlaneWarps), kPlaneWarps * 32, 0, st>>>(
+          logits, d_file, d_block, n_files, p, total_blocks, bits, starts, ends, table, capacity);
   } else {
     decode_count_kernel<<<total_blocks, kDecodeBlock, 0, st>>>(logits, d_file, d_block, n_files, p, bits, starts, ends);
   }
   rc = launch_status("decode count pass");
   if (rc != SEGMA_OK) return rc;
-  const long long n_counts = (long long)total_blocks * n_labels;
-  if (n_counts <= 4 * kScanTile) {
+  if (plane_tiles) {
+    plane_tile_sums_kernel<<<plane_tiles, 256, 0, st>>>(starts, ends, n_counts, d_tiles);
+    plane_scan_kernel<<<plane_tiles, 256, 0, st>>>(starts, ends, n_counts, d_tiles, plane_tiles, count);
+  } else if (n_counts <= 4 * kScanTile) {
     decode_scan_kernel<<<1, kScanThreads, 0, st>>>(starts, ends, n_counts, count);
   } else {  // long inputs: scan in parallel
     const int n_tiles = (int)ceil_div_ll(n_counts, kScanTile);
@@ -953,7 +1184,14 @@ static int decode_impl(const float* logits, const int64_t* file_offsets, int n_f
   }
   rc = launch_status("decode scan pass");
   if (rc != SEGMA_OK) return rc;
-  if (fast) {
+  if (fast && !onset) {
+    if (n_labels == 4)
+      decode_plane_kernel<true, 4><<<ceil_div(total_blocks, kPlaneWarps), kPlaneWarps * 32, 0, st>>>(
+          logits, d_file, d_block, n_files, p, total_blocks, bits, starts, ends, table, capacity);
+    else
+      decode_plane_kernel<true, 0><<<ceil_div(total_blocks, kPlaneWarps), kPlaneWarps * 32, 0, st>>>(
+          logits, d_file, d_block, n_files, p, total_blocks, bits, starts, ends, table, capacity);
+  } else if (fast) {  // hysteresis keeps its activity bytes
     decode_fast_kernel<1><<<total_blocks, kFastThreads, 0, st>>>(
         logits, d_file, d_block, d_bfile, p, reinterpret_cast<uint8_t*>(bits), starts, ends, table, capacity);
   } else {

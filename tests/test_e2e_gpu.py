@@ -90,6 +90,38 @@ def test_whisper_small_dims_few_windows(cuda):
     _check_logits(got, ref, "whisper-small dims")
 
 
+def test_config2_full_size_properties(cuda):
+    """BASELINE config 2 at its full size (Whisper-small dims, one 1 h file, batch 128), checked through
+    size-independent properties: the frame count of the reference's geometry, the prefix property of the batching
+    (the first 128-window batch does not depend on what follows it), and interval decoding that is bit-exact against
+    the reference's create_intervals restated on the host boolean mask."""
+    dims = synth.WHISPER_SMALL
+    sd = synth.surgical_hydra_state_dict(dims, seed=0)
+    le = MultiLabelEncoder(list(LABELS))
+    model = Models["surgical_hydra"].from_state_dict(sd, le, make_config("surgical_hydra"))
+    n = 57_600_000
+    pcm = synth.synth_audio(n, 0)
+    logits = apply_model_on_audio(pcm, model, INFERENCE_SETTINGS, "cuda", batch_size=128)
+    assert logits.shape == (179_999, len(LABELS)) and logits.dtype == torch.float32   # SURVEY 8a: 904 windows + tail
+    assert torch.isfinite(logits).all()
+    # prefix property: 128 full windows on their own reproduce the first batch bit for bit
+    n_prefix = 63_680 * 128 + 320
+    first = apply_model_on_audio(pcm[:n_prefix], model, INFERENCE_SETTINGS, "cuda", batch_size=128)
+    assert first.shape[0] == 199 * 128
+    assert torch.equal(first, logits[: 199 * 128])
+    # decode: fused device path == reference semantics on the thresholded mask
+    thr = default_thresholds(le)
+    mask = apply_thresholds(logits, thr, "cuda")
+    got = decode_logits(logits, thr, le)
+    ref = O.create_intervals(mask.cpu().numpy(), list(le.base_labels))
+    assert got == ref
+    assert got == create_intervals(mask, INFERENCE_SETTINGS, le)
+    for lab in le.base_labels:  # per label: time-ordered, disjoint, inside the file
+        iv = [(s, e) for s, e, l in got if l == lab]
+        assert all(0 <= s < e <= 320 * 179_999 for s, e in iv)
+        assert all(a[1] < b[0] for a, b in zip(iv, iv[1:]))
+
+
 def test_overlapping_windows_stitch(cuda):
     dims = synth.WHISPER_TEST
     sd = synth.hydra_whisper_state_dict(dims, seed=5)

@@ -32,15 +32,25 @@ o_qkv = torch.empty((M, 3 * d), dtype=torch.float16, device="cuda")
 o_mid = torch.empty((M, ffn), dtype=torch.float16, device="cuda")
 o_res = torch.empty((M, d), dtype=torch.float32, device="cuda")
 flops = {"qkv": 2.0 * M * d * 3 * d, "out": 2.0 * M * d * d, "fc1": 2.0 * M * d * ffn, "fc2": 2.0 * M * d * ffn}
+# The clock governor of a power-capped B200 moves in steps every 30-70 ms: each case runs long enough (about 0.4 s of
+# warm-up, then 0.4 s timed) to be measured at its own steady-state clock rather than at its predecessor's.
 for name, fn in cases.items():
-    for _ in range(3):
-        fn()
+    fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(20):
+    for _ in range(10):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    t = e0.elapsed_time(e1) / 20 * 1e-3
-    print(f"{name:28s} {t * 1e6:8.1f} us  {flops[name[:3]] / t / 1e12:7.1f} TFLOP/s")
+    iters = max(20, int(400.0 / (e0.elapsed_time(e1) / 10)))
+    for _ in range(iters):
+        fn()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / iters * 1e-3
+    print(f"{name:28s} {t * 1e6:8.1f} us  {flops[name[:3]] / t / 1e12:7.1f} TFLOP/s  ({iters} iterations)")

@@ -385,10 +385,10 @@ __global__ void __launch_bounds__(kDecodeBlock) decode_write_kernel(
   }
 }
 
-// ---- fast path for C <= 8 labels: 4 frames per thread, one activity byte per frame ---------------------------
-// Pass 1 streams the logits once (4 x 128-bit loads per thread for C = 4), keeps one byte of activity bits
-// per frame for pass 3, and counts run starts / ends per label with byte-packed warp reductions (a warp
-// holds at most 128 boundaries per label, so four labels share one 32-bit word).
+// ---- byte path for C <= 8 labels (hysteresis): 4 frames per thread, one activity byte per frame ---------------
+// The resolved hysteresis state arrives as one byte of activity bits per frame; run starts / ends per label are
+// counted with byte-packed warp reductions (a warp holds at most 128 boundaries per label, so four labels share one
+// 32-bit word) and ranked the same way in the write pass.
 constexpr int kFastThreads = 256;
 constexpr int kFastFrames = 4;                             // consecutive frames per thread
 constexpr int kFastBlock = kFastThreads * kFastFrames;     // 1024 frames per block (== kDecodeBlock)
@@ -437,8 +437,8 @@ __device__ __forceinline__ FrameBits neighbour_bits(uint32_t cur, uint32_t halo_
   return fb;
 }
 
-// MODE 0: count pass from logits (stores the activity bytes), 1: write pass from the activity bytes,
-// 2: count pass from activity bytes produced elsewhere (hysteresis)
+// MODE 1: write pass from the activity bytes, 2: count pass from the activity bytes (both after hyst_resolve_kernel;
+// the plain-threshold decoder uses decode_plane_kernel below)
 template <int MODE>
 __global__ void __launch_bounds__(kFastThreads) decode_fast_kernel(
     const float* __restrict__ logits, const long long* __restrict__ file_offsets,
@@ -463,37 +463,23 @@ __global__ void __launch_bounds__(kFastThreads) decode_fast_kernel(
   }
 
   constexpr bool kWrite = MODE == 1;
-  constexpr bool kFromBits = MODE != 0;
   uint32_t cur = 0;
-  if (kFromBits) {
-    if (frame0 + kFastFrames <= f_end && ((reinterpret_cast<uintptr_t>(bits + frame0) & 3) == 0)) {
-      cur = *reinterpret_cast<const uint32_t*>(bits + frame0);
-    } else {
-#pragma unroll
-      for (int i = 0; i < kFastFrames; ++i)
-        if (frame0 + i < f_end) cur |= static_cast<uint32_t>(bits[frame0 + i]) << (8 * i);
-    }
+  if (frame0 + kFastFrames <= f_end && ((reinterpret_cast<uintptr_t>(bits + frame0) & 3) == 0)) {
+    cur = *reinterpret_cast<const uint32_t*>(bits + frame0);
   } else {
 #pragma unroll
     for (int i = 0; i < kFastFrames; ++i)
-      if (frame0 + i < f_end) cur |= frame_bits(logits, frame0 + i, p) << (8 * i);
-    if (frame0 + kFastFrames <= f_end && ((reinterpret_cast<uintptr_t>(bits + frame0) & 3) == 0)) {
-      *reinterpret_cast<uint32_t*>(bits + frame0) = cur;
-    } else {
-#pragma unroll
-      for (int i = 0; i < kFastFrames; ++i)
-        if (frame0 + i < f_end) bits[frame0 + i] = static_cast<uint8_t>(cur >> (8 * i));
-    }
+      if (frame0 + i < f_end) cur |= static_cast<uint32_t>(bits[frame0 + i]) << (8 * i);
   }
   // block halos: the frame before the block and the frame after it (inside the same file)
   uint32_t halo_prev = 0, halo_next = 0;
   if (threadIdx.x == 0) {
     const long long pf = frame0 - 1;
-    if (pf >= f_begin) halo_prev = kFromBits ? bits[pf] : frame_bits(logits, pf, p);
+    if (pf >= f_begin) halo_prev = bits[pf];
   }
   if (threadIdx.x == kFastThreads - 1) {
     const long long nf = f_begin + (long long)(local_block + 1) * kFastBlock;
-    if (nf < f_end) halo_next = kFromBits ? bits[nf] : frame_bits(logits, nf, p);
+    if (nf < f_end) halo_next = bits[nf];
   }
   if (lane == 0) s_edge_lo[warp] = cur & 0xffu;
   if (lane == 31) s_edge_hi[warp] = cur >> 24;

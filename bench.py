@@ -167,6 +167,9 @@ def run_gpu(args):
     from segma_b200.models import Models
     from segma_b200.thresholds import logit_cut
 
+    # NCCL writes its version banner (NCCL_DEBUG=VERSION and up) to stdout unless told otherwise; stdout carries the
+    # single JSON line of this script
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, world, local = init_from_env("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

@@ -127,7 +127,8 @@ def test_cast_f16(cuda):
 
 
 # ---- attention -----------------------------------------------------------------------------------------
-@pytest.mark.parametrize("T,H,B,nq", [(199, 2, 3, 199), (1500, 2, 2, 1500), (1500, 12, 1, 199), (64, 1, 1, 64), (65, 3, 2, 65)])
+@pytest.mark.parametrize("T,H,B,nq", [(199, 2, 3, 199), (1500, 2, 2, 1500), (1500, 12, 1, 199), (64, 1, 1, 64), (65, 3, 2, 65),
+                                      (1, 1, 1, 1), (31, 2, 1, 31), (32, 1, 2, 32), (33, 1, 1, 20), (129, 2, 1, 129)])
 def test_attention(cuda, T, H, B, nq):
     d = H * 64
     qkv = _rand((B * T, 3 * d), 16).to(torch.float16)
@@ -137,6 +138,26 @@ def test_attention(cuda, T, H, B, nq):
     ref = (torch.softmax(q @ k.transpose(-1, -2), -1) @ v).permute(0, 2, 1, 3).reshape(B, T, d)
     got = out.view(B, T, d)[:, :nq]
     _close(got, ref[:, :nq], 3e-3, 3e-3, f"attention T={T}")
+
+
+@pytest.mark.parametrize("T", [199, 1500])
+def test_attention_reference_max_rescale(cuda, T):
+    """Scores that keep growing along the key axis (every later chunk beats the running reference max by far more than
+    the 2^10 laziness bound, up to values whose exponentials overflow fp16) exercise the in-place rescale of O and l."""
+    H, B = 2, 1
+    d = H * 64
+    g = torch.Generator().manual_seed(31)
+    qkv = torch.randn((B * T, 3 * d), generator=g)
+    ramp = torch.linspace(-1.0, 1.0, T)[:, None]
+    qkv[:, :d] = 0.9 + 0.05 * qkv[:, :d]                       # q: almost constant direction
+    qkv[:, d:2 * d] = ramp * 1.2 + 0.05 * qkv[:, d:2 * d]     # k: grows with the key index -> scores span about +-70
+    qkv = qkv.to(torch.float16)
+    out = ops.attention(qkv.to(cuda), B, T, H)
+    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s_ = q @ k.transpose(-1, -2)
+    assert s_.max() - s_.min() > 100
+    ref = (torch.softmax(s_, -1) @ v).permute(0, 2, 1, 3).reshape(B * T, d)
+    _close(out, ref, 3e-3, 3e-3, f"attention with growing scores T={T}")
 
 
 @pytest.mark.parametrize("T,padded", [(199, False), (199, True), (300, True), (64, True)])

@@ -163,9 +163,12 @@ __device__ __forceinline__ uint64_t gelu_erf_pair(uint64_t x2) {
   return f2_fma(f2_mul(ax, f2_splat(0.5f)), erf_abs, hx);  // 0.5 x (1 + sign(x) erf_abs)
 }
 
+// two fp32 -> packed fp16, round to nearest, saturating to +-65504 instead of overflowing to infinity (an activation
+// outside the fp16 range then stays a large finite number instead of poisoning the next softmax / LayerNorm)
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-  __half2 v = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 
 // one lane of a converged warp (the same lane every time): issue point of TMA / tcgen05 instructions.  Keeping the

@@ -126,6 +126,17 @@ def test_cast_f16(cuda):
     assert torch.equal(dst, x.to(torch.float16))
 
 
+def test_linear_fp16_output_saturates(cuda):
+    """Results outside the fp16 range are stored as +-65504, not infinity (a deliberate, documented divergence from a
+    plain fp16 cast: the fp32 reference holds a finite value there too)."""
+    a = torch.full((128, 64), 100.0, dtype=torch.float16, device=cuda)
+    w = torch.full((32, 64), 100.0, dtype=torch.float16, device=cuda)
+    w[16:] = -100.0
+    out = ops.linear(a, w)
+    assert torch.isfinite(out).all()
+    assert (out[:, :16] == 65504.0).all() and (out[:, 16:] == -65504.0).all()
+
+
 # ---- attention -----------------------------------------------------------------------------------------
 @pytest.mark.parametrize("T,H,B,nq", [(199, 2, 3, 199), (1500, 2, 2, 1500), (1500, 12, 1, 199), (64, 1, 1, 64), (65, 3, 2, 65),
                                       (1, 1, 1, 1), (31, 2, 1, 31), (32, 1, 2, 32), (33, 1, 1, 20), (129, 2, 1, 129)])

@@ -326,6 +326,26 @@ def test_decode_multi_file_and_overflow(cuda):
     assert np.array_equal(table, np.concatenate(rows))
 
 
+@pytest.mark.parametrize("C", [1, 4, 5, 8])
+def test_decode_multi_file_logit_mode_runs_across_blocks(cuda, C):
+    """Logit-domain cuts (the product's mode) on several files of awkward lengths, with runs long enough to span the
+    1024-frame blocks and the 32-frame words of the bit-plane kernels."""
+    rng = np.random.default_rng(40 + C)
+    lens = [1023, 1024, 1025, 0, 31, 32, 33, 7000, 2048, 1]
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    n = int(offs[-1])
+    base = rng.standard_normal((n // 211 + 1, C)).repeat(211, axis=0)[:n] + 0.2 * rng.standard_normal((n, C))
+    logits = torch.from_numpy(base.astype(np.float32))
+    cuts = [0.1 * c - 0.2 for c in range(C)]
+    table = ops.decode_intervals(logits.to(cuda), cuts, file_offsets=offs, mode=ops.DECODE_LOGIT).cpu().numpy()
+    rows = []
+    for f, (a, b) in enumerate(zip(offs[:-1], offs[1:])):
+        mask = (logits[a:b] > torch.tensor(cuts)).numpy()
+        t = O.interval_table(mask, C)
+        rows.append(np.concatenate([np.full((t.shape[0], 1), f), t], axis=1))
+    assert np.array_equal(table, np.concatenate(rows))
+
+
 def test_decode_logit_cut_mode(cuda):
     from segma_b200.thresholds import logit_cut
 

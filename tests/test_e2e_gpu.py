@@ -263,7 +263,9 @@ def _composed_oracle(pcm, forward, win, step, batch_size, whisper, frames_per_wi
     return O.stitch_mean(wins, offs, n_frames)
 
 
-@pytest.mark.parametrize("win_s,overlap", [(2, 0.5), (3, 0.75), (4, 0.9), (6, 0.5), (8, 0.75)])
+# BASELINE config 5: the full window x overlap grid (thresholds 0.3 / 0.5 / 0.7 are swept inside the test)
+@pytest.mark.parametrize("win_s", [2, 3, 4, 6, 8])
+@pytest.mark.parametrize("overlap", [0.5, 0.75, 0.9])
 def test_sweep_waveform_model(cuda, win_s, overlap):
     sd = synth.hubert_hydra_state_dict(synth.W2V2_TEST, seed=5)
     le = MultiLabelEncoder(list(LABELS))

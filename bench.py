@@ -348,8 +348,9 @@ def run_gpu(args):
         "roofline": {"bound": "tensor", "kernel": "gemm_tc5_kernel (tcgen05 GEMM + implicit conv)",
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                      # dram__bytes_read+write per launch, mean of the four layer GEMMs (QKV, out-proj, fc1, fc2) of a
-                     # 128-window batch from profiles/r01c_prof_gemm_ncu_full.txt; their algorithmic bytes: 1.62e9
-                     "traffic": 1.58e9 if args.workload == "whisper" else None, "launches": n_gemm, "avg_launch_ms": g_ms / max(n_gemm, 1),
+                     # 128-window batch from profiles/r01e_prof_gemm_ncu_full.txt (1.13 + 1.42 + 1.43 + 2.39 GB) / 4; their
+                     # algorithmic bytes: 1.62e9
+                     "traffic": 1.59e9 if args.workload == "whisper" else None, "launches": n_gemm, "avg_launch_ms": g_ms / max(n_gemm, 1),
                      "share_of_step": (g_ms / 1e3) / (dev_s / args.steps), "peak_source": peak_src},
         "cpu_baseline": cpu,
         "side_kernels": side,

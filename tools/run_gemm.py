@@ -20,11 +20,17 @@ cases = {
     "fc2  n768 k3072 +src f32": lambda: ops.linear(hmid, w_2, b_o, add_src=res, out=o_res),
     "fc1  n3072 k768 (no gelu)": lambda: ops.linear(x, w_1, b_1, out=o_mid),
     "qkv  n2304 k768 (gelu)": lambda: ops.linear(x, w_qkv, b_qkv, gelu=True, out=o_qkv),
+    # cuBLAS on the same shapes (plain GEMM, no epilogue), as the energy-efficiency yardstick under the power cap
+    "qkv  cublas": lambda: torch.mm(x, w_qkv_t, out=o_qkv),
+    "fc1  cublas": lambda: torch.mm(x, w_1_t, out=o_mid),
+    "fc2  cublas": lambda: torch.mm(hmid, w_2_t, out=o_f16),
 }
 w_qkv = (torch.randn((3 * d, d), device="cuda", generator=g) * 0.03).to(torch.float16)
 w_o = (torch.randn((d, d), device="cuda", generator=g) * 0.03).to(torch.float16)
 w_1 = (torch.randn((ffn, d), device="cuda", generator=g) * 0.03).to(torch.float16)
 w_2 = (torch.randn((d, ffn), device="cuda", generator=g) * 0.03).to(torch.float16)
+w_qkv_t, w_1_t, w_2_t = w_qkv.t(), w_1.t(), w_2.t()
+o_f16 = torch.empty((M, d), dtype=torch.float16, device="cuda")
 b_qkv = torch.randn(3 * d, device="cuda", generator=g)
 b_o = torch.randn(d, device="cuda", generator=g)
 b_1 = torch.randn(ffn, device="cuda", generator=g)

@@ -28,6 +28,10 @@ constexpr int kBK = 64;  // 128 bytes of fp16: one swizzle row
 // GELU epilogue without residual, whose smaller register footprint leaves room for the extra warps)
 constexpr int kEpiPitch = 36;  // floats per staged accumulator row (32 + 4 pad: conflict-free 128-bit access)
 constexpr int kEpiRows = 16;   // rows staged per round (half a warp's accumulator rows)
+constexpr int kEpiF16Pitch = 80;  // bytes per staged fp16 row (32 values + 16 B pad: conflict-free 128-bit writes)
+constexpr int kEpiWarpBytes = 32 * kEpiF16Pitch;  // per-warp staging tile: 32 fp16 rows (>= 16 fp32 rows of 144 B)
+static_assert(kEpiWarpBytes >= kEpiRows * kEpiPitch * 4, "staging tile too small");
+constexpr int kFlagEpiRegs = 1 << 16;  // internal: bias / GELU on the accumulator registers, fp16 staging
 
 struct GemmKernelArgs {
   int batch, rows_per_batch, tiles_per_batch;
@@ -59,7 +63,7 @@ struct GemmCfg {
   static constexpr int kTmemCols = BN == 128 ? 256 : 512;
   static constexpr int kAccStride = BN == 192 ? 256 : BN;  // column offset between the two accumulators
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                    kEW * kEpiRows * kEpiPitch * 4 /*epilogue transpose tiles*/;
+                                    kEW * kEpiWarpBytes /*epilogue transpose tiles*/;
 };
 
 template <int BN, bool kCta2, int kEW, bool kAddSrc>
@@ -194,7 +198,9 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int cgrp = (warp - 2) >> 2;   // which of the quadrant's kEW/4 warps: chunks cgrp, cgrp + kEW/4, ...
     const bool out_f32 = (p.flags & SEGMA_GEMM_OUT_F32) != 0;
     const bool do_gelu = (p.flags & SEGMA_GEMM_GELU) != 0;
-    float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256) + (warp - 2) * (kEpiRows * kEpiPitch);
+    unsigned char* stg_bytes = smem + Cfg::kStages * Cfg::kStageBytes + 256 + (warp - 2) * kEpiWarpBytes;
+    float* stg = reinterpret_cast<float*>(stg_bytes);
+    const bool epi_regs = !kAddSrc && !out_f32 && (p.flags & kFlagEpiRegs) != 0;
     const int sub_r = lane >> 3;   // row within a group of 4
     const int c4 = lane & 7;       // float4 column within the 32-column chunk
     int it = 0;
@@ -229,9 +235,44 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                          : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
+        uint32_t acc[32];
+        if (!kAddSrc && epi_regs) {
+          // fp16 output without a residual: bias and GELU run on the accumulator registers (this lane's row, 32
+          // independent columns), the result is packed to fp16 first and only then transposed through shared memory
+          // (half the staging bytes of the fp32 route) for row-wise 128-bit stores
+          tmem_ld_32x32(t_addr + chunk * 32, acc);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bq = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + q);  // same address in every lane
+            uint64_t v01 = f2_add(f2_pack(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1])), f2_pack(bq.x, bq.y));
+            uint64_t v23 = f2_add(f2_pack(__uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3])), f2_pack(bq.z, bq.w));
+            if (do_gelu) { v01 = gelu_erf_pair(v01); v23 = gelu_erf_pair(v23); }
+            float a, b;
+            f2_unpack(v01, a, b);
+            pk[2 * q] = pack_f16x2(a, b);
+            f2_unpack(v23, a, b);
+            pk[2 * q + 1] = pack_f16x2(a, b);
+          }
+          uint4* my_row = reinterpret_cast<uint4*>(stg_bytes + lane * kEpiF16Pitch);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) my_row[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          __syncwarp();
+          const int seg = lane & 3;  // 16-byte segment of the 64-byte row
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + (lane >> 2);
+            const uint4 v = *reinterpret_cast<const uint4*>(stg_bytes + rr * kEpiF16Pitch + seg * 16);
+            if (r_base + rr < p.rows_per_batch)
+              *reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + (out_row0 + rr) * p.ldo + nc + seg * 8) = v;
+          }
+          __syncwarp();
+          continue;
+        }
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + c4);
-        uint32_t acc[32];
         tmem_ld_32x32(t_addr + chunk * 32, acc);
         tmem_ld_wait();
 #pragma unroll
@@ -435,6 +476,10 @@ int segma_gemm_f16(const segma_gemm_args* a, void* stream) {
   ka.out_row_offset = a->out_row_offset;
   ka.ldo = a->ldo;
   ka.flags = a->flags;
+  {  // A/B switch for the epilogue route of fp16 outputs without a residual (read per call: tools flip it in-process)
+    const char* env = getenv("SEGMA_GEMM_EPI_REGS");
+    if (env ? atoi(env) != 0 : true) ka.flags |= kFlagEpiRegs;
+  }
 
   // A map: stride-s convolutions view s consecutive input rows as one map row of s*c channels
   const int in_rows = a->a_rows_per_batch > 0 ? a->a_rows_per_batch : a->rows_per_batch;

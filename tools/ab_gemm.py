@@ -21,9 +21,17 @@ b_qkv = torch.randn(3 * d, device="cuda", generator=g)
 b_1 = torch.randn(ffn, device="cuda", generator=g)
 o_qkv = torch.empty((M, 3 * d), dtype=torch.float16, device="cuda")
 o_mid = torch.empty((M, ffn), dtype=torch.float16, device="cuda")
+hmid = torch.randn((M, ffn), device="cuda", generator=g).to(torch.float16)
+resid = torch.randn((M, d), device="cuda", generator=g)
+w_o = (torch.randn((d, d), device="cuda", generator=g) * 0.03).to(torch.float16)
+w_2 = (torch.randn((d, ffn), device="cuda", generator=g) * 0.03).to(torch.float16)
+b_o = torch.randn(d, device="cuda", generator=g)
+o_res = torch.empty((M, d), dtype=torch.float32, device="cuda")
 cases = {
     "qkv  n2304 k768": lambda: ops.linear(x, w_qkv, b_qkv, out=o_qkv),
     "fc1  n3072 k768 gelu": lambda: ops.linear(x, w_1, b_1, gelu=True, out=o_mid),
+    "out  n768 k768 +src f32": lambda: ops.linear(x, w_o, b_o, add_src=resid, out=o_res),
+    "fc2  n768 k3072 +src f32": lambda: ops.linear(hmid, w_2, b_o, add_src=resid, out=o_res),
 }
 
 

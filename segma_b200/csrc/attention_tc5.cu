@@ -5,17 +5,18 @@
 // modeling_whisper.py:338-352; 1500 positions, no mask) and torchaudio SelfAttention
 // (site-packages/torchaudio/models/wav2vec2/components.py:305-307; 199 positions).
 //
-// One CTA owns 128 query rows of one (window, head) and walks the keys in tiles of 64; four CTAs are
-// resident per SM (48 KB of shared memory, 128 TMEM columns each) so that one CTA's softmax overlaps the others'
-// MMAs and barrier hand-offs.  Per key tile:
+// One CTA owns 128 query rows of one (window, head); four CTAs are resident per SM (48 KB of shared memory, 128 TMEM
+// columns each) so that one CTA's softmax overlaps the others' MMAs and barrier hand-offs.  K and V arrive in tiles
+// of 64 keys; scores are produced and consumed in chunks of 32 keys, in two TMEM buffers:
 //   warp 0      TMA: Q once, then the K and V tiles (64 x 64, 128B swizzle, two buffers each), straight from the
 //               fused QKV activation through 3-D tensor maps (column block selects q / k / v and the head)
-//   warp 1      one lane issues  O += P_{j-1} V_{j-1}  (M128 N64 K64; P read from tensor memory, V as an MN-major
-//               shared-memory B operand) and  S = Q K_j^T (M128 N64 K64) back to back, then one tcgen05.commit
+//   warp 1      converged; one elected lane issues, per chunk t,  O += P_t V_t  (M128 N64 K32; P read from tensor
+//               memory, V as an MN-major shared-memory B operand) and  S_{t+2} = Q K_{t+2}^T  (M128 N32 K64) into the
+//               buffer P_t just left, so the softmax of chunk t+1 overlaps both
 //   warps 2-5   one thread per query row, 32 keys at a time: tcgen05.ld of the scores, exp2 against the running
-//               reference max (rescaling O and l only when a chunk's probabilities sum to more than 2^10), P -> fp16 pairs stored with tcgen05.st over the score columns just consumed
-// Scores and probabilities never leave tensor memory / registers; shared memory only carries Q, K and V, which is
-// what bounds the M128 N64 MMAs (A and B operand fetch), so P as a shared-memory operand would cost a third more.
+//               reference max (rescaling O and l only when a chunk's probabilities sum to more than 2^10), P -> fp16
+//               pairs stored with tcgen05.st over the score columns just consumed
+// Scores and probabilities never leave tensor memory / registers; shared memory only carries Q, K and V.
 #include "common.cuh"
 
 namespace segma {

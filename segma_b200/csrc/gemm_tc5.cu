@@ -6,11 +6,13 @@
 // and nn.Conv1d of the Whisper stem (modeling_whisper.py:619-625) / wav2vec2 feature extractor
 // (components.py:77-99) to cuBLASLt / cuDNN.
 //
-// Structure (persistent, warp-specialised, one CTA per SM):
-//   warp 0      TMA producer: 128B-swizzled A (128 x 64) and W (BN x 64) tiles into a multi-stage ring
-//   warp 1      allocates TMEM, one elected lane issues tcgen05.mma (M=128, N=BN, K=16) per 32 bytes of K
-//   warps 2-9   epilogue: tcgen05.ld of the fp32 accumulator (double-buffered in TMEM so the next tile's
-//               MMAs overlap), + bias, exact-erf GELU, + fp32 residual / position table, fp16 or fp32 store
+// Structure (persistent, warp-specialised, one CTA per SM; 256-wide tiles run on CTA pairs, cta_group::2, M = 256):
+//   warp 0      TMA producer: 128B-swizzled A (128 x 64) and W (BN x 64, or half of it per CTA of a pair) tiles into a
+//               multi-stage ring
+//   warp 1      allocates TMEM, one lane issues tcgen05.mma (M=128 or 256, N=BN, K=16) per 32 bytes of K
+//   warps 2-..  8 or 16 epilogue warps: tcgen05.ld of the fp32 accumulator (double-buffered in TMEM so the next
+//               tile's MMAs overlap), + bias, exact-erf GELU, + fp32 residual / position table, fp16 or fp32 store
+//               through a per-warp shared-memory transpose (fp16 outputs without a residual are narrowed first)
 // A strided Conv1d is the same loop with the K axis split into taps: tap j of a stride-s convolution reads
 // the activation map (rows merged s at a time) at column block (j % s) * C and row offset j / s, so no
 // im2col buffer is ever written.

@@ -385,173 +385,12 @@ __global__ void __launch_bounds__(kDecodeBlock) decode_write_kernel(
   }
 }
 
-// ---- byte path for C <= 8 labels (hysteresis): 4 frames per thread, one activity byte per frame ---------------
-// The resolved hysteresis state arrives as one byte of activity bits per frame; run starts / ends per label are
-// counted with byte-packed warp reductions (a warp holds at most 128 boundaries per label, so four labels share one
-// 32-bit word) and ranked the same way in the write pass.
+// ---- tiling of the hysteresis kernels (C <= 8): 4 frames per thread, one activity byte per frame --------------
 constexpr int kFastThreads = 256;
 constexpr int kFastFrames = 4;                             // consecutive frames per thread
 constexpr int kFastBlock = kFastThreads * kFastFrames;     // 1024 frames per block (== kDecodeBlock)
 
-__device__ __forceinline__ uint32_t packed_warp_sum(uint32_t v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ uint32_t packed_warp_excl_scan(uint32_t v, int lane) {
-  uint32_t x = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += t;
-  }
-  return x - v;
-}
-// bit c of every frame byte -> count of set bits among the 4 frames, packed one byte per label (labels lo..lo+3)
-__device__ __forceinline__ uint32_t packed_counts(uint32_t flags4, int lo) {
-  uint32_t out = 0;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) out |= static_cast<uint32_t>(__popc(flags4 & (0x01010101u << (lo + c)))) << (8 * c);
-  return out;
-}
-
-// activity bytes of this thread's 4 frames plus the neighbouring frames on either side
-struct FrameBits {
-  uint32_t cur;   // byte i = frame i of the thread
-  uint32_t prev;  // byte i = frame i-1
-  uint32_t next;  // byte i = frame i+1
-};
-
-__device__ __forceinline__ FrameBits neighbour_bits(uint32_t cur, uint32_t halo_prev, uint32_t halo_next, int lane,
-                                                    const uint32_t* s_edge_lo, const uint32_t* s_edge_hi, int warp,
-                                                    int n_warps) {
-  // byte 3 of the previous thread / byte 0 of the next thread, across warps through shared memory
-  uint32_t left = __shfl_up_sync(0xffffffffu, cur >> 24, 1);
-  uint32_t right = __shfl_down_sync(0xffffffffu, cur & 0xffu, 1);
-  if (lane == 0) left = warp == 0 ? halo_prev : s_edge_hi[warp - 1];
-  if (lane == 31) right = warp == n_warps - 1 ? halo_next : s_edge_lo[warp + 1];
-  FrameBits fb;
-  fb.cur = cur;
-  fb.prev = (cur << 8) | (left & 0xffu);
-  fb.next = (cur >> 8) | ((right & 0xffu) << 24);
-  return fb;
-}
-
-// MODE 1: write pass from the activity bytes, 2: count pass from the activity bytes (both after hyst_resolve_kernel;
-// the plain-threshold decoder uses decode_plane_kernel below)
-template <int MODE>
-__global__ void __launch_bounds__(kFastThreads) decode_fast_kernel(
-    const float* __restrict__ logits, const long long* __restrict__ file_offsets,
-    const int* __restrict__ block_offsets, const int* __restrict__ block_file, DecodeParams p,
-    uint8_t* __restrict__ bits, int* __restrict__ start_counts, int* __restrict__ end_counts,
-    int32_t* __restrict__ table, long long capacity) {
-  __shared__ uint32_t s_edge_lo[kFastThreads / 32], s_edge_hi[kFastThreads / 32];
-  __shared__ uint32_t s_warp[4][kFastThreads / 32];  // [starts lo, starts hi, ends lo, ends hi][warp]
-  const int file = __ldg(block_file + blockIdx.x);
-  const int local_block = blockIdx.x - block_offsets[file];
-  const int nblk_file = block_offsets[file + 1] - block_offsets[file];
-  const long long f_begin = file_offsets[file], f_end = file_offsets[file + 1];
-  const long long frame0 = f_begin + (long long)local_block * kFastBlock + threadIdx.x * kFastFrames;
-  const int lane = lane_id(), warp = threadIdx.x >> 5;
-  constexpr int n_warps = kFastThreads / 32;
-  // write pass: fetch this block's scanned row offsets now, so the load overlaps the rest of the dependent chain
-  int my_base = 0;
-  if (MODE == 1 && threadIdx.x < 2 * p.C) {
-    const int which = threadIdx.x / p.C, c = threadIdx.x - which * p.C;
-    const long long idx = (long long)p.C * block_offsets[file] + (long long)c * nblk_file + local_block;
-    my_base = __ldg((which == 0 ? start_counts : end_counts) + idx);  // exclusive-scanned by pass 2
-  }
-
-  constexpr bool kWrite = MODE == 1;
-  uint32_t cur = 0;
-  if (frame0 + kFastFrames <= f_end && ((reinterpret_cast<uintptr_t>(bits + frame0) & 3) == 0)) {
-    cur = *reinterpret_cast<const uint32_t*>(bits + frame0);
-  } else {
-#pragma unroll
-    for (int i = 0; i < kFastFrames; ++i)
-      if (frame0 + i < f_end) cur |= static_cast<uint32_t>(bits[frame0 + i]) << (8 * i);
-  }
-  // block halos: the frame before the block and the frame after it (inside the same file)
-  uint32_t halo_prev = 0, halo_next = 0;
-  if (threadIdx.x == 0) {
-    const long long pf = frame0 - 1;
-    if (pf >= f_begin) halo_prev = bits[pf];
-  }
-  if (threadIdx.x == kFastThreads - 1) {
-    const long long nf = f_begin + (long long)(local_block + 1) * kFastBlock;
-    if (nf < f_end) halo_next = bits[nf];
-  }
-  if (lane == 0) s_edge_lo[warp] = cur & 0xffu;
-  if (lane == 31) s_edge_hi[warp] = cur >> 24;
-  __syncthreads();
-  const FrameBits fb = neighbour_bits(cur, halo_prev, halo_next, lane, s_edge_lo, s_edge_hi, warp, n_warps);
-  const uint32_t starts = fb.cur & ~fb.prev, ends = fb.cur & ~fb.next;
-  const uint32_t cs_lo = packed_counts(starts, 0), ce_lo = packed_counts(ends, 0);
-  const uint32_t cs_hi = p.C > 4 ? packed_counts(starts, 4) : 0u, ce_hi = p.C > 4 ? packed_counts(ends, 4) : 0u;
-
-  if (!kWrite) {
-    const uint32_t ws_lo = packed_warp_sum(cs_lo), we_lo = packed_warp_sum(ce_lo);
-    const uint32_t ws_hi = p.C > 4 ? packed_warp_sum(cs_hi) : 0u, we_hi = p.C > 4 ? packed_warp_sum(ce_hi) : 0u;
-    if (lane == 0) { s_warp[0][warp] = ws_lo; s_warp[1][warp] = ws_hi; s_warp[2][warp] = we_lo; s_warp[3][warp] = we_hi; }
-    __syncthreads();
-    if (threadIdx.x < 2 * p.C) {
-      const int which = threadIdx.x / p.C, c = threadIdx.x - which * p.C;  // 0 = starts, 1 = ends
-      int total = 0;
-      for (int w = 0; w < n_warps; ++w) total += (s_warp[which * 2 + (c >> 2)][w] >> (8 * (c & 3))) & 0xff;
-      const long long idx = (long long)p.C * block_offsets[file] + (long long)c * nblk_file + local_block;
-      (which == 0 ? start_counts : end_counts)[idx] = total;
-    }
-    return;
-  }
-
-  // ---- write pass: rank of this thread's first boundary of each label inside the block ----
-  const uint32_t xs_lo = packed_warp_excl_scan(cs_lo, lane), xe_lo = packed_warp_excl_scan(ce_lo, lane);
-  const uint32_t xs_hi = p.C > 4 ? packed_warp_excl_scan(cs_hi, lane) : 0u, xe_hi = p.C > 4 ? packed_warp_excl_scan(ce_hi, lane) : 0u;
-  if (lane == 31) {
-    s_warp[0][warp] = xs_lo + cs_lo; s_warp[1][warp] = xs_hi + cs_hi;
-    s_warp[2][warp] = xe_lo + ce_lo; s_warp[3][warp] = xe_hi + ce_hi;
-  }
-  __syncthreads();
-  // s_first[which][c][w]: table row of the first start / end of label c emitted by warp w of this block
-  __shared__ int s_first[2][8][n_warps];
-  if (threadIdx.x < 2 * p.C) {
-    const int which = threadIdx.x / p.C, c = threadIdx.x - which * p.C;
-    int run = my_base;
-    for (int w = 0; w < n_warps; ++w) {
-      s_first[which][c][w] = run;
-      run += (s_warp[2 * which + (c >> 2)][w] >> (8 * (c & 3))) & 0xff;
-    }
-  }
-  __syncthreads();
-  const int rel0 = static_cast<int>(frame0 - f_begin);
-  const unsigned cap = capacity > 0x7fffffffll ? 0x7fffffffu : static_cast<unsigned>(capacity);
-  for (int c = 0; c < p.C; ++c) {
-    const uint32_t m = 0x01010101u << c;
-    const uint32_t sb = starts & m, eb = ends & m;
-    if (!(sb | eb)) continue;  // most threads hold no boundary of this label
-    const int word = c >> 2, sh = 8 * (c & 3);
-    unsigned row_s = static_cast<unsigned>(s_first[0][c][warp]) + (((word ? xs_hi : xs_lo) >> sh) & 0xff);
-    unsigned row_e = static_cast<unsigned>(s_first[1][c][warp]) + (((word ? xe_hi : xe_lo) >> sh) & 0xff);
-#pragma unroll
-    for (int i = 0; i < kFastFrames; ++i) {
-      if ((sb >> (8 * i)) & 0xffu) {
-        if (row_s < cap) {
-          int* t = table + 4ll * row_s;
-          t[0] = file;
-          t[1] = c;
-          t[2] = (rel0 + i) * SEGMA_FRAME_SAMPLES;
-        }
-        ++row_s;
-      }
-      if ((eb >> (8 * i)) & 0xffu) {
-        if (row_e < cap) table[4ll * row_e + 3] = (rel0 + i + 1) * SEGMA_FRAME_SAMPLES;
-        ++row_e;
-      }
-    }
-  }
-}
-
-// ---- bit-plane path for C <= 8 labels (plain thresholds): one warp per 1024-frame block -----------------------
+// ---- bit-plane path for C <= 8 labels: one warp per 1024-frame block ----------------------------------------
 // Count pass: lane l reads frame 32 k + l of the block (one coalesced 128-bit load per frame row for C = 4), a ballot
 // per label turns 32 frames into one word, and lane k keeps the words of step k: after 32 steps lane k holds, for every
 // label, the activity of frames [32 k, 32 k + 32) as a bit mask.  Run starts / ends are then word operations
@@ -654,8 +493,8 @@ template <bool kWrite, int kC>
 __global__ void __launch_bounds__(kPlaneWarps * 32) decode_plane_kernel(
     const float* __restrict__ logits, const long long* __restrict__ file_offsets,
     const int* __restrict__ block_offsets, int n_files, DecodeParams p, int total_blocks,
-    uint32_t* __restrict__ planes, int* __restrict__ start_counts, int* __restrict__ end_counts,
-    int32_t* __restrict__ table, long long capacity) {
+    const uint8_t* __restrict__ act, uint32_t* __restrict__ planes, int* __restrict__ start_counts,
+    int* __restrict__ end_counts, int32_t* __restrict__ table, long long capacity) {
   const int lane = lane_id();
   const int blk = blockIdx.x * kPlaneWarps + (threadIdx.x >> 5);
   if (blk >= total_blocks) return;  // warp-uniform
@@ -682,7 +521,7 @@ __global__ void __launch_bounds__(kPlaneWarps * 32) decode_plane_kernel(
 #pragma unroll
     for (int c = 0; c < kMaxC; ++c) w[c] = 0;
     const int n_here = (int)min((long long)kDecodeBlock, f_end - base);  // frames of this block that exist
-    if (kC == 4 && p.mode == SEGMA_DECODE_LOGIT) {  // the product's configuration: four compares and ballots per step
+    if (kC == 4 && p.mode == SEGMA_DECODE_LOGIT && act == nullptr) {  // the product's configuration: four compares and ballots per step
       const float4* rows = reinterpret_cast<const float4*>(logits) + base;
       const float t0 = p.thr[0], t1 = p.thr[1], t2 = p.thr[2], t3 = p.thr[3];
 #pragma unroll 1
@@ -705,7 +544,9 @@ __global__ void __launch_bounds__(kPlaneWarps * 32) decode_plane_kernel(
 #pragma unroll 4
       for (int k = 0; k < 32; ++k) {
         if (32 * k >= n_here) break;  // warp-uniform
-        const uint32_t bits = 32 * k + lane < n_here ? frame_bits(logits, base + 32 * k + lane, p) : 0u;
+        // act: activity bytes resolved by the hysteresis kernels instead of thresholded logits
+        uint32_t bits = 0;
+        if (32 * k + lane < n_here) bits = act ? act[base + 32 * k + lane] : frame_bits(logits, base + 32 * k + lane, p);
 #pragma unroll
         for (int c = 0; c < kMaxC; ++c) {
           if (c < C) {
@@ -715,8 +556,8 @@ __global__ void __launch_bounds__(kPlaneWarps * 32) decode_plane_kernel(
         }
       }
     }
-    if (base - 1 >= f_begin) prev_bits = frame_bits(logits, base - 1, p);            // same address in every lane
-    if (base + kDecodeBlock < f_end) next_bits = frame_bits(logits, base + kDecodeBlock, p);
+    if (base - 1 >= f_begin) prev_bits = act ? act[base - 1] : frame_bits(logits, base - 1, p);  // same address in every lane
+    if (base + kDecodeBlock < f_end) next_bits = act ? act[base + kDecodeBlock] : frame_bits(logits, base + kDecodeBlock, p);
   } else {
 #pragma unroll
     for (int c = 0; c < kMaxC; ++c) {
@@ -1005,7 +846,7 @@ __global__ void __launch_bounds__(kPostThreads) filter_intervals_kernel(const in
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct DecodeLayout {
-  size_t bits_off, starts_off, ends_off, file_off, block_off, codes_off, summary_off, carry_off, bfile_off, tiles_off, total;
+  size_t bits_off, act_off, starts_off, ends_off, file_off, block_off, codes_off, summary_off, carry_off, bfile_off, tiles_off, total;
   long long n_count;
 };
 
@@ -1016,6 +857,7 @@ static DecodeLayout decode_layout(long long n_frames, int n_files, int C) {
   size_t off = 0;
   // one word per frame (generic path), one byte per frame (byte path) or C x 128 bytes per block (bit planes)
   L.bits_off = off; off = align_up(off + std::max(sizeof(uint32_t) * (size_t)n_frames, (size_t)max_blocks * C * 128), 256);
+  L.act_off = off; off = align_up(off + (size_t)n_frames, 256);  // hysteresis: resolved activity bytes
   L.starts_off = off; off = align_up(off + sizeof(int) * (size_t)L.n_count, 256);
   L.ends_off = off; off = align_up(off + sizeof(int) * (size_t)L.n_count, 256);
   L.file_off = off; off = align_up(off + sizeof(long long) * (size_t)(n_files + 1), 256);
@@ -1115,10 +957,11 @@ static int decode_impl(const float* logits, const int64_t* file_offsets, int n_f
   int* d_bfile = reinterpret_cast<int*>(ws + L.bfile_off);
   int* d_tiles = reinterpret_cast<int*>(ws + L.tiles_off);
   // pageable-source async copies are staged before returning, so block_offsets may go out of scope
-  const bool fast = n_labels <= 8;  // bit planes (plain thresholds) or one activity byte per frame (hysteresis)
+  const bool fast = n_labels <= 8;  // bit planes (built from thresholded logits, or from the resolved hysteresis bytes)
+  const uint8_t* act = nullptr;
   const long long n_counts = (long long)total_blocks * n_labels;
-  // plain thresholds on long inputs: two-kernel scan over tiles of 2048 block counts
-  const int plane_tiles = (fast && !onset && n_counts > 4 * kScanTile) ? (int)ceil_div_ll(n_counts, kPlaneScanTile) : 0;
+  // long inputs: two-kernel scan over tiles of 2048 block counts
+  const int plane_tiles = (fast && n_counts > 4 * kScanTile) ? (int)ceil_div_ll(n_counts, kPlaneScanTile) : 0;
   if (!fast || onset) block_file_kernel<<<ceil_div(total_blocks, 256), 256, 0, st>>>(d_block, n_files, total_blocks, d_bfile);
   static_assert(kFastBlock == kDecodeBlock, "both paths tile files in blocks of 1024 frames");
   if (onset) {
@@ -1139,19 +982,19 @@ static int decode_impl(const float* logits, const int64_t* file_offsets, int n_f
     hyst_carry_kernel<<<ceil_div(n_files, 128), 128, 0, st>>>(summary, d_block, n_files, carry);
     rc = launch_status("hyst_carry_kernel");
     if (rc != SEGMA_OK) return rc;
-    hyst_resolve_kernel<<<total_blocks, kFastThreads, 0, st>>>(codes, d_file, d_block, d_bfile, n_labels, carry,
-                                                             reinterpret_cast<uint8_t*>(bits));
+    uint8_t* act_out = reinterpret_cast<uint8_t*>(ws + L.act_off);
+    hyst_resolve_kernel<<<total_blocks, kFastThreads, 0, st>>>(codes, d_file, d_block, d_bfile, n_labels, carry, act_out);
+    act = act_out;
     rc = launch_status("hyst_resolve_kernel");
     if (rc != SEGMA_OK) return rc;
-    decode_fast_kernel<2><<<total_blocks, kFastThreads, 0, st>>>(
-        logits, d_file, d_block, d_bfile, p, reinterpret_cast<uint8_t*>(bits), starts, ends, table, capacity);
-  } else if (fast) {
+  }
+  if (fast) {
     if (n_labels == 4)
       decode_plane_kernel<false, 4><<<ceil_div(total_blocks, kPlaneWarps), kPlaneWarps * 32, 0, st>>>(
-          logits, d_file, d_block, n_files, p, total_blocks, bits, starts, ends, table, capacity);
+          logits, d_file, d_block, n_files, p, total_blocks, act, bits, starts, ends, table, capacity);
     else
       decode_plane_kernel<false, 0><<<ceil_div(total_blocks, kPlaneWarps), kPlaneWarps * 32, 0, st>>>(
-          logits, d_file, d_block, n_files, p, total_blocks, bits, starts, ends, table, capacity);
+          logits, d_file, d_block, n_files, p, total_blocks, act, bits, starts, ends, table, capacity);
   } else {
     decode_count_kernel<<<total_blocks, kDecodeBlock, 0, st>>>(logits, d_file, d_block, n_files, p, bits, starts, ends);
   }
@@ -1170,16 +1013,13 @@ static int decode_impl(const float* logits, const int64_t* file_offsets, int n_f
   }
   rc = launch_status("decode scan pass");
   if (rc != SEGMA_OK) return rc;
-  if (fast && !onset) {
+  if (fast) {
     if (n_labels == 4)
       decode_plane_kernel<true, 4><<<ceil_div(total_blocks, kPlaneWarps), kPlaneWarps * 32, 0, st>>>(
-          logits, d_file, d_block, n_files, p, total_blocks, bits, starts, ends, table, capacity);
+          logits, d_file, d_block, n_files, p, total_blocks, nullptr, bits, starts, ends, table, capacity);
     else
       decode_plane_kernel<true, 0><<<ceil_div(total_blocks, kPlaneWarps), kPlaneWarps * 32, 0, st>>>(
-          logits, d_file, d_block, n_files, p, total_blocks, bits, starts, ends, table, capacity);
-  } else if (fast) {  // hysteresis keeps its activity bytes
-    decode_fast_kernel<1><<<total_blocks, kFastThreads, 0, st>>>(
-        logits, d_file, d_block, d_bfile, p, reinterpret_cast<uint8_t*>(bits), starts, ends, table, capacity);
+          logits, d_file, d_block, n_files, p, total_blocks, nullptr, bits, starts, ends, table, capacity);
   } else {
     decode_write_kernel<<<total_blocks, kDecodeBlock, 0, st>>>(bits, d_file, d_block, n_files, n_labels, starts, ends,
                                                                table, capacity);

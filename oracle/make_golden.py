@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the REFERENCE itself
 (/root/reference, imported through oracle/ref_shim.py) on seeded synthetic inputs.
 
-    python oracle/make_golden.py
+    python oracle/make_golden.py [geometry logmel intervals models models_large whisper_config2 postprocess tuning]
 
 Inputs are not stored: every fixture records the seeds, and tests regenerate audio and weights with
 ``segma_b200.synth``.  Outputs are the reference's own: ``ConvolutionSettings`` values, the Whisper
@@ -174,11 +174,168 @@ def intervals():
     np.savez(OUT / "intervals.npz", **out)
 
 
+def _hubert_reference_model(le, wavlm: bool, dims, seed):
+    """The reference's ``SurgicalHydraHubert`` (torchaudio ``wavlm_base`` swapped in for WavLM)."""
+    sub = SurgicalHydraLightHuBERTConfig(wav_encoder="none", encoder_layers=[], reduction="weighted", classifier=256, freeze_encoder=True)
+    m = Models["surgical_hubert_hydra"](le, ref_shim.make_config("surgical_hubert_hydra", sub), train=False).eval()
+    if wavlm:
+        import torchaudio
+
+        m.wav2vec2 = torchaudio.models.wavlm_base().eval()
+    torch.nn.Module.load_state_dict(m, synth.hubert_hydra_state_dict(dims, seed=seed), strict=True)
+    return m
+
+
+def models_large():
+    """HuBERT-base / WavLM-base+ dims on 26 windows + tail (20 800 label decisions each: enough to resolve the
+    99.9 % agreement bar) through the reference's own ``apply_model_on_audio``."""
+    le = MultiLabelEncoder(list(LABELS))
+    cs = ConvolutionSettings((320,), (320,), (0,))
+    n, audio_seed, bs = 63680 * 26 + 320 + 8320, 31, 128
+    pcm = synth.synth_audio(n, audio_seed)
+    audio = ref_shim.InMemoryAudio()
+    audio.add("/mem/large.wav", pcm)
+    audio.patch()
+    out = {"meta": np.array([n, audio_seed, bs])}
+    for key, wavlm, dims, seed in (("hubert_logits", False, synth.HUBERT_BASE, 5), ("wavlm_logits", True, synth.WAVLM_BASE, 6)):
+        m = _hubert_reference_model(le, wavlm, dims, seed)
+        out[key] = inf.apply_model_on_audio(Path("/mem/large.wav"), m, cs, "cpu", batch_size=bs).numpy()
+        assert out[key].shape == ((n - 400) // 320 + 1, 4), out[key].shape
+    np.savez_compressed(OUT / "models_large.npz", **out)
+
+
+def whisper_config2():
+    """BASELINE config 2's model (Whisper-small dims ``surgical_hydra``, the weights bench.py uses) on one full
+    128-window batch + a remainder batch of 8 + the tail, composed from the reference's own classes: the LSTM
+    recurrence runs over all 128 windows of the first forward call (surgical_hydra.py:57-60,101)."""
+    le = MultiLabelEncoder(list(LABELS))
+    dims = synth.WHISPER_SMALL
+    enc_dir = _whisper_dir(dims)
+    cfg = ref_shim.make_config("surgical_hydra", SurgicalHydraConfig(encoder=enc_dir, encoder_layers=[], reduction="weighted",
+                                                                      lstm=LSTMConfig(128, 2, True, 0.5), classifier=256))
+    m = Models["surgical_hydra"](le, cfg).eval()
+    m.load_state_dict(synth.surgical_hydra_state_dict(dims, seed=0), strict=True)
+    n, audio_seed, bs = 63680 * 136 + 33280, 2, 128
+    logits = _compose_whisper_file(m, synth.synth_audio(n, audio_seed), bs).numpy()
+    assert logits.shape == (136 * 199 + 103, 4), logits.shape
+    np.savez_compressed(OUT / "whisper_config2.npz", logits=logits, meta=np.array([n, audio_seed, bs]))
+
+
+#: the insertion sequences of /root/reference/tests/test_interval.py (every ``Intervals()`` block of its 20 tests),
+#: labels as in the tests; the expected lists are NOT copied -- they are produced by running the reference class
+INTERVAL_KAT_INPUTS = [
+    [],
+    [(0, 10, "a")],
+    [(0, 10, "a"), (10, 20, "a")],
+    [(0, 5, "b"), (5, 10, "b"), (10, 15, "b")],
+    [(0, 10, "a"), (5, 15, "a")],
+    [(0, 20, "a"), (5, 10, "a")],
+    [(0, 10, "a"), (8, 20, "a")],
+    [(0, 10, "a"), (15, 25, "a")],
+    [(0, 5, "a"), (10, 15, "a"), (20, 25, "a")],
+    [(0, 10, "a"), (10, 20, "b")],
+    [(0, 15, "a"), (10, 20, "b")],
+    [(0, 10, "a"), (5, 15, "b"), (10, 20, "a"), (12, 18, "b")],
+    [(0, 10, 1), (10, 20, 1)],
+    [(0, 10, 1), (5, 15, 2), (10, 20, 1)],
+    [(0, 10, "a"), (5, 15, 1), (10, 20, "a"), (15, 25, 1)],
+    [(5, 5, "a"), (5, 5, "a")],
+    [(5, 5, "a"), (5, 10, "a")],
+    [(20, 30, "a"), (0, 10, "a"), (10, 20, "a")],
+    [(15, 20, "b"), (5, 10, "a"), (0, 5, "a"), (10, 15, "b")],
+    [(i, i + 10, "a") for i in range(0, 50, 5)],
+    [(-10, 0, "a"), (0, 10, "a")],
+    [(-20, -10, "a"), (-15, -5, "a")],
+    [(0, 1000000, "a"), (1000000, 2000000, "a")],
+    [(0, 5, "a"), (10, 15, "a"), (5, 10, "a"), (7, 12, "b")],
+    [(0, 20, "a"), (5, 10, "a"), (12, 15, "a")],
+    [(0, 10, "a"), (0, 10, "a"), (0, 10, "a")],
+    [(0, 10, "a"), (11, 20, "a")],
+    [(0, 10, "a-b"), (10, 20, "a-b")],
+    [(0, 10, "label with spaces"), (5, 15, "label with spaces")],
+    [(0, 10, ""), (10, 20, "")],
+]
+
+
+def postprocess():
+    """the reference's ``Intervals`` struct (src/segma/structs/interval.py:8-54) run on the
+    insertion sequences of its own tests and on interval lists decoded from random masks (inserted in a shuffled
+    order, with nested / overlapping extras); stored as JSON because labels mix ints and strings."""
+    import json
+
+    from segma.structs.interval import Intervals
+
+    cs = ConvolutionSettings((320,), (320,), (0,))
+    le = MultiLabelEncoder(list(LABELS))
+    cases = []
+    for seq in INTERVAL_KAT_INPUTS:
+        iv = Intervals()
+        states = []
+        for item in seq:
+            iv.add(item)
+            states.append([list(t) for t in iv.intervals])
+        cases.append({"adds": [list(t) for t in seq], "after_each_add": states, "final": [list(t) for t in iv.intervals]})
+    rng = np.random.default_rng(7)
+    for nf, p in [(400, 0.5), (2000, 0.85), (3000, 0.2)]:
+        mask = rng.random((nf, 4)) < p
+        decoded = inf.create_intervals(torch.from_numpy(mask), cs, le)
+        extra = [(int(s) + 160, int(e) + 7 * 320, lab) for s, e, lab in decoded[::9]]  # overlapping / bridging rows
+        seq = decoded + extra
+        order = rng.permutation(len(seq))
+        iv = Intervals()
+        for j in order:
+            iv.add(seq[int(j)])
+        cases.append({"adds": [list(seq[int(j)]) for j in order], "final": [list(t) for t in iv.intervals]})
+    (OUT / "postprocess.json").write_text(json.dumps({"source": "segma.structs.interval.Intervals", "cases": cases}))
+
+
+def tuning():
+    """``tune_multilabel`` and ``rttm_to_tensor`` of /root/reference/scripts/tune.py (imported with
+    ``ruamel`` stubbed) on seeded logits / a seeded RTTM."""
+    import importlib.util
+    import math
+    import types
+
+    if "ruamel" not in sys.modules:
+        ru = types.ModuleType("ruamel")
+        ru.yaml = types.ModuleType("ruamel.yaml")
+        ru.yaml.YAML = object
+        sys.modules["ruamel"], sys.modules["ruamel.yaml"] = ru, ru.yaml
+    spec = importlib.util.spec_from_file_location("segma_ref_tune", "/root/reference/scripts/tune.py")
+    tune = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tune)
+    out = {}
+    for name, n, seed, precision in (("p10", 50_000, 0, 0.1), ("p100", 50_000, 1, 0.01), ("p10_rare", 3_000, 2, 0.1)):
+        g = torch.Generator().manual_seed(seed)
+        truth = (torch.rand((n, 4), generator=g) < torch.tensor([0.3, 0.05, 0.5, 0.0])).float()
+        logits = (truth * 2 - 1) * 1.5 + torch.randn((n, 4), generator=g) * 1.7
+        n_steps = int(1 / precision)
+        thresholds = torch.linspace(0, 1, steps=n_steps).round(decimals=int(math.log10(n_steps)))
+        tune.n_steps = n_steps  # the function reads the script's module-level n_steps (tune.py:246)
+        best = tune.tune_multilabel({"val": {"true": truth, "pred": logits}}, thresholds, list(LABELS))
+        out[f"{name}_meta"] = np.array([n, seed, n_steps])
+        out[f"{name}_thresholds"] = thresholds.numpy()
+        out[f"{name}_best"] = np.array([best[lab]["lower_bound"] for lab in LABELS], dtype=np.float64)
+    with tempfile.TemporaryDirectory() as tmp:
+        rng = np.random.default_rng(3)
+        lines = []
+        for _ in range(40):
+            s, d = rng.uniform(0, 60), rng.uniform(0.05, 4)
+            lab = ["KCHI", "OCH", "MAL", "FEM", "SPEECH"][int(rng.integers(0, 5))]
+            lines.append(f"SPEAKER f <NA> {round(float(s), 8)} {round(float(d), 8)} <NA> <NA> {lab} <NA> <NA>")
+        p = Path(tmp) / "f.rttm"
+        p.write_text("\n".join(lines) + "\n")
+        out["rttm_text"] = np.array("\n".join(lines) + "\n")
+        out["rttm_tensor"] = tune.rttm_to_tensor(p, list(LABELS)).numpy().astype(np.uint8)
+    np.savez_compressed(OUT / "tuning.npz", **out)
+
+
+
 if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
-    geometry()
-    logmel()
-    intervals()
-    models()
-    for p in sorted(OUT.glob("*.npz")):
+    ALL = {"geometry": geometry, "logmel": logmel, "intervals": intervals, "models": models, "models_large": models_large,
+           "whisper_config2": whisper_config2, "postprocess": postprocess, "tuning": tuning}
+    for name in (sys.argv[1:] or list(ALL)):
+        ALL[name]()
+    for p in sorted(OUT.glob("*.np*")) + sorted(OUT.glob("*.json")):
         print(p.name, p.stat().st_size)

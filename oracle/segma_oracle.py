@@ -147,16 +147,18 @@ def _lin(x, sd, name):
 
 
 def _mha(q, k, v, n_heads, bias=None):
-    """softmax(q k^T + bias) v with (B, T, d) inputs; q is already scaled."""
+    """softmax(q k^T + bias) v with (B, T, d) inputs; q is already scaled.  Dispatched the way the
+    reference's third-party modules do it -- ``F.scaled_dot_product_attention`` with ``scale=1.0``
+    (site-packages/transformers/integrations/sdpa_attention.py:92 as selected by modeling_whisper.py:338-350;
+    site-packages/torchaudio/models/wav2vec2/components.py:305, wavlm_attention.py:204 with the gated bias as
+    ``attn_mask``) -- so the CPU arm of bench.py costs what the reference's CPU path costs instead of
+    materialising the (B, H, T, T) score tensor."""
     B, T, d = q.shape
     hd = d // n_heads
     q = q.view(B, T, n_heads, hd).transpose(1, 2)
     k = k.view(B, -1, n_heads, hd).transpose(1, 2)
     v = v.view(B, -1, n_heads, hd).transpose(1, 2)
-    s = q @ k.transpose(-1, -2)
-    if bias is not None:
-        s = s + bias
-    o = torch.softmax(s, dim=-1) @ v
+    o = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, dropout_p=0.0, is_causal=False, scale=1.0)
     return o.transpose(1, 2).reshape(B, T, d)
 
 
@@ -259,7 +261,8 @@ W2V2_KERNELS = (10, 3, 3, 3, 3, 2, 2)
 W2V2_STRIDES = (5, 2, 2, 2, 2, 2, 2)
 
 
-def w2v2_feature_extractor(sd: dict, x: torch.Tensor, prefix: str = "wav2vec2.feature_extractor.") -> torch.Tensor:
+def w2v2_feature_extractor(sd: dict, x: torch.Tensor, prefix: str = "wav2vec2.feature_extractor.",
+                           trace: list | None = None) -> torch.Tensor:
     """torchaudio ``FeatureExtractor`` with GroupNorm on layer 0 only
     (site-packages/torchaudio/models/wav2vec2/components.py:77-99,117-143): (B, n) -> (B, T, 512)."""
     h = x.unsqueeze(1)
@@ -270,6 +273,8 @@ def w2v2_feature_extractor(sd: dict, x: torch.Tensor, prefix: str = "wav2vec2.fe
             h = F.group_norm(h, c, sd[f"{prefix}conv_layers.0.layer_norm.weight"],
                              sd[f"{prefix}conv_layers.0.layer_norm.bias"], 1e-5)
         h = F.gelu(h)
+        if trace is not None:
+            trace.append((f"conv{i}", h.transpose(1, 2)))
     return h.transpose(1, 2)
 
 
@@ -300,7 +305,8 @@ def wavlm_position_bias(rel_attn_embed: torch.Tensor, T: int, num_buckets: int =
     return F.embedding(buckets, rel_attn_embed).permute(2, 0, 1)
 
 
-def w2v2_encoder_last(sd: dict, feats: torch.Tensor, prefix: str = "wav2vec2.encoder.") -> torch.Tensor:
+def w2v2_encoder_last(sd: dict, feats: torch.Tensor, prefix: str = "wav2vec2.encoder.",
+                      trace: list | None = None) -> torch.Tensor:
     """``Encoder.extract_features(x, None)[-1]`` for the base (post-LN) architecture
     (components.py:171-183 projection, 220-234 pos-conv, 421-428 preprocess, 363-401 layer,
     263-310 attention; WavLM attention wavlm_attention.py:166-211).  (B, T, 512) -> (B, T, 768)."""
@@ -315,8 +321,14 @@ def w2v2_encoder_last(sd: dict, feats: torch.Tensor, prefix: str = "wav2vec2.enc
     pc = F.conv1d(x.transpose(1, 2), w, sd[t + "pos_conv_embed.conv.bias"], padding=k // 2, groups=d // w.shape[1])
     if k % 2 == 0:
         pc = pc[..., :-1]
+    if trace is not None:
+        trace.append(("proj", x))
     x = x + F.gelu(pc.transpose(1, 2))
+    if trace is not None:
+        trace.append(("posconv_sum", x))
     x = _ln(x, sd, t + "layer_norm")
+    if trace is not None:
+        trace.append(("ln0", x))
     wavlm = (t + "layers.0.attention.attention.in_proj_weight") in sd
     pos_bias = None
     if wavlm:
@@ -345,15 +357,18 @@ def w2v2_encoder_last(sd: dict, feats: torch.Tensor, prefix: str = "wav2vec2.enc
         x = _ln(x + a, sd, lp + "layer_norm")
         f = _lin(F.gelu(_lin(x, sd, lp + "feed_forward.intermediate_dense")), sd, lp + "feed_forward.output_dense")
         x = _ln(x + f, sd, lp + "final_layer_norm")
+        if trace is not None:
+            trace.append((f"layer{i}", x))
         i += 1
     return x
 
 
-def hubert_hydra_forward(sd: dict, x: torch.Tensor, labels) -> torch.Tensor:
+def hubert_hydra_forward(sd: dict, x: torch.Tensor, labels, trace: list | None = None) -> torch.Tensor:
     """``SurgicalHydraHubert.forward`` (src/segma/models/hubert/surgical_hydra.py:87-101):
-    ``(B, n_samples)`` -> ``(B, T, 1, C)``; dropout is identity in eval."""
-    feats = w2v2_feature_extractor(sd, x)
-    return _heads(sd, w2v2_encoder_last(sd, feats), labels)
+    ``(B, n_samples)`` -> ``(B, T, 1, C)``; dropout is identity in eval.  ``trace`` collects (stage, tensor)
+    pairs for the per-stage diagnosis of the CUDA path (tools/diag_w2v2.py)."""
+    feats = w2v2_feature_extractor(sd, x, trace=trace)
+    return _heads(sd, w2v2_encoder_last(sd, feats, trace=trace), labels)
 
 
 # ----------------------------------------------------------------------------------------
@@ -475,6 +490,25 @@ def hysteresis_mask(logits: torch.Tensor, offset_cuts, onset_cuts) -> np.ndarray
                 state = False
             out[f, c] = state
     return out
+
+
+def intervals_reduce(intervals: list) -> list:
+    """``Intervals._reduce_per_label`` (src/segma/structs/interval.py:19-45): per label, sort and fuse every
+    interval whose start is <= the running end (overlapping, nested or touching); then ``sorted()`` over all labels."""
+    by_label: dict = {}
+    for s, e, lab in intervals:
+        by_label.setdefault(lab, []).append((s, e, lab))
+    out = []
+    for lab, ivs in by_label.items():
+        ivs.sort()
+        cur = [ivs[0]]
+        for s, e, _ in ivs[1:]:
+            if s <= cur[-1][1]:
+                cur[-1] = (cur[-1][0], max(cur[-1][1], e), lab)
+            else:
+                cur.append((s, e, lab))
+        out += cur
+    return sorted(out)
 
 
 def postprocess_table(table: np.ndarray, max_gap: int, min_dur: int) -> np.ndarray:

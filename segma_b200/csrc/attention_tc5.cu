@@ -350,13 +350,13 @@ int launch_attention_tc5(const void* qkv, int n_windows, int T, int n_heads, int
   if (rc != SEGMA_OK) return rc;
   rc = make_f16_map(&map_kv, qkv, 3, dims, strides, kAtK);
   if (rc != SEGMA_OK) return rc;
-  static bool attr_set = false;
+  static PerDeviceFlag attr_set;
   // SEGMA_ATTN_POLY=1 moves a quarter of the exponentials from the MUFU to the FMA pipe (ex2_poly_pair).  Measured
   // slower on B200 (0.370 vs 0.333 ms for 32 windows): the softmax warps are latency-bound, not MUFU-bound, so the
   // longer instruction stream costs more than the freed MUFU slots give back.  Kept as a switch for re-measurement.
   static bool poly = false;
   constexpr int kRelMaxT = 1024;  // the Toeplitz slice (T + 128 floats) must leave room for four CTAs per SM
-  if (!attr_set) {
+  if (!attr_set.here()) {
     SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<0, 0x0000u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
     SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<0, 0x2222u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
     SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<1, 0u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
@@ -364,7 +364,7 @@ int launch_attention_tc5(const void* qkv, int n_windows, int T, int n_heads, int
                                        kAtSmem + 4 * (kRelMaxT + kAtQ)));
     const char* env = getenv("SEGMA_ATTN_POLY");
     poly = env && atoi(env) != 0;
-    attr_set = true;
+    attr_set.here() = true;
   }
   if (bias_mode == 2 && T > kRelMaxT) {
     set_last_error("segma_attention_rel: T=%d exceeds %d", T, kRelMaxT);

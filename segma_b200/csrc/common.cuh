@@ -40,6 +40,19 @@ inline int launch_status(const char* kernel) {
 
 int device_sm_count();
 
+// State that must be set up once per CUDA device (function attributes, __device__ tables, cached device properties):
+// a process may drive several devices, so "done" flags are kept per device ordinal, not per process.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return d;
+}
+struct PerDeviceFlag {
+  bool done[kMaxDevices] = {};
+  bool& here() { return done[current_device()]; }
+};
+
 constexpr int kWarp = 32;
 
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -4,6 +4,7 @@
 // NumPy/Python run extraction of create_intervals (237-263).  All three are HBM-bound streaming
 // passes: one coalesced read of the logits, warp-shuffle/ballot run-boundary detection, a block
 // offset scan, and a compacted int32 table write.
+#include <climits>
 #include <algorithm>
 #include <vector>
 
@@ -777,40 +778,87 @@ __device__ __forceinline__ int block_incl_scan(int v, int* s_warp, int lane, int
   return r;
 }
 
+// Segmented running maximum of the interval ends: (flag, val) pairs under (a then b) -> (a.flag | b.flag,
+// b.flag ? b.val : max(a.val, b.val)); flag marks the first row of a (file, label) segment.
+struct SegMax { int flag, val; };
+__device__ __forceinline__ SegMax segmax(SegMax a, SegMax b) {
+  return SegMax{a.flag | b.flag, b.flag ? b.val : max(a.val, b.val)};
+}
+
+__device__ __forceinline__ SegMax block_incl_segmax(SegMax v, int* s_flag, int* s_val, int lane, int warp) {
+  SegMax x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    SegMax t{__shfl_up_sync(0xffffffffu, x.flag, o), __shfl_up_sync(0xffffffffu, x.val, o)};
+    if (lane >= o) x = segmax(t, x);
+  }
+  if (lane == 31) { s_flag[warp] = x.flag; s_val[warp] = x.val; }
+  __syncthreads();
+  if (warp == 0) {
+    SegMax y{s_flag[lane], s_val[lane]};
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      SegMax t{__shfl_up_sync(0xffffffffu, y.flag, o), __shfl_up_sync(0xffffffffu, y.val, o)};
+      if (lane >= o) y = segmax(t, y);
+    }
+    s_flag[lane] = y.flag;  // inclusive over warps 0..lane
+    s_val[lane] = y.val;
+  }
+  __syncthreads();
+  if (warp > 0) x = segmax(SegMax{s_flag[warp - 1], s_val[warp - 1]}, x);
+  __syncthreads();
+  return x;
+}
+
+// Rows sorted by (file, label, start).  A row opens a new interval when its (file, label) differs from the previous
+// row's or its start lies more than max_gap past the largest end seen so far in that (file, label) -- the reference's
+// `s <= ret[-1][1]` test (interval.py:26-31) generalised by the gap -- so overlapping and nested rows merge too; the
+// merged end is that running maximum.
 __global__ void __launch_bounds__(kPostThreads) merge_intervals_kernel(const int4* __restrict__ in, long long n,
                                                                        int max_gap, int4* __restrict__ merged,
                                                                        int* __restrict__ n_merged) {
-  __shared__ int s_warp[32];
-  __shared__ int s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
+  __shared__ int s_warp[32], s_flag[32], s_val[32];
+  __shared__ int s_incl[kPostThreads];
+  __shared__ int s_carry, s_carry_end;
+  if (threadIdx.x == 0) { s_carry = 0; s_carry_end = INT_MIN; }
   __syncthreads();
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   for (long long base = 0; base < n; base += kPostThreads) {
     const long long i = base + threadIdx.x;
-    int head = 0, last = 0;
-    int4 row = make_int4(0, 0, 0, 0);
+    int4 row = make_int4(0, 0, 0, INT_MIN);
+    int key_head = 0;
     if (i < n) {
       row = in[i];
       if (i == 0) {
-        head = 1;
+        key_head = 1;
       } else {
         const int4 pr = in[i - 1];
-        head = (pr.x != row.x || pr.y != row.y || row.z - pr.w > max_gap) ? 1 : 0;
+        key_head = (pr.x != row.x || pr.y != row.y) ? 1 : 0;
       }
+    }
+    SegMax m = block_incl_segmax(SegMax{key_head, row.w}, s_flag, s_val, lane, warp);
+    const int carry_end = s_carry_end;
+    if (!m.flag) m.val = max(m.val, carry_end);  // same (file, label) as the last row of the previous chunk
+    s_incl[threadIdx.x] = m.val;
+    __syncthreads();
+    int head = 0, last = 0;
+    if (i < n) {
+      const int before = threadIdx.x > 0 ? s_incl[threadIdx.x - 1] : carry_end;
+      head = (key_head || (long long)row.z - before > max_gap) ? 1 : 0;
       if (i == n - 1) {
         last = 1;
       } else {
         const int4 nx = in[i + 1];
-        last = (nx.x != row.x || nx.y != row.y || nx.z - row.w > max_gap) ? 1 : 0;
+        last = (nx.x != row.x || nx.y != row.y || (long long)nx.z - m.val > max_gap) ? 1 : 0;
       }
     }
     const int g = s_carry + block_incl_scan(head, s_warp, lane, warp) - 1;  // group index of row i
     if (i < n) {
       if (head) { merged[g].x = row.x; merged[g].y = row.y; merged[g].z = row.z; }
-      if (last) merged[g].w = row.w;
+      if (last) merged[g].w = m.val;
     }
     __syncthreads();
-    if (threadIdx.x == kPostThreads - 1) s_carry = g + 1;
+    if (threadIdx.x == kPostThreads - 1) { s_carry = g + 1; s_carry_end = m.val; }
     __syncthreads();
   }
   if (threadIdx.x == 0) *n_merged = s_carry;

@@ -384,23 +384,23 @@ int make_f16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* d
 
 // CTAs of the persistent grid: one per SM, or fewer when SEGMA_GEMM_MAX_CTAS leaves SMs to a concurrent kernel
 static int gemm_cta_limit() {
-  static int limit = 0;
-  if (limit == 0) {
-    limit = device_sm_count();
+  static int env_limit = -1;
+  if (env_limit < 0) {
     const char* env = getenv("SEGMA_GEMM_MAX_CTAS");
-    if (env && atoi(env) > 0) limit = std::min(limit, atoi(env));
+    env_limit = env && atoi(env) > 0 ? atoi(env) : 0;
   }
-  return limit;
+  const int sms = device_sm_count();
+  return env_limit > 0 ? std::min(sms, env_limit) : sms;
 }
 
 template <int BN, bool kCta2, int kEW, bool kAddSrc>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, GemmKernelArgs& ka, cudaStream_t st) {
   using Cfg = GemmCfg<BN, kCta2, kEW>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  if (!attr_set.here()) {
     SEGMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc5_kernel<BN, kCta2, kEW, kAddSrc>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
+    attr_set.here() = true;
   }
   ka.n_tiles = ceil_div(ka.n, BN);
   const int units_per_batch = kCta2 ? (ka.tiles_per_batch + 1) / 2 : ka.tiles_per_batch;

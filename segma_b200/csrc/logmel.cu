@@ -46,7 +46,7 @@ struct MelTables {
 __device__ MelTables g_tab;
 
 static std::mutex g_tab_mutex;
-static bool g_tab_ready = false;
+static PerDeviceFlag g_tab_ready;  // the __device__ tables exist once per device
 static std::vector<float> g_mel_dense;  // (201, 80) row-major, active filterbank
 
 static double hz_to_mel(double f) {
@@ -98,13 +98,13 @@ static int upload_tables_locked() {
     for (int i = 0; i < len; ++i) h.mel_w[m][i] = g_mel_dense[(size_t)(first + i) * kMels + m];
   }
   SEGMA_CUDA_OK(cudaMemcpyToSymbol(g_tab, &h, sizeof(h)));
-  g_tab_ready = true;
+  g_tab_ready.here() = true;
   return SEGMA_OK;
 }
 
 static int ensure_tables() {
   std::lock_guard<std::mutex> lock(g_tab_mutex);
-  if (g_tab_ready) return SEGMA_OK;
+  if (g_tab_ready.here()) return SEGMA_OK;
   if (g_mel_dense.empty()) default_mel(g_mel_dense);
   return upload_tables_locked();
 }
@@ -466,6 +466,7 @@ int segma_logmel_set_filters(const float* mel_201x80) {
   SEGMA_REQUIRE(mel_201x80 != nullptr, "segma_logmel_set_filters: NULL matrix");
   std::lock_guard<std::mutex> lock(g_tab_mutex);
   g_mel_dense.assign(mel_201x80, mel_201x80 + (size_t)kBins * kMels);
+  for (bool& ready : g_tab_ready.done) ready = false;  // other devices pick the new filterbank up on their next call
   return upload_tables_locked();
 }
 
@@ -496,10 +497,10 @@ int segma_logmel(const float* pcm, int64_t pcm_len, int n_windows, int win_len, 
   float* logspec = reinterpret_cast<float*>(static_cast<char*>(scratch) + head);
   SEGMA_CUDA_OK(cudaMemsetAsync(win_max, 0, (size_t)n_windows * sizeof(uint32_t), st));
   const size_t smem = sizeof(float2) * kGroup * kHalf + sizeof(float) * std::max(kStage, kGroup * kBins) + sizeof(SmemTables);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  if (!attr_set.here()) {
     SEGMA_CUDA_OK(cudaFuncSetAttribute(logmel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set.here() = true;
   }
   const int groups = nvp / kGroup;
   const int grid_a = std::min(n_windows * groups, 4 * device_sm_count());

@@ -180,10 +180,10 @@ int segma_lstm_layer(const float* pre, const float* w_hh_t, int n_steps, int n_r
     }
     case 128: {
       constexpr int kSmem = 128 * 512 * 2 + 128 * 4 * 4 + kLstmRowsSmem * 512 * 4;
-      static bool attr_set = false;
-      if (!attr_set) {
+      static PerDeviceFlag attr_set;
+      if (!attr_set.here()) {
         SEGMA_CUDA_OK(cudaFuncSetAttribute(lstm_layer_smem_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-        attr_set = true;
+        attr_set.here() = true;
       }
       lstm_layer_smem_kernel<128><<<grid_s, 512, kSmem, st>>>(pre, w_hh_t, n_steps, n_rows, n_dirs, out, ob);
       break;

@@ -31,6 +31,30 @@ def _f32(t: torch.Tensor, device) -> torch.Tensor:
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
+def resolve_device(device) -> torch.device:
+    """``"cuda"`` / ``cuda:N`` -> a device with an explicit index (the current one when none is given)."""
+    dev = torch.device(device)
+    if dev.type == "cuda" and dev.index is None and torch.cuda.is_available():
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def move_to(obj, device):
+    """Packed weights (tensors nested in lists / dicts / small holder objects) -> ``device``."""
+    if isinstance(obj, torch.Tensor):
+        return obj.to(device)
+    if isinstance(obj, list):
+        return [move_to(v, device) for v in obj]
+    if isinstance(obj, tuple):
+        return tuple(move_to(v, device) for v in obj)
+    if isinstance(obj, dict):
+        return {k: move_to(v, device) for k, v in obj.items()}
+    if isinstance(obj, (_LstmLayer, LstmHeads)):
+        for k, v in vars(obj).items():
+            setattr(obj, k, move_to(v, device))
+    return obj
+
+
 @dataclass
 class _LstmLayer:
     w_ih: torch.Tensor  # (n_dirs*4H, in) fp16
@@ -72,8 +96,9 @@ class LstmHeads:
 class WhisperEngine:
     def __init__(self, sd: dict, labels, *, kind: str = "surgical_hydra", encoder_layers=None,
                  reduction: str = "weighted", n_keep: int = 199, device="cuda", prefix: str = "w_encoder."):
-        ops.device_check()
-        self.device = torch.device(device)
+        self.device = resolve_device(device)
+        with torch.cuda.device(self.device):
+            ops.device_check()
         self.kind = kind
         self.labels = tuple(labels)
         self.n_keep = n_keep
@@ -129,6 +154,18 @@ class WhisperEngine:
         self.tail = LstmHeads(sd, labels, dev)
         self._slots: dict[int, tuple[int, dict]] = {}  # workspace slot -> (capacity in windows, buffers)
         self._ws: dict[str, torch.Tensor] = {}
+
+    def to(self, device) -> "WhisperEngine":
+        """Move the packed weights to another CUDA device; workspaces are re-created there on demand."""
+        device = resolve_device(device)
+        if device != self.device:
+            for k, v in vars(self).items():
+                if k not in ("_slots", "_ws", "device"):
+                    setattr(self, k, move_to(v, device))
+            self._slots, self._ws, self.device = {}, {}, device
+            with torch.cuda.device(device):
+                ops.device_check()
+        return self
 
     # ---- workspace -------------------------------------------------------------------------------
     def _reserve(self, n: int, slot: int = 0) -> None:
@@ -197,27 +234,29 @@ class WhisperEngine:
         """Windows ``pcm[start + i*step : +win_len]``, i < n, of a device-resident 1-D fp32 signal ->
         ``logits[(frame_offset + i*step_frames + r), :]`` for r < n_keep.  ``slot`` selects the workspace
         (batches running concurrently on different streams use different slots)."""
-        self._reserve(n, slot)
-        ws = self._ws
-        need = ops.logmel_scratch_bytes(n, win_len)
-        if ws["mel_scratch"].numel() < need:
-            ws["mel_scratch"] = torch.empty(need, dtype=torch.uint8, device=self.device)
-        view = pcm[start:]
-        ops.logmel_into(view, n, win_len, step, ws["mel_tm"], ws["mel_scratch"])
-        self.encode_tm(ws["mel_tm"], n)
-        keep = self.n_keep if n_keep is None else n_keep
-        self.tail.run(ws["mix"][:n].view(n * self.n_keep, self.d), ws["mix_f16"][: n * self.n_keep], n, self.n_keep,
-                      logits, frame_offset, step_frames, keep)
+        with torch.cuda.device(self.device):
+            self._reserve(n, slot)
+            ws = self._ws
+            need = ops.logmel_scratch_bytes(n, win_len)
+            if ws["mel_scratch"].numel() < need:
+                ws["mel_scratch"] = torch.empty(need, dtype=torch.uint8, device=self.device)
+            view = pcm[start:]
+            ops.logmel_into(view, n, win_len, step, ws["mel_tm"], ws["mel_scratch"])
+            self.encode_tm(ws["mel_tm"], n)
+            keep = self.n_keep if n_keep is None else n_keep
+            self.tail.run(ws["mix"][:n].view(n * self.n_keep, self.d), ws["mix_f16"][: n * self.n_keep], n, self.n_keep,
+                          logits, frame_offset, step_frames, keep)
 
     def forward_features(self, feats: torch.Tensor) -> torch.Tensor:
         """Drop-in ``model.forward``: (B, 80, 3000) fp32 log-mel -> (B, n_keep, 1, C) fp32 logits."""
         n = feats.shape[0]
-        self._reserve(n)
-        ws = self._ws
-        tm = ws["mel_tm"][:n]
-        tm[:, 1:-1] = feats.to(self.device).transpose(1, 2).to(torch.float16)  # layout change only
-        self.encode_tm(ws["mel_tm"], n)
-        logits = torch.empty((n * self.n_keep, len(self.labels)), dtype=torch.float32, device=self.device)
-        self.tail.run(ws["mix"][:n].view(n * self.n_keep, self.d), ws["mix_f16"][: n * self.n_keep], n, self.n_keep,
-                      logits, 0, self.n_keep, self.n_keep)
+        with torch.cuda.device(self.device):
+            self._reserve(n)
+            ws = self._ws
+            tm = ws["mel_tm"][:n]
+            tm[:, 1:-1] = feats.to(self.device).transpose(1, 2).to(torch.float16)  # layout change only
+            self.encode_tm(ws["mel_tm"], n)
+            logits = torch.empty((n * self.n_keep, len(self.labels)), dtype=torch.float32, device=self.device)
+            self.tail.run(ws["mix"][:n].view(n * self.n_keep, self.d), ws["mix_f16"][: n * self.n_keep], n, self.n_keep,
+                          logits, 0, self.n_keep, self.n_keep)
         return logits.view(n, self.n_keep, 1, len(self.labels))

@@ -15,6 +15,7 @@ import math
 import torch
 
 from . import ops
+from .engine import move_to, resolve_device
 
 HEAD_DIM = 64
 CONV_KERNELS = (10, 3, 3, 3, 3, 2, 2)
@@ -66,8 +67,9 @@ def wavlm_relative_bias(rel_attn_embed: torch.Tensor, T: int, num_buckets: int, 
 
 class W2V2Engine:
     def __init__(self, sd: dict, labels, device="cuda", prefix: str = "wav2vec2."):
-        ops.device_check()
-        dev = self.device = torch.device(device)
+        dev = self.device = resolve_device(device)
+        with torch.cuda.device(dev):
+            ops.device_check()
         self.labels = tuple(labels)
         fe = prefix + "feature_extractor."
         w0 = sd[fe + "conv_layers.0.conv.weight"]
@@ -137,6 +139,12 @@ class W2V2Engine:
         self.head_w = _f32(torch.cat([sd[f"task_heads.linear_head_{lab}.weight"] for lab in labels], dim=0), dev)
         self.head_b = _f32(torch.cat([sd[f"task_heads.linear_head_{lab}.bias"] for lab in labels], dim=0), dev)
         self._ws: dict[tuple[int, int], dict] = {}
+        #: diagnostics only (tools/diag_w2v2.py): when a list, every stage appends (name, copy of its output)
+        self.trace: list | None = None
+
+    def _tr(self, name: str, t: torch.Tensor) -> None:
+        if self.trace is not None:
+            self.trace.append((name, t.detach().float().clone()))
 
     def _pos_bias_for(self, T: int) -> torch.Tensor:
         if T not in self._pos_bias:
@@ -183,9 +191,27 @@ class W2V2Engine:
         self._ws[key] = ws
         return ws
 
+    def to(self, device) -> "W2V2Engine":
+        """Move the packed weights to another CUDA device; workspaces and bias tables are re-created there on demand."""
+        device = resolve_device(device)
+        if device != self.device:
+            for k, v in vars(self).items():
+                if k not in ("_ws", "_pos_bias", "device", "rel_embed"):
+                    setattr(self, k, move_to(v, device))
+            self._ws, self.device = {}, device
+            if self.wavlm:
+                self._pos_bias = {}
+            with torch.cuda.device(device):
+                ops.device_check()
+        return self
+
     def forward_pcm(self, pcm: torch.Tensor, start: int, n: int, win_len: int, step: int, logits: torch.Tensor,
                     frame_offset: int, step_frames: int, n_keep: int | None = None, slot: int = 0) -> None:
         """Windows ``pcm[start + i*step : +win_len]``, i < n -> ``logits[frame_offset + i*step_frames + r]``, r < n_keep."""
+        with torch.cuda.device(self.device):
+            self._forward_pcm(pcm, start, n, win_len, step, logits, frame_offset, step_frames, n_keep, slot)
+
+    def _forward_pcm(self, pcm, start, n, win_len, step, logits, frame_offset, step_frames, n_keep, slot) -> None:
         ws = self._workspace(n, win_len, slot)
         lens, T, C, d = ws["lens"], ws["T"], self.C, self.d
         if T <= 0:
@@ -193,11 +219,13 @@ class W2V2Engine:
         view = pcm[start:]
         act = ws["act"]
         ops.w2v2_layer0(view, n, win_len, step, self.conv0_w, self.gn_g, self.gn_b, ws["ss"], act[0])
+        self._tr("conv0", act[0][:, : lens[0]])
         for i in range(1, 7):
             src = act[i - 1]
             if i < 6:
                 ops.conv1d_tm(src, self.conv_w[i - 1], None, CONV_KERNELS[i], CONV_STRIDES[i], lens[i], gelu=True,
                               out=act[i], out_batch_rows=act[i].shape[1])
+                self._tr(f"conv{i}", act[i][:, : lens[i]])
             else:
                 ops.conv1d_tm(src, self.conv_w[i - 1], None, CONV_KERNELS[i], CONV_STRIDES[i], T, gelu=True,
                               out=ws["feat"].view(n, T, C))
@@ -213,14 +241,18 @@ class W2V2Engine:
                      flags=ops.GEMM_GELU | ops.GEMM_OUT_F32, conv_taps=self.pos_k, conv_stride=1,
                      a_rows_per_batch=xp.shape[1], a_col_per_ntile=bn, a_cols=d, force_bn=bn)
         x, xh, tmp = ws["x"], ws["x_f16"], ws["tmp"]
+        self._tr("conv6", ws["feat"].view(n, T, C))
+        self._tr("proj", ws["x0"].view(n, T, d))
+        self._tr("posconv_sum", tmp.view(n, T, d))
         ops.layernorm(tmp, self.ln0_g, self.ln0_b, out_f16=xh, out_f32=x)
+        self._tr("ln0", x.view(n, T, d))
         rel_bias = pos_bias = None
         if self.wavlm:
             if T <= self.REL_BIAS_MAX_T:
                 rel_bias = self._rel_bias_for(T)
             else:
                 pos_bias = self._pos_bias_for(T)
-        for L in self.layers:
+        for li, L in enumerate(self.layers):
             ops.linear(xh, L["wqkv"], L["bqkv"], out=ws["qkv"])
             if self.wavlm:
                 ops.wavlm_gate(x, T, self.n_heads, L["gate_w"], L["gate_b"], L["gate_c"], ws["gate"])
@@ -233,6 +265,7 @@ class W2V2Engine:
             ops.linear(xh, L["w1"], L["b1"], gelu=True, out=ws["h1"])
             ops.linear(ws["h1"], L["w2"], L["b2"], add_src=x, out=tmp)
             ops.layernorm(tmp, L["ln2_g"], L["ln2_b"], out_f16=xh, out_f32=x)
+            self._tr(f"layer{li}", x.view(n, T, d))
         keep = T if n_keep is None else min(n_keep, T)
         ops.heads(x.view(n, T, d), self.head_w, self.head_b, logits, frame_offset, step_frames, keep)
 

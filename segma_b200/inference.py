@@ -29,6 +29,7 @@ from .config import Config, load_config
 from .encoders import MultiLabelEncoder
 from .geometry import FRAME_SAMPLES, INFERENCE_SETTINGS, Chunkyfier, ConvolutionSettings, conv_frames, plan_windows
 from .io import PcmSource, get_audio_info, get_samples_in_range, stage_to_device
+from .engine import resolve_device
 from .models import BaseSegmentationModel, Models
 from .thresholds import logit_cut
 
@@ -55,7 +56,7 @@ def _cuda_device(device) -> torch.device:
     dev = torch.device("cuda" if device in ("gpu", None) else device)
     if dev.type != "cuda":
         raise ops.SegmaNativeError(f"device '{device}': segma_b200 runs on CUDA (sm_100a) only; there is no CPU path")
-    return dev
+    return resolve_device(dev)
 
 
 def prepare_audio(audio_path, model: BaseSegmentationModel, device, start_f: int, end_f: int | None = None):
@@ -90,6 +91,16 @@ def apply_model_on_audio(
     ``audio_path`` may also be a 1-D float32 array / tensor (host or device).
     """
     dev = _cuda_device(device)
+    engine = model._require_engine()
+    if engine.device != dev:
+        raise ops.SegmaNativeError(f"model weights are on {engine.device} but device={dev} was requested; call model.to(device)")
+    with torch.cuda.device(dev):
+        return _apply_model_on_audio(audio_path, model, engine, conv_settings, dev, batch_size, chunk_duration_s,
+                                     sample_rate, window_step)
+
+
+def _apply_model_on_audio(audio_path, model, engine, conv_settings, dev, batch_size, chunk_duration_s, sample_rate,
+                          window_step) -> torch.Tensor:
     chunk_f = int(chunk_duration_s * sample_rate)
     chunky = Chunkyfier(batch_size, chunk_f, conv_settings)  # same derived quantities as the reference
     step = chunky.step if window_step is None else int(window_step)
@@ -97,7 +108,6 @@ def apply_model_on_audio(
     source = PcmSource(audio_path, dev)
     pcm = source.dev
     n_samples = source.n_samples
-    engine = model._require_engine()
     frames_per_window = model.n_keep if model.family == "whisper" else conv_frames(chunk_f)
     plan = plan_windows(n_samples, chunk_f, batch_size, step, frames_per_window)
     n_labels = model.label_encoder.n_labels
@@ -157,7 +167,8 @@ def apply_thresholds(feature_tensor: torch.Tensor, thresholds: dict[str, dict[st
     bit-identical to the reference's (inference.py:214-234)."""
     bounds = _lower_bounds(thresholds, feature_tensor.shape[-1])
     x = feature_tensor.to(_cuda_device(device), torch.float32).contiguous()
-    return ops.threshold_mask(x, [logit_cut(t) for t in bounds], mode=ops.DECODE_LOGIT)
+    with torch.cuda.device(x.device):
+        return ops.threshold_mask(x, [logit_cut(t) for t in bounds], mode=ops.DECODE_LOGIT)
 
 
 def _table_to_intervals(table: np.ndarray, conv_settings: ConvolutionSettings, labels) -> list[tuple[int, int, str]]:
@@ -179,8 +190,9 @@ def create_intervals(thresholded_features: torch.Tensor, conv_settings: Convolut
     m = torch.as_tensor(thresholded_features)
     if m.numel() == 0:
         return []
-    x = m.to("cuda", torch.float32).contiguous()
-    table = ops.decode_intervals(x, [0.5] * x.shape[-1], mode=ops.DECODE_LOGIT).cpu().numpy()
+    x = m.to(m.device if m.is_cuda else _cuda_device("cuda"), torch.float32).contiguous()
+    with torch.cuda.device(x.device):
+        table = ops.decode_intervals(x, [0.5] * x.shape[-1], mode=ops.DECODE_LOGIT).cpu().numpy()
     return _table_to_intervals(table, conv_settings, label_encoder.base_labels)
 
 
@@ -201,12 +213,13 @@ def decode_logits(logits: torch.Tensor, thresholds: dict, label_encoder: MultiLa
     if hysteresis:
         ups = [float(lab.get("upper_bound", 1.0)) for lab in thresholds.values()]
         onset = [logit_cut(u) if u < 1.0 else logit_cut(lo) for u, lo in zip(ups, bounds)]
-    dev_table = ops.decode_intervals(logits.contiguous(), [logit_cut(t) for t in bounds], file_offsets=file_offsets,
-                                     mode=ops.DECODE_LOGIT, onset=onset)
-    if max_gap_s > 0.0 or min_duration_s > 0.0:
-        dev_table = ops.postprocess_intervals(dev_table.contiguous(), int(round(max_gap_s * 16_000)),
-                                              int(round(min_duration_s * 16_000)))
-    table = dev_table.cpu().numpy()
+    with torch.cuda.device(logits.device):
+        dev_table = ops.decode_intervals(logits.contiguous(), [logit_cut(t) for t in bounds], file_offsets=file_offsets,
+                                         mode=ops.DECODE_LOGIT, onset=onset)
+        if max_gap_s > 0.0 or min_duration_s > 0.0:
+            dev_table = ops.postprocess_intervals(dev_table.contiguous(), int(round(max_gap_s * 16_000)),
+                                                  int(round(min_duration_s * 16_000)))
+        table = dev_table.cpu().numpy()
     labels = label_encoder.base_labels
     if file_offsets is None:
         return _table_to_intervals(table, conv_settings, labels)

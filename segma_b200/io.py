@@ -142,6 +142,17 @@ def write_wav(path, pcm: np.ndarray, sample_rate: int = 16_000, subtype: str = "
 _STAGE_CHUNK = 32 << 20  # bytes per pinned staging buffer
 
 
+_COPY_STREAMS: dict[int, "torch.cuda.Stream"] = {}
+
+
+def _copy_stream_for(device: torch.device) -> "torch.cuda.Stream":
+    """One H2D staging stream per device, shared by all files (not one per file)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _COPY_STREAMS:
+        _COPY_STREAMS[idx] = torch.cuda.Stream(device=device)
+    return _COPY_STREAMS[idx]
+
+
 class PcmSource:
     """A file's samples as a 1-D float32 device tensor that is filled progressively.
 
@@ -191,9 +202,13 @@ class PcmSource:
                 self._buf_events = [None, None]
                 self._turn = 0
         code, _, t_dt = self._fmt
-        self.dev = torch.empty(self.n_samples, dtype=torch.float32, device=self.device)
-        self._raw = self.dev if code == ops.PCM_F32 else torch.empty(self.n_samples, dtype=t_dt, device=self.device)
-        self._copy_stream = torch.cuda.Stream(device=self.device)
+        with torch.cuda.device(self.device):
+            self.dev = torch.empty(self.n_samples, dtype=torch.float32, device=self.device)
+            self._raw = self.dev if code == ops.PCM_F32 else torch.empty(self.n_samples, dtype=t_dt, device=self.device)
+            # The caching allocator may hand back blocks whose previous owner (an earlier file's PCM, logits or
+            # scratch) still has kernels queued on the current stream: the copy stream must not write them earlier.
+            self._copy_stream = _copy_stream_for(self.device)
+            self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))
 
     def ensure(self, upto: int) -> None:
         upto = min(int(upto), self.n_samples)
@@ -227,7 +242,8 @@ class PcmSource:
                 pos += cnt
         main.wait_stream(self._copy_stream)
         if code != ops.PCM_F32:
-            ops.pcm_to_f32(self._raw[a:upto], code, out=self.dev[a:upto])
+            with torch.cuda.device(self.device):
+                ops.pcm_to_f32(self._raw[a:upto], code, out=self.dev[a:upto])
         self._done = upto
         if self._done >= self.n_samples and self._file is not None:
             self._file.close()

@@ -18,7 +18,7 @@ import torch
 from . import ops
 from .config import Config
 from .encoders import MultiLabelEncoder
-from .engine import WhisperEngine
+from .engine import WhisperEngine, resolve_device
 from .geometry import ConvolutionSettings
 
 
@@ -43,10 +43,12 @@ class BaseSegmentationModel:
         return self
 
     def to(self, device):
-        device = torch.device(device)
+        device = torch.device("cuda" if device == "gpu" else device)
         if device.type != "cuda":
             raise ops.SegmaNativeError("segma_b200 models run on CUDA (sm_100a) only; there is no CPU path")
-        self.device = device
+        self.device = resolve_device(device)
+        if self.engine is not None:
+            self.engine.to(self.device)  # weights packed by load_from_checkpoint follow the model (inference.py:440)
         return self
 
     def __call__(self, x):
@@ -101,7 +103,8 @@ class _WhisperFamily(BaseSegmentationModel):
         """1-D waveform -> (1, 80, 3000) log-mel, the Whisper feature extractor of hydra.py:197-201 on the GPU."""
         x = torch.as_tensor(audio_t, dtype=torch.float32).reshape(-1).to(self.device).contiguous()
         n = min(x.numel(), 480_000 - 400)
-        f32, _ = ops.logmel(x, 1, n, n)
+        with torch.cuda.device(x.device):
+            f32, _ = ops.logmel(x, 1, n, n)
         return f32
 
 

@@ -68,6 +68,11 @@ def _stream() -> int:
 def _dev(t: torch.Tensor, dtype, name: str) -> int:
     if not t.is_cuda:
         raise SegmaNativeError(f"{name} must be a CUDA tensor (segma_b200 has no CPU path)")
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the current device's stream; engines and the inference entry points select the tensors'
+        # device themselves (torch.cuda.device), direct callers of ops must do the same
+        raise SegmaNativeError(f"{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                               f"wrap the call in torch.cuda.device({t.device.index})")
     if t.dtype != dtype:
         raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
     return t.data_ptr()

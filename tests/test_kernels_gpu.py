@@ -472,18 +472,46 @@ def test_postprocess_intervals(cuda):
         assert np.array_equal(got, O.postprocess_table(table, gap, dur)), (gap, dur)
 
 
-def test_merge_semantics_of_the_reference_interval_struct(cuda):
-    """Known answers of the reference's tests/test_interval.py (adjacent and overlapping intervals of one label
-    merge, different labels never do), expressed on the (file, label, start, end) table."""
-    def run(rows):
-        t = torch.tensor(sorted(rows, key=lambda r: (r[0], r[1], r[2])), dtype=torch.int32, device=cuda)
-        return [tuple(r) for r in ops.postprocess_intervals(t, 0, 0).cpu().tolist()]
+def test_intervals_struct_vs_reference_golden(cuda):
+    """``segma_b200.structs.Intervals`` (merge on the device) against what the reference's own ``Intervals`` produced
+    for every insertion sequence of /root/reference/tests/test_interval.py -- after each ``add`` -- and for shuffled
+    decode tables with overlapping / bridging extras (tests/golden/postprocess.json, oracle/make_golden.py)."""
+    import json
+    from pathlib import Path
 
-    assert run([(0, 0, 0, 10), (0, 0, 10, 20)]) == [(0, 0, 0, 20)]
-    assert run([(0, 1, 0, 5), (0, 1, 5, 10), (0, 1, 10, 15)]) == [(0, 1, 0, 15)]
-    assert run([(0, 0, 0, 10), (0, 0, 15, 25)]) == [(0, 0, 0, 10), (0, 0, 15, 25)]
-    assert run([(0, 0, 0, 10), (0, 1, 10, 20)]) == [(0, 0, 0, 10), (0, 1, 10, 20)]
-    assert run([(0, 0, 0, 10), (1, 0, 10, 20)]) == [(0, 0, 0, 10), (1, 0, 10, 20)]
+    from segma_b200.structs import Intervals
+
+    cases = json.loads((Path(__file__).parent / "golden" / "postprocess.json").read_text())["cases"]
+    assert len(cases) >= 30
+    for case in cases:
+        adds = [tuple(r) for r in case["adds"]]
+        if "after_each_add" in case:
+            iv = Intervals()
+            assert iv.intervals == [] and len(iv) == 0
+            for item, state in zip(adds, case["after_each_add"]):
+                iv.add(item)
+                assert iv.intervals == [tuple(r) for r in state]
+        iv = Intervals()
+        iv.extend(adds)
+        assert iv.intervals == [tuple(r) for r in case["final"]]
+        assert list(iv) == iv.intervals and len(iv) == len(case["final"])
+
+
+def test_postprocess_overlapping_rows_across_chunks(cuda):
+    """Nested and overlapping rows (running maximum of the ends) over more rows than one scan chunk of 1024."""
+    rng = np.random.default_rng(11)
+    rows = []
+    for f in range(2):
+        for c in range(3):
+            starts = np.sort(rng.integers(0, 400_000, size=int(rng.integers(900, 2600))))
+            for s in starts:
+                rows.append((f, c, int(s), int(s) + int(rng.integers(0, 900))))
+    table = np.array(rows, dtype=np.int32)
+    for gap, dur in [(0, 0), (50, 0), (0, 400), (120, 1000)]:
+        got = ops.postprocess_intervals(torch.from_numpy(table).to(cuda), gap, dur).cpu().numpy()
+        want = O.postprocess_table(table, gap, dur)
+        assert np.array_equal(got, want), (gap, dur)
+        assert 0 < want.shape[0] < table.shape[0]
 
 
 def test_decode_long_input_parallel_scan(cuda):

@@ -82,3 +82,20 @@ def test_device_tuning_equals_oracle(cuda, precision, n):
     f1 = tuning.f1_from_histogram(hist)
     for k, t in enumerate(sorted(float(t) for t in thr)):
         assert np.allclose(f1[k].numpy(), O.f1_per_label(truth, logits.sigmoid() > torch.tensor(t)), atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["p10", "p100", "p10_rare"])
+def test_device_tuning_equals_reference_golden(cuda, name):
+    """The histogram path against thresholds the reference's own ``tune_multilabel`` chose (tests/golden/tuning.npz,
+    generated from /root/reference/scripts/tune.py by oracle/make_golden.py::tuning)."""
+    from pathlib import Path
+
+    g = np.load(Path(__file__).parent / "golden" / "tuning.npz")
+    n, seed, n_steps = (int(v) for v in g[f"{name}_meta"])
+    gen = torch.Generator().manual_seed(seed)
+    truth = (torch.rand((n, 4), generator=gen) < torch.tensor([0.3, 0.05, 0.5, 0.0])).float()
+    logits = (truth * 2 - 1) * 1.5 + torch.randn((n, 4), generator=gen) * 1.7
+    thr = torch.from_numpy(g[f"{name}_thresholds"])
+    best = tuning.tune_multilabel({"val": {"true": truth, "pred": logits}}, thr, LABELS, n_steps)
+    assert [best[lab]["lower_bound"] for lab in LABELS] == g[f"{name}_best"].tolist()

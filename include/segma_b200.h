@@ -167,12 +167,19 @@ SEGMA_API int segma_attention_rel(const void* qkv, int n_windows, int T, int n_h
 /* fp32 -> fp16 copy of a (rows, cols) matrix with row strides. */
 SEGMA_API int segma_cast_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
 
+/* fp32 (rows, cols) -> fp16 (rows, 3*cols) = [hi | lo | hi], hi = fp16(x), lo = fp16(x - hi): the A operand of a
+ * split-precision GEMM against a weight packed as [W_hi | W_hi | W_lo] (K = 3*cols).  Used for the LSTM input
+ * projection (nn.LSTM's x W_ih^T, src/segma/models/whisper/surgical_hydra.py:57-60,101), whose rounding error is
+ * otherwise a systematic perturbation that adds up along the 128-step recurrence. */
+SEGMA_API int segma_cast_f16_split(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
+
 /* ---- LSTM over the window axis + per-label heads ---------------------------------------------
  * One direction-pair of one nn.LSTM layer (src/segma/models/whisper/hydra.py:48-51,81): the
  * sequence axis is the window batch (n_steps), the LSTM "batch" is the n_rows kept frames.
  *   pre   [dev] fp32 (n_steps, n_rows, n_dirs*4H): x W_ih^T + b_ih + b_hh, gate order i,f,g,o,
  *         forward direction first
- *   w_hh_t[dev] fp32 (n_dirs, H, 4H): W_hh transposed
+ *   w_hh_t[dev] fp32 (n_dirs, H, 4H): W_hh transposed; kept at fp32 precision on the SM (H = 64: fp32 in shared
+ *         memory; H = 128: fp16 hi in shared memory + fp16 lo in registers; H = 256: fp32 through L2)
  *   out   [dev] fp32 (n_steps, n_rows, n_dirs*H); out_f16 same shape or NULL
  */
 SEGMA_API int segma_lstm_layer(const float* pre, const float* w_hh_t, int n_steps, int n_rows, int hidden, int n_dirs,

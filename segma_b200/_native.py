@@ -62,6 +62,7 @@ SIGNATURES = {
     "segma_attention": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "segma_attention_rel": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "segma_cast_f16": (_i, [_vp, _i64, _vp, _i64, _i64, _i, _vp]),
+    "segma_cast_f16_split": (_i, [_vp, _i64, _vp, _i64, _i64, _i, _vp]),
     "segma_lstm_layer": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "segma_heads": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i64, _i, _vp]),
     "segma_stitch": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i64, _vp]),

@@ -90,6 +90,32 @@ __global__ void __launch_bounds__(256) cast_f16_kernel(const float* __restrict__
   }
 }
 
+// fp32 -> [hi | lo | hi] fp16 with hi = fp16(x), lo = fp16(x - hi): the A operand of a split-precision GEMM whose
+// weight is laid out [W_hi | W_hi | W_lo], so that x W^T = hi W_hi + lo W_hi + hi W_lo carries ~22 bits of both
+// operands through the fp16 tensor cores (the dropped lo W_lo term is 2^-22 relative).
+__global__ void __launch_bounds__(256) cast_f16_split_kernel(const float* __restrict__ src, long long lds,
+                                                               __half* __restrict__ dst, long long ldd,
+                                                               long long rows, int cols) {
+  const int quads = cols / 4;
+  const long long total = rows * quads;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / quads;
+    const int q = (int)(i - r * quads);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + r * lds) + q);
+    const __half hx = __float2half(v.x), hy = __float2half(v.y), hz = __float2half(v.z), hw = __float2half(v.w);
+    uint2 hi, lo;
+    hi.x = pack_f16x2(__half2float(hx), __half2float(hy));
+    hi.y = pack_f16x2(__half2float(hz), __half2float(hw));
+    lo.x = pack_f16x2(v.x - __half2float(hx), v.y - __half2float(hy));
+    lo.y = pack_f16x2(v.z - __half2float(hz), v.w - __half2float(hw));
+    __half* row = dst + r * ldd;
+    reinterpret_cast<uint2*>(row)[q] = hi;
+    reinterpret_cast<uint2*>(row + cols)[q] = lo;
+    reinterpret_cast<uint2*>(row + 2 * cols)[q] = hi;
+  }
+}
+
 // integer PCM -> float32 in [-1, 1) exactly as the host decode does (x / 2^15, x / 2^31): the file's samples
 // cross PCIe in their native width and are widened on the device
 template <typename T>
@@ -172,6 +198,18 @@ int segma_cast_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_
   const int grid = (int)std::min<long long>(ceil_div_ll(total, 256), (long long)device_sm_count() * 16);
   cast_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, lds, static_cast<__half*>(dst), ldd, rows, cols);
   return launch_status("cast_f16_kernel");
+}
+
+int segma_cast_f16_split(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream) {
+  SEGMA_REQUIRE(rows >= 0 && cols > 0, "segma_cast_f16_split: bad shape");
+  if (rows == 0) return SEGMA_OK;
+  SEGMA_REQUIRE(src && dst, "segma_cast_f16_split: NULL buffer");
+  SEGMA_REQUIRE(cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ldd >= 3 * (int64_t)cols,
+                "segma_cast_f16_split: cols and strides must be multiples of 4, ldd >= 3 * cols");
+  const long long total = rows * (cols / 4);
+  const int grid = (int)std::min<long long>(ceil_div_ll(total, 256), (long long)device_sm_count() * 16);
+  cast_f16_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, lds, static_cast<__half*>(dst), ldd, rows, cols);
+  return launch_status("cast_f16_split_kernel");
 }
 
 }  // extern "C"

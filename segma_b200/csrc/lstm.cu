@@ -4,8 +4,11 @@
 // surgical_hydra.py:57-60), so the (B, T, d) encoder output is consumed as (seq = B windows, batch = T
 // frames): the recurrence runs across the <= batch_size windows of one forward call and the kept frames
 // are independent rows (SURVEY.md finding 6).  The input projection x W_ih^T + b is a tcgen05 GEMM
-// (gemm_tc5.cu); this kernel runs the sequential part: each CTA owns R frames of one direction, keeps
-// h in shared memory and c in registers, and walks the n_steps windows.  fp32 throughout.
+// (gemm_tc5.cu) on a split-precision operand pair (segma_cast_f16_split); this kernel runs the sequential part:
+// each CTA owns R frames of one direction, keeps h in shared memory and c in registers, and walks the n_steps
+// windows.  fp32 throughout (W_hh at 22+ bits, see lstm_layer_smem_kernel).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace segma {
@@ -74,12 +77,16 @@ __global__ void __launch_bounds__(4 * H) lstm_layer_kernel(const float* __restri
   }
 }
 
-// Same recurrence with W_hh resident in shared memory as fp16 (H <= 128: 128 KB), R = 3 frames per CTA so
-// that 2 x ceil(199 / 3) = 134 CTAs cover the 148 SMs in one wave.  Per step a thread owns one gate column:
-// 128 (LDS.16 + cvt + R FMAs), then the pointwise cell update; the fetch of W_hh no longer depends on L2
-// latency, which bounded the kernel above at ~11 us per step.  The rounding of W_hh to fp16 matches the
-// precision of W_ih (an fp16 tensor-core operand); h, c and the gate pre-activations stay fp32.
+// Same recurrence with W_hh resident on the SM, R = 3 frames per CTA so that 2 x ceil(199 / 3) = 134 CTAs cover the
+// 148 SMs in one wave.  Per step a thread owns one gate column: H x (weight fetch + R FMAs), then the pointwise cell
+// update; the fetch of W_hh no longer depends on L2 latency, which bounded the kernel above at ~11 us per step.
+// The weights keep fp32 precision -- the recurrence runs over up to batch_size = 128 windows, and a rounded W_hh is a
+// systematic perturbation that adds up along it:
+//   H = 64  : fp32 in shared memory (64 KB)
+//   H = 128 : fp32 does not fit (256 KB), so w = hi + lo * 2^-11 with hi = fp16(w) in shared memory (128 KB) and
+//             lo = fp16((w - hi) * 2^11) in 64 registers of the thread that owns the column (22 significant bits)
 constexpr int kLstmRowsSmem = 3;
+constexpr float kLoScale = 2048.0f;
 
 template <int H>
 __global__ void __launch_bounds__(4 * H) lstm_layer_smem_kernel(const float* __restrict__ pre,
@@ -88,14 +95,29 @@ __global__ void __launch_bounds__(4 * H) lstm_layer_smem_kernel(const float* __r
                                                                  __half* __restrict__ out_f16) {
   constexpr int R = kLstmRowsSmem;
   constexpr int G = 4 * H;
+  constexpr bool kSplit = H > 64;
+  using WT = typename std::conditional<kSplit, __half, float>::type;
   extern __shared__ __align__(16) unsigned char lstm_smem[];
-  __half* s_w = reinterpret_cast<__half*>(lstm_smem);                 // [H][G]
-  float* s_h = reinterpret_cast<float*>(lstm_smem + sizeof(__half) * H * G);  // [H][4] (R padded to 4)
-  float* s_g = s_h + H * 4;                                          // [R][G]
+  WT* s_w = reinterpret_cast<WT*>(lstm_smem);                            // [H][G]
+  float* s_h = reinterpret_cast<float*>(lstm_smem + sizeof(WT) * H * G);  // [H][4] (R padded to 4)
+  float* s_g = s_h + H * 4;                                               // [R][G]
   const int dir = blockIdx.y;
   const int r0 = blockIdx.x * R;
   const int j = threadIdx.x;
-  for (int k = 0; k < H; ++k) s_w[k * G + j] = __float2half(__ldg(w_hh_t + ((long long)dir * H + k) * G + j));
+  __half2 w_lo[kSplit ? H / 2 : 1];
+  if (kSplit) {
+#pragma unroll
+    for (int k = 0; k < H; k += 2) {
+      const float w0 = __ldg(w_hh_t + ((long long)dir * H + k) * G + j);
+      const float w1 = __ldg(w_hh_t + ((long long)dir * H + k + 1) * G + j);
+      const __half h0 = __float2half(w0), h1 = __float2half(w1);
+      s_w[k * G + j] = h0;
+      s_w[(k + 1) * G + j] = h1;
+      w_lo[k / 2] = __floats2half2_rn((w0 - __half2float(h0)) * kLoScale, (w1 - __half2float(h1)) * kLoScale);
+    }
+  } else {
+    for (int k = 0; k < H; ++k) s_w[k * G + j] = __ldg(w_hh_t + ((long long)dir * H + k) * G + j);
+  }
   for (int i = j; i < H * 4; i += G) s_h[i] = 0.f;
   float c_state = 0.f;
   __syncthreads();
@@ -108,13 +130,30 @@ __global__ void __launch_bounds__(4 * H) lstm_layer_smem_kernel(const float* __r
       const int row = r0 + r;
       acc[r] = row < n_rows ? __ldg(pre + ((long long)s * n_rows + row) * (n_dirs * G) + dir * G + j) : 0.f;
     }
+    if (kSplit) {
+#pragma unroll
+      for (int k = 0; k < H; k += 2) {
+        const float2 lo = __half22float2(w_lo[k / 2]);
+        const float wa = fmaf(lo.x, 1.0f / kLoScale, __half2float(s_w[k * G + j]));
+        const float wb = fmaf(lo.y, 1.0f / kLoScale, __half2float(s_w[(k + 1) * G + j]));
+        const float4 ha = *reinterpret_cast<const float4*>(s_h + k * 4);
+        const float4 hb = *reinterpret_cast<const float4*>(s_h + k * 4 + 4);
+        acc[0] = fmaf(wa, ha.x, acc[0]);
+        acc[1] = fmaf(wa, ha.y, acc[1]);
+        acc[2] = fmaf(wa, ha.z, acc[2]);
+        acc[0] = fmaf(wb, hb.x, acc[0]);
+        acc[1] = fmaf(wb, hb.y, acc[1]);
+        acc[2] = fmaf(wb, hb.z, acc[2]);
+      }
+    } else {
 #pragma unroll 16
-    for (int k = 0; k < H; ++k) {
-      const float wk = __half2float(s_w[k * G + j]);
-      const float4 hv = *reinterpret_cast<const float4*>(s_h + k * 4);
-      acc[0] = fmaf(wk, hv.x, acc[0]);
-      acc[1] = fmaf(wk, hv.y, acc[1]);
-      acc[2] = fmaf(wk, hv.z, acc[2]);
+      for (int k = 0; k < H; ++k) {
+        const float wk = s_w[k * G + j];
+        const float4 hv = *reinterpret_cast<const float4*>(s_h + k * 4);
+        acc[0] = fmaf(wk, hv.x, acc[0]);
+        acc[1] = fmaf(wk, hv.y, acc[1]);
+        acc[2] = fmaf(wk, hv.z, acc[2]);
+      }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) s_g[r * G + j] = acc[r];
@@ -174,7 +213,12 @@ int segma_lstm_layer(const float* pre, const float* w_hh_t, int n_steps, int n_r
   dim3 grid_s(ceil_div(n_rows, kLstmRowsSmem), n_dirs);
   switch (hidden) {
     case 64: {
-      constexpr int kSmem = 64 * 256 * 2 + 64 * 4 * 4 + kLstmRowsSmem * 256 * 4;
+      constexpr int kSmem = 64 * 256 * 4 + 64 * 4 * 4 + kLstmRowsSmem * 256 * 4;  // fp32 weights
+      static PerDeviceFlag attr_set;
+      if (!attr_set.here()) {
+        SEGMA_CUDA_OK(cudaFuncSetAttribute(lstm_layer_smem_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        attr_set.here() = true;
+      }
       lstm_layer_smem_kernel<64><<<grid_s, 256, kSmem, st>>>(pre, w_hh_t, n_steps, n_rows, n_dirs, out, ob);
       break;
     }
@@ -188,6 +232,7 @@ int segma_lstm_layer(const float* pre, const float* w_hh_t, int n_steps, int n_r
       lstm_layer_smem_kernel<128><<<grid_s, 512, kSmem, st>>>(pre, w_hh_t, n_steps, n_rows, n_dirs, out, ob);
       break;
     }
+    // H = 256: W_hh (1 MB per direction in fp32) stays in L2, read with __ldg every step
     case 256: lstm_layer_kernel<256><<<grid, 1024, 0, st>>>(pre, w_hh_t, n_steps, n_rows, n_dirs, out, ob); break;
     default:
       set_last_error("segma_lstm_layer: hidden size %d not supported (64, 128, 256)", hidden);

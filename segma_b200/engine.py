@@ -57,7 +57,7 @@ def move_to(obj, device):
 
 @dataclass
 class _LstmLayer:
-    w_ih: torch.Tensor  # (n_dirs*4H, in) fp16
+    w_ih: torch.Tensor  # (n_dirs*4H, 3*in) fp16, split precision [W_hi | W_hi | W_lo]
     bias: torch.Tensor  # (n_dirs*4H) fp32 = b_ih + b_hh
     w_hh_t: torch.Tensor  # (n_dirs, H, 4H) fp32
 
@@ -73,7 +73,10 @@ class LstmHeads:
             w_ih = torch.cat([sd[f"{prefix}weight_ih_l{layer}{s}"] for s in sufs], dim=0)
             bias = torch.cat([sd[f"{prefix}bias_ih_l{layer}{s}"] + sd[f"{prefix}bias_hh_l{layer}{s}"] for s in sufs])
             w_hh_t = torch.stack([sd[f"{prefix}weight_hh_l{layer}{s}"].T.contiguous() for s in sufs])
-            self.layers.append(_LstmLayer(_f16(w_ih, device), _f32(bias, device), _f32(w_hh_t, device)))
+            # The recurrence runs over up to batch_size windows and the windows of a file resemble each other, so a
+            # rounded W_ih / input is a *systematic* perturbation that adds up along it: the input projection runs at
+            # split precision (hi + lo fp16 halves of both operands, one GEMM over K = 3 * in).
+            self.layers.append(_LstmLayer(ops.split_weight(w_ih).to(device), _f32(bias, device), _f32(w_hh_t, device)))
             layer += 1
         self.hidden = self.layers[0].w_hh_t.shape[1] if self.layers else 0
         self.n_dirs = self.layers[0].w_hh_t.shape[0] if self.layers else 0
@@ -81,16 +84,18 @@ class LstmHeads:
         self.head_b = _f32(torch.cat([sd[f"task_heads.linear_head_{lab}.bias"] for lab in labels], dim=0), device)
         self.n_labels = len(labels)
 
-    def run(self, feat_f32: torch.Tensor, feat_f16: torch.Tensor, n_steps: int, n_rows: int, logits: torch.Tensor,
+    def run(self, feat_f32: torch.Tensor, n_steps: int, n_rows: int, logits: torch.Tensor,
             frame_offset: int, step_frames: int, n_keep: int) -> None:
-        """feat_* (n_steps*n_rows, F): LSTM input (fp16 copy for the tensor-core projection)."""
-        cur_f32, cur_f16 = feat_f32, feat_f16
+        """feat_f32 (n_steps*n_rows, F): LSTM input; each layer's input is split into fp16 hi / lo halves for the
+        tensor-core projection."""
+        cur = feat_f32
         for lay in self.layers:
-            pre = ops.linear(cur_f16, lay.w_ih, lay.bias, out_f32=True)
-            out_f16 = torch.empty((n_steps, n_rows, self.n_dirs * self.hidden), dtype=torch.float16, device=pre.device)
-            cur_f32 = ops.lstm_layer(pre.view(n_steps, n_rows, -1), lay.w_hh_t, self.hidden, out_f16=out_f16)
-            cur_f16 = out_f16.view(n_steps * n_rows, -1)
-        ops.heads(cur_f32.view(n_steps, n_rows, -1), self.head_w, self.head_b, logits, frame_offset, step_frames, n_keep)
+            rows, feat = cur.shape
+            a = torch.empty((rows, 3 * feat), dtype=torch.float16, device=cur.device)
+            ops.cast_f16_split(cur, a)
+            pre = ops.linear(a, lay.w_ih, lay.bias, out_f32=True)
+            cur = ops.lstm_layer(pre.view(n_steps, n_rows, -1), lay.w_hh_t, self.hidden).view(rows, -1)
+        ops.heads(cur.view(n_steps, n_rows, -1), self.head_w, self.head_b, logits, frame_offset, step_frames, n_keep)
 
 
 class WhisperEngine:
@@ -185,14 +190,13 @@ class WhisperEngine:
         ws["att"] = torch.empty((M, d), dtype=torch.float16, device=dev)
         ws["h1"] = torch.empty((M, self.ffn), dtype=torch.float16, device=dev)
         ws["mix"] = torch.empty((n, self.n_keep, d), dtype=torch.float32, device=dev)
-        ws["mix_f16"] = torch.empty((n * self.n_keep, d), dtype=torch.float16, device=dev)
         ws["mel_scratch"] = torch.empty(max(ops.logmel_scratch_bytes(n, 64_000 * 2), 1), dtype=torch.uint8, device=dev)
         self._slots[slot] = (n, ws)
         self._ws = ws
 
     # ---- stages ------------------------------------------------------------------------------------
     def encode_tm(self, mel_tm: torch.Tensor, n: int) -> None:
-        """(n, 3002, 80) fp16 padded time-major log-mel -> ws['mix'] (n, n_keep, d) fp32 (+ fp16 copy)."""
+        """(n, 3002, 80) fp16 padded time-major log-mel -> ws['mix'] (n, n_keep, d) fp32."""
         ws, d, T = self._ws, self.d, N_CTX
         M = n * T
         x, xn, qkv, att, h1, mix = ws["x"][:M], ws["xn"][:M], ws["qkv"][:M], ws["att"][:M], ws["h1"][:M], ws["mix"][:n]
@@ -227,7 +231,6 @@ class WhisperEngine:
                 ops.linear_rows(h1, n, T, keep, L["w2"], L["b2"], x, add_src=x)
         ops.layernorm(x, self.lnf_g, self.lnf_b, mix=mix, period=T, n_keep=keep, w_in=0.0,
                       w_out=self.mix_w[-1], mix_init=not mixed, only_kept=True)
-        ops.cast_f16(mix.view(n * self.n_keep, d), ws["mix_f16"][: n * self.n_keep])
 
     def forward_pcm(self, pcm: torch.Tensor, start: int, n: int, win_len: int, step: int, logits: torch.Tensor,
                     frame_offset: int, step_frames: int, n_keep: int | None = None, slot: int = 0) -> None:
@@ -244,8 +247,8 @@ class WhisperEngine:
             ops.logmel_into(view, n, win_len, step, ws["mel_tm"], ws["mel_scratch"])
             self.encode_tm(ws["mel_tm"], n)
             keep = self.n_keep if n_keep is None else n_keep
-            self.tail.run(ws["mix"][:n].view(n * self.n_keep, self.d), ws["mix_f16"][: n * self.n_keep], n, self.n_keep,
-                          logits, frame_offset, step_frames, keep)
+            self.tail.run(ws["mix"][:n].view(n * self.n_keep, self.d), n, self.n_keep, logits, frame_offset, step_frames,
+                          keep)
 
     def forward_features(self, feats: torch.Tensor) -> torch.Tensor:
         """Drop-in ``model.forward``: (B, 80, 3000) fp32 log-mel -> (B, n_keep, 1, C) fp32 logits."""
@@ -257,6 +260,5 @@ class WhisperEngine:
             tm[:, 1:-1] = feats.to(self.device).transpose(1, 2).to(torch.float16)  # layout change only
             self.encode_tm(ws["mel_tm"], n)
             logits = torch.empty((n * self.n_keep, len(self.labels)), dtype=torch.float32, device=self.device)
-            self.tail.run(ws["mix"][:n].view(n * self.n_keep, self.d), ws["mix_f16"][: n * self.n_keep], n, self.n_keep,
-                          logits, 0, self.n_keep, self.n_keep)
+            self.tail.run(ws["mix"][:n].view(n * self.n_keep, self.d), n, self.n_keep, logits, 0, self.n_keep, self.n_keep)
         return logits.view(n, self.n_keep, 1, len(self.labels))

@@ -43,6 +43,8 @@ __all__ = [
 #: so overlapping batches buys nothing (2.26 vs 2.22 audio-h/s); the default stays strictly serial.
 N_STREAMS = int(os.environ.get("SEGMA_STREAMS", "1"))
 _STREAMS: dict[tuple, list] = {}
+#: files queued on the device before the host waits for the oldest one's interval table
+MAX_FILES_IN_FLIGHT = 4
 
 
 def _side_streams(dev: torch.device, n: int):
@@ -239,25 +241,69 @@ def default_thresholds(label_encoder: MultiLabelEncoder) -> dict:
     return {label: {"lower_bound": 0.5, "upper_bound": 1.0} for label in label_encoder._labels}
 
 
+_D2H_STREAMS: dict[int, "torch.cuda.Stream"] = {}
+
+
+def _d2h_stream(dev: torch.device) -> "torch.cuda.Stream":
+    if dev.index not in _D2H_STREAMS:
+        _D2H_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    return _D2H_STREAMS[dev.index]
+
+
+class _FileJob:
+    """One file in flight: everything is queued on the device, nothing has been waited for yet.  The interval table
+    (worst-case sized, a few MB per hour of audio), its row count and -- if asked for -- the logits travel to pinned
+    host memory on a side stream, so the main stream never stalls on a per-file read-back."""
+
+    def __init__(self, audio_path, model, config, batch_size, device, thresholds, save_logits, window_step):
+        self.stem = Path(audio_path).stem if not isinstance(audio_path, (np.ndarray, torch.Tensor)) else "audio"
+        self.model = model
+        dev = _cuda_device(device)
+        logits = apply_model_on_audio(audio_path=audio_path, model=model, batch_size=batch_size,
+                                      chunk_duration_s=config.audio.chunk_duration_s, conv_settings=INFERENCE_SETTINGS,
+                                      device=dev, window_step=window_step)
+        bounds = _lower_bounds(thresholds, logits.shape[-1])
+        with torch.cuda.device(dev):
+            self.table, self.count = ops.decode_intervals_async(logits, [logit_cut(t) for t in bounds], mode=ops.DECODE_LOGIT)
+            main, side = torch.cuda.current_stream(dev), _d2h_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self.host_count = torch.empty(1, dtype=torch.int32).pin_memory()
+                self.host_table = torch.empty(self.table.shape, dtype=torch.int32).pin_memory()
+                self.host_count.copy_(self.count, non_blocking=True)
+                self.host_table.copy_(self.table, non_blocking=True)
+                self.host_logits = None
+                if save_logits:
+                    self.host_logits = torch.empty(logits.shape, dtype=torch.float32).pin_memory()
+                    self.host_logits.copy_(logits, non_blocking=True)
+                self.done = torch.cuda.Event()
+                self.done.record(side)
+            for t in (logits, self.table, self.count):
+                t.record_stream(side)
+
+    def finish(self, output_p) -> list[tuple[int, int, str]]:
+        """Wait for this file's copies only, then format: RTTM (+ logits file), as inference.py:333-357."""
+        self.done.synchronize()
+        le = self.model.label_encoder
+        n = int(self.host_count[0])
+        intervals = _table_to_intervals(self.host_table[:n].numpy(), INFERENCE_SETTINGS, le.base_labels)
+        if self.host_logits is not None:
+            logits_out_p = Path(output_p) / "logits"
+            logits_out_p.mkdir(parents=True, exist_ok=True)
+            torch.save({le.inv_transform(i): self.host_logits[:, i].clone() for i in range(le.n_labels)},
+                       f"{logits_out_p}/{self.stem}-logits_dict_t.pt")
+        if output_p is not None:
+            write_intervals(intervals=intervals, audio_path=Path(self.stem), output_p=output_p)
+        return intervals
+
+
 def infer_file(audio_path, model: BaseSegmentationModel, output_p: Path, config: Config, batch_size: int,
                device="cuda", thresholds: None | dict = None, save_logits: bool = False, window_step: int | None = None):
     """Window, forward, threshold, decode and write one file (inference.py:286-357). Returns the intervals."""
     if thresholds is None:
         thresholds = default_thresholds(model.label_encoder)
-    logits_t = apply_model_on_audio(audio_path=audio_path, model=model, batch_size=batch_size,
-                                    chunk_duration_s=config.audio.chunk_duration_s, conv_settings=INFERENCE_SETTINGS,
-                                    device=device, window_step=window_step)
-    stem = Path(audio_path).stem if not isinstance(audio_path, (np.ndarray, torch.Tensor)) else "audio"
-    if save_logits:
-        logits_out_p = Path(output_p) / "logits"
-        logits_out_p.mkdir(parents=True, exist_ok=True)
-        host = logits_t.cpu()
-        torch.save({model.label_encoder.inv_transform(i): host[:, i].clone() for i in range(model.label_encoder.n_labels)},
-                   f"{logits_out_p}/{stem}-logits_dict_t.pt")
-    intervals = decode_logits(logits_t, thresholds, model.label_encoder, INFERENCE_SETTINGS)
-    if output_p is not None:
-        write_intervals(intervals=intervals, audio_path=Path(stem), output_p=output_p)
-    return intervals
+    job = _FileJob(audio_path, model, config, batch_size, device, thresholds, save_logits, window_step)
+    return job.finish(output_p)
 
 
 def get_list_of_files_to_process(wavs: Path, recursive: bool = False, uris: Path | None = None) -> tuple[list[Path], int]:
@@ -307,14 +353,22 @@ def run_inference_on_audios(config, uris, wavs, checkpoint, output, thresholds, 
 
         sizes = [get_audio_info(p).n_samples for p in files]
         mine = [files[i] for i in assign_files(sizes, shard[1])[shard[0]]]
+    if not thresholds:
+        thresholds = default_thresholds(model.label_encoder)
+    # Files are queued back to back: file i's interval table comes back on a side stream and is formatted on the host
+    # while the device already runs file i + 1 ... i + MAX_FILES_IN_FLIGHT (the reference loop is serial, 442-458).
+    in_flight: list[_FileJob] = []
     for i, audio_path in enumerate(mine, 1):
         s = f"({i:>{len(str(n_files))}}/{n_files}) - running inference for file: '{audio_path.stem}'"
         if logger:
             logger.info(s)
         else:
             print(f"[log] - {s}", flush=True)
-        infer_file(audio_path=audio_path, model=model, output_p=output, config=cfg, batch_size=batch_size,
-                   device=device, thresholds=thresholds, save_logits=save_logits)
+        in_flight.append(_FileJob(audio_path, model, cfg, batch_size, device, thresholds, save_logits, None))
+        while len(in_flight) > MAX_FILES_IN_FLIGHT:
+            in_flight.pop(0).finish(output)
+    for job in in_flight:
+        job.finish(output)
     return mine
 
 

@@ -211,6 +211,22 @@ def cast_f16(src: torch.Tensor, dst: torch.Tensor) -> None:
                                dst.stride(0), rows, cols, _stream())
 
 
+def cast_f16_split(src: torch.Tensor, dst: torch.Tensor) -> None:
+    """(rows, cols) fp32 -> (rows, 3*cols) fp16 ``[hi | lo | hi]`` (see ``split_weight``)."""
+    rows, cols = src.shape
+    assert dst.shape == (rows, 3 * cols)
+    _call("segma_cast_f16_split", 1, _lib().segma_cast_f16_split, _dev(src, torch.float32, "src"), src.stride(0),
+          _dev(dst, torch.float16, "dst"), dst.stride(0), rows, cols, _stream())
+
+
+def split_weight(w: torch.Tensor) -> torch.Tensor:
+    """(N, K) fp32 weight -> (N, 3K) fp16 ``[W_hi | W_hi | W_lo]`` matching ``cast_f16_split``'s ``[hi | lo | hi]``."""
+    w = w.detach().float()
+    hi = w.to(torch.float16)
+    lo = (w - hi.float()).to(torch.float16)
+    return torch.cat([hi, hi, lo], dim=1).contiguous()
+
+
 def attention(qkv: torch.Tensor, n_windows: int, T: int, n_heads: int, *, n_query=None, gate=None, pos_bias=None,
               rel_bias=None, out=None) -> torch.Tensor:
     """``pos_bias`` (H, T, T) or, for a Toeplitz table, ``rel_bias`` (H, 2T-1) with bias[i, j] = rel[j - i + T - 1]."""
@@ -308,6 +324,37 @@ def decode_intervals(logits: torch.Tensor, thresholds, *, file_offsets=None, mod
         if total <= cap:
             return table[:total]
         cap = total
+
+
+def decode_intervals_async(logits: torch.Tensor, thresholds, *, file_offsets=None, mode: int = DECODE_SIGMOID,
+                           onset=None) -> tuple[torch.Tensor, torch.Tensor]:
+    """``decode_intervals`` without the host read-back: returns ``(table, count)`` where ``table`` has room for the
+    worst case (alternating frames: ceil(n_f / 2) runs per label and file) and ``count`` is a 1-element int32 device
+    tensor; rows ``[count:]`` are undefined.  Nothing synchronises, so files can be queued back to back."""
+    lib = _lib()
+    n, C_ = logits.shape
+    assert logits.is_contiguous()
+    offs = [0, n] if file_offsets is None else [int(v) for v in file_offsets]
+    n_files = len(offs) - 1
+    assert offs[-1] == n
+    off_arr = (C.c_int64 * len(offs))(*offs)
+    thr = (C.c_float * C_)(*[float(t) for t in thresholds])
+    ws_bytes = lib.segma_decode_workspace_bytes(n, n_files, C_)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=logits.device)
+    count = torch.zeros(1, dtype=torch.int32, device=logits.device)
+    cap = max(1, C_ * (n // 2 + n_files))
+    table = torch.empty((cap, 4), dtype=torch.int32, device=logits.device)
+    if n == 0:
+        return table, count
+    if onset is None:
+        _call("segma_decode_intervals", 3, lib.segma_decode_intervals, _dev(logits, torch.float32, "logits"), off_arr,
+              n_files, C_, thr, mode, table.data_ptr(), cap, count.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+    else:
+        hi = (C.c_float * C_)(*[float(t) for t in onset])
+        _call("segma_decode_intervals_hysteresis", 6, lib.segma_decode_intervals_hysteresis,
+              _dev(logits, torch.float32, "logits"), off_arr, n_files, C_, thr, hi, table.data_ptr(), cap,
+              count.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+    return table, count
 
 
 # ---- wav2vec2 / WavLM ------------------------------------------------------------------------------

@@ -7,16 +7,21 @@ Workload (`config.workload`): Whisper-small-dims encoder + segma LSTM/linear hea
 80-bin log-mel, one 1 h synthetic 16 kHz file per step and per GPU, 4 s windows at the reference's step
 (905 forward windows, 179 999 frames), batch 128, default 0.5 thresholds, intervals decoded on the device.
 A step = the whole hot path over one file: window -> log-mel -> encoder -> LSTM -> heads -> logits on the
-file timeline -> threshold + run-length decode -> interval table (+ NCCL all-gather of tables for N > 1).
+file timeline -> threshold + run-length decode -> interval table.  Nothing is read back between steps; after the
+last step the row counts are read once and (N > 1) the tables are all-gathered once over NCCL, inside the timed region.
 
   value  : device-timed (CUDA events), PCM already resident in HBM.
-  e2e    : the same through the public API (`apply_model_on_audio` + `decode_logits`) from pinned host
-           PCM: H2D copy of the file and D2H read of the interval table inside the timed region.
+  e2e    : the same through the public per-file API (what `infer_file` / `run_inference_on_audios` run) from pinned
+           host PCM: every step's H2D copy of its file and D2H read of its interval table inside the timed region.
   roofline: the dominant kernel (tcgen05 GEMM / implicit conv), algorithmic FLOPs / CUDA-event time of its
            launches inside the timed region, against the measured sustained bf16 cuBLAS peak.
   cpu_baseline: the oracle (reference arithmetic in torch fp32) on this box's host cores on a bounded
            sample of the same workload.
-`--impl reference` times that CPU arm alone (all host threads), same metric / unit / config.
+  gpu_eager_baseline: the reference's own modules (transformers WhisperEncoder, nn.LSTM, nn.Linear) in torch eager on
+           the same GPU -- the library kernels (cuBLASLt / cuDNN / SDPA / cuFFT) the hand-written ones replace.
+  workloads: HuBERT-base / WavLM-base+ dims (BASELINE configs 1 and 3 models), 3 steps of 1 h each.
+`--workload corpus`: BASELINE config 4 in miniature (skewed file durations, file-sharded, strong scaling).
+`--impl reference` times the CPU arm alone (all host threads), same metric / unit / config.
 """
 from __future__ import annotations
 
@@ -146,77 +151,177 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["sec_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": _config(args.gpus, res["audio_s"]),
-        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"]},
+        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"],
+                         "calibration": _calibration()},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ---- torch-eager-on-B200 arm: the reference's own module stack on the GPU ---------------
+def eager_gpu_baseline(dev, sd, n_windows: int = 128) -> dict:
+    """The reference path as torch 2.11 eager dispatches it on this GPU: transformers' ``WhisperEncoder`` (SDPA),
+    ``nn.LSTM`` read sequence-first (the reference never sets batch_first), per-label ``nn.Linear`` heads -- composed
+    as /root/reference/src/segma/models/whisper/surgical_hydra.py:80-109 composes them -- with the log-mel hook
+    restated in torch on the device (torch.stft -> mel -> log10 -> clamp, feature_extraction_whisper.py:135-164).
+    cuFFT / cuDNN / cuBLASLt / flash SDPA: the library kernels the hand-written ones have to beat.  One 128-window
+    batch per step (the reference's default), 1 warm-up + 2 timed steps per precision."""
+    import numpy as np
+    import torch
+    from torch import nn
+    from transformers import WhisperConfig
+    from transformers.models.whisper.modeling_whisper import WhisperEncoder
+
+    from segma_b200 import ops, synth
+
+    cfg = WhisperConfig(d_model=768, encoder_layers=12, encoder_attention_heads=12, encoder_ffn_dim=3072, decoder_layers=1,
+                        decoder_attention_heads=2, decoder_ffn_dim=64, vocab_size=100)
+    enc = WhisperEncoder(cfg).eval()
+    enc.load_state_dict({k[len("w_encoder."):]: v for k, v in sd.items() if k.startswith("w_encoder.")}, strict=True)
+    lstm = nn.LSTM(input_size=768, hidden_size=128, num_layers=2, bidirectional=True).eval()
+    lstm.load_state_dict({k[len("lstm_shared."):]: v for k, v in sd.items() if k.startswith("lstm_shared.")}, strict=True)
+    heads = nn.ModuleList([nn.Linear(256, 1) for _ in LABELS]).eval()
+    for h, lab in zip(heads, LABELS):
+        h.load_state_dict({"weight": sd[f"task_heads.linear_head_{lab}.weight"], "bias": sd[f"task_heads.linear_head_{lab}.bias"]})
+    enc, lstm, heads = enc.to(dev), lstm.to(dev), heads.to(dev)
+    lw = torch.softmax(sd["layer_weights"], 0).to(dev)
+    mel = torch.from_numpy(np.ascontiguousarray(ops.mel_filters().T)).to(dev)  # (80, 201), same filterbank values
+    hann = torch.hann_window(400, device=dev)
+    n = STEP_SAMPLES * (n_windows - 1) + WIN
+    pcm = torch.from_numpy(synth.synth_audio(n, 0)).to(dev)
+
+    def step():
+        wins = pcm.unfold(0, WIN, STEP_SAMPLES)  # (n_windows, 64000), inference.py:148-152
+        x = torch.zeros((n_windows, 480_000), device=dev)
+        x[:, :WIN] = wins
+        st = torch.stft(x, 400, 160, window=hann, return_complex=True)
+        spec = mel @ (st[..., :-1].abs() ** 2)
+        log_spec = torch.clamp(spec, min=1e-10).log10()
+        log_spec = torch.maximum(log_spec, log_spec.amax(dim=(1, 2), keepdim=True) - 8.0)
+        feats = (log_spec + 4.0) / 4.0
+        hs = enc(feats, output_hidden_states=True).hidden_states[1:]
+        mix = torch.einsum("l,l...->...", lw.to(hs[0].dtype), torch.stack(list(hs), dim=0))
+        out, _ = lstm(mix)  # sequence axis = windows
+        out = out[:, :199]
+        logits = torch.stack([h(out) for h in heads], dim=-1).reshape(-1, len(LABELS))
+        return (logits.float().sigmoid() > 0.5)
+
+    res = {"windows_per_step": n_windows, "audio_s_per_step": n / 16_000,
+           "what": "transformers WhisperEncoder (sdpa) + nn.LSTM + nn.Linear heads + torch.stft log-mel, torch eager, "
+                   "weights and audio as in the main arm; thresholded on the device, no interval decode"}
+    for name, ctx in (("fp32", None), ("bf16_autocast", torch.bfloat16), ("fp16_autocast", torch.float16)):
+        try:
+            with torch.inference_mode():
+                def run():
+                    if ctx is None:
+                        return step()
+                    with torch.autocast("cuda", dtype=ctx):
+                        return step()
+                run()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(2):
+                    run()
+                e1.record()
+                torch.cuda.synchronize()
+            sec = e0.elapsed_time(e1) / 2e3
+            res[name] = {"value": n / 16_000 / 3600.0 / sec, "unit": UNIT, "ms_per_128_windows": sec * 1e3}
+        except Exception as e:  # noqa: BLE001  (an arm that cannot run is reported, not hidden)
+            res[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    del enc, lstm, heads
+    torch.cuda.empty_cache()
+    return res
+
+
 # ---- GPU arm ---------------------------------------------------------------------------------------------
-def run_gpu(args):
+def _peaks():
+    try:
+        return json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:  # noqa: BLE001
+        return {}
+
+
+def _traffic():
+    """DRAM bytes per launch of the dominant kernel from this round's ``ncu --set full`` capture (ncu cannot run inside
+    the bench; tools/ncu_full_summary.py writes the file from the capture of the same command)."""
+    try:
+        return json.loads((ROOT / "profiles" / "r02_gemm_traffic.json").read_text())
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def measure_model_workload(args, workload: str, steps: int, warmup: int, rank: int, world: int, dev, with_e2e: bool = True):
+    """One model workload: K timed steps (one file of ``args.hours`` h per GPU per step) + the final exchange."""
     import torch
     import torch.distributed as dist
 
     from segma_b200 import ops, synth
     from segma_b200.config import make_config
-    from segma_b200.distributed import gather_file_tables, init_from_env
+    from segma_b200.distributed import gather_corpus_tables
     from segma_b200.encoders import MultiLabelEncoder
     from segma_b200.geometry import INFERENCE_SETTINGS
-    from segma_b200.inference import apply_model_on_audio, default_thresholds
+    from segma_b200.inference import MAX_FILES_IN_FLIGHT, _FileJob, apply_model_on_audio, default_thresholds
     from segma_b200.models import Models
     from segma_b200.thresholds import logit_cut
 
-    # NCCL writes its version banner (NCCL_DEBUG=VERSION and up) to stdout unless told otherwise; stdout carries the
-    # single JSON line of this script
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    rank, world, local = init_from_env("nccl")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    ops.device_check()
     n_samples = int(args.hours * HOUR_SAMPLES)
     audio_s = n_samples / 16_000
-
     le = MultiLabelEncoder(list(LABELS))
-    kind, _, gflop_per_window = WORKLOADS[args.workload]
+    kind, _, gflop_per_window = WORKLOADS[workload]
     cfg = make_config(kind)
-    if args.workload == "whisper":
+    if workload == "whisper":
         sd = synth.surgical_hydra_state_dict(synth.WHISPER_SMALL, seed=0)
     else:
-        sd = synth.hubert_hydra_state_dict(synth.WAVLM_BASE if args.workload == "wavlm" else synth.HUBERT_BASE, seed=0)
+        sd = synth.hubert_hydra_state_dict(synth.WAVLM_BASE if workload == "wavlm" else synth.HUBERT_BASE, seed=0)
     model = Models[kind].from_state_dict(sd, le, cfg).to(dev)
-    thr = default_thresholds(le)
     cuts = [logit_cut(0.5)] * len(LABELS)
-
+    thr = default_thresholds(le)
     host_pcm = torch.from_numpy(synth.synth_audio(n_samples, seed=rank)).pin_memory()
     dev_pcm = host_pcm.to(dev)
-
-    def step_resident():
-        logits = apply_model_on_audio(dev_pcm, model, INFERENCE_SETTINGS, dev, batch_size=BATCH)
-        table = ops.decode_intervals(logits, cuts, mode=ops.DECODE_LOGIT)
-        table[:, 0] = rank
-        return gather_file_tables(table) if world > 1 else table
-
-    def step_e2e():
-        logits = apply_model_on_audio(host_pcm, model, INFERENCE_SETTINGS, dev, batch_size=BATCH)
-        table = ops.decode_intervals(logits, cuts, mode=ops.DECODE_LOGIT)
-        table[:, 0] = rank
-        full = gather_file_tables(table) if world > 1 else table
-        return full.cpu()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def run_steps(src, k, to_host):
+        """k files through the path with nothing read back in between, then the single end-of-run exchange: counts to
+        the host once, tables compacted and all-gathered once (NCCL for world > 1)."""
+        tables, counts = [], []
+        for _ in range(k):
+            logits = apply_model_on_audio(src, model, INFERENCE_SETTINGS, dev, batch_size=BATCH)
+            t, c = ops.decode_intervals_async(logits, cuts, mode=ops.DECODE_LOGIT)
+            tables.append(t)
+            counts.append(c)
+        full = gather_corpus_tables([rank * k + i for i in range(k)], tables, counts, device=dev, gather=world > 1)
+        return full.cpu() if to_host else full
+
+    def run_e2e(src, k, to_host):
+        """The public per-file API from pinned host PCM: every step stages its file over PCIe behind the compute of the
+        previous batches and brings its interval table (and row count) back to the host on a side stream, where it is
+        turned into the reference's ``(start, end, label)`` list; up to MAX_FILES_IN_FLIGHT files are queued before
+        the host waits for the oldest.  For world > 1 the final all-gather of the device tables follows."""
+        jobs, d2h = [], 0
+        for i in range(k):
+            jobs.append(_FileJob(src, model, cfg, BATCH, dev, thr, False, None))
+            if i >= MAX_FILES_IN_FLIGHT:
+                jobs[i - MAX_FILES_IN_FLIGHT].finish(None)
+        for j in jobs[max(0, k - MAX_FILES_IN_FLIGHT):]:
+            j.finish(None)
+        d2h = sum(j.host_table.numel() * 4 + 4 for j in jobs)
+        if world > 1:
+            gather_corpus_tables([rank * k + i for i in range(k)], [j.table for j in jobs], [j.count for j in jobs],
+                                 device=dev, gather=True)
+        return d2h
+
+    def timed(src, k, to_host):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        out = None
-        for _ in range(steps):
-            out = fn()
+        out = (run_e2e if to_host else run_steps)(src, k, to_host)
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -225,40 +330,71 @@ def run_gpu(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms[0].item() / 1e3, ms[1].item() / 1e3, out
 
-    for _ in range(args.warmup):
-        step_resident()
-    step_e2e()
-
-    with ClockSampler(local) as clocks:
+    run_steps(dev_pcm, warmup, False)
+    if with_e2e:
+        run_e2e(host_pcm, 1, True)
+    with ClockSampler(dev.index or 0) as clocks:
         ops.stats.reset()
-        dev_s, _, table = timed(step_resident, args.steps)
+        dev_s, _, table = timed(dev_pcm, steps, False)
         launches = ops.stats.launches
-        _, e2e_wall, table_host = timed(step_e2e, args.steps)
-    n_intervals = int(table.shape[0])
+        e2e_wall, d2h_bytes = None, 0
+        if with_e2e:
+            _, e2e_wall, d2h_bytes = timed(host_pcm, steps, True)
 
-    # roofline of the dominant kernel: a separately timed pass with an event pair around every GEMM launch
+    # roofline of the dominant kernel: a separately timed pass with an event pair around every launch
     ops.stats.reset()
     ops.stats.profile = True
     barrier()
-    step_resident()
+    run_steps(dev_pcm, 1, False)
     torch.cuda.synchronize()
     ops.stats.profile = False
     breakdown = ops.stats.breakdown()
     gemms = [v for k, v in breakdown.items() if k.startswith("segma_gemm_f16")]
     g_ms, g_flops, n_gemm = sum(v["ms"] for v in gemms), sum(v["work"] for v in gemms), sum(v["calls"] for v in gemms)
-    peaks = {}
-    try:
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-    except Exception:  # noqa: BLE001
-        pass
+    executed = sum(v["work"] for k, v in breakdown.items() if k.startswith(("segma_gemm_f16", "segma_attention")))
+    peaks = _peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     achieved_tf = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
-    total_flops_per_step = 905 * gflop_per_window * 1e9 * (n_samples / HOUR_SAMPLES)
+    n_windows = 905 * (n_samples / HOUR_SAMPLES)
+    traffic = _traffic() if workload == "whisper" else None
+    res = {
+        "value": world * (audio_s / 3600.0) * steps / dev_s,
+        "ms_per_step": dev_s / steps * 1e3,
+        "audio_s": audio_s,
+        "launches": launches,
+        "intervals_per_step": int(table.shape[0]) // max(steps * world, 1),
+        # tensor-core FLOPs the launches of one step actually execute (last-layer pruning, tile padding of grouped
+        # convolutions excluded) and the reference's algorithmic count for the same windows, both per GPU
+        "model_tflops_per_gpu": executed / (dev_s / steps) / 1e12,
+        "executed_gflop_per_window": executed / n_windows / 1e9,
+        "algorithmic_gflop_per_window": gflop_per_window,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc5_kernel (tcgen05 GEMM + implicit conv)",
+                     "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                     "traffic": traffic["bytes_per_launch"] if traffic else None,
+                     "traffic_source": traffic["source"] if traffic else None,
+                     "launches": n_gemm, "avg_launch_ms": g_ms / max(n_gemm, 1),
+                     "share_of_step": (g_ms / 1e3) / (dev_s / steps), "peak_source": peak_src},
+        "clocks": clocks.summary(),
+        "breakdown_ms_per_step": {k: [round(v["ms"], 3), round(v["work"] / max(v["ms"], 1e-9) / 1e9, 1)]
+                                  for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])},
+    }
+    if with_e2e:
+        res["e2e"] = {"value": world * (audio_s / 3600.0) * steps / e2e_wall, "unit": UNIT,
+                      "h2d_bytes_per_step": host_pcm.numel() * 4,
+                      "d2h_bytes_per_step": d2h_bytes // steps}
+    return res, dict(model=model, sd=sd, dev_pcm=dev_pcm, cuts=cuts)
 
-    # secondary HBM-bound kernels, timed alone (burst peak): log-mel front end on one 128-window batch and
-    # threshold + run-length decode on a >= 100 h batch of logits
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+
+def measure_side_kernels(dev, ctx) -> dict:
+    """HBM-bound kernels timed alone against the measured copy bandwidth (burst peak): the two front ends on a batch
+    larger than L2 and threshold + run-length decode on >= 200 h of logits."""
+    import torch
+
+    from segma_b200 import ops, synth
+
+    hbm_peak = float(_peaks().get("hbm_gbs", 6650.0))
+    dev_pcm, cuts = ctx["dev_pcm"], ctx["cuts"]
 
     def time_kernel(fn, iters=20):
         for _ in range(3):
@@ -273,94 +409,229 @@ def run_gpu(args):
         return e0.elapsed_time(e1) / iters * 1e-3
 
     side = {}
-    if rank == 0 and not args.no_side_kernels:
-        n_w = 1024  # 1024 windows: 262 MB in + 983 MB out, larger than L2
-        span = STEP_SAMPLES * (n_w - 1) + WIN
-        pcm_side = dev_pcm[:span] if dev_pcm.numel() >= span else torch.randn(span, device=dev) * 0.1
-        out_f32 = torch.empty((n_w, 80, 3000), dtype=torch.float32, device=dev)
-        scratch = torch.empty(ops.logmel_scratch_bytes(n_w, WIN), dtype=torch.uint8, device=dev)
-        lib = ops._lib()
-        st = torch.cuda.current_stream().cuda_stream
-        t_mel = time_kernel(lambda: lib.segma_logmel(pcm_side.data_ptr(), pcm_side.numel(), n_w, WIN, STEP_SAMPLES,
-                                                     out_f32.data_ptr(), None, scratch.data_ptr(), st))
-        mel_bytes = n_w * (4 * WIN + 4 * 80 * 3000)
-        side["logmel"] = {"bound": "hbm", "achieved": mel_bytes / t_mel / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                          "frac": mel_bytes / t_mel / 1e9 / hbm_peak, "us_per_window": t_mel / n_w * 1e6,
-                          "algorithmic_bytes_per_window": 4 * WIN + 4 * 80 * 3000}
-        del out_f32, scratch
-        def speech_like(n_fr):
-            # runs of ~1 s per label (the reference's synthetic annotations are 0.2-3 s long); built in chunks of 100 h
-            parts = []
-            for lo in range(0, n_fr, 18_000_000):
-                m = min(18_000_000, n_fr - lo)
-                parts.append(torch.randn((m // 50, len(LABELS)), device=dev).repeat_interleave(50, dim=0)
-                             + 0.05 * torch.randn((m, len(LABELS)), device=dev))
-            return torch.cat(parts).contiguous()
+    lib = ops._lib()
+    st = torch.cuda.current_stream().cuda_stream
+    n_w = 1024  # 1024 windows: 262 MB in + 983 MB out, larger than L2
+    span = STEP_SAMPLES * (n_w - 1) + WIN
+    pcm_side = dev_pcm[:span] if dev_pcm.numel() >= span else torch.randn(span, device=dev) * 0.1
+    out_f32 = torch.empty((n_w, 80, 3000), dtype=torch.float32, device=dev)
+    scratch = torch.empty(ops.logmel_scratch_bytes(n_w, WIN), dtype=torch.uint8, device=dev)
+    t_mel = time_kernel(lambda: lib.segma_logmel(pcm_side.data_ptr(), pcm_side.numel(), n_w, WIN, STEP_SAMPLES,
+                                                 out_f32.data_ptr(), None, scratch.data_ptr(), st))
+    mel_bytes = n_w * (4 * WIN + 4 * 80 * 3000)
+    side["logmel"] = {"bound": "hbm", "achieved": mel_bytes / t_mel / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                      "frac": mel_bytes / t_mel / 1e9 / hbm_peak, "us_per_window": t_mel / n_w * 1e6,
+                      "algorithmic_bytes_per_window": 4 * WIN + 4 * 80 * 3000}
+    del out_f32, scratch
+    # wav2vec2 / HuBERT / WavLM front end, layer 0: conv(k=10, s=5) + GroupNorm + GELU, 4*64000 B read and the
+    # 2*12799*512 B fp16 activation written per window (SURVEY.md 8d counts the front end's HBM-bound part)
+    n_l0 = 256
+    span0 = STEP_SAMPLES * (n_l0 - 1) + WIN
+    sd0 = synth.hubert_hydra_state_dict(synth.HUBERT_BASE, seed=0)
+    fe = "wav2vec2.feature_extractor.conv_layers.0."
+    w0 = sd0[fe + "conv.weight"].reshape(512, 10).contiguous().to(dev)
+    g0, b0 = sd0[fe + "layer_norm.weight"].to(dev), sd0[fe + "layer_norm.bias"].to(dev)
+    rows0 = (WIN - 10) // 5 + 1
+    act = torch.zeros((n_l0, rows0 + (rows0 & 1), 512), dtype=torch.float16, device=dev)
+    ss = torch.empty((n_l0, 512, 2), dtype=torch.float32, device=dev)
+    t_l0 = time_kernel(lambda: ops.w2v2_layer0(dev_pcm[:span0], n_l0, WIN, STEP_SAMPLES, w0, g0, b0, ss, act), iters=10)
+    l0_bytes = n_l0 * (4 * WIN + 2 * rows0 * 512)
+    side["w2v2_layer0"] = {"bound": "hbm", "achieved": l0_bytes / t_l0 / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": l0_bytes / t_l0 / 1e9 / hbm_peak, "us_per_window": t_l0 / n_l0 * 1e6,
+                           "algorithmic_bytes_per_window": 4 * WIN + 2 * rows0 * 512}
+    del act, ss
 
-        for name, hours, make in (
-            # 1000 h of logits batched (2.9 GB), one file per hour
-            ("decode", 1000, speech_like),
-            # worst case: iid logits, one interval every ~4 frames per label (the 16 B/interval table dominates)
-            ("decode_worst_case", 200, lambda n_fr: torch.randn((n_fr, len(LABELS)), device=dev)),
-        ):
-            n_fr = 180_000 * hours
-            offs = [i * 180_000 for i in range(hours + 1)]
-            big = make(n_fr)
-            tbl = ops.decode_intervals(big, cuts, file_offsets=offs, mode=ops.DECODE_LOGIT)
-            n_iv = int(tbl.shape[0])
-            del tbl
-            # device time of the C-ABI call (its kernels + two small offset uploads), CUDA events around it
-            ops.stats.reset()
-            ops.stats.profile = True
-            for _ in range(5):
-                ops.decode_intervals(big, cuts, file_offsets=offs, mode=ops.DECODE_LOGIT, capacity=n_iv)
-            torch.cuda.synchronize()
-            ops.stats.profile = False
-            evs = [e0.elapsed_time(e1) for nm, e0, e1, _ in ops.stats.events if nm == "segma_decode_intervals"]
-            t_dec = min(evs) * 1e-3
-            dec_bytes = 4 * len(LABELS) * n_fr + 16 * n_iv
-            side[name] = {"bound": "hbm", "achieved": dec_bytes / t_dec / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                          "frac": dec_bytes / t_dec / 1e9 / hbm_peak, "hours_of_logits": hours, "intervals": n_iv,
-                          "ms": t_dec * 1e3,
-                          "note": "device time of one segma_decode_intervals call (count, tile sums, scan, write kernels)"}
-            del big
+    def speech_like(n_fr):
+        # runs of ~1 s per label (the reference's synthetic annotations are 0.2-3 s long); built in chunks of 100 h
+        parts = []
+        for lo in range(0, n_fr, 18_000_000):
+            m = min(18_000_000, n_fr - lo)
+            parts.append(torch.randn((m // 50, len(LABELS)), device=dev).repeat_interleave(50, dim=0)
+                         + 0.05 * torch.randn((m, len(LABELS)), device=dev))
+        return torch.cat(parts).contiguous()
 
-    if rank != 0:
+    for name, hours, make in (
+        # 1000 h of logits batched (2.9 GB), one file per hour
+        ("decode", 1000, speech_like),
+        # worst case: iid logits, one interval every ~4 frames per label (the 16 B/interval table dominates)
+        ("decode_worst_case", 200, lambda n_fr: torch.randn((n_fr, len(LABELS)), device=dev)),
+    ):
+        n_fr = 180_000 * hours
+        offs = [i * 180_000 for i in range(hours + 1)]
+        big = make(n_fr)
+        tbl = ops.decode_intervals(big, cuts, file_offsets=offs, mode=ops.DECODE_LOGIT)
+        n_iv = int(tbl.shape[0])
+        del tbl
+        # device time of the C-ABI call (its kernels + two small offset uploads), CUDA events around it
+        ops.stats.reset()
+        ops.stats.profile = True
+        for _ in range(5):
+            ops.decode_intervals(big, cuts, file_offsets=offs, mode=ops.DECODE_LOGIT, capacity=n_iv)
+        torch.cuda.synchronize()
+        ops.stats.profile = False
+        evs = [e0.elapsed_time(e1) for nm, e0, e1, _ in ops.stats.events if nm == "segma_decode_intervals"]
+        t_dec = min(evs) * 1e-3
+        dec_bytes = 4 * len(LABELS) * n_fr + 16 * n_iv
+        side[name] = {"bound": "hbm", "achieved": dec_bytes / t_dec / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                      "frac": dec_bytes / t_dec / 1e9 / hbm_peak, "hours_of_logits": hours, "intervals": n_iv,
+                      "ms": t_dec * 1e3,
+                      "note": "device time of one segma_decode_intervals call (count, tile sums, scan, write kernels)"}
+        del big
+    return side
+
+
+def measure_corpus(args, rank: int, world: int, dev):
+    """BASELINE config 4 in miniature: a fixed corpus of files with skewed durations (10 s ... 1 h), sharded by file
+    over the ranks (longest first), no exchange until the single final all-gather.  Strong scaling: the corpus does not
+    grow with the number of GPUs."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from segma_b200 import ops, synth
+    from segma_b200.config import make_config
+    from segma_b200.encoders import MultiLabelEncoder
+    from segma_b200.inference import infer_corpus
+    from segma_b200.models import Models
+
+    le = MultiLabelEncoder(list(LABELS))
+    cfg = make_config("surgical_hydra")
+    model = Models["surgical_hydra"].from_state_dict(synth.surgical_hydra_state_dict(synth.WHISPER_SMALL, seed=0), le, cfg).to(dev)
+    rng = np.random.default_rng(4)
+    n_files = args.corpus_files
+    dur_s = np.clip(np.exp(rng.normal(np.log(150.0), 1.3, size=n_files)), 10.0, 3600.0)
+    lens = (dur_s * 16_000).astype(np.int64)
+    pool = torch.from_numpy(synth.synth_audio(HOUR_SAMPLES, seed=0)).pin_memory()
+    offs = rng.integers(0, HOUR_SAMPLES - lens + 1)
+    host_files = [pool[int(o): int(o) + int(n)] for o, n in zip(offs, lens)]
+    dev_pool = pool.to(dev)
+    dev_files = [dev_pool[int(o): int(o) + int(n)] for o, n in zip(offs, lens)]
+    total_h = float(lens.sum()) / 16_000 / 3600.0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(files, k, to_host):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(k):
+            out = infer_corpus(files, model, cfg, BATCH, dev, shard=(rank, world), sizes=lens.tolist())
+            if to_host:
+                out = out.cpu()
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = torch.tensor([e0.elapsed_time(e1), wall * 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms[0].item() / 1e3, ms[1].item() / 1e3, out
+
+    timed(dev_files, max(1, min(args.warmup, 1)), False)
+    with ClockSampler(dev.index or 0) as clocks:
+        ops.stats.reset()
+        dev_s, _, table = timed(dev_files, args.steps, False)
+        launches = ops.stats.launches
+        _, e2e_wall, table_host = timed(host_files, args.steps, True)
+    return {
+        "value": total_h * args.steps / dev_s, "ms_per_step": dev_s / args.steps * 1e3, "launches": launches,
+        "e2e": {"value": total_h * args.steps / e2e_wall, "unit": UNIT, "h2d_bytes_per_step": int(lens.sum()) * 4,
+                "d2h_bytes_per_step": int(table_host.numel()) * 4},
+        "clocks": clocks.summary(), "corpus_hours": total_h, "n_files": n_files, "intervals": int(table.shape[0]),
+        "longest_file_s": float(dur_s.max()), "median_file_s": float(np.median(dur_s)),
+    }
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from segma_b200 import ops
+    from segma_b200.distributed import init_from_env
+
+    # NCCL writes its version banner (NCCL_DEBUG=VERSION and up) to stdout unless told otherwise; stdout carries the
+    # single JSON line of this script
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    rank, world, local = init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ops.device_check()
+
+    if args.workload == "corpus":
+        r = measure_corpus(args, rank, world, dev)
+        if rank == 0:
+            line = {
+                "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f16", "data": "synthetic",
+                "config": {"workload": f"corpus: {r['n_files']} files, {r['corpus_hours']:.2f} h in total, durations log-normal "
+                                       f"(median {r['median_file_s']:.0f} s, longest {r['longest_file_s']:.0f} s), "
+                                       "whisper-small-dims surgical_hydra, 4 s windows step 63680, batch 128",
+                           "parallelism": f"files sharded over {world} GPU(s), longest first; one final interval all-gather",
+                           "l2": "a 230 MB PCM pool and > 3 GB of activations per 128-window batch: larger than L2"},
+                "e2e": r["e2e"], "gpu_launches": r["launches"], "clocks": r["clocks"], "intervals_per_step": r["intervals"],
+            }
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
         return
-    value = world * (audio_s / 3600.0) * args.steps / dev_s
-    e2e_value = world * (audio_s / 3600.0) * args.steps / e2e_wall
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline and args.workload == "whisper":
-        r = cpu_reference_run(args.ref_windows, 1, 0)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    res, ctx = measure_model_workload(args, args.workload, args.steps, args.warmup, rank, world, dev)
+    extras, side, cpu, eager = {}, {}, None, None
+    if world == 1:
+        if not args.no_side_kernels:
+            side = measure_side_kernels(dev, ctx)
+        if args.workload == "whisper" and not args.no_extra_workloads:
+            if not args.no_eager_baseline:
+                eager = eager_gpu_baseline(dev, ctx["sd"])
+            ctx.clear()
+            torch.cuda.empty_cache()
+            for wl in ("hubert", "wavlm"):  # BASELINE configs 1 and 3 models, driver-visible: 3 steps of 1 h each
+                r, c = measure_model_workload(args, wl, 3, 3, rank, world, dev, with_e2e=False)
+                c.clear()
+                torch.cuda.empty_cache()
+                extras[wl] = {"workload": WORKLOADS[wl][1], "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"],
+                              "steps": 3, "warmup": 3, "roofline": r["roofline"], "gpu_launches": r["launches"],
+                              "model_tflops_per_gpu": r["model_tflops_per_gpu"],
+                              "executed_gflop_per_window": r["executed_gflop_per_window"],
+                              "breakdown_ms_per_step": r["breakdown_ms_per_step"]}
+        if not args.no_cpu_baseline and args.workload == "whisper":
+            c = cpu_reference_run(args.ref_windows, 1, 0)
+            cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": "port", "sample": c["sample"],
+                   "calibration": _calibration()}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16",
-        "dtype_detail": "f16 tensor-core operands; f32 accumulation, residual stream, LayerNorm/softmax statistics, LSTM state, logits",
-        "data": "synthetic", "config": _config(world, audio_s, args.workload),
-        "realtime_factor_per_gpu": value * 3600.0 / world,
-        "model_tflops_per_gpu": total_flops_per_step * args.steps / dev_s / 1e12,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host_pcm.numel() * 4,
-                "d2h_bytes_per_step": int(table_host.numel()) * 4 + 4},
-        "gpu_launches": launches,
-        "intervals_per_step": n_intervals,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc5_kernel (tcgen05 GEMM + implicit conv)",
-                     "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                     # dram__bytes_read+write per launch, mean of the four layer GEMMs (QKV, out-proj, fc1, fc2) of a
-                     # 128-window batch from profiles/r01e_prof_gemm_ncu_full.txt (1.13 + 1.42 + 1.43 + 2.39 GB) / 4; their
-                     # algorithmic bytes: 1.62e9
-                     "traffic": 1.59e9 if args.workload == "whisper" else None, "launches": n_gemm, "avg_launch_ms": g_ms / max(n_gemm, 1),
-                     "share_of_step": (g_ms / 1e3) / (dev_s / args.steps), "peak_source": peak_src},
-        "cpu_baseline": cpu,
-        "side_kernels": side,
-        "clocks": clocks.summary(),
-        "breakdown_ms_per_step": {k: [round(v["ms"], 3), round(v["work"] / max(v["ms"], 1e-9) / 1e9, 1)]
-                                  for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])},
+        "dtype_detail": "f16 tensor-core operands; f32 accumulation, residual stream, LayerNorm/softmax statistics, LSTM "
+                        "(input projection and recurrence at fp32 level), logits",
+        "data": "synthetic", "config": _config(world, res["audio_s"], args.workload),
+        "realtime_factor_per_gpu": res["value"] * 3600.0 / world,
+        "model_tflops_per_gpu": res["model_tflops_per_gpu"],
+        "executed_gflop_per_window": res["executed_gflop_per_window"],
+        "algorithmic_gflop_per_window": res["algorithmic_gflop_per_window"],
+        "e2e": res["e2e"], "gpu_launches": res["launches"], "intervals_per_step": res["intervals_per_step"],
+        "roofline": res["roofline"], "cpu_baseline": cpu, "gpu_eager_baseline": eager, "side_kernels": side,
+        "workloads": extras, "clocks": res["clocks"], "breakdown_ms_per_step": res["breakdown_ms_per_step"],
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _calibration():
+    """Port / reference time ratio of the CPU arm, measured where the reference is mounted (oracle/calibrate_port.py)."""
+    try:
+        return json.loads((ROOT / "oracle" / "calibration.json").read_text())
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def main():
@@ -372,9 +643,13 @@ def main():
     ap.add_argument("--hours", type=float, default=1.0, help="audio hours per GPU per step")
     ap.add_argument("--ref-windows", type=int, default=16, help="windows per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="whisper", choices=sorted(WORKLOADS),
-                    help="whisper = BASELINE config 2 (the headline); hubert / wavlm = configs 1 and 3 models, informational")
-    ap.add_argument("--no-side-kernels", action="store_true", help="skip the log-mel / decode roofline measurements")
+    ap.add_argument("--workload", default="whisper", choices=sorted(WORKLOADS) + ["corpus"],
+                    help="whisper = BASELINE config 2 (the headline, also reports hubert / wavlm = configs 1 and 3 under "
+                         "'workloads'); corpus = config 4 in miniature (file-sharded, strong scaling)")
+    ap.add_argument("--corpus-files", type=int, default=256, help="files in the corpus workload")
+    ap.add_argument("--no-side-kernels", action="store_true", help="skip the front-end / decode roofline measurements")
+    ap.add_argument("--no-extra-workloads", action="store_true", help="skip the hubert / wavlm lines and the eager arm")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager-on-GPU arm")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -385,7 +660,7 @@ def main():
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                    "--master-addr", "127.0.0.1", "--master-port", "29511", str(Path(__file__).resolve()),
                    "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
-                   "--hours", str(args.hours)]
+                   "--hours", str(args.hours), "--workload", args.workload, "--corpus-files", str(args.corpus_files)]
             sys.exit(subprocess.call(cmd))
         run_gpu(args)
 

@@ -74,3 +74,23 @@ def gather_file_tables(local_table: torch.Tensor, group=None) -> torch.Tensor:
         return full
     order = torch.sort(full[:, 0].to(torch.int64), stable=True).indices
     return full[order]
+
+
+def gather_corpus_tables(file_indices, tables, counts, device=None, gather: bool = True, group=None) -> torch.Tensor:
+    """The single exchange step at the end of a sharded corpus run.
+
+    ``tables[k]`` is the worst-case-sized int32 ``(cap_k, 4)`` table of this rank's k-th file (global index
+    ``file_indices[k]``) and ``counts[k]`` the 1-element tensor with its valid row count, both still where the decode
+    kernel left them.  Reads all counts back at once (the only host synchronisation of the run), compacts, stamps the
+    global file index into column 0 and all-gathers; every rank returns the same table ordered by file, label, time."""
+    if device is None:
+        device = tables[0].device if tables else torch.device("cpu")
+    parts = []
+    if tables:
+        host_counts = torch.cat([c.reshape(1) for c in counts]).cpu().tolist()
+        for i, t, c in zip(file_indices, tables, host_counts):
+            part = t[:c].clone()
+            part[:, 0] = i
+            parts.append(part)
+    local = torch.cat(parts) if parts else torch.empty((0, 4), dtype=torch.int32, device=device)
+    return gather_file_tables(local, group) if gather else local

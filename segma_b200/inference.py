@@ -35,7 +35,8 @@ from .thresholds import logit_cut
 
 __all__ = [
     "Chunkyfier", "prepare_audio", "apply_model_on_audio", "apply_thresholds", "create_intervals",
-    "decode_logits", "write_intervals", "infer_file", "get_list_of_files_to_process", "run_inference_on_audios",
+    "decode_logits", "write_intervals", "infer_file", "infer_corpus", "get_list_of_files_to_process",
+    "run_inference_on_audios",
 ]
 
 
@@ -304,6 +305,40 @@ def infer_file(audio_path, model: BaseSegmentationModel, output_p: Path, config:
         thresholds = default_thresholds(model.label_encoder)
     job = _FileJob(audio_path, model, config, batch_size, device, thresholds, save_logits, window_step)
     return job.finish(output_p)
+
+
+def infer_corpus(audios, model: BaseSegmentationModel, config: Config, batch_size: int = 128, device="cuda",
+                 thresholds: None | dict = None, shard: tuple[int, int] | None = None, sizes=None,
+                 window_step: int | None = None, gather: bool = True) -> torch.Tensor:
+    """A whole corpus -> one int32 ``(n_intervals, 4)`` device table ``(file, label, start_sample, end_sample)`` with
+    ``file`` the index into ``audios``, ordered by file, then label, then time.
+
+    The multi-GPU form of the reference's serial file loop (inference.py:442-458): with
+    ``shard=(rank, world_size)`` each rank runs only its files (``distributed.assign_files`` over ``sizes``, longest
+    first), nothing is exchanged while files are processed and nothing is read back per file -- every file's table stays
+    on the device at its worst-case size with its row count -- and at the very end the counts are read once, the tables
+    compacted and all-gathered once (``distributed.gather_file_tables``, NCCL).  ``audios`` holds paths or 1-D arrays."""
+    from .distributed import assign_files, gather_corpus_tables
+
+    if thresholds is None:
+        thresholds = default_thresholds(model.label_encoder)
+    dev = _cuda_device(device)
+    mine = list(range(len(audios)))
+    if shard is not None:
+        if sizes is None:
+            sizes = [a.shape[-1] if isinstance(a, (np.ndarray, torch.Tensor)) else get_audio_info(a).n_samples for a in audios]
+        mine = assign_files(list(sizes), shard[1])[shard[0]]
+    cuts = [logit_cut(t) for t in _lower_bounds(thresholds, model.label_encoder.n_labels)]
+    tables, counts = [], []
+    for i in mine:
+        logits = apply_model_on_audio(audios[i], model, INFERENCE_SETTINGS, dev, batch_size=batch_size,
+                                      chunk_duration_s=config.audio.chunk_duration_s, window_step=window_step)
+        with torch.cuda.device(dev):
+            table, count = ops.decode_intervals_async(logits, cuts, mode=ops.DECODE_LOGIT)
+        tables.append(table)
+        counts.append(count)
+    with torch.cuda.device(dev):
+        return gather_corpus_tables(mine, tables, counts, device=dev, gather=gather and shard is not None and shard[1] > 1)
 
 
 def get_list_of_files_to_process(wavs: Path, recursive: bool = False, uris: Path | None = None) -> tuple[list[Path], int]:

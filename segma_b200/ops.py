@@ -238,7 +238,8 @@ def attention(qkv: torch.Tensor, n_windows: int, T: int, n_heads: int, *, n_quer
         assert rel_bias.is_contiguous() and rel_bias.shape == (n_heads, 2 * T - 1)
         _call("segma_attention_rel", 1, _lib().segma_attention_rel, _dev(qkv, torch.float16, "qkv"), n_windows, T, n_heads,
               T if n_query is None else n_query, _ptr(gate, torch.float32, "gate"),
-              _ptr(rel_bias, torch.float32, "rel_bias"), _dev(out, torch.float16, "out"), _stream())
+              _ptr(rel_bias, torch.float32, "rel_bias"), _dev(out, torch.float16, "out"), _stream(),
+              work=4.0 * n_windows * n_heads * (T if n_query is None else n_query) * T * 64)
         return out
     pb_ld = 0
     if pos_bias is not None:
@@ -247,7 +248,8 @@ def attention(qkv: torch.Tensor, n_windows: int, T: int, n_heads: int, *, n_quer
         pb_ld = pos_bias.stride(1)
     _call("segma_attention", 1, _lib().segma_attention, _dev(qkv, torch.float16, "qkv"), n_windows, T, n_heads,
           T if n_query is None else n_query, _ptr(gate, torch.float32, "gate"), _ptr(pos_bias, torch.float32, "pos_bias"),
-          pb_ld, _dev(out, torch.float16, "out"), _stream())
+          pb_ld, _dev(out, torch.float16, "out"), _stream(),
+          work=4.0 * n_windows * n_heads * (T if n_query is None else n_query) * T * 64)
     return out
 
 

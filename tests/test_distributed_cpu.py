@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from segma_b200.distributed import all_gather_tables, assign_files, gather_file_tables
+from segma_b200.distributed import all_gather_tables, assign_files, gather_corpus_tables, gather_file_tables
 
 
 def test_assign_files_is_balanced_and_complete():
@@ -47,6 +47,16 @@ def _worker(rank, world, port, out_dir):
         all_gather_tables(torch.zeros((0, 4), dtype=torch.int32))
     full = gather_file_tables(table)
     np.save(os.path.join(out_dir, f"r{rank}.npy"), full.numpy())
+    # end-of-run exchange of a sharded corpus: per-file worst-case tables + device-side counts, one gather
+    tables, counts = [], []
+    for f in files:
+        n = f + 1 + rank
+        t = torch.full((n + 7, 4), -1, dtype=torch.int32)  # capacity > count: rows beyond the count are junk
+        t[:n] = torch.tensor([(0, k % 4, 320 * k, 320 * (k + 1)) for k in range(n)], dtype=torch.int32)
+        tables.append(t)
+        counts.append(torch.tensor([n], dtype=torch.int32))
+    corpus = gather_corpus_tables(files, tables, counts)
+    assert torch.equal(corpus, full)
     dist.destroy_process_group()
 
 

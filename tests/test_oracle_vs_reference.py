@@ -90,3 +90,15 @@ def test_hubert_file_level_through_reference_driver(ref):
     got = O.apply_model_on_audio(torch.from_numpy(pcm), lambda w: O.hubert_hydra_forward(sd, w, LABELS), 4, batch_size=128)
     assert got.shape == want.shape == ((n - 400) // 320 + 1, 4)
     assert (got - want).abs().max() <= 1e-4 * max(1.0, want.abs().max().item())
+
+
+def test_port_costs_what_the_reference_costs(ref):
+    """bench.py's CPU arm times the oracle port in place of the reference (which cannot travel to the GPU box): the
+    port must not be slower than the reference's own ``SurgicalHydra.forward`` by more than 10 % (best of alternating
+    rounds), or the reported GPU / CPU ratio would be inflated.  Same logits to 1e-5."""
+    from oracle.calibrate_port import measure
+
+    res = measure(n_windows=4, rounds=3)
+    print(res)
+    assert res["max_abs_logit_diff"] <= 1e-5
+    assert 0.75 <= res["port_over_reference"] <= 1.10, res

@@ -89,14 +89,17 @@ def load(build_if_missing: bool = True):
     from . import build as _build
 
     path = _build.LIB_PATH
-    if not path.exists():
+    if not path.exists() or not _build.is_current():
+        # missing, or built from other sources than the ones in the tree (a stale library would be called with this
+        # file's argument lists): rebuild, or refuse
+        what = "missing" if not path.exists() else "older than its sources"
         if not build_if_missing:
-            raise SegmaNativeError(f"{path} is missing: run `python -m segma_b200.build`")
+            raise SegmaNativeError(f"{path} is {what}: run `python -m segma_b200.build`")
         try:
             _build.build()
         except Exception as e:  # noqa: BLE001
             raise SegmaNativeError(
-                f"libsegma_b200.so is missing and could not be built ({e}); segma_b200 has no CPU fallback"
+                f"libsegma_b200.so is {what} and could not be built ({e}); segma_b200 has no CPU fallback"
             ) from e
     lib = C.CDLL(str(path))
     for name, (res, args) in SIGNATURES.items():

@@ -94,6 +94,7 @@ class W2V2Engine:
         w = v * (g / v.norm(dim=(0, 1), keepdim=True))  # (d, cg, K)
         cg, K = w.shape[1], w.shape[2]
         self.pos_k = K
+        self.pos_cg = cg
         self.pos_pad = K // 2
         bn = next((b for b in (192, 256, 128) if d % b == 0 and b % cg == 0), None)
         assert bn is not None, f"no N tile fits positional-conv groups of {cg} channels in d={d}"
@@ -239,7 +240,8 @@ class W2V2Engine:
         ops.gemm_raw(xp.data_ptr(), xp.shape[1] * d, d, n, T, self.pos_k * bn, self.pos_w, d, ws["tmp"].data_ptr(), d,
                      bias=self.pos_b, add_src_ptr=ws["x0"].data_ptr(), add_batch_rows=T, out_batch_rows=T,
                      flags=ops.GEMM_GELU | ops.GEMM_OUT_F32, conv_taps=self.pos_k, conv_stride=1,
-                     a_rows_per_batch=xp.shape[1], a_col_per_ntile=bn, a_cols=d, force_bn=bn)
+                     a_rows_per_batch=xp.shape[1], a_col_per_ntile=bn, a_cols=d, force_bn=bn,
+                     work=2.0 * n * T * d * self.pos_k * self.pos_cg)  # algorithmic: each output sees its group only
         x, xh, tmp = ws["x"], ws["x_f16"], ws["tmp"]
         self._tr("conv6", ws["feat"].view(n, T, C))
         self._tr("proj", ws["x0"].view(n, T, d))

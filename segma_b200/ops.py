@@ -130,7 +130,9 @@ def set_mel_filters(mel: np.ndarray) -> None:
 # ---- GEMM / conv ---------------------------------------------------------------------------------
 def gemm_raw(a_ptr, a_batch_stride, a_row_stride, batch, rows_per_batch, k, w, n, out_ptr, ldo, *, bias=None,
              add_src_ptr=None, add_batch_rows=0, out_batch_rows=None, out_row_offset=0, flags=0, conv_taps=0,
-             conv_stride=0, a_rows_per_batch=0, a_col_per_ntile=0, a_cols=0, force_bn=0) -> None:
+             conv_stride=0, a_rows_per_batch=0, a_col_per_ntile=0, a_cols=0, force_bn=0, work=None) -> None:
+    """``work``: algorithmic FLOPs of the launch for the roofline accounting when they differ from 2*M*N*K of the
+    launched shape (a grouped convolution packed with zero blocks executes more than it computes)."""
     args = GemmArgs(
         a=a_ptr, a_batch_stride=a_batch_stride, a_row_stride=a_row_stride, batch=batch,
         rows_per_batch=rows_per_batch, a_rows_per_batch=a_rows_per_batch, k=k, conv_taps=conv_taps,
@@ -143,7 +145,8 @@ def gemm_raw(a_ptr, a_batch_stride, a_row_stride, batch, rows_per_batch, k, w, n
     if stats.profile:
         name += f"[n{n} k{k}{' conv' if conv_taps > 1 else ''}{' gelu' if flags & GEMM_GELU else ''}" \
                 f"{' +src' if add_src_ptr else ''}{' f32' if flags & GEMM_OUT_F32 else ''}]"
-    _call(name, 1, _lib().segma_gemm_f16, C.byref(args), _stream(), work=2.0 * batch * rows_per_batch * n * k)
+    _call(name, 1, _lib().segma_gemm_f16, C.byref(args), _stream(),
+          work=2.0 * batch * rows_per_batch * n * k if work is None else work)
 
 
 def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, gelu=False, add_src=None, out=None, out_f32=False,
@@ -365,10 +368,11 @@ def w2v2_layer0(pcm_view: torch.Tensor, n_windows: int, win_len: int, step: int,
     """out (n_windows, out_rows, C) fp16 = gelu(GroupNorm(conv_k10_s5(window)))."""
     C_ = w.shape[0]
     assert out.is_contiguous() and out.shape[0] >= n_windows and out.shape[2] == C_
+    rows0 = (win_len - 10) // 5 + 1
     _call("segma_w2v2_layer0", 2, _lib().segma_w2v2_layer0, _dev(pcm_view, torch.float32, "pcm"), pcm_view.numel(),
           n_windows, win_len, step, _dev(w, torch.float32, "w"), _dev(gamma, torch.float32, "gamma"),
           _dev(beta, torch.float32, "beta"), C_, scale_shift.data_ptr(), _dev(out, torch.float16, "out"), out.shape[1],
-          _stream())
+          _stream(), work=2.0 * n_windows * rows0 * C_ * 10)
 
 
 def wavlm_gate(x: torch.Tensor, T: int, n_heads: int, gate_w, gate_b, gate_const, gate: torch.Tensor) -> None:

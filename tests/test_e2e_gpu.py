@@ -32,9 +32,19 @@ def _report(got, ref):
     return err.max().item(), err.mean().item(), std, agree
 
 
-def _check_logits(got, ref, what, min_agreement=MIN_LABEL_AGREEMENT, max_rtol=LOGIT_RTOL_OF_STD):
+#: below this many label decisions one flipped frame is worth more than 0.01 %: the rate cannot be resolved to 99.9 %
+#: (2 636 decisions: one flip = 0.038 %), so short fixtures are held to 99.8 % and every model is also run on a
+#: fixture of >= 20 000 decisions that is held to the 99.9 % of north_star
+RESOLVING_SAMPLE = 10_000
+SMALL_SAMPLE_AGREEMENT = 0.998
+
+
+def _check_logits(got, ref, what, min_agreement=None, max_rtol=LOGIT_RTOL_OF_STD):
     mx, mean, std, agree = _report(got, ref)
-    print(f"{what}: max|err| {mx:.4g} mean|err| {mean:.4g} logit std {std:.4g} label agreement {agree:.5f}")
+    if min_agreement is None:
+        min_agreement = MIN_LABEL_AGREEMENT if ref.numel() >= RESOLVING_SAMPLE else SMALL_SAMPLE_AGREEMENT
+    print(f"{what}: {ref.numel()} decisions, max|err| {mx:.4g} mean|err| {mean:.4g} logit std {std:.4g} "
+          f"label agreement {agree:.5f} (bar {min_agreement})")
     assert mx <= max_rtol * max(std, 1.0), f"{what}: max logit error {mx} vs std {std}"
     assert agree >= min_agreement, f"{what}: frame-label agreement {agree}"
 
@@ -202,14 +212,12 @@ def test_w2v2_family_file_level_small(cuda, dims, seed):
     got = apply_model_on_audio(pcm, model, INFERENCE_SETTINGS, "cuda", batch_size=2).cpu()
     ref = O.apply_model_on_audio(torch.from_numpy(pcm), lambda w: O.hubert_hydra_forward(sd, w, LABELS), 4, batch_size=2)
     assert got.shape == ref.shape == ((n - 400) // 320 + 1, 4)
-    # 2 636 decisions of a tiny random model whose logits hug the threshold: a handful of flips is the fp16
-    # noise floor (|err| ~ 1e-3 of the spread); the base-size models below are held to 99.9 %
-    _check_logits(got, ref, f"w2v2 wavlm={dims.wavlm} file-level", min_agreement=0.998)
+    _check_logits(got, ref, f"w2v2 wavlm={dims.wavlm} file-level")
     # forward drop-in on (B, n_samples)
     wav = torch.stack([torch.from_numpy(synth.synth_audio(64000, s)) for s in range(2)])
     out = model(wav)
     assert out.shape == (2, 199, 1, 4)
-    _check_logits(out.cpu(), O.hubert_hydra_forward(sd, wav, LABELS), "w2v2 forward drop-in", min_agreement=0.998)
+    _check_logits(out.cpu(), O.hubert_hydra_forward(sd, wav, LABELS), "w2v2 forward drop-in")
 
 
 @pytest.mark.parametrize("key,dims,seed", [("hubert_logits", synth.HUBERT_BASE, 5), ("wavlm_logits", synth.WAVLM_BASE, 6)])
@@ -349,7 +357,7 @@ def test_sweep_waveform_model(cuda, win_s, overlap):
                                window_step=step)
     ref = _composed_oracle(pcm, lambda w: O.hubert_hydra_forward(sd, w, LABELS), win, step, 4, False, F_)
     assert got.shape == ref.shape
-    _check_logits(got.cpu(), ref, f"sweep {win_s}s overlap {overlap}", min_agreement=0.998)
+    _check_logits(got.cpu(), ref, f"sweep {win_s}s overlap {overlap}")
     for t in (0.3, 0.5, 0.7):  # decoding of the product's own logits is bit-exact at every threshold
         thr = {lab: {"lower_bound": t, "upper_bound": 1.0} for lab in LABELS}
         mask = O.apply_thresholds(got.cpu(), [t] * 4)
@@ -415,7 +423,7 @@ def test_infer_file_on_wav_writes_reference_artefacts(cuda, tmp_path):
     # the int16 file was decoded exactly like the host path would
     pcm16 = np.clip(np.round(pcm * 32768.0), -32768, 32767).astype(np.int16).astype(np.float32) / 32768.0
     ref = O.apply_model_on_audio(torch.from_numpy(pcm16), lambda w: O.hubert_hydra_forward(sd, w, LABELS), 4, batch_size=2)
-    _check_logits(logits, ref, "infer_file on int16 wav", min_agreement=0.998)
+    _check_logits(logits, ref, "infer_file on int16 wav")
 
 
 def test_run_inference_on_audios_cli_path(cuda, tmp_path, capsys):

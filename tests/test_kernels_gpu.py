@@ -404,10 +404,12 @@ def test_decode_logit_cut_mode(cuda):
 
 
 # ---- wav2vec2 front end / WavLM gate / grouped positional conv -----------------------------------------------
-@pytest.mark.parametrize("L,C", [(64000, 128), (33280, 512), (400, 128)])
-def test_w2v2_layer0(cuda, L, C):
+@pytest.mark.parametrize("L,C,gain", [(64000, 128, 1.0), (33280, 512, 1.0), (400, 128, 1.0), (64000, 512, 1e-3), (16000, 128, 3e-5)])
+def test_w2v2_layer0(cuda, L, C, gain):
+    """``gain``: quiet recordings (down to -90 dB) must come out as well as loud ones -- GroupNorm rescales them to
+    unit variance, so the statistics (fp64 second moments of the input) are what matters."""
     n_win, step = 3, 1000
-    pcm = torch.from_numpy(synth.synth_audio(L + (n_win - 1) * step, 31))
+    pcm = torch.from_numpy(synth.synth_audio(L + (n_win - 1) * step, 31)) * gain
     w = _rand((C, 1, 10), 32, 0.5)
     g, b = 1 + 0.1 * _rand((C,), 33), 0.1 * _rand((C,), 34)
     T0 = (L - 10) // 5 + 1
@@ -418,7 +420,7 @@ def test_w2v2_layer0(cuda, L, C):
     wins = torch.stack([pcm[i * step: i * step + L] for i in range(n_win)])
     y = F.conv1d(wins.unsqueeze(1), w, None, stride=5)
     ref = F.gelu(F.group_norm(y, C, g, b, 1e-5)).transpose(1, 2)
-    _close(out[:, :T0], ref, 2e-3, 2e-3, "layer 0")
+    _close(out[:, :T0], ref, 1e-3, 1e-3, "layer 0")  # fp16 output rounding (2^-11) dominates
     assert (out[:, T0:] == 0).all()
 
 

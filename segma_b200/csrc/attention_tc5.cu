@@ -17,6 +17,8 @@
 //               reference max (rescaling O and l only when a chunk's probabilities sum to more than 2^10), P -> fp16
 //               pairs stored with tcgen05.st over the score columns just consumed
 // Scores and probabilities never leave tensor memory / registers; shared memory only carries Q, K and V.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace segma {
@@ -354,16 +356,18 @@ int launch_attention_tc5(const void* qkv, int n_windows, int T, int n_heads, int
   // SEGMA_ATTN_POLY=1 moves a quarter of the exponentials from the MUFU to the FMA pipe (ex2_poly_pair).  Measured
   // slower on B200 (0.370 vs 0.333 ms for 32 windows): the softmax warps are latency-bound, not MUFU-bound, so the
   // longer instruction stream costs more than the freed MUFU slots give back.  Kept as a switch for re-measurement.
-  static bool poly = false;
+  static unsigned poly = 0;
   constexpr int kRelMaxT = 1024;  // the Toeplitz slice (T + 128 floats) must leave room for four CTAs per SM
   if (!attr_set.here()) {
     SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<0, 0x0000u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
     SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<0, 0x2222u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<0, 0x2A2Au>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<0, 0xAAAAu>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
     SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<1, 0u>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
     SEGMA_CUDA_OK(cudaFuncSetAttribute(attention_tc5_kernel<2, 0u>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kAtSmem + 4 * (kRelMaxT + kAtQ)));
     const char* env = getenv("SEGMA_ATTN_POLY");
-    poly = env && atoi(env) != 0;
+    poly = env ? (unsigned)strtoul(env, nullptr, 0) : 0u;
     attr_set.here() = true;
   }
   if (bias_mode == 2 && T > kRelMaxT) {
@@ -376,7 +380,9 @@ int launch_attention_tc5(const void* qkv, int n_windows, int T, int n_heads, int
                                                                     pos_bias, pb_ld, static_cast<__half*>(out))
   if (bias_mode == 2) SEGMA_ATTN_LAUNCH(2, 0u, kAtSmem + 4 * (T + kAtQ));
   else if (bias_mode == 1) SEGMA_ATTN_LAUNCH(1, 0u, kAtSmem);
-  else if (poly) SEGMA_ATTN_LAUNCH(0, 0x2222u, kAtSmem);
+  else if (poly == 1 || poly == 0x2222u) SEGMA_ATTN_LAUNCH(0, 0x2222u, kAtSmem);  // 4 of 16 key pairs
+  else if (poly == 0x2A2Au) SEGMA_ATTN_LAUNCH(0, 0x2A2Au, kAtSmem);                // 6 of 16
+  else if (poly == 0xAAAAu) SEGMA_ATTN_LAUNCH(0, 0xAAAAu, kAtSmem);                // 8 of 16
   else SEGMA_ATTN_LAUNCH(0, 0x0000u, kAtSmem);
 #undef SEGMA_ATTN_LAUNCH
   return launch_status("attention_tc5_kernel");

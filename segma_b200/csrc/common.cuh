@@ -107,23 +107,22 @@ __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
-// 2^x for a pair on the FMA pipe instead of the MUFU: round-to-nearest split x = n + f, |f| <= 0.5, a degree-4
-// minimax polynomial for 2^f (relative error 2.7e-6) and n added into the exponent field.  x is clamped to
-// [-126, 126]: the result stays a finite non-negative float, and anything above 2^16 still overflows fp16.
+// 2^x for a pair on the FMA pipe instead of the MUFU: round-to-nearest split x = n + f, |f| <= 0.5, a degree-3
+// minimax polynomial for 2^f (relative error 7.5e-5: the result is stored as fp16, 4.9e-4) and n added into the
+// exponent field (one shift-add per element).  Ten instructions per pair.  x is clamped from below at -30 (2^-30
+// rounds to zero in fp16 and keeps the exponent arithmetic in range); callers guarantee x <= ~16.
 __device__ __forceinline__ void ex2_poly_pair(uint64_t x2, float& p0, float& p1) {
   float x0, x1;
   f2_unpack(x2, x0, x1);
-  x0 = fminf(fmaxf(x0, -126.f), 126.f);
-  x1 = fminf(fmaxf(x1, -126.f), 126.f);
+  x0 = fmaxf(x0, -30.f);
+  x1 = fmaxf(x1, -30.f);
   const uint64_t xc = f2_pack(x0, x1);
   const uint64_t t = f2_add(xc, f2_pack(12582912.f, 12582912.f));     // 1.5 * 2^23: low mantissa bits = n
   const uint64_t r = f2_add(t, f2_pack(-12582912.f, -12582912.f));    // n as a float
   const uint64_t f = f2_fma(r, f2_pack(-1.f, -1.f), xc);
-  uint64_t y = f2_fma(f2_pack(0.009570102207362652f, 0.009570102207362652f), f,
-                      f2_pack(0.05591785907745361f, 0.05591785907745361f));
-  y = f2_fma(y, f, f2_pack(0.240247443318367f, 0.240247443318367f));
-  y = f2_fma(y, f, f2_pack(0.6931217908859253f, 0.6931217908859253f));
-  y = f2_fma(y, f, f2_pack(0.9999992847442627f, 0.9999992847442627f));
+  uint64_t y = f2_fma(f2_pack(0.0551716475f, 0.0551716475f), f, f2_pack(0.2426111206f, 0.2426111206f));
+  y = f2_fma(y, f, f2_pack(0.6932609894f, 0.6932609894f));
+  y = f2_fma(y, f, f2_pack(0.9999280737f, 0.9999280737f));
   float y0, y1, t0, t1;
   f2_unpack(y, y0, y1);
   f2_unpack(t, t0, t1);

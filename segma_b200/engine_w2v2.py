@@ -38,6 +38,20 @@ def conv_lengths(n_samples: int) -> list[int]:
     return out
 
 
+def _pos_conv_weight(sd: dict, p: str) -> torch.Tensor:
+    """The positional convolution's effective kernel.  torchaudio wraps it in weight-norm over dim 2
+    (components.py:194-234): checkpoints hold ``parametrizations.weight.original0/1`` (g, v) with current torch,
+    ``weight_g`` / ``weight_v`` when saved by older torch / torchaudio (torch's load hook converts those), or a plain
+    ``weight`` after ``remove_weight_norm`` / script export.  w = g * v / ||v||, the norm over dims (0, 1)."""
+    for kg, kv in (("parametrizations.weight.original0", "parametrizations.weight.original1"), ("weight_g", "weight_v")):
+        if p + kg in sd and p + kv in sd:
+            g, v = sd[p + kg].float(), sd[p + kv].float()
+            return v * (g / v.norm(dim=(0, 1), keepdim=True))
+    if p + "weight" in sd:
+        return sd[p + "weight"].float()
+    raise KeyError(f"no positional-convolution weight under '{p}' (parametrizations.weight.original0/1, weight_g/v or weight)")
+
+
 def _even(v: int) -> int:
     return v + (v & 1)
 
@@ -89,9 +103,7 @@ class W2V2Engine:
         assert d % 128 == 0
         t = enc + "transformer."
         # positional convolution: fold weight-norm, then lay the grouped kernel out for N tiles of whole groups
-        g = sd[t + "pos_conv_embed.conv.parametrizations.weight.original0"].float()
-        v = sd[t + "pos_conv_embed.conv.parametrizations.weight.original1"].float()
-        w = v * (g / v.norm(dim=(0, 1), keepdim=True))  # (d, cg, K)
+        w = _pos_conv_weight(sd, t + "pos_conv_embed.conv.")  # (d, cg, K)
         cg, K = w.shape[1], w.shape[2]
         self.pos_k = K
         self.pos_cg = cg

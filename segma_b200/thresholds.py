@@ -64,7 +64,9 @@ def _bisect(active, t: np.float32) -> int | float:
 @lru_cache(maxsize=256)
 def logit_cut(threshold: float) -> float:
     t = np.float32(threshold)
-    if not (t >= 0.0):  # negative (or nan) thresholds: every finite logit is active
+    if np.isnan(t):  # ``sigmoid(x) > nan`` is false for every frame
+        return math.inf
+    if t < 0.0:  # negative thresholds: every finite logit is active
         return -math.inf
     lo = _bisect(_active, t)
     if isinstance(lo, float):

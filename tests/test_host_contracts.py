@@ -184,3 +184,35 @@ def test_wavlm_relative_bias_is_the_toeplitz_form_of_the_table():
         assert rel.shape == (12, 2 * T - 1)
         idx = torch.arange(T)[None, :] - torch.arange(T)[:, None] + T - 1
         assert torch.equal(rel[:, idx], pb)
+
+
+def test_nan_threshold_activates_nothing():
+    """``sigmoid(x) > nan`` is False for every frame in the reference (inference.py:228-234)."""
+    import math
+
+    from segma_b200.thresholds import logit_cut
+
+    assert logit_cut(float("nan")) == math.inf
+    assert logit_cut(-0.1) == -math.inf
+    assert logit_cut(1.0) == math.inf
+
+
+def test_positional_conv_weight_from_any_checkpoint_flavour():
+    """weight-norm parametrisation keys of current torch, ``weight_g`` / ``weight_v`` of older checkpoints, or a plain
+    ``weight``: all give the same effective kernel (torchaudio components.py:194-234)."""
+    import torch
+
+    from segma_b200.engine_w2v2 import _pos_conv_weight
+
+    g = torch.rand(1, 1, 8) + 0.5
+    v = torch.randn(16, 4, 8)
+    w = v * (g / v.norm(dim=(0, 1), keepdim=True))
+    p = "enc.pos_conv_embed.conv."
+    a = _pos_conv_weight({p + "parametrizations.weight.original0": g, p + "parametrizations.weight.original1": v}, p)
+    b = _pos_conv_weight({p + "weight_g": g, p + "weight_v": v}, p)
+    c = _pos_conv_weight({p + "weight": w}, p)
+    assert torch.equal(a, w) and torch.equal(b, w) and torch.equal(c, w)
+    import pytest
+
+    with pytest.raises(KeyError):
+        _pos_conv_weight({}, p)

@@ -176,7 +176,8 @@ def test_attention_reference_max_rescale(cuda, T):
 
 @pytest.mark.parametrize("T,padded", [(199, False), (199, True), (300, True), (64, True)])
 def test_attention_wavlm_bias(cuda, T, padded):
-    """padded=True: bias rows at a 16-byte pitch -> tcgen05 kernel; False: unpadded table -> mma.sync kernel."""
+    """padded=True: bias rows at a 16-byte pitch, what the one (tcgen05) kernel reads with 128-bit loads;
+    False: an unpadded table with 796-byte rows is rejected -- there is no second backend to fall to."""
     H, B = 2, 2
     d = H * 64
     qkv = _rand((B * T, 3 * d), 17).to(torch.float16)
@@ -189,6 +190,10 @@ def test_attention_wavlm_bias(cuda, T, padded):
         buf = torch.zeros((H, T, ld), device=cuda)
         buf[:, :, :T] = pos_dev
         pos_dev = buf[:, :, :T]
+    else:
+        with pytest.raises(ops.SegmaNativeError, match="16-byte aligned"):
+            ops.attention(qkv.to(cuda), B, T, H, gate=gate.to(cuda), pos_bias=pos_dev)
+        return
     out = ops.attention(qkv.to(cuda), B, T, H, gate=gate.to(cuda), pos_bias=pos_dev)
     q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
     s = q @ k.transpose(-1, -2) + gate[..., None] * pos[None]
@@ -334,13 +339,15 @@ def test_stitch(cuda, F_, sf, nw, tail):
 
 
 @pytest.mark.parametrize("n,C,p", [(1, 4, 1.0), (5, 4, 0.5), (1024, 4, 0.5), (1025, 4, 0.3), (100_000, 4, 0.5), (4097, 3, 0.9),
-                                   (3000, 7, 0.1), (2048, 4, 0.0), (2048, 4, 1.0)])
+                                   (3000, 7, 0.1), (2048, 4, 0.0), (2048, 4, 1.0), (5000, 12, 0.4), (1025, 9, 0.6)])
 def test_decode_intervals_bit_exact(cuda, n, C, p):
+    """C <= 8 runs the bit-plane kernels (``decode_plane_kernel``), more labels the word-per-frame kernels
+    (``decode_count_kernel`` / ``decode_write_kernel``)."""
     rng = np.random.default_rng(n + C)
     # blocky logits so that runs of every length occur
     base = rng.standard_normal((n // 7 + 1, C)).repeat(7, axis=0)[:n] + 0.3 * rng.standard_normal((n, C))
     logits = torch.from_numpy((base + (2 * p - 1) * 3).astype(np.float32))
-    thr = [0.5, 0.3, 0.7, 0.5, 0.45, 0.55, 0.6][:C]
+    thr = [0.5, 0.3, 0.7, 0.5, 0.45, 0.55, 0.6, 0.5, 0.35, 0.65, 0.5, 0.4][:C]
     mask_ref = O.apply_thresholds(logits, thr)
     mask = ops.threshold_mask(logits.to(cuda), thr)
     assert torch.equal(mask.cpu(), mask_ref)

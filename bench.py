@@ -65,6 +65,27 @@ def _config(n_gpus: int, audio_s: float, workload: str = "whisper") -> dict:
     }
 
 
+# ---- stdout carries exactly one JSON line -------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def protect_stdout() -> None:
+    """Libraries write banners to file descriptor 1 (NCCL prints its version there at NCCL_DEBUG=VERSION unless
+    NCCL_DEBUG_FILE says otherwise; torchrun children inherit the descriptor): keep a private copy of stdout for the
+    result line and point descriptor 1 at stderr for everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 # ---- clocks ---------------------------------------------------------------------------------------------
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -156,7 +177,7 @@ def run_reference(args):
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---- torch-eager-on-B200 arm: the reference's own module stack on the GPU ---------------
@@ -574,7 +595,7 @@ def run_gpu(args):
                            "l2": "a 230 MB PCM pool and > 3 GB of activations per 128-window batch: larger than L2"},
                 "e2e": r["e2e"], "gpu_launches": r["launches"], "clocks": r["clocks"], "intervals_per_step": r["intervals"],
             }
-            print(json.dumps(line), flush=True)
+            emit(line)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -621,7 +642,7 @@ def run_gpu(args):
         "roofline": res["roofline"], "cpu_baseline": cpu, "gpu_eager_baseline": eager, "side_kernels": side,
         "workloads": extras, "clocks": res["clocks"], "breakdown_ms_per_step": res["breakdown_ms_per_step"],
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -651,6 +672,8 @@ def main():
     ap.add_argument("--no-extra-workloads", action="store_true", help="skip the hubert / wavlm lines and the eager arm")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager-on-GPU arm")
     args = ap.parse_args()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.gpus == 1 or args.impl == "reference":
+        protect_stdout()  # (the convenience launcher below leaves stdout to the ranks it spawns)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -122,13 +122,25 @@ __global__ void __launch_bounds__(4 * H) lstm_layer_smem_kernel(const float* __r
   float c_state = 0.f;
   __syncthreads();
   const int pr = j / H, pu = j - pr * H;  // pointwise item of this thread (valid if pr < R)
+  // the input pre-activations of step t + 1 are fetched while step t runs: their HBM / L2 latency (about a
+  // microsecond, 128 times per launch) would otherwise sit at the head of every step's dependency chain
+  float nxt[R];
+  {
+    const int s0 = dir == 0 ? 0 : n_steps - 1;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      nxt[r] = r0 + r < n_rows ? __ldg(pre + ((long long)s0 * n_rows + r0 + r) * (n_dirs * G) + dir * G + j) : 0.f;
+  }
   for (int step = 0; step < n_steps; ++step) {
     const int s = dir == 0 ? step : n_steps - 1 - step;
     float acc[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int row = r0 + r;
-      acc[r] = row < n_rows ? __ldg(pre + ((long long)s * n_rows + row) * (n_dirs * G) + dir * G + j) : 0.f;
+    for (int r = 0; r < R; ++r) acc[r] = nxt[r];
+    if (step + 1 < n_steps) {
+      const int s1 = dir == 0 ? step + 1 : n_steps - 2 - step;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        nxt[r] = r0 + r < n_rows ? __ldg(pre + ((long long)s1 * n_rows + r0 + r) * (n_dirs * G) + dir * G + j) : 0.f;
     }
     if (kSplit) {
 #pragma unroll

@@ -1,7 +1,7 @@
 #!/bin/bash
 # launch list (per-launch device time) and full captures of the two dominant kernels for a short bench run
 mkdir -p gpurun_out
-CMD="python bench.py --steps 1 --warmup 3 --hours 0.15 --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 3 --hours 0.15 --no-cpu-baseline --no-extra-workloads --no-side-kernels"
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 &&

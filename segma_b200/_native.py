@@ -86,17 +86,20 @@ def load(build_if_missing: bool = True):
     global _LIB
     if _LIB is not None:
         return _LIB
+    import os
+
     from . import build as _build
 
-    path = _build.LIB_PATH
-    if not path.exists() or not _build.is_current():
+    debug = os.environ.get("SEGMA_DEBUG", "0") not in ("", "0")  # the same kernels with device-side bounds asserts
+    path = _build.DEBUG_LIB_PATH if debug else _build.LIB_PATH
+    if not path.exists() or not _build.is_current(debug):
         # missing, or built from other sources than the ones in the tree (a stale library would be called with this
         # file's argument lists): rebuild, or refuse
         what = "missing" if not path.exists() else "older than its sources"
         if not build_if_missing:
             raise SegmaNativeError(f"{path} is {what}: run `python -m segma_b200.build`")
         try:
-            _build.build()
+            _build.build(debug=debug)
         except Exception as e:  # noqa: BLE001
             raise SegmaNativeError(
                 f"libsegma_b200.so is {what} and could not be built ({e}); segma_b200 has no CPU fallback"

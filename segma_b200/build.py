@@ -21,6 +21,10 @@ INCLUDE = PKG_DIR.parent / "include"
 LIB_DIR = PKG_DIR / "lib"
 LIB_PATH = LIB_DIR / "libsegma_b200.so"
 OBJ_DIR = PKG_DIR / "build"
+#: the same sources with -DSEGMA_DEBUG (device-side bounds asserts); loaded instead of the product library when
+#: SEGMA_DEBUG=1 is set (compute-sanitizer is not available on the GPU pool)
+DEBUG_LIB_PATH = LIB_DIR / "libsegma_b200_debug.so"
+DEBUG_OBJ_DIR = PKG_DIR / "build_debug"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -51,21 +55,24 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def is_current() -> bool:
-    stamp = LIB_DIR / "build.sha256"
-    return LIB_PATH.exists() and stamp.exists() and stamp.read_text().strip() == _digest()
+def is_current(debug: bool = False) -> bool:
+    stamp = LIB_DIR / ("build_debug.sha256" if debug else "build.sha256")
+    lib = DEBUG_LIB_PATH if debug else LIB_PATH
+    return lib.exists() and stamp.exists() and stamp.read_text().strip() == _digest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and is_current():
-        return LIB_PATH
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> Path:
+    lib_path, obj_dir = (DEBUG_LIB_PATH, DEBUG_OBJ_DIR) if debug else (LIB_PATH, OBJ_DIR)
+    if not force and is_current(debug):
+        return lib_path
     nvcc = _nvcc()
-    OBJ_DIR.mkdir(exist_ok=True)
+    obj_dir.mkdir(exist_ok=True)
     LIB_DIR.mkdir(exist_ok=True)
+    flags = NVCC_FLAGS + (["-DSEGMA_DEBUG"] if debug else [])
 
     def compile_one(src: Path) -> Path:
-        obj = OBJ_DIR / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
+        obj = obj_dir / (src.stem + ".o")
+        cmd = [nvcc, *flags, "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -75,15 +82,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, len(sources()))) as ex:
         objs = list(ex.map(compile_one, sources()))
-    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a",
+    cmd = [nvcc, "-shared", "-o", str(lib_path), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a",
            "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    (LIB_DIR / "build.sha256").write_text(_digest() + "\n")
-    return LIB_PATH
+    (LIB_DIR / ("build_debug.sha256" if debug else "build.sha256")).write_text(_digest() + "\n")
+    return lib_path
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose=True)
+    path = build(force="--force" in sys.argv, verbose=True, debug="--debug" in sys.argv)
     print(f"built {path}")

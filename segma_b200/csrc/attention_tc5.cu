@@ -317,6 +317,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       tmem_ld_32x32(tmem_o + lane_addr + c * 32, ov);
       tmem_ld_wait();
       if (q_row < n_query) {
+        SEGMA_DEV_ASSERT(q_row < T && h < n_heads && l_run > 0.f);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 pk;

@@ -2,6 +2,7 @@
 // wrappers over the PTX the kernels are written in (mbarrier, TMA, tcgen05/TMEM, cp.async, mma.sync).
 #pragma once
 
+#include <cstdio>
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -28,6 +29,22 @@ int check_cuda(cudaError_t e, const char* what);
       return SEGMA_ERR_INVALID_ARGUMENT;                           \
     }                                                              \
   } while (0)
+
+// Device-side bounds checks of the debug build (`python -m segma_b200.build --debug`, loaded with SEGMA_DEBUG=1):
+// compute-sanitizer is closed on the GPU pool, so the kernels carry their own index asserts; a failed one prints the
+// expression and traps (the launch then reports an error).  They compile to nothing in the product library.
+#ifdef SEGMA_DEBUG
+#define SEGMA_DEV_ASSERT(cond)                                                                              \
+  do {                                                                                                      \
+    if (!(cond)) {                                                                                          \
+      printf("segma_b200 device assert failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, \
+             (int)blockIdx.x, (int)threadIdx.x);                                                            \
+      __trap();                                                                                             \
+    }                                                                                                       \
+  } while (0)
+#else
+#define SEGMA_DEV_ASSERT(cond) ((void)0)
+#endif
 
 inline int launch_status(const char* kernel) {
   cudaError_t e = cudaGetLastError();

@@ -883,6 +883,7 @@ __global__ void __launch_bounds__(kPostThreads) filter_intervals_kernel(const in
       keep = (row.w - row.z >= min_dur) ? 1 : 0;
     }
     const int pos = s_carry + block_incl_scan(keep, s_warp, lane, warp) - 1;
+    SEGMA_DEV_ASSERT(!keep || (row.w >= row.z && pos >= 0));
     if (keep && pos < capacity) out[pos] = row;
     __syncthreads();
     if (threadIdx.x == kPostThreads - 1) s_carry = pos + 1;

@@ -267,8 +267,10 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           for (int it = 0; it < 4; ++it) {
             const int rr = it * 8 + (lane >> 2);
             const uint4 v = *reinterpret_cast<const uint4*>(stg_bytes + rr * kEpiF16Pitch + seg * 16);
-            if (r_base + rr < p.rows_per_batch)
+            if (r_base + rr < p.rows_per_batch) {
+              SEGMA_DEV_ASSERT(nc + seg * 8 + 8 <= p.n && out_row0 + rr >= 0 && b < p.batch);
               *reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + (out_row0 + rr) * p.ldo + nc + seg * 8) = v;
+            }
           }
           __syncwarp();
           continue;
@@ -302,6 +304,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
             if (kAddSrc && p.add_src) { v.x += src4[g].x; v.y += src4[g].y; v.z += src4[g].z; v.w += src4[g].w; }
             if (r_base + rr < p.rows_per_batch) {
+              SEGMA_DEV_ASSERT(nc + c4 * 4 + 4 <= p.n && out_row0 + rr >= 0 && b < p.batch && n_tile < p.n_tiles);
               const long long o = (out_row0 + rr) * p.ldo + nc;
               if (out_f32) {
                 reinterpret_cast<float4*>(static_cast<float*>(p.out) + o)[c4] = v;

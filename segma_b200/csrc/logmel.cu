@@ -351,6 +351,7 @@ __global__ void __launch_bounds__(kThreadsA, 4) logmel_power_kernel(const float*
           for (int i = 0; i < len; ++i) acc = fmaf(g_tab.mel_w[m][i], pp[i], acc);
         }
         const float v = 0.30102999566398120f * __log2f(fmaxf(acc, 1e-10f));  // log10
+        SEGMA_DEV_ASSERT(win < n_windows && m < kMels && t < nvp);
         logspec[((long long)win * kMels + m) * nvp + t] = v;
         local_max = fmaxf(local_max, v);
       }

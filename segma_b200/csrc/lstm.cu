@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(4 * H) lstm_layer_smem_kernel(const float* __r
       s_h[pu * 4 + pr] = h;
       const int row = r0 + pr;
       if (row < n_rows) {
+        SEGMA_DEV_ASSERT(s >= 0 && s < n_steps && pu < H && isfinite(h));
         const long long o = ((long long)s * n_rows + row) * (n_dirs * H) + dir * H + pu;
         out[o] = h;
         if (out_f16) out_f16[o] = __float2half(h);

@@ -83,3 +83,16 @@ def test_product_does_not_import_the_oracle():
     pkg = ROOT / "segma_b200"
     for f in pkg.rglob("*.py"):
         assert "oracle" not in re.sub(r'""".*?"""', "", f.read_text(), flags=re.S).replace("# oracle", ""), f
+
+
+def test_debug_flavour_builds_and_exports_the_same_abi():
+    """``python -m segma_b200.build --debug``: the same sources with device-side bounds asserts (SEGMA_DEBUG=1 loads
+    it; compute-sanitizer is closed on the GPU pool).  Same symbols as the product library."""
+    import ctypes
+
+    from segma_b200 import _native, build
+
+    path = build.build(debug=True)
+    assert path.name == "libsegma_b200_debug.so" and path.exists()
+    lib = ctypes.CDLL(str(path))
+    assert not [name for name in _native.SIGNATURES if not hasattr(lib, name)]

@@ -516,11 +516,16 @@ def measure_corpus(args, rank: int, world: int, dev):
     from segma_b200.models import Models
 
     le = MultiLabelEncoder(list(LABELS))
-    cfg = make_config("surgical_hydra")
-    model = Models["surgical_hydra"].from_state_dict(synth.surgical_hydra_state_dict(synth.WHISPER_SMALL, seed=0), le, cfg).to(dev)
+    kind, desc, _ = WORKLOADS[args.corpus_model]
+    cfg = make_config(kind)
+    if args.corpus_model == "whisper":
+        sd = synth.surgical_hydra_state_dict(synth.WHISPER_SMALL, seed=0)
+    else:
+        sd = synth.hubert_hydra_state_dict(synth.WAVLM_BASE if args.corpus_model == "wavlm" else synth.HUBERT_BASE, seed=0)
+    model = Models[kind].from_state_dict(sd, le, cfg).to(dev)
     rng = np.random.default_rng(4)
     n_files = args.corpus_files
-    dur_s = np.clip(np.exp(rng.normal(np.log(150.0), 1.3, size=n_files)), 10.0, 3600.0)
+    dur_s = np.clip(np.exp(rng.normal(np.log(args.corpus_median_s), 1.3, size=n_files)), min(10.0, args.corpus_median_s), 3600.0)
     lens = (dur_s * 16_000).astype(np.int64)
     pool = torch.from_numpy(synth.synth_audio(HOUR_SAMPLES, seed=0)).pin_memory()
     offs = rng.integers(0, HOUR_SAMPLES - lens + 1)
@@ -562,7 +567,7 @@ def measure_corpus(args, rank: int, world: int, dev):
         "e2e": {"value": total_h * args.steps / e2e_wall, "unit": UNIT, "h2d_bytes_per_step": int(lens.sum()) * 4,
                 "d2h_bytes_per_step": int(table_host.numel()) * 4},
         "clocks": clocks.summary(), "corpus_hours": total_h, "n_files": n_files, "intervals": int(table.shape[0]),
-        "longest_file_s": float(dur_s.max()), "median_file_s": float(np.median(dur_s)),
+        "longest_file_s": float(dur_s.max()), "median_file_s": float(np.median(dur_s)), "model": desc,
     }
 
 
@@ -590,7 +595,7 @@ def run_gpu(args):
                 "dtype": "f16", "data": "synthetic",
                 "config": {"workload": f"corpus: {r['n_files']} files, {r['corpus_hours']:.2f} h in total, durations log-normal "
                                        f"(median {r['median_file_s']:.0f} s, longest {r['longest_file_s']:.0f} s), "
-                                       "whisper-small-dims surgical_hydra, 4 s windows step 63680, batch 128",
+                                       f"{r['model']}, 4 s windows step 63680, batch 128",
                            "parallelism": f"files sharded over {world} GPU(s), longest first; one final interval all-gather",
                            "l2": "a 230 MB PCM pool and > 3 GB of activations per 128-window batch: larger than L2"},
                 "e2e": r["e2e"], "gpu_launches": r["launches"], "clocks": r["clocks"], "intervals_per_step": r["intervals"],
@@ -668,6 +673,8 @@ def main():
                     help="whisper = BASELINE config 2 (the headline, also reports hubert / wavlm = configs 1 and 3 under "
                          "'workloads'); corpus = config 4 in miniature (file-sharded, strong scaling)")
     ap.add_argument("--corpus-files", type=int, default=256, help="files in the corpus workload")
+    ap.add_argument("--corpus-model", default="whisper", choices=sorted(WORKLOADS), help="model of the corpus workload")
+    ap.add_argument("--corpus-median-s", type=float, default=150.0, help="median file duration of the corpus workload")
     ap.add_argument("--no-side-kernels", action="store_true", help="skip the front-end / decode roofline measurements")
     ap.add_argument("--no-extra-workloads", action="store_true", help="skip the hubert / wavlm lines and the eager arm")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager-on-GPU arm")
@@ -683,7 +690,8 @@ def main():
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                    "--master-addr", "127.0.0.1", "--master-port", "29511", str(Path(__file__).resolve()),
                    "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
-                   "--hours", str(args.hours), "--workload", args.workload, "--corpus-files", str(args.corpus_files)]
+                   "--hours", str(args.hours), "--workload", args.workload, "--corpus-files", str(args.corpus_files),
+                   "--corpus-model", args.corpus_model, "--corpus-median-s", str(args.corpus_median_s)]
             sys.exit(subprocess.call(cmd))
         run_gpu(args)
 

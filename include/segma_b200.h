@@ -79,6 +79,11 @@ SEGMA_API int segma_logmel_get_filters(float* mel_201x80);
 SEGMA_API int segma_w2v2_layer0(const float* pcm, int64_t pcm_len, int n_windows, int win_len, int64_t step, const float* w,
                       const float* gamma, const float* beta, int channels, void* scale_shift, void* out,
                       int out_rows, void* stream);
+/* The same with window w starting at sample win_offsets[w] ([dev] int64): windows of several files packed into one
+ * call (the wav2vec2-family windows are independent of each other). */
+SEGMA_API int segma_w2v2_layer0_at(const float* pcm, int64_t pcm_len, int n_windows, int win_len, const int64_t* win_offsets,
+                         const float* w, const float* gamma, const float* beta, int channels, void* scale_shift,
+                         void* out, int out_rows, void* stream);
 
 /* WavLM gate on the relative-position bias (site-packages/torchaudio/models/wav2vec2/wavlm_attention.py:185-193):
  * x fp32 (rows = n_windows*T, n_heads*64) layer input; gate_w (8, 64), gate_b (8), gate_const (n_heads);
@@ -190,6 +195,9 @@ SEGMA_API int segma_lstm_layer(const float* pre, const float* w_hh_t, int n_step
  * onto the file timeline when windows tile it, or per window (step_frames = n_keep) for stitching. */
 SEGMA_API int segma_heads(const float* feat, int n_steps, int n_rows, int n_feat, int n_keep, const float* w, const float* b,
                 int n_labels, float* logits, int64_t frame_offset, int step_frames, void* stream);
+/* The same with window s writing frames frame_offsets[s] + r ([dev] int64): packed windows of several files. */
+SEGMA_API int segma_heads_at(const float* feat, int n_steps, int n_rows, int n_feat, int n_keep, const float* w, const float* b,
+                   int n_labels, float* logits, const int64_t* frame_offsets, void* stream);
 
 /* ---- stitching and interval decoding --------------------------------------------------------
  * Overlap-add of per-window frame logits onto the file timeline: out[g] = mean over the windows

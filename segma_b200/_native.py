@@ -56,6 +56,7 @@ SIGNATURES = {
     "segma_logmel_set_filters": (_i, [_vp]),
     "segma_logmel_get_filters": (_i, [_vp]),
     "segma_w2v2_layer0": (_i, [_vp, _i64, _i, _i, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "segma_w2v2_layer0_at": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "segma_wavlm_gate": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "segma_gemm_f16": (_i, [C.POINTER(GemmArgs), _vp]),
     "segma_layernorm": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _f, _f, _i, _i, _vp]),
@@ -65,6 +66,7 @@ SIGNATURES = {
     "segma_cast_f16_split": (_i, [_vp, _i64, _vp, _i64, _i64, _i, _vp]),
     "segma_lstm_layer": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "segma_heads": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i64, _i, _vp]),
+    "segma_heads_at": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "segma_stitch": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i64, _vp]),
     "segma_decode_workspace_bytes": (_sz, [_i64, _i, _i]),
     "segma_decode_intervals": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i64, _vp, _vp, _sz, _vp]),

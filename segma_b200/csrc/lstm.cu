@@ -194,13 +194,15 @@ __global__ void __launch_bounds__(4 * H) lstm_layer_smem_kernel(const float* __r
 __global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ feat, int n_steps, int n_rows,
                                                      int n_feat, int n_keep, const float* __restrict__ w,
                                                      const float* __restrict__ b, int C, float* __restrict__ logits,
-                                                     long long frame_offset, int step_frames) {
+                                                     long long frame_offset, int step_frames,
+                                                     const long long* __restrict__ frame_offsets) {
   const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wid >= (long long)n_steps * n_keep) return;
   const int s = (int)(wid / n_keep), r = (int)(wid - (long long)s * n_keep);
   const int lane = lane_id();
   const float* f = feat + ((long long)s * n_rows + r) * n_feat;
-  float* dst = logits + (frame_offset + (long long)s * step_frames + r) * C;
+  // window s writes frames frame_offset + s * step_frames + r, or frame_offsets[s] + r for windows packed from several files
+  float* dst = logits + ((frame_offsets ? frame_offsets[s] : frame_offset + (long long)s * step_frames) + r) * C;
   for (int c = 0; c < C; ++c) {
     float acc = 0.f;
     for (int k = lane; k < n_feat; k += 32) acc = fmaf(__ldg(f + k), __ldg(w + (long long)c * n_feat + k), acc);
@@ -262,7 +264,20 @@ int segma_heads(const float* feat, int n_steps, int n_rows, int n_feat, int n_ke
   SEGMA_REQUIRE(feat && w && b && logits, "segma_heads: NULL buffer");
   const long long warps = (long long)n_steps * n_keep;
   heads_kernel<<<(unsigned)ceil_div_ll(warps, 8), 256, 0, (cudaStream_t)stream>>>(
-      feat, n_steps, n_rows, n_feat, n_keep, w, b, n_labels, logits, frame_offset, step_frames);
+      feat, n_steps, n_rows, n_feat, n_keep, w, b, n_labels, logits, frame_offset, step_frames, nullptr);
+  return launch_status("heads_kernel");
+}
+
+int segma_heads_at(const float* feat, int n_steps, int n_rows, int n_feat, int n_keep, const float* w, const float* b,
+                   int n_labels, float* logits, const int64_t* frame_offsets, void* stream) {
+  SEGMA_REQUIRE(n_steps >= 0 && n_rows > 0 && n_feat > 0 && n_keep >= 0 && n_keep <= n_rows && n_labels > 0,
+                "segma_heads_at: bad shape");
+  if (n_steps == 0 || n_keep == 0) return SEGMA_OK;
+  SEGMA_REQUIRE(feat && w && b && logits && frame_offsets, "segma_heads_at: NULL buffer");
+  const long long warps = (long long)n_steps * n_keep;
+  heads_kernel<<<(unsigned)ceil_div_ll(warps, 8), 256, 0, (cudaStream_t)stream>>>(
+      feat, n_steps, n_rows, n_feat, n_keep, w, b, n_labels, logits, 0, 0,
+      reinterpret_cast<const long long*>(frame_offsets));
   return launch_status("heads_kernel");
 }
 

@@ -20,15 +20,18 @@ constexpr int kStatsThreads = 256;
 constexpr int kPairs = kL0K * (kL0K + 1) / 2;  // 55
 
 __global__ void __launch_bounds__(kStatsThreads) w2v2_l0_stats_kernel(
-    const float* __restrict__ pcm, long long pcm_len, int win_len, long long step, const float* __restrict__ w,
+    const float* __restrict__ pcm, long long pcm_len, int win_len, long long step,
+    const long long* __restrict__ win_offsets, const float* __restrict__ w,
     const float* __restrict__ gamma, const float* __restrict__ beta, int C, float2* __restrict__ scale_shift) {
   __shared__ double s_sum[kL0K + kPairs];
   __shared__ double s_part[kStatsThreads / 32][kL0K + kPairs];
   const int win = blockIdx.x;
-  long long avail = pcm_len - (long long)win * step;
+  // window w starts at sample w * step, or at win_offsets[w] when windows of several files are packed into one call
+  const long long w_off = win_offsets ? win_offsets[win] : (long long)win * step;
+  long long avail = pcm_len - w_off;
   if (avail > win_len) avail = win_len;
   const int T0 = avail >= kL0K ? (int)((avail - kL0K) / kL0S + 1) : 0;
-  const float* x = pcm + (long long)win * step;
+  const float* x = pcm + w_off;
   double acc[kL0K + kPairs];
 #pragma unroll
   for (int i = 0; i < kL0K + kPairs; ++i) acc[i] = 0.0;
@@ -98,15 +101,17 @@ constexpr int kL0Threads = 256;
 
 // out[b][t][c] = gelu(conv(x)[t][c] * scale + shift) as fp16, time-major with `out_rows` rows per window
 __global__ void __launch_bounds__(kL0Threads) w2v2_l0_apply_kernel(
-    const float* __restrict__ pcm, long long pcm_len, int win_len, long long step, const float* __restrict__ w,
+    const float* __restrict__ pcm, long long pcm_len, int win_len, long long step,
+    const long long* __restrict__ win_offsets, const float* __restrict__ w,
     const float2* __restrict__ scale_shift, int C, __half* __restrict__ out, int out_rows) {
   __shared__ float s_x[kL0TimeTile * kL0S + kL0K];
   const int win = blockIdx.y;
   const int t0 = blockIdx.x * kL0TimeTile;
-  long long avail = pcm_len - (long long)win * step;
+  const long long w_off = win_offsets ? win_offsets[win] : (long long)win * step;
+  long long avail = pcm_len - w_off;
   if (avail > win_len) avail = win_len;
   const int T0 = avail >= kL0K ? (int)((avail - kL0K) / kL0S + 1) : 0;
-  const float* x = pcm + (long long)win * step;
+  const float* x = pcm + w_off;
   for (int i = threadIdx.x; i < kL0TimeTile * kL0S + kL0K; i += kL0Threads) {
     const long long n = (long long)t0 * kL0S + i;
     s_x[i] = n < avail ? __ldg(x + n) : 0.f;
@@ -199,9 +204,9 @@ using namespace segma;
 
 extern "C" {
 
-int segma_w2v2_layer0(const float* pcm, int64_t pcm_len, int n_windows, int win_len, int64_t step, const float* w,
-                      const float* gamma, const float* beta, int channels, void* scale_shift, void* out,
-                      int out_rows, void* stream) {
+static int w2v2_layer0_impl(const float* pcm, int64_t pcm_len, int n_windows, int win_len, int64_t step,
+                           const int64_t* win_offsets, const float* w, const float* gamma, const float* beta, int channels,
+                           void* scale_shift, void* out, int out_rows, void* stream) {
   SEGMA_REQUIRE(n_windows >= 0, "segma_w2v2_layer0: negative n_windows");
   if (n_windows == 0) return SEGMA_OK;
   SEGMA_REQUIRE(pcm && w && gamma && beta && scale_shift && out, "segma_w2v2_layer0: NULL buffer");
@@ -211,15 +216,31 @@ int segma_w2v2_layer0(const float* pcm, int64_t pcm_len, int n_windows, int win_
   SEGMA_REQUIRE(out_rows >= T0, "segma_w2v2_layer0: out_rows %d < %d conv outputs", out_rows, T0);
   SEGMA_REQUIRE(n_windows <= 65535, "segma_w2v2_layer0: at most 65535 windows per call");
   cudaStream_t st = (cudaStream_t)stream;
-  w2v2_l0_stats_kernel<<<n_windows, kStatsThreads, 0, st>>>(pcm, pcm_len, win_len, step, w, gamma, beta, channels,
+  const long long* offs = reinterpret_cast<const long long*>(win_offsets);
+  w2v2_l0_stats_kernel<<<n_windows, kStatsThreads, 0, st>>>(pcm, pcm_len, win_len, step, offs, w, gamma, beta, channels,
                                                             static_cast<float2*>(scale_shift));
   int rc = launch_status("w2v2_l0_stats_kernel");
   if (rc != SEGMA_OK) return rc;
   dim3 grid(ceil_div(out_rows, kL0TimeTile), n_windows);
-  w2v2_l0_apply_kernel<<<grid, kL0Threads, 0, st>>>(pcm, pcm_len, win_len, step, w,
+  w2v2_l0_apply_kernel<<<grid, kL0Threads, 0, st>>>(pcm, pcm_len, win_len, step, offs, w,
                                                     static_cast<const float2*>(scale_shift), channels,
                                                     static_cast<__half*>(out), out_rows);
   return launch_status("w2v2_l0_apply_kernel");
+}
+
+int segma_w2v2_layer0(const float* pcm, int64_t pcm_len, int n_windows, int win_len, int64_t step, const float* w,
+                      const float* gamma, const float* beta, int channels, void* scale_shift, void* out,
+                      int out_rows, void* stream) {
+  return w2v2_layer0_impl(pcm, pcm_len, n_windows, win_len, step, nullptr, w, gamma, beta, channels, scale_shift, out,
+                          out_rows, stream);
+}
+
+int segma_w2v2_layer0_at(const float* pcm, int64_t pcm_len, int n_windows, int win_len, const int64_t* win_offsets,
+                         const float* w, const float* gamma, const float* beta, int channels, void* scale_shift,
+                         void* out, int out_rows, void* stream) {
+  SEGMA_REQUIRE(win_offsets != nullptr, "segma_w2v2_layer0_at: NULL win_offsets");
+  return w2v2_layer0_impl(pcm, pcm_len, n_windows, win_len, 0, win_offsets, w, gamma, beta, channels, scale_shift, out,
+                          out_rows, stream);
 }
 
 int segma_wavlm_gate(const float* x, int64_t rows, int T, int n_heads, const float* gate_w, const float* gate_b,

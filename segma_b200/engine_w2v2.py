@@ -224,14 +224,23 @@ class W2V2Engine:
         with torch.cuda.device(self.device):
             self._forward_pcm(pcm, start, n, win_len, step, logits, frame_offset, step_frames, n_keep, slot)
 
-    def _forward_pcm(self, pcm, start, n, win_len, step, logits, frame_offset, step_frames, n_keep, slot) -> None:
+    def forward_windows(self, pcm: torch.Tensor, win_offsets: torch.Tensor, n: int, win_len: int, logits: torch.Tensor,
+                        frame_offsets: torch.Tensor, n_keep: int | None = None, slot: int = 0) -> None:
+        """Windows ``pcm[win_offsets[i] : +win_len]`` -> ``logits[frame_offsets[i] + r]``, r < n_keep, for int64 device
+        tables of n offsets: the windows of this model family are independent of each other (no LSTM over the window
+        axis), so windows of several files can share one forward call."""
+        with torch.cuda.device(self.device):
+            self._forward_pcm(pcm, 0, n, win_len, 0, logits, 0, 0, n_keep, slot, win_offsets, frame_offsets)
+
+    def _forward_pcm(self, pcm, start, n, win_len, step, logits, frame_offset, step_frames, n_keep, slot,
+                     win_offsets=None, frame_offsets=None) -> None:
         ws = self._workspace(n, win_len, slot)
         lens, T, C, d = ws["lens"], ws["T"], self.C, self.d
         if T <= 0:
             return
         view = pcm[start:]
         act = ws["act"]
-        ops.w2v2_layer0(view, n, win_len, step, self.conv0_w, self.gn_g, self.gn_b, ws["ss"], act[0])
+        ops.w2v2_layer0(view, n, win_len, step, self.conv0_w, self.gn_g, self.gn_b, ws["ss"], act[0], win_offsets=win_offsets)
         self._tr("conv0", act[0][:, : lens[0]])
         for i in range(1, 7):
             src = act[i - 1]
@@ -281,7 +290,7 @@ class W2V2Engine:
             ops.layernorm(tmp, L["ln2_g"], L["ln2_b"], out_f16=xh, out_f32=x)
             self._tr(f"layer{li}", x.view(n, T, d))
         keep = T if n_keep is None else min(n_keep, T)
-        ops.heads(x.view(n, T, d), self.head_w, self.head_b, logits, frame_offset, step_frames, keep)
+        ops.heads(x.view(n, T, d), self.head_w, self.head_b, logits, frame_offset, step_frames, keep, frame_offsets=frame_offsets)
 
     def forward_waveforms(self, wav: torch.Tensor) -> torch.Tensor:
         """Drop-in ``model.forward``: (B, n_samples) fp32 -> (B, T, 1, C) fp32 logits."""

@@ -34,7 +34,7 @@ from .models import BaseSegmentationModel, Models
 from .thresholds import logit_cut
 
 __all__ = [
-    "Chunkyfier", "prepare_audio", "apply_model_on_audio", "apply_thresholds", "create_intervals",
+    "Chunkyfier", "prepare_audio", "apply_model_on_audio", "apply_model_on_audios", "apply_thresholds", "create_intervals",
     "decode_logits", "write_intervals", "infer_file", "infer_corpus", "get_list_of_files_to_process",
     "run_inference_on_audios",
 ]
@@ -157,6 +157,82 @@ def _apply_model_on_audio(audio_path, model, engine, conv_settings, dev, batch_s
     n_full = sum(b.n_windows for b in plan.batches if not b.is_tail)
     tail_frames = next((b.frames_per_window for b in plan.batches if b.is_tail), 0)
     return ops.stitch(win_logits, n_full, frames_per_window, sf, tail_frames, plan.n_frames)
+
+
+#: windows per packed group of files (a few forward calls of ``batch_size`` windows) and its PCM budget
+PACK_MAX_WINDOWS = 1024
+
+
+def apply_model_on_audios(audios, model: BaseSegmentationModel, conv_settings: ConvolutionSettings = INFERENCE_SETTINGS,
+                          device: Literal["cuda", "gpu"] = "cuda", batch_size: int = 128, chunk_duration_s: float = 4.0,
+                          sample_rate: int = 16_000) -> list[torch.Tensor]:
+    """``apply_model_on_audio`` for several files at once: one ``(n_frames_f, n_classes)`` logits tensor per file.
+
+    For the wav2vec2 family (HuBERT / WavLM: no recurrence over the window axis, so a window's logits do not depend
+    on what else is in its forward call) the windows of all files are packed into forward calls of ``batch_size``
+    windows regardless of file boundaries, and tails of equal length share a call: a corpus of short clips runs at the
+    batch efficiency of long files instead of one partial batch + one tail per file (the reference loops over files,
+    inference.py:442-458, and over a file's batches, 138-206).  Results are the same bits as file-by-file calls.
+    Whisper-family models couple the windows of a call through the LSTM (SURVEY.md finding 6): their batch boundaries
+    are part of the result, so files are processed one after the other."""
+    dev = _cuda_device(device)
+    if model.family != "wav2vec2":
+        return [apply_model_on_audio(a, model, conv_settings, dev, batch_size, chunk_duration_s, sample_rate) for a in audios]
+    engine = model._require_engine()
+    if engine.device != dev:
+        raise ops.SegmaNativeError(f"model weights are on {engine.device} but device={dev} was requested; call model.to(device)")
+    from .io import audio_n_samples
+
+    chunk_f = int(chunk_duration_s * sample_rate)
+    step = Chunkyfier(batch_size, chunk_f, conv_settings).step
+    fpw = conv_frames(chunk_f)
+    n_labels = model.label_encoder.n_labels
+    out: list[torch.Tensor] = []
+    with torch.cuda.device(dev):
+        group: list[tuple] = []  # (audio, n_samples, plan)
+        n_win = 0
+
+        def flush():
+            nonlocal group, n_win
+            if not group:
+                return
+            pcm_off = np.concatenate(([0], np.cumsum([g[1] for g in group]))).astype(np.int64)
+            frm_off = np.concatenate(([0], np.cumsum([g[2].n_frames for g in group]))).astype(np.int64)
+            pcm_all = torch.empty(int(pcm_off[-1]), dtype=torch.float32, device=dev)
+            logits = torch.empty((int(frm_off[-1]), n_labels), dtype=torch.float32, device=dev)
+            full_w, full_f, tails = [], [], {}
+            for k, (audio, n_s, plan) in enumerate(group):
+                if n_s > 0:
+                    PcmSource(audio, dev, dev_out=pcm_all[int(pcm_off[k]): int(pcm_off[k + 1])]).all()
+                for b in plan.batches:
+                    if b.is_tail:
+                        tails.setdefault((b.win_len, b.frames_per_window), []).append(
+                            (pcm_off[k] + b.start_sample, frm_off[k] + b.first_window * plan.step_frames))
+                    else:
+                        for i in range(b.n_windows):
+                            full_w.append(pcm_off[k] + b.start_sample + i * step)
+                            full_f.append(frm_off[k] + (b.first_window + i) * plan.step_frames)
+            calls = [(chunk_f, fpw, full_w[i: i + batch_size], full_f[i: i + batch_size]) for i in range(0, len(full_w), batch_size)]
+            for (wl, keep), items in tails.items():
+                for i in range(0, len(items), batch_size):
+                    part = items[i: i + batch_size]
+                    calls.append((wl, keep, [p[0] for p in part], [p[1] for p in part]))
+            for wl, keep, w_offs, f_offs in calls:
+                tab = torch.tensor([w_offs, f_offs], dtype=torch.int64).to(dev, non_blocking=True)
+                engine.forward_windows(pcm_all, tab[0], len(w_offs), wl, logits, tab[1], keep)
+            for k in range(len(group)):
+                out.append(logits[int(frm_off[k]): int(frm_off[k + 1])])
+            group, n_win = [], 0
+
+        for a in audios:
+            n_s = audio_n_samples(a)
+            plan = plan_windows(n_s, chunk_f, batch_size, step, fpw)
+            if group and n_win + plan.n_windows > PACK_MAX_WINDOWS:
+                flush()
+            group.append((a, n_s, plan))
+            n_win += plan.n_windows
+        flush()
+    return out
 
 
 def _lower_bounds(thresholds: dict, n_labels: int) -> list[float]:
@@ -330,11 +406,17 @@ def infer_corpus(audios, model: BaseSegmentationModel, config: Config, batch_siz
         mine = assign_files(list(sizes), shard[1])[shard[0]]
     cuts = [logit_cut(t) for t in _lower_bounds(thresholds, model.label_encoder.n_labels)]
     tables, counts = [], []
-    for i in mine:
-        logits = apply_model_on_audio(audios[i], model, INFERENCE_SETTINGS, dev, batch_size=batch_size,
-                                      chunk_duration_s=config.audio.chunk_duration_s, window_step=window_step)
+    if model.family == "wav2vec2" and window_step is None and os.environ.get("SEGMA_PACK_FILES", "1") != "0":
+        # independent windows: packed across files into full forward calls (apply_model_on_audios)
+        all_logits = apply_model_on_audios([audios[i] for i in mine], model, INFERENCE_SETTINGS, dev, batch_size=batch_size,
+                                           chunk_duration_s=config.audio.chunk_duration_s)
+    else:
+        all_logits = (apply_model_on_audio(audios[i], model, INFERENCE_SETTINGS, dev, batch_size=batch_size,
+                                           chunk_duration_s=config.audio.chunk_duration_s, window_step=window_step)
+                      for i in mine)
+    for logits in all_logits:
         with torch.cuda.device(dev):
-            table, count = ops.decode_intervals_async(logits, cuts, mode=ops.DECODE_LOGIT)
+            table, count = ops.decode_intervals_async(logits.contiguous(), cuts, mode=ops.DECODE_LOGIT)
         tables.append(table)
         counts.append(count)
     with torch.cuda.device(dev):

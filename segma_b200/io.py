@@ -161,7 +161,9 @@ class PcmSource:
     batches instead of preceding the whole file.  Sources: a device tensor (nothing to do), a pinned or
     pageable host array, or a mono PCM16 / PCM32 / float32 WAV file read in its stored width."""
 
-    def __init__(self, audio_p, device):
+    def __init__(self, audio_p, device, dev_out: torch.Tensor | None = None):
+        """``dev_out``: a 1-D float32 device tensor of exactly this file's length to stage into (a slice of a buffer that
+        packs several files); by default the source allocates its own."""
         from . import ops
 
         self._ops = ops
@@ -173,6 +175,9 @@ class PcmSource:
         if isinstance(arr, torch.Tensor) and arr.is_cuda:
             self.dev = arr.reshape(-1).to(torch.float32).contiguous()
             self.n_samples = self._done = self.dev.numel()
+            if dev_out is not None:
+                dev_out.copy_(self.dev)
+                self.dev = dev_out
             return
         if arr is not None:
             host = torch.as_tensor(arr).reshape(-1)
@@ -203,7 +208,9 @@ class PcmSource:
                 self._turn = 0
         code, _, t_dt = self._fmt
         with torch.cuda.device(self.device):
-            self.dev = torch.empty(self.n_samples, dtype=torch.float32, device=self.device)
+            if dev_out is not None:
+                assert dev_out.numel() == self.n_samples and dev_out.dtype == torch.float32 and dev_out.is_contiguous()
+            self.dev = dev_out if dev_out is not None else torch.empty(self.n_samples, dtype=torch.float32, device=self.device)
             self._raw = self.dev if code == ops.PCM_F32 else torch.empty(self.n_samples, dtype=t_dt, device=self.device)
             # The caching allocator may hand back blocks whose previous owner (an earlier file's PCM, logits or
             # scratch) still has kernels queued on the current stream: the copy stream must not write them earlier.
@@ -252,6 +259,15 @@ class PcmSource:
     def all(self) -> torch.Tensor:
         self.ensure(self.n_samples)
         return self.dev
+
+
+def audio_n_samples(audio_p) -> int:
+    """Samples of a file or array without staging it."""
+    if isinstance(audio_p, torch.Tensor):
+        return int(audio_p.numel())
+    if isinstance(audio_p, np.ndarray):
+        return int(audio_p.size)
+    return int(get_audio_info(audio_p).n_samples)
 
 
 def stage_to_device(audio_p, device) -> torch.Tensor:

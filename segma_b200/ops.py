@@ -270,9 +270,15 @@ def lstm_layer(pre: torch.Tensor, w_hh_t: torch.Tensor, hidden: int, *, out=None
 
 
 def heads(feat: torch.Tensor, w: torch.Tensor, b: torch.Tensor, logits: torch.Tensor, frame_offset: int,
-          step_frames: int, n_keep: int) -> None:
+          step_frames: int, n_keep: int, frame_offsets: torch.Tensor | None = None) -> None:
     n_steps, n_rows, n_feat = feat.shape
     assert feat.is_contiguous() and w.is_contiguous() and logits.is_contiguous()
+    if frame_offsets is not None:  # window s writes frames frame_offsets[s] + r (packed windows of several files)
+        assert frame_offsets.numel() >= n_steps and frame_offsets.is_contiguous()
+        _call("segma_heads", 1, _lib().segma_heads_at, _dev(feat, torch.float32, "feat"), n_steps, n_rows, n_feat, n_keep,
+              _dev(w, torch.float32, "w"), _dev(b, torch.float32, "b"), w.shape[0], _dev(logits, torch.float32, "logits"),
+              _dev(frame_offsets, torch.int64, "frame_offsets"), _stream())
+        return
     _call("segma_heads", 1, _lib().segma_heads, _dev(feat, torch.float32, "feat"), n_steps, n_rows, n_feat, n_keep,
                            _dev(w, torch.float32, "w"), _dev(b, torch.float32, "b"), w.shape[0],
                            _dev(logits, torch.float32, "logits"), frame_offset, step_frames, _stream())
@@ -364,15 +370,24 @@ def decode_intervals_async(logits: torch.Tensor, thresholds, *, file_offsets=Non
 
 # ---- wav2vec2 / WavLM ------------------------------------------------------------------------------
 def w2v2_layer0(pcm_view: torch.Tensor, n_windows: int, win_len: int, step: int, w: torch.Tensor, gamma, beta,
-                scale_shift: torch.Tensor, out: torch.Tensor) -> None:
-    """out (n_windows, out_rows, C) fp16 = gelu(GroupNorm(conv_k10_s5(window)))."""
+                scale_shift: torch.Tensor, out: torch.Tensor, win_offsets: torch.Tensor | None = None) -> None:
+    """out (n_windows, out_rows, C) fp16 = gelu(GroupNorm(conv_k10_s5(window))); window i starts at sample
+    ``i * step`` of ``pcm_view``, or at ``win_offsets[i]`` (int64 device tensor) for packed windows of several files."""
     C_ = w.shape[0]
     assert out.is_contiguous() and out.shape[0] >= n_windows and out.shape[2] == C_
     rows0 = (win_len - 10) // 5 + 1
-    _call("segma_w2v2_layer0", 2, _lib().segma_w2v2_layer0, _dev(pcm_view, torch.float32, "pcm"), pcm_view.numel(),
-          n_windows, win_len, step, _dev(w, torch.float32, "w"), _dev(gamma, torch.float32, "gamma"),
-          _dev(beta, torch.float32, "beta"), C_, scale_shift.data_ptr(), _dev(out, torch.float16, "out"), out.shape[1],
-          _stream(), work=2.0 * n_windows * rows0 * C_ * 10)
+    work = 2.0 * n_windows * rows0 * C_ * 10
+    if win_offsets is None:
+        _call("segma_w2v2_layer0", 2, _lib().segma_w2v2_layer0, _dev(pcm_view, torch.float32, "pcm"), pcm_view.numel(),
+              n_windows, win_len, step, _dev(w, torch.float32, "w"), _dev(gamma, torch.float32, "gamma"),
+              _dev(beta, torch.float32, "beta"), C_, scale_shift.data_ptr(), _dev(out, torch.float16, "out"), out.shape[1],
+              _stream(), work=work)
+    else:
+        assert win_offsets.numel() >= n_windows and win_offsets.is_contiguous()
+        _call("segma_w2v2_layer0", 2, _lib().segma_w2v2_layer0_at, _dev(pcm_view, torch.float32, "pcm"), pcm_view.numel(),
+              n_windows, win_len, _dev(win_offsets, torch.int64, "win_offsets"), _dev(w, torch.float32, "w"),
+              _dev(gamma, torch.float32, "gamma"), _dev(beta, torch.float32, "beta"), C_, scale_shift.data_ptr(),
+              _dev(out, torch.float16, "out"), out.shape[1], _stream(), work=work)
 
 
 def wavlm_gate(x: torch.Tensor, T: int, n_heads: int, gate_w, gate_b, gate_const, gate: torch.Tensor) -> None:

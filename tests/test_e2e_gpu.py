@@ -463,3 +463,36 @@ def test_run_inference_on_audios_cli_path(cuda, tmp_path, capsys):
         assert len(rttm) == len(want)
         assert rttm[:3] == [f"SPEAKER {name} <NA> {round(s / 16000, 8)} {round((e - s) / 16000, 8)} <NA> <NA> {lab} <NA> <NA>"
                             for s, e, lab in want[:3]]
+
+
+def test_packed_windows_of_several_files_equal_file_by_file(cuda):
+    """``apply_model_on_audios`` packs the (independent) windows of wav2vec2-family models across file boundaries into
+    full forward calls and lets tails of equal length share a call: the logits are the same bits as file-by-file
+    ``apply_model_on_audio``, and ``infer_corpus`` returns the same table as decoding each file on its own."""
+    from segma_b200.inference import apply_model_on_audios, infer_corpus
+
+    sd = synth.hubert_hydra_state_dict(synth.W2V2_TEST, seed=5)
+    le = MultiLabelEncoder(list(LABELS))
+    cfg = make_config("surgical_hubert_hydra")
+    model = Models["surgical_hubert_hydra"].from_state_dict(sd, le, cfg)
+    lens = [64000 + 63680 * 2 + 9000, 300, 64000, 70_000, 64000 + 63680 + 9000, 5000, 63680 * 4 + 320 + 70_000 - 64000, 0, 12_345]
+    files = [synth.synth_audio(n, 60 + i) if n else np.zeros(0, dtype=np.float32) for i, n in enumerate(lens)]
+    packed = apply_model_on_audios(files, model, INFERENCE_SETTINGS, "cuda", batch_size=3)
+    assert len(packed) == len(files)
+    for f, got in zip(files, packed):
+        want = apply_model_on_audio(f, model, INFERENCE_SETTINGS, "cuda", batch_size=3)
+        assert got.shape == want.shape == (max((f.size - 400) // 320 + 1, 0) if f.size >= 400 else 0, 4)
+        assert torch.equal(got, want)
+    table = infer_corpus(files, model, cfg, batch_size=3, device="cuda").cpu().numpy()
+    thr = default_thresholds(le)
+    rows = []
+    for i, f in enumerate(files):
+        iv = decode_logits(apply_model_on_audio(f, model, INFERENCE_SETTINGS, "cuda", batch_size=3), thr, le)
+        rows += [(i, LABELS.index(lab), s, e) for s, e, lab in iv]
+    assert table.tolist() == [list(r) for r in rows]
+    # Whisper-family models are never packed (the LSTM couples the windows of a call): one file after the other
+    sdw = synth.hydra_whisper_state_dict(synth.WHISPER_TEST, seed=7)
+    mw = Models["hydra_whisper"].from_state_dict(sdw, le, make_config("hydra_whisper"))
+    two = [synth.synth_audio(64000 + 63680 + 3000, 80), synth.synth_audio(64000, 81)]
+    for f, got in zip(two, apply_model_on_audios(two, mw, INFERENCE_SETTINGS, "cuda", batch_size=2)):
+        assert torch.equal(got, apply_model_on_audio(f, mw, INFERENCE_SETTINGS, "cuda", batch_size=2))

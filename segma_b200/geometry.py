@@ -213,3 +213,48 @@ def plan_windows(
         batches.append(WindowBatch(n_fit, 1, tail_start, tail_len, f_tail, is_tail=True))
         n_frames = max(n_frames, n_fit * (step // FRAME_SAMPLES) + f_tail)
     return WindowPlan(n_samples, win_len, step, frames_per_window, batch_size, tuple(batches), n_frames)
+
+
+@dataclass(frozen=True)
+class PackedCall:
+    """One forward call over windows of several files (models without coupling between the windows of a call)."""
+
+    win_len: int  # samples per window (a tail length for tail calls)
+    frames_per_window: int  # frames kept per window
+    sample_offsets: tuple[int, ...]  # first sample of each window in the packed PCM buffer
+    frame_offsets: tuple[int, ...]  # first frame of each window in the packed logits buffer
+
+
+def plan_packed_calls(n_samples: list[int], win_len: int = 64_000, batch_size: int = 128, step: int | None = None,
+                      frames_per_window: int | None = None):
+    """Files laid end to end in one PCM buffer and one logits buffer -> ``(calls, pcm_offsets, frame_offsets)``.
+
+    Every file keeps exactly the windows of ``plan_windows`` (the reference's, inference.py:129-206); only their
+    grouping into forward calls changes: full windows of all files fill calls of ``batch_size`` in file order, tails of
+    equal length share calls.  ``pcm_offsets[k]`` / ``frame_offsets[k]`` are file k's first sample / frame
+    (both lists end with the totals)."""
+    plans = [plan_windows(n, win_len, batch_size, step, frames_per_window) for n in n_samples]
+    pcm_off, frm_off = [0], [0]
+    for n, pl in zip(n_samples, plans):
+        pcm_off.append(pcm_off[-1] + n)
+        frm_off.append(frm_off[-1] + pl.n_frames)
+    full_w, full_f, tails = [], [], {}
+    for k, pl in enumerate(plans):
+        for b in pl.batches:
+            if b.is_tail:
+                tails.setdefault((b.win_len, b.frames_per_window), []).append(
+                    (pcm_off[k] + b.start_sample, frm_off[k] + b.first_window * pl.step_frames))
+            else:
+                for i in range(b.n_windows):
+                    full_w.append(pcm_off[k] + b.start_sample + i * pl.step)
+                    full_f.append(frm_off[k] + (b.first_window + i) * pl.step_frames)
+    calls = []
+    if full_w:
+        fpw = plans[0].frames_per_window
+        for i in range(0, len(full_w), batch_size):
+            calls.append(PackedCall(win_len, fpw, tuple(full_w[i: i + batch_size]), tuple(full_f[i: i + batch_size])))
+    for (wl, keep), items in tails.items():
+        for i in range(0, len(items), batch_size):
+            part = items[i: i + batch_size]
+            calls.append(PackedCall(wl, keep, tuple(p[0] for p in part), tuple(p[1] for p in part)))
+    return calls, pcm_off, frm_off

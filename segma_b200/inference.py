@@ -27,7 +27,8 @@ from . import ops
 from .annotation import rttm_line
 from .config import Config, load_config
 from .encoders import MultiLabelEncoder
-from .geometry import FRAME_SAMPLES, INFERENCE_SETTINGS, Chunkyfier, ConvolutionSettings, conv_frames, plan_windows
+from .geometry import (FRAME_SAMPLES, INFERENCE_SETTINGS, Chunkyfier, ConvolutionSettings, conv_frames, plan_packed_calls,
+                       plan_windows)
 from .io import PcmSource, get_audio_info, get_samples_in_range, stage_to_device
 from .engine import resolve_device
 from .models import BaseSegmentationModel, Models
@@ -196,30 +197,15 @@ def apply_model_on_audios(audios, model: BaseSegmentationModel, conv_settings: C
             nonlocal group, n_win
             if not group:
                 return
-            pcm_off = np.concatenate(([0], np.cumsum([g[1] for g in group]))).astype(np.int64)
-            frm_off = np.concatenate(([0], np.cumsum([g[2].n_frames for g in group]))).astype(np.int64)
+            calls, pcm_off, frm_off = plan_packed_calls([g[1] for g in group], chunk_f, batch_size, step, fpw)
             pcm_all = torch.empty(int(pcm_off[-1]), dtype=torch.float32, device=dev)
             logits = torch.empty((int(frm_off[-1]), n_labels), dtype=torch.float32, device=dev)
-            full_w, full_f, tails = [], [], {}
-            for k, (audio, n_s, plan) in enumerate(group):
+            for k, (audio, n_s, _) in enumerate(group):
                 if n_s > 0:
                     PcmSource(audio, dev, dev_out=pcm_all[int(pcm_off[k]): int(pcm_off[k + 1])]).all()
-                for b in plan.batches:
-                    if b.is_tail:
-                        tails.setdefault((b.win_len, b.frames_per_window), []).append(
-                            (pcm_off[k] + b.start_sample, frm_off[k] + b.first_window * plan.step_frames))
-                    else:
-                        for i in range(b.n_windows):
-                            full_w.append(pcm_off[k] + b.start_sample + i * step)
-                            full_f.append(frm_off[k] + (b.first_window + i) * plan.step_frames)
-            calls = [(chunk_f, fpw, full_w[i: i + batch_size], full_f[i: i + batch_size]) for i in range(0, len(full_w), batch_size)]
-            for (wl, keep), items in tails.items():
-                for i in range(0, len(items), batch_size):
-                    part = items[i: i + batch_size]
-                    calls.append((wl, keep, [p[0] for p in part], [p[1] for p in part]))
-            for wl, keep, w_offs, f_offs in calls:
-                tab = torch.tensor([w_offs, f_offs], dtype=torch.int64).to(dev, non_blocking=True)
-                engine.forward_windows(pcm_all, tab[0], len(w_offs), wl, logits, tab[1], keep)
+            for c in calls:
+                tab = torch.tensor([c.sample_offsets, c.frame_offsets], dtype=torch.int64).to(dev, non_blocking=True)
+                engine.forward_windows(pcm_all, tab[0], len(c.sample_offsets), c.win_len, logits, tab[1], c.frames_per_window)
             for k in range(len(group)):
                 out.append(logits[int(frm_off[k]): int(frm_off[k + 1])])
             group, n_win = [], 0

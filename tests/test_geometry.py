@@ -95,3 +95,30 @@ def test_bad_steps_rejected():
         plan_windows(100_000, 64000, 4, step=1000)
     with pytest.raises(ValueError):
         plan_windows(100_000, 64000, 4, step=64000 + 320)
+
+
+def test_packed_calls_keep_every_files_windows():
+    """Cross-file packing (models whose windows are independent): each file keeps exactly the windows and frames of
+    ``plan_windows``; full windows of all files fill calls of ``batch_size``, tails of equal length share calls."""
+    from segma_b200.geometry import plan_packed_calls, plan_windows
+
+    lens = [64000 + 63680 * 2 + 9000, 300, 64000, 70_000, 64000 + 63680 + 9000, 5000, 0, 70_000, 12_345]
+    calls, pcm_off, frm_off = plan_packed_calls(lens, 64_000, 3)
+    assert pcm_off == [0] + list(np.cumsum(lens)) and len(frm_off) == len(lens) + 1
+    # every frame of every file is written exactly once
+    hits = np.zeros(frm_off[-1], dtype=int)
+    for c in calls:
+        assert 0 < len(c.sample_offsets) <= 3 and len(c.sample_offsets) == len(c.frame_offsets)
+        for w, f in zip(c.sample_offsets, c.frame_offsets):
+            hits[f: f + c.frames_per_window] += 1
+            k = int(np.searchsorted(pcm_off, w, side="right")) - 1
+            assert w + c.win_len <= pcm_off[k + 1]  # a window never crosses into the next file
+            assert frm_off[k] <= f and f + c.frames_per_window <= frm_off[k + 1]
+    assert (hits == 1).all()
+    for k, n in enumerate(lens):
+        assert frm_off[k + 1] - frm_off[k] == plan_windows(n, 64_000, 3).n_frames == (max((n - 400) // 320 + 1, 0) if n >= 400 else 0)
+    full = [c for c in calls if c.win_len == 64_000]
+    assert sum(len(c.sample_offsets) for c in full) == sum(max((n - 64000) // 63680 + 1, 0) if n >= 64000 else 0 for n in lens)
+    assert all(len(c.sample_offsets) == 3 for c in full[:-1])  # packed across file boundaries
+    tails = [c for c in calls if c.win_len != 64_000]
+    assert any(len(c.sample_offsets) == 2 for c in tails)  # the two 9000-sample tails (and the two 6320-sample ones) share a call

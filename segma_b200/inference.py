@@ -47,6 +47,10 @@ N_STREAMS = int(os.environ.get("SEGMA_STREAMS", "1"))
 _STREAMS: dict[tuple, list] = {}
 #: files queued on the device before the host waits for the oldest one's interval table
 MAX_FILES_IN_FLIGHT = 4
+#: ``infer_corpus``: streams that short files (fewer than SMALL_FILE_WINDOWS windows) of a Whisper-family corpus take
+#: turns on; their forward calls are too small to fill the GPU one at a time
+FILE_STREAMS = int(os.environ.get("SEGMA_FILE_STREAMS", "4"))
+SMALL_FILE_WINDOWS = 32
 
 
 def _side_streams(dev: torch.device, n: int):
@@ -86,6 +90,7 @@ def apply_model_on_audio(
     chunk_duration_s: float = 4.0,
     sample_rate: int = 16_000,
     window_step: int | None = None,
+    slot_base: int = 0,
 ) -> torch.Tensor:
     """Apply model on audio, return a ``(n_frames, n_classes)`` fp32 tensor of raw logits on the device.
 
@@ -100,11 +105,11 @@ def apply_model_on_audio(
         raise ops.SegmaNativeError(f"model weights are on {engine.device} but device={dev} was requested; call model.to(device)")
     with torch.cuda.device(dev):
         return _apply_model_on_audio(audio_path, model, engine, conv_settings, dev, batch_size, chunk_duration_s,
-                                     sample_rate, window_step)
+                                     sample_rate, window_step, slot_base)
 
 
 def _apply_model_on_audio(audio_path, model, engine, conv_settings, dev, batch_size, chunk_duration_s, sample_rate,
-                          window_step) -> torch.Tensor:
+                          window_step, slot_base=0) -> torch.Tensor:
     chunk_f = int(chunk_duration_s * sample_rate)
     chunky = Chunkyfier(batch_size, chunk_f, conv_settings)  # same derived quantities as the reference
     step = chunky.step if window_step is None else int(window_step)
@@ -143,11 +148,11 @@ def _apply_model_on_audio(audio_path, model, engine, conv_settings, dev, batch_s
         with torch.cuda.stream(lanes[i % n_lanes]):
             if tiled:
                 engine.forward_pcm(pcm, b.start_sample, b.n_windows, b.win_len, step, logits, b.first_window * sf, sf,
-                                   b.frames_per_window, slot=i % n_lanes)
+                                   b.frames_per_window, slot=slot_base + i % n_lanes)
             else:
                 engine.forward_pcm(pcm, b.start_sample, b.n_windows, b.win_len, step, win_logits,
                                    b.first_window * frames_per_window, frames_per_window, b.frames_per_window,
-                                   slot=i % n_lanes)
+                                   slot=slot_base + i % n_lanes)
     for st in lanes:
         if st is not main:
             main.wait_stream(st)
@@ -397,14 +402,42 @@ def infer_corpus(audios, model: BaseSegmentationModel, config: Config, batch_siz
         all_logits = apply_model_on_audios([audios[i] for i in mine], model, INFERENCE_SETTINGS, dev, batch_size=batch_size,
                                            chunk_duration_s=config.audio.chunk_duration_s)
     else:
-        all_logits = (apply_model_on_audio(audios[i], model, INFERENCE_SETTINGS, dev, batch_size=batch_size,
-                                           chunk_duration_s=config.audio.chunk_duration_s, window_step=window_step)
-                      for i in mine)
-    for logits in all_logits:
-        with torch.cuda.device(dev):
-            table, count = ops.decode_intervals_async(logits.contiguous(), cuts, mode=ops.DECODE_LOGIT)
-        tables.append(table)
-        counts.append(count)
+        all_logits = None
+    if all_logits is not None:
+        for logits in all_logits:
+            with torch.cuda.device(dev):
+                table, count = ops.decode_intervals_async(logits.contiguous(), cuts, mode=ops.DECODE_LOGIT)
+            tables.append(table)
+            counts.append(count)
+    else:
+        # Files that cannot be packed (the LSTM couples the windows of a call) are independent of each other all the
+        # same: short files, whose forward calls are too small to fill 148 SMs, take turns on FILE_STREAMS streams, each
+        # with its own workspace slot; long files run alone on the main stream.
+        from .io import audio_n_samples
+
+        main = torch.cuda.current_stream(dev)
+        lanes = _side_streams(dev, FILE_STREAMS) if FILE_STREAMS > 1 else []
+        for st in lanes:
+            st.wait_stream(main)
+        chunk_f = int(config.audio.chunk_duration_s * 16_000)
+        turn = 0
+        for i in mine:
+            small = lanes and audio_n_samples(audios[i]) < SMALL_FILE_WINDOWS * chunk_f
+            lane = turn % FILE_STREAMS if small else -1
+            turn += 1 if small else 0
+            with torch.cuda.stream(lanes[lane] if small else main):
+                logits = apply_model_on_audio(audios[i], model, INFERENCE_SETTINGS, dev, batch_size=batch_size,
+                                              chunk_duration_s=config.audio.chunk_duration_s, window_step=window_step,
+                                              slot_base=(1 + lane) * max(N_STREAMS, 1) if small else 0)
+                with torch.cuda.device(dev):
+                    table, count = ops.decode_intervals_async(logits, cuts, mode=ops.DECODE_LOGIT)
+            if small:  # allocated on the lane's stream, consumed by the final exchange on the main stream
+                table.record_stream(main)
+                count.record_stream(main)
+            tables.append(table)
+            counts.append(count)
+        for st in lanes:
+            main.wait_stream(st)
     with torch.cuda.device(dev):
         return gather_corpus_tables(mine, tables, counts, device=dev, gather=gather and shard is not None and shard[1] > 1)
 

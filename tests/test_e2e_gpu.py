@@ -490,9 +490,18 @@ def test_packed_windows_of_several_files_equal_file_by_file(cuda):
         iv = decode_logits(apply_model_on_audio(f, model, INFERENCE_SETTINGS, "cuda", batch_size=3), thr, le)
         rows += [(i, LABELS.index(lab), s, e) for s, e, lab in iv]
     assert table.tolist() == [list(r) for r in rows]
-    # Whisper-family models are never packed (the LSTM couples the windows of a call): one file after the other
+    # Whisper-family corpus: short files take turns on several streams (infer_corpus), same table as one by one
     sdw = synth.hydra_whisper_state_dict(synth.WHISPER_TEST, seed=7)
-    mw = Models["hydra_whisper"].from_state_dict(sdw, le, make_config("hydra_whisper"))
+    cfgw = make_config("hydra_whisper")
+    mw = Models["hydra_whisper"].from_state_dict(sdw, le, cfgw)
+    small = [synth.synth_audio(n, 90 + i) for i, n in enumerate([64000 + 5000, 70_000, 63680 * 2 + 64000, 9000, 64000, 63680 + 64000 + 700, 30_000])]
+    tw = infer_corpus(small, mw, cfgw, batch_size=2, device="cuda").cpu().numpy()
+    rows = []
+    for i, f in enumerate(small):
+        iv = decode_logits(apply_model_on_audio(f, mw, INFERENCE_SETTINGS, "cuda", batch_size=2), thr, le)
+        rows += [(i, LABELS.index(lab), s, e) for s, e, lab in iv]
+    assert tw.tolist() == [list(r) for r in rows]
+    # Whisper-family models are never packed (the LSTM couples the windows of a call): one file after the other
     two = [synth.synth_audio(64000 + 63680 + 3000, 80), synth.synth_audio(64000, 81)]
     for f, got in zip(two, apply_model_on_audios(two, mw, INFERENCE_SETTINGS, "cuda", batch_size=2)):
         assert torch.equal(got, apply_model_on_audio(f, mw, INFERENCE_SETTINGS, "cuda", batch_size=2))

@@ -323,13 +323,13 @@ class _FileJob:
     (worst-case sized, a few MB per hour of audio), its row count and -- if asked for -- the logits travel to pinned
     host memory on a side stream, so the main stream never stalls on a per-file read-back."""
 
-    def __init__(self, audio_path, model, config, batch_size, device, thresholds, save_logits, window_step):
+    def __init__(self, audio_path, model, config, batch_size, device, thresholds, save_logits, window_step, slot_base=0):
         self.stem = Path(audio_path).stem if not isinstance(audio_path, (np.ndarray, torch.Tensor)) else "audio"
         self.model = model
         dev = _cuda_device(device)
         logits = apply_model_on_audio(audio_path=audio_path, model=model, batch_size=batch_size,
                                       chunk_duration_s=config.audio.chunk_duration_s, conv_settings=INFERENCE_SETTINGS,
-                                      device=dev, window_step=window_step)
+                                      device=dev, window_step=window_step, slot_base=slot_base)
         bounds = _lower_bounds(thresholds, logits.shape[-1])
         with torch.cuda.device(dev):
             self.table, self.count = ops.decode_intervals_async(logits, [logit_cut(t) for t in bounds], mode=ops.DECODE_LOGIT)
@@ -493,18 +493,35 @@ def run_inference_on_audios(config, uris, wavs, checkpoint, output, thresholds, 
         thresholds = default_thresholds(model.label_encoder)
     # Files are queued back to back: file i's interval table comes back on a side stream and is formatted on the host
     # while the device already runs file i + 1 ... i + MAX_FILES_IN_FLIGHT (the reference loop is serial, 442-458).
+    # Short files (forward calls too small to fill the GPU) take turns on FILE_STREAMS streams, as in infer_corpus.
+    from .io import audio_n_samples
+
+    dev = _cuda_device(device)
+    main = torch.cuda.current_stream(dev)
+    lanes = _side_streams(dev, FILE_STREAMS) if FILE_STREAMS > 1 else []
+    for st in lanes:
+        st.wait_stream(main)
+    small_below = SMALL_FILE_WINDOWS * cfg.audio.chunk_duration_f
     in_flight: list[_FileJob] = []
+    turn = 0
     for i, audio_path in enumerate(mine, 1):
         s = f"({i:>{len(str(n_files))}}/{n_files}) - running inference for file: '{audio_path.stem}'"
         if logger:
             logger.info(s)
         else:
             print(f"[log] - {s}", flush=True)
-        in_flight.append(_FileJob(audio_path, model, cfg, batch_size, device, thresholds, save_logits, None))
-        while len(in_flight) > MAX_FILES_IN_FLIGHT:
+        small = bool(lanes) and audio_n_samples(audio_path) < small_below
+        lane = turn % FILE_STREAMS if small else -1
+        turn += 1 if small else 0
+        with torch.cuda.stream(lanes[lane] if small else main):
+            in_flight.append(_FileJob(audio_path, model, cfg, batch_size, device, thresholds, save_logits, None,
+                                      slot_base=(1 + lane) * max(N_STREAMS, 1) if small else 0))
+        while len(in_flight) > max(MAX_FILES_IN_FLIGHT, FILE_STREAMS):
             in_flight.pop(0).finish(output)
     for job in in_flight:
         job.finish(output)
+    for st in lanes:
+        main.wait_stream(st)
     return mine
 
 

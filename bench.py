@@ -331,7 +331,7 @@ def measure_model_workload(args, workload: str, steps: int, warmup: int, rank: i
                 jobs[i - MAX_FILES_IN_FLIGHT].finish(None)
         for j in jobs[max(0, k - MAX_FILES_IN_FLIGHT):]:
             j.finish(None)
-        d2h = sum(j.host_table.numel() * 4 + 4 for j in jobs)
+        d2h = sum(j.table.numel() * 4 + 4 for j in jobs)  # the worst-case sized table + its row count, per file
         if world > 1:
             gather_corpus_tables([rank * k + i for i in range(k)], [j.table for j in jobs], [j.count for j in jobs],
                                  device=dev, gather=True)

@@ -318,6 +318,25 @@ def _d2h_stream(dev: torch.device) -> "torch.cuda.Stream":
     return _D2H_STREAMS[dev.index]
 
 
+class _PinnedPool:
+    """Page-locked host buffers for the per-file read-backs, recycled by size class: ``cudaHostAlloc`` costs a fraction
+    of a millisecond, which a corpus of short clips would otherwise pay three times per file."""
+
+    def __init__(self):
+        self._free: dict[int, list[torch.Tensor]] = {}
+
+    def take(self, nbytes: int) -> torch.Tensor:
+        size = 1 << max(int(nbytes - 1).bit_length(), 8)
+        bucket = self._free.setdefault(size, [])
+        return bucket.pop() if bucket else torch.empty(size, dtype=torch.uint8).pin_memory()
+
+    def give(self, buf: torch.Tensor) -> None:
+        self._free.setdefault(buf.numel(), []).append(buf)
+
+
+_PINNED = _PinnedPool()
+
+
 class _FileJob:
     """One file in flight: everything is queued on the device, nothing has been waited for yet.  The interval table
     (worst-case sized, a few MB per hour of audio), its row count and -- if asked for -- the logits travel to pinned
@@ -336,13 +355,15 @@ class _FileJob:
             main, side = torch.cuda.current_stream(dev), _d2h_stream(dev)
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                self.host_count = torch.empty(1, dtype=torch.int32).pin_memory()
-                self.host_table = torch.empty(self.table.shape, dtype=torch.int32).pin_memory()
+                self._bufs = [_PINNED.take(4), _PINNED.take(max(self.table.numel(), 1) * 4)]
+                self.host_count = self._bufs[0][:4].view(torch.int32)
+                self.host_table = self._bufs[1][: self.table.numel() * 4].view(torch.int32).view(self.table.shape)
                 self.host_count.copy_(self.count, non_blocking=True)
                 self.host_table.copy_(self.table, non_blocking=True)
                 self.host_logits = None
                 if save_logits:
-                    self.host_logits = torch.empty(logits.shape, dtype=torch.float32).pin_memory()
+                    self._bufs.append(_PINNED.take(max(logits.numel(), 1) * 4))
+                    self.host_logits = self._bufs[2][: logits.numel() * 4].view(torch.float32).view(logits.shape)
                     self.host_logits.copy_(logits, non_blocking=True)
                 self.done = torch.cuda.Event()
                 self.done.record(side)
@@ -362,6 +383,9 @@ class _FileJob:
                        f"{logits_out_p}/{self.stem}-logits_dict_t.pt")
         if output_p is not None:
             write_intervals(intervals=intervals, audio_path=Path(self.stem), output_p=output_p)
+        for buf in self._bufs:  # everything has been copied out of the pinned buffers (numpy -> Python ints, clone)
+            _PINNED.give(buf)
+        self._bufs, self.host_table, self.host_count, self.host_logits = [], None, None, None
         return intervals
 
 

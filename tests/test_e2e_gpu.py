@@ -505,3 +505,55 @@ def test_packed_windows_of_several_files_equal_file_by_file(cuda):
     two = [synth.synth_audio(64000 + 63680 + 3000, 80), synth.synth_audio(64000, 81)]
     for f, got in zip(two, apply_model_on_audios(two, mw, INFERENCE_SETTINGS, "cuda", batch_size=2)):
         assert torch.equal(got, apply_model_on_audio(f, mw, INFERENCE_SETTINGS, "cuda", batch_size=2))
+
+
+# ---- the reference's own forward tests (tests/test_models.py:37-71), widened over dims, labels and LSTM shapes ------------
+@pytest.mark.parametrize("kind,dims,lstm,labels", [
+    ("surgical_hydra", synth.WHISPER_TEST, synth.LSTMDims(), ("aa", "bb", "cc")),            # the reference's 3 labels
+    ("hydra_whisper", synth.WHISPER_TEST, synth.LSTMDims(), ("aa", "bb", "cc")),
+    ("surgical_hydra", synth.WHISPER_TINY, synth.LSTMDims(64, 1, False), ("only",)),          # d=384: 128-wide N tiles; 1 label
+    ("hydra_whisper", synth.WHISPER_BASE, synth.LSTMDims(256, 1, True), tuple("abcdefg")),    # d=512; H=256 (L2-resident W_hh)
+    ("surgical_hydra", synth.WHISPER_TEST, synth.LSTMDims(128, 3, True), tuple("abcdefghijkl")),  # 3 LSTM layers, 12 labels
+])
+def test_whisper_based_forward_like_the_reference_tests(cuda, kind, dims, lstm, labels):
+    """``model(x_t)`` on ``torch.ones((2, 80, 3000))`` as /root/reference/tests/test_models.py:37-53 calls it (the
+    reference only checks that it runs; here the logits are compared with the oracle), over encoder widths that take
+    different GEMM tile shapes, LSTM shapes that take different recurrence kernels, and 1 ... 12 labels (decode kernels
+    for C <= 8 and C > 8)."""
+    make = synth.surgical_hydra_state_dict if kind == "surgical_hydra" else synth.hydra_whisper_state_dict
+    sd = make(dims, lstm=lstm, labels=labels, seed=21)
+    le = MultiLabelEncoder(list(labels))
+    cfg = make_config(kind, {"lstm": {"hidden_size": lstm.hidden_size, "num_layers": lstm.num_layers,
+                                      "bidirectional": lstm.bidirectional, "dropout": 0.5}}, classes=labels)
+    model = Models[kind].from_state_dict(sd, le, cfg)
+    x_t = torch.ones((2, 80, 3000))
+    out = model(x_t)
+    fwd = O.surgical_hydra_forward if kind == "surgical_hydra" else O.hydra_whisper_forward
+    ref = fwd(sd, x_t, labels)
+    if isinstance(out, dict):  # HydraWhisper returns the per-head dict (hydra.py:83-87)
+        assert list(out) == [f"linear_head_{lab}" for lab in labels]
+        out = torch.stack([out[f"linear_head_{lab}"] for lab in labels], dim=-1)
+    assert out.shape == ref.shape == (2, 199, 1, len(labels))
+    _check_logits(out.cpu().reshape(-1, len(labels)), ref.reshape(-1, len(labels)), f"{kind} d={dims.d_model} H={lstm.hidden_size}")
+    # a real signal through the same model, file level, decoded: intervals bit-exact on the product's own logits
+    pcm = synth.synth_audio(64000 + 63680 + 9000, 33)
+    logits = apply_model_on_audio(pcm, model, INFERENCE_SETTINGS, "cuda", batch_size=2)
+    thr = default_thresholds(le)
+    mask = O.apply_thresholds(logits.cpu(), [0.5] * len(labels))
+    assert decode_logits(logits, thr, le) == O.create_intervals(mask.numpy(), list(le.base_labels))
+
+
+def test_wavlm_based_forward_like_the_reference_tests(cuda):
+    """``model(torch.ones((2, 32_000)))`` on raw audio (/root/reference/tests/test_models.py:56-71), 3 labels; constant
+    audio makes GroupNorm's variance zero in layer 0 (the io fixture's degenerate case)."""
+    labels = ("aa", "bb", "cc")
+    for dims, seed in ((synth.W2V2_TEST, 22), (synth.WAVLM_TEST, 23)):
+        sd = synth.hubert_hydra_state_dict(dims, labels=labels, seed=seed)
+        model = Models["surgical_hubert_hydra"].from_state_dict(sd, MultiLabelEncoder(list(labels)),
+                                                                make_config("surgical_hubert_hydra", classes=labels))
+        x_t = torch.ones((2, 32_000))
+        out = model(x_t)
+        ref = O.hubert_hydra_forward(sd, x_t, labels)
+        assert out.shape == ref.shape == (2, 99, 1, 3)
+        assert torch.isfinite(out).all()
+        assert (out.cpu() - ref).abs().max() <= 0.01 * max(1.0, ref.abs().max().item())

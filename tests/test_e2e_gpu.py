@@ -557,3 +557,59 @@ def test_wavlm_based_forward_like_the_reference_tests(cuda):
         assert out.shape == ref.shape == (2, 99, 1, 3)
         assert torch.isfinite(out).all()
         assert (out.cpu() - ref).abs().max() <= 0.01 * max(1.0, ref.abs().max().item())
+
+
+# ---- BASELINE configs 1 and 3 at their stated sizes ---------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["hubert", "whisper_tiny"])
+def test_config1_180s_file_vs_oracle(cuda, which):
+    """BASELINE config 1: the smallest models on a 180 s file = 2 880 000 samples -> 45 windows in one
+    remainder batch + a 14 400-sample tail = 8 999 frames, against the CPU oracle on every logit (35 996 decisions: the
+    99.9 % bar resolves)."""
+    n = 2_880_000
+    pcm = synth.synth_audio(n, 5)
+    le = MultiLabelEncoder(list(LABELS))
+    if which == "hubert":
+        sd = synth.hubert_hydra_state_dict(synth.HUBERT_BASE, seed=5)
+        model = Models["surgical_hubert_hydra"].from_state_dict(sd, le, make_config("surgical_hubert_hydra"))
+        fwd, whisper = (lambda w: O.hubert_hydra_forward(sd, w, LABELS)), False
+    else:
+        sd = synth.surgical_hydra_state_dict(synth.WHISPER_TINY, seed=6)
+        model = Models["surgical_hydra"].from_state_dict(sd, le, make_config("surgical_hydra"))
+        fwd, whisper = (lambda f: O.surgical_hydra_forward(sd, f, LABELS)), True
+    got = apply_model_on_audio(pcm, model, INFERENCE_SETTINGS, "cuda", batch_size=128).cpu()
+    assert got.shape == (8_999, 4)
+    torch.set_num_threads(16)
+    ref = O.apply_model_on_audio(torch.from_numpy(pcm), fwd, 4, batch_size=128, whisper=whisper)
+    _check_logits(got, ref, f"config 1, {which}, 180 s file")
+    thr = default_thresholds(le)
+    assert decode_logits(got.cuda(), thr, le) == O.create_intervals(O.apply_thresholds(got, [0.5] * 4).numpy(), LABELS)
+
+
+def test_config3_full_size_properties(cuda):
+    """BASELINE config 3 at size: WavLM-base+ dims on hours of audio (two 1 h files and a few short ones through the
+    corpus driver), checked through size-independent properties: the reference's frame count per file, independence of
+    the files (the packed corpus path gives each file the logits it gets on its own), and interval decoding that is
+    bit-exact against the reference's create_intervals restated on the thresholded mask."""
+    from segma_b200.inference import apply_model_on_audios, infer_corpus
+
+    sd = synth.hubert_hydra_state_dict(synth.WAVLM_BASE, seed=6)
+    le = MultiLabelEncoder(list(LABELS))
+    cfg = make_config("surgical_hubert_hydra")
+    model = Models["surgical_hubert_hydra"].from_state_dict(sd, le, cfg)
+    hour = synth.synth_audio(57_600_000, 0)
+    files = [hour, hour[1_000_000:1_000_000 + 700_000], hour[::-1].copy(), hour[5_000_000:5_064_000], hour[:33_280]]
+    per_file = apply_model_on_audios(files, model, INFERENCE_SETTINGS, "cuda", batch_size=128)
+    assert [t.shape[0] for t in per_file] == [(f.size - 400) // 320 + 1 for f in files]
+    assert per_file[0].shape == (179_999, 4) and all(torch.isfinite(t).all() for t in per_file)
+    for k in (1, 3, 4):  # short files: the same bits as on their own
+        assert torch.equal(per_file[k], apply_model_on_audio(files[k], model, INFERENCE_SETTINGS, "cuda", batch_size=128))
+    # a window's logits do not depend on its neighbours: the first 10 windows of the hour alone
+    head = apply_model_on_audio(hour[: 63_680 * 10 + 320], model, INFERENCE_SETTINGS, "cuda", batch_size=128)
+    assert torch.equal(head, per_file[0][: head.shape[0]])
+    thr = default_thresholds(le)
+    table = infer_corpus(files, model, cfg, batch_size=128, device="cuda").cpu().numpy()
+    rows = []
+    for i, t in enumerate(per_file):
+        mask = O.apply_thresholds(t.cpu(), [0.5] * 4)
+        rows += [(i, LABELS.index(lab), s, e) for s, e, lab in O.create_intervals(mask.numpy(), LABELS)]
+    assert table.shape[0] == len(rows) and table.tolist() == [list(r) for r in rows]

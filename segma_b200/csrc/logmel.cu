@@ -271,9 +271,13 @@ __global__ void __launch_bounds__(kThreadsA, 4) logmel_power_kernel(const float*
           v[t] = make_float2(x.x * h.x, x.y * h.y);
         }
         dft8(v);
-        float2* z = Z + f * kHalf + j * 8;  // expand(j, 1, 8) = 8 j
+        // Output t of butterfly j is element 8 j + t of the sequence.  Stored transposed, at t * 25 + j: consecutive
+        // threads (consecutive j) then write consecutive 8-byte words -- the natural position 8 j + t puts the 16 lanes
+        // of a half-warp on two bank groups (an 8-way conflict on every store).  The first radix-5 pass reads its
+        // inputs i = jj + 40 s at (i % 8) * 25 + i / 8 = (jj % 8) * 25 + jj / 8 + 5 s.
+        float2* z = Z + f * kHalf + j;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) z[t] = v[t];
+        for (int t = 0; t < 8; ++t) z[t * 25] = v[t];
         j += kThreadsA % 25;   // 160 = 6 * 25 + 10
         f += kThreadsA / 25;
         if (j >= 25) { j -= 25; ++f; }
@@ -293,16 +297,19 @@ __global__ void __launch_bounds__(kThreadsA, 4) logmel_power_kernel(const float*
         const float2 w1 = tab.tw200[tw_step], w2 = tab.tw200[2 * tw_step], w3 = tab.tw200[3 * tw_step],
                      w4 = tab.tw200[4 * tw_step];
         const int out0 = (j / Ns) * Ns * 5 + k;
+        // inputs j + 40 s: pass 0 reads the transposed layout the radix-8 stage wrote, pass 1 the natural one
+        const int in0 = pass == 0 ? (j & 7) * 25 + (j >> 3) : j;
+        const int in_step = pass == 0 ? 5 : 40;
         constexpr int kIter = (kGroup * 40) / kThreadsA;  // 8 butterflies per thread
         float2 v[kIter][5];
 #pragma unroll
         for (int it = 0; it < kIter; ++it) {
-          const float2* z = Z + (fb + 4 * it) * kHalf + j;
+          const float2* z = Z + (fb + 4 * it) * kHalf + in0;
           v[it][0] = z[0];
-          v[it][1] = cmul(z[40], w1);
-          v[it][2] = cmul(z[80], w2);
-          v[it][3] = cmul(z[120], w3);
-          v[it][4] = cmul(z[160], w4);
+          v[it][1] = cmul(z[in_step], w1);
+          v[it][2] = cmul(z[2 * in_step], w2);
+          v[it][3] = cmul(z[3 * in_step], w3);
+          v[it][4] = cmul(z[4 * in_step], w4);
         }
         __syncthreads();
 #pragma unroll

@@ -165,6 +165,7 @@ class W2V2Engine:
             ld = (T + 3) // 4 * 4  # rows padded to 16 bytes for the tcgen05 kernel's 128-bit loads
             padded = torch.zeros((pb.shape[0], T, ld), dtype=torch.float32, device=self.device)
             padded[:, :, :T] = pb.to(self.device)
+            torch.cuda.current_stream(self.device).synchronize()  # cached for every stream that runs this engine later
             self._pos_bias[T] = padded[:, :, :T]  # (H, T, T) view with row stride ld
         return self._pos_bias[T]
 
@@ -174,6 +175,7 @@ class W2V2Engine:
         key = -T
         if key not in self._pos_bias:
             self._pos_bias[key] = wavlm_relative_bias(self.rel_embed, T, self.rel_embed.shape[0]).to(self.device)
+            torch.cuda.current_stream(self.device).synchronize()  # cached for every stream that runs this engine later
         return self._pos_bias[key]
 
     def _workspace(self, n: int, win_len: int, slot: int = 0) -> dict:

@@ -607,27 +607,42 @@ def run_gpu(args):
 
     res, ctx = measure_model_workload(args, args.workload, args.steps, args.warmup, rank, world, dev)
     extras, side, cpu, eager = {}, {}, None, None
+    def attempt(what, fn):
+        """The headline numbers are already measured: a side measurement that cannot run is reported, not fatal."""
+        try:
+            return fn()
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] {what} failed: {type(e).__name__}: {e}", file=sys.stderr, flush=True)
+            return {"error": f"{type(e).__name__}: {e}"[:300]}
+
     if world == 1:
         if not args.no_side_kernels:
-            side = measure_side_kernels(dev, ctx)
+            side = attempt("side kernels", lambda: measure_side_kernels(dev, ctx))
         if args.workload == "whisper" and not args.no_extra_workloads:
             if not args.no_eager_baseline:
-                eager = eager_gpu_baseline(dev, ctx["sd"])
+                eager = attempt("torch-eager arm", lambda: eager_gpu_baseline(dev, ctx["sd"]))
             ctx.clear()
             torch.cuda.empty_cache()
-            for wl in ("hubert", "wavlm"):  # BASELINE configs 1 and 3 models, driver-visible: 3 steps of 1 h each
+
+            def extra(wl):
                 r, c = measure_model_workload(args, wl, 3, 3, rank, world, dev, with_e2e=False)
                 c.clear()
                 torch.cuda.empty_cache()
-                extras[wl] = {"workload": WORKLOADS[wl][1], "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"],
-                              "steps": 3, "warmup": 3, "roofline": r["roofline"], "gpu_launches": r["launches"],
-                              "model_tflops_per_gpu": r["model_tflops_per_gpu"],
-                              "executed_gflop_per_window": r["executed_gflop_per_window"],
-                              "breakdown_ms_per_step": r["breakdown_ms_per_step"]}
+                return {"workload": WORKLOADS[wl][1], "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"],
+                        "steps": 3, "warmup": 3, "roofline": r["roofline"], "gpu_launches": r["launches"],
+                        "model_tflops_per_gpu": r["model_tflops_per_gpu"],
+                        "executed_gflop_per_window": r["executed_gflop_per_window"],
+                        "breakdown_ms_per_step": r["breakdown_ms_per_step"]}
+
+            for wl in ("hubert", "wavlm"):  # BASELINE configs 1 and 3 models, driver-visible: 3 steps of 1 h each
+                extras[wl] = attempt(f"workload {wl}", lambda wl=wl: extra(wl))
         if not args.no_cpu_baseline and args.workload == "whisper":
-            c = cpu_reference_run(args.ref_windows, 1, 0)
-            cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": "port", "sample": c["sample"],
-                   "calibration": _calibration()}
+            def cpu_arm():
+                c = cpu_reference_run(args.ref_windows, 1, 0)
+                return {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": "port", "sample": c["sample"],
+                        "calibration": _calibration()}
+
+            cpu = attempt("cpu baseline", cpu_arm)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

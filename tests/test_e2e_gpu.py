@@ -613,3 +613,27 @@ def test_config3_full_size_properties(cuda):
         mask = O.apply_thresholds(t.cpu(), [0.5] * 4)
         rows += [(i, LABELS.index(lab), s, e) for s, e, lab in O.create_intervals(mask.numpy(), LABELS)]
     assert table.shape[0] == len(rows) and table.tolist() == [list(r) for r in rows]
+
+
+def test_second_device_in_one_process(cuda):
+    """A process may drive more than one GPU: ``model.to("cuda:1")`` moves the packed weights, every entry point runs
+    on the device it is given whatever the current device is, and the library's per-device state (function attributes,
+    mel tables, SM count) is set up per device.  Same logits on both devices, bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    le = MultiLabelEncoder(list(LABELS))
+    pcm = synth.synth_audio(64000 + 63680 * 2 + 9000, 17)
+    thr = default_thresholds(le)
+    for kind, sd in (("surgical_hydra", synth.surgical_hydra_state_dict(synth.WHISPER_TEST, seed=3)),
+                     ("surgical_hubert_hydra", synth.hubert_hydra_state_dict(synth.WAVLM_TEST, seed=6))):
+        model = Models[kind].from_state_dict(sd, le, make_config(kind))
+        a = apply_model_on_audio(pcm, model, INFERENCE_SETTINGS, "cuda:0", batch_size=2)
+        iv0 = decode_logits(a, thr, le)
+        model.to("cuda:1")
+        assert torch.cuda.current_device() == 0
+        b = apply_model_on_audio(pcm, model, INFERENCE_SETTINGS, "cuda:1", batch_size=2)
+        assert b.device == torch.device("cuda", 1) and torch.cuda.current_device() == 0
+        assert torch.equal(a.cpu(), b.cpu())
+        assert decode_logits(b, thr, le) == iv0
+        with pytest.raises(Exception):  # weights on cuda:1, asked for cuda:0: refused, not silently wrong
+            apply_model_on_audio(pcm, model, INFERENCE_SETTINGS, "cuda:0", batch_size=2)

@@ -76,21 +76,46 @@ def gather_file_tables(local_table: torch.Tensor, group=None) -> torch.Tensor:
     return full[order]
 
 
-def gather_corpus_tables(file_indices, tables, counts, device=None, gather: bool = True, group=None) -> torch.Tensor:
+def merge_split_files(table: torch.Tensor, merge_fn=None) -> torch.Tensor:
+    """Rows of files whose window batches were decoded in several pieces (on several ranks) -> the table of the whole
+    files.  Sorted by (file, label, start); a run of active frames that crosses a piece boundary arrives as two intervals
+    that touch (end == next start) and is fused by the gap-0 merge of the interval post-processing kernel -- inside one
+    piece two intervals of a label never touch (at least one inactive frame lies between them), so nothing else merges."""
+    if table.shape[0] == 0:
+        return table
+    order = torch.sort(table[:, 2], stable=True).indices
+    order = order[torch.sort(table[order, 1], stable=True).indices]
+    order = order[torch.sort(table[order, 0], stable=True).indices]
+    table = table[order].contiguous()
+    if merge_fn is None:
+        from . import ops
+
+        merge_fn = lambda t: ops.postprocess_intervals(t, 0, 0)  # noqa: E731
+    return merge_fn(table)
+
+
+def gather_corpus_tables(file_indices, tables, counts, device=None, gather: bool = True, group=None,
+                         sample_offsets=None, merge_split: bool = False, merge_fn=None) -> torch.Tensor:
     """The single exchange step at the end of a sharded corpus run.
 
-    ``tables[k]`` is the worst-case-sized int32 ``(cap_k, 4)`` table of this rank's k-th file (global index
-    ``file_indices[k]``) and ``counts[k]`` the 1-element tensor with its valid row count, both still where the decode
-    kernel left them.  Reads all counts back at once (the only host synchronisation of the run), compacts, stamps the
-    global file index into column 0 and all-gathers; every rank returns the same table ordered by file, label, time."""
+    ``tables[k]`` is the worst-case-sized int32 ``(cap_k, 4)`` table of this rank's k-th work unit (a file, or a range
+    of a file's window batches; global file index ``file_indices[k]``, first sample ``sample_offsets[k]``) and
+    ``counts[k]`` the 1-element tensor with its valid row count, both still where the decode kernel left them.  Reads all
+    counts back at once (the only host synchronisation of the run), compacts, stamps the global file index into column
+    0, shifts the pieces of split files to their place on the file timeline and all-gathers; with ``merge_split`` the
+    pieces are then fused (``merge_split_files``).  Every rank returns the same table ordered by file, label, time."""
     if device is None:
         device = tables[0].device if tables else torch.device("cpu")
     parts = []
     if tables:
         host_counts = torch.cat([c.reshape(1) for c in counts]).cpu().tolist()
-        for i, t, c in zip(file_indices, tables, host_counts):
+        offs = sample_offsets if sample_offsets is not None else [0] * len(tables)
+        for i, t, c, off in zip(file_indices, tables, host_counts, offs):
             part = t[:c].clone()
             part[:, 0] = i
+            if off:
+                part[:, 2:4] += int(off)
             parts.append(part)
     local = torch.cat(parts) if parts else torch.empty((0, 4), dtype=torch.int32, device=device)
-    return gather_file_tables(local, group) if gather else local
+    full = gather_file_tables(local, group) if gather else local
+    return merge_split_files(full, merge_fn) if merge_split else full

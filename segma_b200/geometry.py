@@ -258,3 +258,63 @@ def plan_packed_calls(n_samples: list[int], win_len: int = 64_000, batch_size: i
             part = items[i: i + batch_size]
             calls.append(PackedCall(wl, keep, tuple(p[0] for p in part), tuple(p[1] for p in part)))
     return calls, pcm_off, frm_off
+
+
+@dataclass(frozen=True)
+class WorkUnit:
+    """A contiguous range of forward calls (window batches) of one file: the atomic work item of the multi-GPU
+    partition (batches are independent of one another -- the LSTM couples the windows *inside* a call only)."""
+
+    file: int
+    batch_lo: int
+    batch_hi: int  # exclusive
+    n_windows: int
+    whole_file: bool
+
+
+def batch_frame_range(plan: WindowPlan, lo: int, hi: int) -> tuple[int, int]:
+    """Frames ``[f_lo, f_hi)`` of the file timeline that batches ``[lo, hi)`` of a tiled plan write."""
+    assert plan.step_frames == plan.frames_per_window, "batch ranges need windows that tile the frame grid"
+    bs = plan.batches[lo:hi]
+    if not bs:
+        return 0, 0
+    f_lo = bs[0].first_window * plan.step_frames
+    last = bs[-1]
+    f_hi = plan.n_frames if last.is_tail else (last.first_window + last.n_windows) * plan.step_frames
+    return f_lo, f_hi
+
+
+def plan_work_units(n_samples: list[int], world_size: int, win_len: int = 64_000, batch_size: int = 128,
+                    step: int | None = None, frames_per_window: int | None = None) -> list[WorkUnit]:
+    """Files -> work units for ``world_size`` ranks.  A file stays whole unless it alone would unbalance the ranks
+    (more than half of a rank's fair share of windows): then it is cut into contiguous batch ranges of about a quarter of
+    that share.  Batch boundaries are never moved -- they are part of the result for the Whisper family."""
+    plans = [plan_windows(n, win_len, batch_size, step, frames_per_window) for n in n_samples]
+    total = sum(p.n_windows for p in plans)
+    share = max(total / max(world_size, 1), 1.0)
+    units: list[WorkUnit] = []
+    for f, pl in enumerate(plans):
+        nb = len(pl.batches)
+        if world_size <= 1 or nb <= 1 or pl.n_windows <= share / 2:
+            units.append(WorkUnit(f, 0, nb, pl.n_windows, True))
+            continue
+        per = max(1, round(share / 4 / batch_size))  # batches per unit
+        for lo in range(0, nb, per):
+            hi = min(lo + per, nb)
+            units.append(WorkUnit(f, lo, hi, sum(b.n_windows for b in pl.batches[lo:hi]), False))
+    return units
+
+
+def assign_units(units: list[WorkUnit], world_size: int) -> list[list[WorkUnit]]:
+    """Longest-processing-time-first assignment of work units to ranks (deterministic); each rank's units come back in
+    (file, batch) order."""
+    import heapq
+
+    heap = [(0, r) for r in range(world_size)]
+    heapq.heapify(heap)
+    out: list[list[WorkUnit]] = [[] for _ in range(world_size)]
+    for u in sorted(units, key=lambda u: (-u.n_windows, u.file, u.batch_lo)):
+        load, r = heapq.heappop(heap)
+        out[r].append(u)
+        heapq.heappush(heap, (load + max(u.n_windows, 1), r))
+    return [sorted(v, key=lambda u: (u.file, u.batch_lo)) for v in out]

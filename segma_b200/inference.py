@@ -27,8 +27,8 @@ from . import ops
 from .annotation import rttm_line
 from .config import Config, load_config
 from .encoders import MultiLabelEncoder
-from .geometry import (FRAME_SAMPLES, INFERENCE_SETTINGS, Chunkyfier, ConvolutionSettings, conv_frames, plan_packed_calls,
-                       plan_windows)
+from .geometry import (FRAME_SAMPLES, INFERENCE_SETTINGS, Chunkyfier, ConvolutionSettings, assign_units, batch_frame_range,
+                       conv_frames, plan_packed_calls, plan_windows, plan_work_units)
 from .io import PcmSource, get_audio_info, get_samples_in_range, stage_to_device
 from .engine import resolve_device
 from .models import BaseSegmentationModel, Models
@@ -91,13 +91,16 @@ def apply_model_on_audio(
     sample_rate: int = 16_000,
     window_step: int | None = None,
     slot_base: int = 0,
+    batch_range: tuple[int, int] | None = None,
 ) -> torch.Tensor:
     """Apply model on audio, return a ``(n_frames, n_classes)`` fp32 tensor of raw logits on the device.
 
     Windows and batches are exactly the reference's (inference.py:129-206): ``batch_size`` consecutive
     windows per forward call, one remainder batch, then the tail alone -- the LSTM of the Whisper-family
     models couples the windows of a call, so batch boundaries are part of the result (SURVEY.md finding 6).
-    ``audio_path`` may also be a 1-D float32 array / tensor (host or device).
+    ``audio_path`` may also be a 1-D float32 array / tensor (host or device).  ``batch_range=(lo, hi)`` runs only
+    forward calls lo ... hi-1 of the file and returns the logits of the frames they cover
+    (``geometry.batch_frame_range``): a rank's share of a very long file.
     """
     dev = _cuda_device(device)
     engine = model._require_engine()
@@ -105,11 +108,11 @@ def apply_model_on_audio(
         raise ops.SegmaNativeError(f"model weights are on {engine.device} but device={dev} was requested; call model.to(device)")
     with torch.cuda.device(dev):
         return _apply_model_on_audio(audio_path, model, engine, conv_settings, dev, batch_size, chunk_duration_s,
-                                     sample_rate, window_step, slot_base)
+                                     sample_rate, window_step, slot_base, batch_range)
 
 
 def _apply_model_on_audio(audio_path, model, engine, conv_settings, dev, batch_size, chunk_duration_s, sample_rate,
-                          window_step, slot_base=0) -> torch.Tensor:
+                          window_step, slot_base=0, batch_range=None) -> torch.Tensor:
     chunk_f = int(chunk_duration_s * sample_rate)
     chunky = Chunkyfier(batch_size, chunk_f, conv_settings)  # same derived quantities as the reference
     step = chunky.step if window_step is None else int(window_step)
@@ -124,8 +127,17 @@ def _apply_model_on_audio(audio_path, model, engine, conv_settings, dev, batch_s
     tiled = sf == frames_per_window  # windows tile the frame grid: stitching is concatenation
     if plan.n_frames == 0:
         return torch.zeros((0, n_labels), dtype=torch.float32, device=dev)
+    batches, f_lo = plan.batches, 0
+    if batch_range is not None:
+        if not tiled:
+            raise ValueError("batch_range needs windows that tile the frame grid (no window_step overlap)")
+        batches = plan.batches[batch_range[0]: batch_range[1]]
+        f_lo, f_hi = batch_frame_range(plan, *batch_range)
+        if not batches:
+            return torch.zeros((0, n_labels), dtype=torch.float32, device=dev)
+        source.skip_to(batches[0].start_sample)
     if tiled:
-        logits = torch.empty((plan.n_frames, n_labels), dtype=torch.float32, device=dev)
+        logits = torch.empty((plan.n_frames if batch_range is None else f_hi - f_lo, n_labels), dtype=torch.float32, device=dev)
     else:
         n_full = sum(b.n_windows for b in plan.batches if not b.is_tail)
         tail = next((b for b in plan.batches if b.is_tail), None)
@@ -135,19 +147,19 @@ def _apply_model_on_audio(audio_path, model, engine, conv_settings, dev, batch_s
     # batches alternate between two streams / workspace slots: one batch's HBM- and latency-bound kernels
     # (LayerNorm, LSTM, heads) and kernel tails overlap the other's tensor-core kernels.
     main = torch.cuda.current_stream(dev)
-    n_lanes = max(1, min(N_STREAMS, len(plan.batches)))
+    n_lanes = max(1, min(N_STREAMS, len(batches)))
     lanes = _side_streams(dev, n_lanes) if n_lanes > 1 else [main]
     for st in lanes:
         if st is not main:
             st.wait_stream(main)
     target = logits if tiled else win_logits
-    for i, b in enumerate(plan.batches):
+    for i, b in enumerate(batches):
         source.ensure(b.start_sample + (b.n_windows - 1) * step + b.win_len)
         if lanes[i % n_lanes] is not main:
             lanes[i % n_lanes].wait_stream(main)
         with torch.cuda.stream(lanes[i % n_lanes]):
             if tiled:
-                engine.forward_pcm(pcm, b.start_sample, b.n_windows, b.win_len, step, logits, b.first_window * sf, sf,
+                engine.forward_pcm(pcm, b.start_sample, b.n_windows, b.win_len, step, logits, b.first_window * sf - f_lo, sf,
                                    b.frames_per_window, slot=slot_base + i % n_lanes)
             else:
                 engine.forward_pcm(pcm, b.start_sample, b.n_windows, b.win_len, step, win_logits,
@@ -406,65 +418,78 @@ def infer_corpus(audios, model: BaseSegmentationModel, config: Config, batch_siz
     ``file`` the index into ``audios``, ordered by file, then label, then time.
 
     The multi-GPU form of the reference's serial file loop (inference.py:442-458): with
-    ``shard=(rank, world_size)`` each rank runs only its files (``distributed.assign_files`` over ``sizes``, longest
-    first), nothing is exchanged while files are processed and nothing is read back per file -- every file's table stays
-    on the device at its worst-case size with its row count -- and at the very end the counts are read once, the tables
-    compacted and all-gathered once (``distributed.gather_file_tables``, NCCL).  ``audios`` holds paths or 1-D arrays."""
-    from .distributed import assign_files, gather_corpus_tables
+    ``shard=(rank, world_size)`` the work is partitioned by audio file and by window batch -- files are assigned longest
+    first, and a file that alone would unbalance the ranks is cut into contiguous ranges of its forward calls
+    (``geometry.plan_work_units``; batch boundaries never move, they are part of the result).  Nothing is exchanged while
+    the units run and nothing is read back per unit: every table stays on the device at its worst-case size with its row
+    count.  At the very end the counts are read once, the tables compacted, shifted to their place on the file timeline
+    and all-gathered once (NCCL); runs that cross a cut are fused by the gap-0 interval merge
+    (``distributed.merge_split_files``).  ``audios`` holds paths or 1-D arrays."""
+    from .distributed import gather_corpus_tables
+    from .io import audio_n_samples
 
     if thresholds is None:
         thresholds = default_thresholds(model.label_encoder)
     dev = _cuda_device(device)
-    mine = list(range(len(audios)))
-    if shard is not None:
-        if sizes is None:
-            sizes = [a.shape[-1] if isinstance(a, (np.ndarray, torch.Tensor)) else get_audio_info(a).n_samples for a in audios]
-        mine = assign_files(list(sizes), shard[1])[shard[0]]
+    chunk_f = int(config.audio.chunk_duration_s * 16_000)
+    fpw = model.n_keep if model.family == "whisper" else conv_frames(chunk_f)
+    world = shard[1] if shard is not None else 1
+    if sizes is None:
+        sizes = [audio_n_samples(a) for a in audios]
+    step = Chunkyfier(batch_size, chunk_f, INFERENCE_SETTINGS).step if window_step is None else int(window_step)
+    units = plan_work_units(list(sizes), world if window_step is None else 1, chunk_f, batch_size, step, fpw)
+    mine = assign_units(units, world)[shard[0]] if shard is not None else units
+    any_split = any(not u.whole_file for u in units)
     cuts = [logit_cut(t) for t in _lower_bounds(thresholds, model.label_encoder.n_labels)]
-    tables, counts = [], []
-    if model.family == "wav2vec2" and window_step is None and os.environ.get("SEGMA_PACK_FILES", "1") != "0":
-        # independent windows: packed across files into full forward calls (apply_model_on_audios)
-        all_logits = apply_model_on_audios([audios[i] for i in mine], model, INFERENCE_SETTINGS, dev, batch_size=batch_size,
-                                           chunk_duration_s=config.audio.chunk_duration_s)
-    else:
-        all_logits = None
-    if all_logits is not None:
-        for logits in all_logits:
+    results: dict[int, tuple] = {}  # position in `mine` -> (table, count)
+    pack = model.family == "wav2vec2" and window_step is None and os.environ.get("SEGMA_PACK_FILES", "1") != "0"
+    if pack:
+        # independent windows: whole files are packed across file boundaries into full forward calls
+        whole = [k for k, u in enumerate(mine) if u.whole_file]
+        packed = apply_model_on_audios([audios[mine[k].file] for k in whole], model, INFERENCE_SETTINGS, dev,
+                                       batch_size=batch_size, chunk_duration_s=config.audio.chunk_duration_s)
+        for k, logits in zip(whole, packed):
             with torch.cuda.device(dev):
-                table, count = ops.decode_intervals_async(logits.contiguous(), cuts, mode=ops.DECODE_LOGIT)
-            tables.append(table)
-            counts.append(count)
-    else:
-        # Files that cannot be packed (the LSTM couples the windows of a call) are independent of each other all the
-        # same: short files, whose forward calls are too small to fill 148 SMs, take turns on FILE_STREAMS streams, each
-        # with its own workspace slot; long files run alone on the main stream.
-        from .io import audio_n_samples
-
-        main = torch.cuda.current_stream(dev)
-        lanes = _side_streams(dev, FILE_STREAMS) if FILE_STREAMS > 1 else []
-        for st in lanes:
-            st.wait_stream(main)
-        chunk_f = int(config.audio.chunk_duration_s * 16_000)
-        turn = 0
-        for i in mine:
-            small = lanes and audio_n_samples(audios[i]) < SMALL_FILE_WINDOWS * chunk_f
-            lane = turn % FILE_STREAMS if small else -1
-            turn += 1 if small else 0
-            with torch.cuda.stream(lanes[lane] if small else main):
-                logits = apply_model_on_audio(audios[i], model, INFERENCE_SETTINGS, dev, batch_size=batch_size,
-                                              chunk_duration_s=config.audio.chunk_duration_s, window_step=window_step,
-                                              slot_base=(1 + lane) * max(N_STREAMS, 1) if small else 0)
-                with torch.cuda.device(dev):
-                    table, count = ops.decode_intervals_async(logits, cuts, mode=ops.DECODE_LOGIT)
-            if small:  # allocated on the lane's stream, consumed by the final exchange on the main stream
-                table.record_stream(main)
-                count.record_stream(main)
-            tables.append(table)
-            counts.append(count)
-        for st in lanes:
-            main.wait_stream(st)
+                results[k] = ops.decode_intervals_async(logits.contiguous(), cuts, mode=ops.DECODE_LOGIT)
+    # Everything else runs unit by unit.  Units are independent of each other: short ones, whose forward calls are too
+    # small to fill 148 SMs, take turns on FILE_STREAMS streams, each with its own workspace slot; long ones run alone
+    # on the main stream.
+    main = torch.cuda.current_stream(dev)
+    lanes = _side_streams(dev, FILE_STREAMS) if FILE_STREAMS > 1 else []
+    for st in lanes:
+        st.wait_stream(main)
+    turn = 0
+    for k, u in enumerate(mine):
+        if k in results:
+            continue
+        small = bool(lanes) and u.n_windows < SMALL_FILE_WINDOWS
+        lane = turn % FILE_STREAMS if small else -1
+        turn += 1 if small else 0
+        with torch.cuda.stream(lanes[lane] if small else main):
+            logits = apply_model_on_audio(audios[u.file], model, INFERENCE_SETTINGS, dev, batch_size=batch_size,
+                                          chunk_duration_s=config.audio.chunk_duration_s, window_step=window_step,
+                                          slot_base=(1 + lane) * max(N_STREAMS, 1) if small else 0,
+                                          batch_range=None if u.whole_file else (u.batch_lo, u.batch_hi))
+            with torch.cuda.device(dev):
+                table, count = ops.decode_intervals_async(logits, cuts, mode=ops.DECODE_LOGIT)
+        if small:  # allocated on the lane's stream, consumed by the final exchange on the main stream
+            table.record_stream(main)
+            count.record_stream(main)
+        results[k] = (table, count)
+    for st in lanes:
+        main.wait_stream(st)
+    offsets = []
+    for u in mine:  # first sample of the unit on its file's timeline
+        if u.whole_file:
+            offsets.append(0)
+        else:
+            plan = plan_windows(sizes[u.file], chunk_f, batch_size, step, fpw)
+            offsets.append(batch_frame_range(plan, u.batch_lo, u.batch_hi)[0] * FRAME_SAMPLES)
     with torch.cuda.device(dev):
-        return gather_corpus_tables(mine, tables, counts, device=dev, gather=gather and shard is not None and shard[1] > 1)
+        return gather_corpus_tables([u.file for u in mine], [results[k][0] for k in range(len(mine))],
+                                    [results[k][1] for k in range(len(mine))], device=dev,
+                                    gather=gather and shard is not None and shard[1] > 1, sample_offsets=offsets,
+                                    merge_split=any_split and gather)
 
 
 def get_list_of_files_to_process(wavs: Path, recursive: bool = False, uris: Path | None = None) -> tuple[list[Path], int]:

@@ -217,6 +217,16 @@ class PcmSource:
             self._copy_stream = _copy_stream_for(self.device)
             self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))
 
+    def skip_to(self, first_sample: int) -> None:
+        """Samples before ``first_sample`` will not be read by anyone (a rank that runs only some batches of the
+        file): do not stage them."""
+        first_sample = min(int(first_sample), self.n_samples)
+        if first_sample <= self._done:
+            return
+        if self._file is not None:
+            self._file.seek((first_sample - self._done) * self._fmt[1].itemsize, 1)
+        self._done = first_sample
+
     def ensure(self, upto: int) -> None:
         upto = min(int(upto), self.n_samples)
         if upto <= self._done:

@@ -57,7 +57,44 @@ def _worker(rank, world, port, out_dir):
         counts.append(torch.tensor([n], dtype=torch.int32))
     corpus = gather_corpus_tables(files, tables, counts)
     assert torch.equal(corpus, full)
+    # a file cut into batch ranges across the ranks: pieces carry their sample offset, touching runs fuse after the gather
+    whole = _split_file_truth()
+    pieces = _cut(whole, [0, 6400, 12800, 32000])
+    mine = [k for k in range(len(pieces)) if k % world == rank]
+    tables, counts = [], []
+    for k in mine:
+        t = torch.full((len(pieces[k][1]) + 3, 4), -7, dtype=torch.int32)
+        t[:len(pieces[k][1])] = torch.tensor(pieces[k][1], dtype=torch.int32).reshape(-1, 4)
+        tables.append(t)
+        counts.append(torch.tensor([len(pieces[k][1])], dtype=torch.int32))
+    merged = gather_corpus_tables([3] * len(mine), tables, counts, sample_offsets=[pieces[k][0] for k in mine],
+                                  merge_split=True, merge_fn=_merge_touching)
+    assert merged.tolist() == [[3, lab, s, e] for lab, s, e in whole], (merged.tolist(), whole)
     dist.destroy_process_group()
+
+
+def _split_file_truth():
+    """(label, start, end) of one file, sorted by label then time; several runs cross the cuts at 6400 / 12800."""
+    return [(0, 0, 640), (0, 3200, 9600), (0, 12160, 12800), (1, 6400, 6720), (1, 9600, 20000), (2, 320, 31680), (3, 12800, 13120)]
+
+
+def _cut(whole, edges):
+    """Decode the file piece by piece: every interval is clipped to the piece and given piece-relative samples."""
+    out = []
+    for lo, hi in zip(edges, edges[1:]):
+        rows = [(0, lab, max(s, lo) - lo, min(e, hi) - lo) for lab, s, e in whole if s < hi and e > lo]
+        out.append((lo, rows))
+    return out
+
+
+def _merge_touching(table):
+    rows = []
+    for f, lab, s, e in table.tolist():
+        if rows and rows[-1][0] == f and rows[-1][1] == lab and rows[-1][3] >= s:
+            rows[-1][3] = max(rows[-1][3], e)
+        else:
+            rows.append([f, lab, s, e])
+    return torch.tensor(rows, dtype=torch.int32).reshape(-1, 4)
 
 
 def test_interval_table_all_gather_world2(tmp_path):

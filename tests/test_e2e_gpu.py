@@ -12,7 +12,7 @@ from segma_b200 import synth
 from segma_b200.config import make_config
 from segma_b200.encoders import MultiLabelEncoder
 from segma_b200.inference import apply_model_on_audio, apply_thresholds, create_intervals, decode_logits, default_thresholds
-from segma_b200.geometry import INFERENCE_SETTINGS
+from segma_b200.geometry import INFERENCE_SETTINGS, plan_windows
 from segma_b200.models import Models
 
 pytestmark = pytest.mark.gpu
@@ -505,6 +505,48 @@ def test_packed_windows_of_several_files_equal_file_by_file(cuda):
     two = [synth.synth_audio(64000 + 63680 + 3000, 80), synth.synth_audio(64000, 81)]
     for f, got in zip(two, apply_model_on_audios(two, mw, INFERENCE_SETTINGS, "cuda", batch_size=2)):
         assert torch.equal(got, apply_model_on_audio(f, mw, INFERENCE_SETTINGS, "cuda", batch_size=2))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["hydra_whisper", "surgical_hubert_hydra"])
+def test_corpus_partitioned_by_file_and_window_batch(cuda, kind):
+    """Multi-GPU partition by audio file *and* window batch, emulated rank by rank on one GPU: a long file
+    is cut into batch ranges, each rank decodes its units on their own, and the shifted + merged pieces equal the table
+    of a single process bit for bit; the logits of a batch range are the same bits as that slice of the whole file."""
+    from segma_b200.distributed import merge_split_files
+    from segma_b200.geometry import assign_units, batch_frame_range, plan_work_units
+    from segma_b200.inference import infer_corpus
+
+    le = MultiLabelEncoder(list(LABELS))
+    cfg = make_config(kind)
+    if kind == "hydra_whisper":
+        model = Models[kind].from_state_dict(synth.hydra_whisper_state_dict(synth.WHISPER_TEST, seed=7), le, cfg)
+        fpw = model.n_keep
+    else:
+        model = Models[kind].from_state_dict(synth.hubert_hydra_state_dict(synth.W2V2_TEST, seed=5), le, cfg)
+        fpw = 199
+    bs = 2
+    lens = [63680 * 21 + 64000 + 7000, 64000, 300, 63680 * 2 + 64000, 70_000, 63680 * 9 + 320 * 30, 12_345]
+    files = [synth.synth_audio(n, 40 + i) for i, n in enumerate(lens)]
+    # make activity cross the cuts: thresholds low enough that long runs exist
+    thr = {lab: {"lower_bound": 0.35, "upper_bound": 1.0} for lab in LABELS}
+    whole = infer_corpus(files, model, cfg, batch_size=bs, device="cuda", thresholds=thr).cpu()
+    for world in (2, 4):
+        units = plan_work_units(lens, world, 64000, bs, 63680, fpw)
+        assert any(not u.whole_file for u in units), "the long file must be cut for this test to mean anything"
+        parts = [infer_corpus(files, model, cfg, batch_size=bs, device="cuda", thresholds=thr, shard=(r, world), gather=False)
+                 for r in range(world)]
+        assert sum(p.shape[0] for p in parts) >= whole.shape[0]
+        merged = merge_split_files(torch.cat(parts)).cpu()
+        assert torch.equal(merged, whole), (world, merged.shape, whole.shape)
+    # the logits of one unit are that slice of the whole file's logits
+    full = apply_model_on_audio(files[0], model, INFERENCE_SETTINGS, "cuda", batch_size=bs)
+    plan = plan_windows(lens[0], 64000, bs, 63680, fpw)
+    for lo, hi in ((0, 3), (3, 4), (len(plan.batches) - 2, len(plan.batches))):
+        f_lo, f_hi = batch_frame_range(plan, lo, hi)
+        got = apply_model_on_audio(files[0], model, INFERENCE_SETTINGS, "cuda", batch_size=bs, batch_range=(lo, hi))
+        assert got.shape[0] == f_hi - f_lo and torch.equal(got, full[f_lo:f_hi])
+    assert assign_units(units, 4) == assign_units(units, 4)
 
 
 # ---- the reference's own forward tests (tests/test_models.py:37-71), widened over dims, labels and LSTM shapes ------------

@@ -122,3 +122,39 @@ def test_packed_calls_keep_every_files_windows():
     assert all(len(c.sample_offsets) == 3 for c in full[:-1])  # packed across file boundaries
     tails = [c for c in calls if c.win_len != 64_000]
     assert any(len(c.sample_offsets) == 2 for c in tails)  # the two 9000-sample tails (and the two 6320-sample ones) share a call
+
+
+def test_work_units_cover_every_batch_once_and_balance():
+    """Multi-GPU partition by audio file and window batch: the units of a file are contiguous batch ranges that cover
+    its plan exactly once; small files stay whole; one very long file no longer pins the slowest rank."""
+    from segma_b200.geometry import assign_units, batch_frame_range, plan_work_units
+
+    hour = 57_600_000
+    sizes = [hour * 6, hour // 60, 300, 64000, hour // 10, 0, 63680 * 128 + 320]
+    for world in (1, 2, 4, 8):
+        units = plan_work_units(sizes, world, 64000, 128, 63680, 199)
+        for f, n in enumerate(sizes):
+            plan = plan_windows(n, 64000, 128, 63680, 199)
+            mine = [u for u in units if u.file == f]
+            assert [u.batch_lo for u in mine] == sorted(u.batch_lo for u in mine)
+            assert mine[0].batch_lo == 0 and mine[-1].batch_hi == len(plan.batches)
+            assert all(a.batch_hi == b.batch_lo for a, b in zip(mine, mine[1:]))
+            assert sum(u.n_windows for u in mine) == plan.n_windows
+            assert all(u.whole_file == (len(mine) == 1) for u in mine)
+            if len(mine) > 1:  # frame ranges of the pieces tile the file's frame grid
+                ranges = [batch_frame_range(plan, u.batch_lo, u.batch_hi) for u in mine]
+                assert ranges[0][0] == 0 and ranges[-1][1] == plan.n_frames
+                assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        parts = assign_units(units, world)
+        assert sorted((u.file, u.batch_lo) for p in parts for u in p) == sorted((u.file, u.batch_lo) for u in units)
+        assert assign_units(units, world) == parts  # deterministic
+        loads = [sum(u.n_windows for u in p) for p in parts]
+        if world > 1:
+            assert len([u for u in units if u.file == 0]) > world  # the 6 h file is cut
+            assert max(loads) <= 1.15 * (sum(loads) / world), loads  # whole files would give world x the mean
+    # a corpus of equal files is left alone: whole files, 125 per rank
+    units = plan_work_units([hour] * 1000, 8, 64000, 128, 63680, 199)
+    assert all(u.whole_file for u in units) and [len(p) for p in assign_units(units, 8)] == [125] * 8
+    # one file, eight ranks: every rank gets work
+    units = plan_work_units([hour], 8, 64000, 128, 63680, 199)
+    assert all(len(p) >= 1 for p in assign_units(units, 8))

@@ -5,8 +5,9 @@
 Every rank builds the same small corpus of wav files (seeded), then
   1. ``run_inference_on_audios(..., shard=(rank, world))``: each rank writes the RTTMs of its own files
      (``distributed.assign_files``, longest first); together they cover the corpus exactly once;
-  2. ``infer_corpus(..., shard=(rank, world))``: the table every rank gets from the final NCCL all-gather equals the table a
-     single process computes for the whole corpus, and equals the RTTMs of step 1.
+  2. ``infer_corpus(..., shard=(rank, world))``: work is partitioned by file and -- for the one long file -- by window batch
+     (``geometry.plan_work_units``); the table every rank gets from the final NCCL all-gather (+ merge of the pieces)
+     equals the table a single process computes for the whole corpus, and equals the RTTMs of step 1.
 """
 import os
 import sys
@@ -34,7 +35,8 @@ def main():
     kind = sys.argv[1] if len(sys.argv) > 1 else "surgical_hydra"
     root = Path(tempfile.gettempdir()) / f"segma_mg_{os.environ.get('MASTER_PORT', '0')}"
     wavs = root / "wav"
-    lens = [64000 * 3 + 5000, 300, 64000, 70_000, 63680 * 6 + 9000, 5000, 63680 * 2 + 64000, 12_345, 64000 * 9, 40_000]
+    lens = [64000 * 3 + 5000, 300, 64000, 70_000, 63680 * 6 + 9000, 5000, 63680 * 2 + 64000, 12_345, 64000 * 9, 40_000,
+            63680 * 44 + 64000 + 9000]  # the last one is long enough to be cut into window-batch ranges across the ranks
     if rank == 0:
         wavs.mkdir(parents=True, exist_ok=True)
         for i, n in enumerate(lens):
@@ -72,8 +74,11 @@ def main():
         dist.all_gather_object(gathered, int(table.shape[0]))
         assert len(set(gathered)) == 1
     if rank == 0:
+        from segma_b200.geometry import assign_units, plan_work_units
+        units = plan_work_units(sizes, world, 64000, 4, 63680, model.n_keep if model.family == "whisper" else 199)
         print(f"multi-GPU check ok: world {world}, {len(files)} files, {whole.shape[0]} intervals, model {kind}; "
-              f"files per rank {[len(v) for v in assign_files(sizes, world)]}")
+              f"files per rank {[len(v) for v in assign_files(sizes, world)]}; work units per rank "
+              f"{[len(v) for v in assign_units(units, world)]} ({sum(not u.whole_file for u in units)} pieces of cut files)")
     if world > 1:
         dist.destroy_process_group()
 

@@ -14,6 +14,7 @@
 // (constant beyond the last frame that touches audio), optionally also as the fp16 time-major tile
 // the conv-stem GEMM consumes.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -41,6 +42,8 @@ struct MelTables {
   int mel_k0[kMels];
   int mel_len[kMels];
   float mel_w[kMels][kMaxTaps];
+  float2 tw20[20][20];             // [c][b] = exp(-2 pi i b c / 400): twiddle between the two radix-20 passes
+  float2 mel_w2[kMels][kMaxTaps];  // (w / 4, w / 4): filter taps for a pair of frames (the 1/4 of the unpacked power)
 };
 
 __device__ MelTables g_tab;
@@ -95,8 +98,14 @@ static int upload_tables_locked() {
     }
     h.mel_k0[m] = first;
     h.mel_len[m] = len;
-    for (int i = 0; i < len; ++i) h.mel_w[m][i] = g_mel_dense[(size_t)(first + i) * kMels + m];
+    for (int i = 0; i < len; ++i) {
+      h.mel_w[m][i] = g_mel_dense[(size_t)(first + i) * kMels + m];
+      h.mel_w2[m][i] = make_float2(0.25f * h.mel_w[m][i], 0.25f * h.mel_w[m][i]);
+    }
   }
+  for (int c = 0; c < 20; ++c)
+    for (int b = 0; b < 20; ++b)
+      h.tw20[c][b] = make_float2((float)std::cos(two_pi * (b * c) / kNfft), (float)-std::sin(two_pi * (b * c) / kNfft));
   SEGMA_CUDA_OK(cudaMemcpyToSymbol(g_tab, &h, sizeof(h)));
   g_tab_ready.here() = true;
   return SEGMA_OK;
@@ -451,6 +460,429 @@ __global__ void __launch_bounds__(256) logmel_finish_tm_kernel(const float* __re
   }
 }
 
+
+// ---- fused kernel: one cluster of four CTAs per window ------------------------------------------------------
+// Transform.  Two frames A, B ride one 400-point complex FFT (z = h x_A + i h x_B) done as 20 x 20: with n = 20 a + b
+// and k = c + 20 d,  Z[c + 20 d] = sum_b W20^{bd} ( W400^{bc} sum_a W20^{ac} z[20 a + b] ).  A thread owns one
+// 20-point DFT per pass (Good-Thomas 4 x 5: no inner twiddles, all in registers), so a frame pair needs one exchange
+// through shared memory between the passes and one to bring Z[k] and Z[400 - k] together for
+// |X_A[k]|^2 = |Z[k] + conj Z[400-k]|^2 / 4,  |X_B[k]|^2 = |Z[k] - conj Z[400-k]|^2 / 4  (the 1/4 sits in the mel taps).
+// A group of 16 frames = 8 pairs x 20 threads = 160 threads, every thread busy in both passes.
+// Finish.  The four CTAs of a cluster take the window's frame groups in turn, leave the unclamped log10 mel values in
+// the (L2-resident) scratch, exchange their maxima through distributed shared memory and then each write a quarter
+// of the window's output -- clamp, scale and the constant tail -- so that one window's stores overlap the other
+// resident clusters' transforms and no second kernel re-reads anything from HBM.
+constexpr int kCl = 4;                         // CTAs per window
+constexpr int kPairs = kGroup / 2;             // frame pairs per group
+constexpr int kThreadsF = kPairs * 20;         // 160
+constexpr int kChunkPad = kHop + 10;           // staged samples: 160-sample chunks 170 words apart, which puts the
+                                               // 20 lanes of pair p on banks 20 p + b (conflict-free pass-1 loads)
+constexpr int kStageChunks = (kStage + kHop - 1) / kHop;
+constexpr int kStageWords = kStageChunks * kChunkPad;
+constexpr int kEL = 21;                        // exchange rows [c][b], odd stride: pass 2 reads columns conflict-free
+constexpr int kEP = 20 * kEL;                  // 420 = 4 mod 16: the 8 pairs of a warp fall on distinct 8-byte banks
+constexpr int kZP = 404;                       // spectrum of a pair, natural order, same residue
+constexpr int kPP = kBins;                     // (P_A, P_B)[k] of a pair
+constexpr int kTmTileF = 32;
+constexpr int kR1Bytes = kPairs * kEP * 8;     // stage / exchange / spectrum / transpose tile share one region
+static_assert(kPairs * kZP * 8 <= kR1Bytes && kMels * (kTmTileF + 1) * 4 <= kR1Bytes,
+              "shared region too small");
+static_assert(kMels % kCl == 0 && kThreadsF % 20 == 0, "row split");
+static_assert(kR1Bytes % 16 == 0 && (kStageWords * 4) % 16 == 0, "shared-memory carve-up alignment");
+constexpr int kFusedSmem = kR1Bytes + kStageWords * 4 + kPairs * kPP * 8 + kNfft * 4 + 400 * 8;  // + Hann, twiddles
+
+// Complex numbers as packed fp32 pairs (re, im): additions, real scalings and fused multiply-adds of a whole complex
+// number are one FADD2 / FMUL2 / FFMA2 (two fp32 lanes per issue slot on sm_100); multiplications by -i are written on
+// the scalar halves and cost nothing extra.
+typedef uint64_t cpx;
+__device__ __forceinline__ cpx cpx_make(float re, float im) { return f2_pack(re, im); }
+__device__ __forceinline__ cpx cpx_sub(cpx a, cpx b) {
+  cpx r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+__device__ __forceinline__ void dft4(cpx& x0, cpx& x1, cpx& x2, cpx& x3) {
+  const cpx t0 = f2_add(x0, x2), t1 = cpx_sub(x0, x2), t2 = f2_add(x1, x3), t3 = cpx_sub(x1, x3);
+  x0 = f2_add(t0, t2);
+  x2 = cpx_sub(t0, t2);
+  float t1x, t1y, t3x, t3y;
+  f2_unpack(t1, t1x, t1y);
+  f2_unpack(t3, t3x, t3y);
+  x1 = cpx_make(t1x + t3y, t1y - t3x);   // t1 - i t3
+  x3 = cpx_make(t1x - t3y, t1y + t3x);   // t1 + i t3
+}
+
+__device__ __forceinline__ void dft5(cpx (&v)[5]) {
+  const float c1 = 0.30901699437494742410f;   // cos(2pi/5)
+  const float c2 = -0.80901699437494742410f;  // cos(4pi/5)
+  const float s1 = 0.95105651629515357212f;   // sin(2pi/5)
+  const float s2 = 0.58778525229247312917f;   // sin(4pi/5)
+  float x1, y1, x2, y2, x3, y3, x4, y4;
+  f2_unpack(v[1], x1, y1);
+  f2_unpack(v[2], x2, y2);
+  f2_unpack(v[3], x3, y3);
+  f2_unpack(v[4], x4, y4);
+  const cpx a1 = f2_add(v[1], v[4]), a2 = f2_add(v[2], v[3]);
+  const cpx r1 = cpx_make(y1 - y4, x4 - x1), r2 = cpx_make(y2 - y3, x3 - x2);  // -i (v1 - v4), -i (v2 - v3)
+  const cpx x0 = v[0];
+  v[0] = f2_add(f2_add(x0, a1), a2);
+  const cpx p1 = f2_fma(f2_splat(c2), a2, f2_fma(f2_splat(c1), a1, x0));
+  const cpx p2 = f2_fma(f2_splat(c1), a2, f2_fma(f2_splat(c2), a1, x0));
+  const cpx q1 = f2_fma(f2_splat(s2), r2, f2_mul(f2_splat(s1), r1));   // -i (s1 b1 + s2 b2)
+  const cpx q2 = f2_fma(f2_splat(-s1), r2, f2_mul(f2_splat(s2), r1));  // -i (s2 b1 - s1 b2)
+  v[1] = f2_add(p1, q1);
+  v[4] = cpx_sub(p1, q1);
+  v[2] = f2_add(p2, q2);
+  v[3] = cpx_sub(p2, q2);
+}
+
+// forward DFT of length 20, natural order in and out: a = 5 a1 + 4 a2, c = 5 c1 + 16 c2 (mod 20), so that
+// W20^{ac} = W4^{a1 c1} W5^{a2 c2} -- four DFT-5 and five DFT-4 without twiddles; the index maps are register renaming
+__device__ __forceinline__ void dft20(cpx (&v)[20]) {
+  cpx u[4][5];
+#pragma unroll
+  for (int a1 = 0; a1 < 4; ++a1)
+#pragma unroll
+    for (int a2 = 0; a2 < 5; ++a2) u[a1][a2] = v[(5 * a1 + 4 * a2) % 20];
+#pragma unroll
+  for (int a1 = 0; a1 < 4; ++a1) dft5(u[a1]);
+#pragma unroll
+  for (int c2 = 0; c2 < 5; ++c2) dft4(u[0][c2], u[1][c2], u[2][c2], u[3][c2]);
+#pragma unroll
+  for (int c1 = 0; c1 < 4; ++c1)
+#pragma unroll
+    for (int c2 = 0; c2 < 5; ++c2) v[(5 * c1 + 16 * c2) % 20] = u[c1][c2];
+}
+
+__device__ __forceinline__ float2 cpx_f2(cpx a) {
+  float2 r;
+  f2_unpack(a, r.x, r.y);
+  return r;
+}
+
+// the unclamped log-mel rows wait in L2 for the finish one window later: written with an evict-last policy, and
+// dropped from L2 without a write-back once they have been read (they never need to reach HBM)
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_f32x2_keep(float* p, float a, float b, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(a), "f"(b), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void l2_discard_128(const void* p) {
+  asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
+
+__device__ __forceinline__ float ld_cluster_f32(const float* own_smem, uint32_t rank) {
+  uint32_t remote;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(own_smem)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// stage samples [s0, s0 + 2800) of the window into 160-sample chunks 170 words apart.  Interior groups of an 8-byte
+// aligned window go through cp.async (no registers, in flight while the previous group is transformed); groups that
+// touch the reflected start, the end of the audio or an odd address take the scalar path.
+__device__ __forceinline__ void stage_group(float* stage, const float* __restrict__ w, long long s0, long long avail,
+                                            bool aligned8, int tid) {
+  if (aligned8 && s0 >= 0 && s0 + kStage <= avail) {
+    const float* src = w + s0 + 2 * tid;
+    float* dst = stage + (tid / 80) * kChunkPad + 2 * (tid % 80);
+#pragma unroll
+    for (int it = 0; it < (kStage / 2 + kThreadsF - 1) / kThreadsF; ++it) {
+      if (it * kThreadsF + tid < kStage / 2) cp_async_8(dst + it * 2 * kChunkPad, src + it * 2 * kThreadsF);
+    }
+  } else {
+    for (int q = tid; q < kStage / 2; q += kThreadsF) {
+      const long long n = s0 + 2 * q;
+      const int chunk = q / (kHop / 2);
+      *reinterpret_cast<float2*>(stage + chunk * kChunkPad + 2 * (q - chunk * (kHop / 2))) =
+          make_float2(sample_at(w, n, avail), sample_at(w, n + 1, avail));
+    }
+  }
+}
+
+__device__ __forceinline__ int window_valid_frames(long long pcm_len, int win, long long step, int win_len,
+                                                   long long& avail) {
+  avail = pcm_len - (long long)win * step;
+  if (avail > win_len) avail = win_len;
+  if (avail <= 0) { avail = 0; return 0; }
+  const long long nv = (avail + 200 + kHop - 1) / kHop;  // frames >= nv see only zeros
+  return nv > kFramesOut ? kFramesOut : (int)nv;
+}
+
+// clamp / scale / constant tail of one window: this CTA's quarter of the outputs
+__device__ __forceinline__ void finish_window(int win, uint32_t rank, int tid, int n_valid, float gmax, int nvp,
+                                              const float* __restrict__ ls, float* __restrict__ out_f32,
+                                              __half* __restrict__ out_tm, unsigned char* r1) {
+  if (gmax == -INFINITY) gmax = -10.f;                  // no frame touches audio
+  if (n_valid < kFramesOut) gmax = fmaxf(gmax, -10.f);  // the zero padding is part of the reference's maximum
+  const float floor_v = gmax - 8.0f;
+  const float fill = (fmaxf(-10.f, floor_v) + 4.0f) / 4.0f;
+  if (out_f32) {
+    constexpr int kRows = kMels / kCl, kQuads = kFramesOut / 4;
+    const int nq = (n_valid + 3) / 4;
+    float4* o = reinterpret_cast<float4*>(out_f32 + ((long long)win * kMels + rank * kRows) * kFramesOut);
+    const float4* src = reinterpret_cast<const float4*>(ls + (long long)rank * kRows * nvp);
+    const int nvq = nvp / 4;
+    // frames that touch audio: clamp and scale what the cluster left in the scratch (four rows in flight per thread)
+    for (int q = tid; q < nq; q += kThreadsF) {
+      const int t = 4 * q;
+#pragma unroll 1
+      for (int row = 0; row < kRows; row += 4) {
+        float4 x[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = __ldcg(src + (row + i) * nvq + q);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 r = make_float4(fill, fill, fill, fill);
+          r.x = (fmaxf(x[i].x, floor_v) + 4.0f) / 4.0f;
+          if (t + 1 < n_valid) r.y = (fmaxf(x[i].y, floor_v) + 4.0f) / 4.0f;
+          if (t + 2 < n_valid) r.z = (fmaxf(x[i].z, floor_v) + 4.0f) / 4.0f;
+          if (t + 3 < n_valid) r.w = (fmaxf(x[i].w, floor_v) + 4.0f) / 4.0f;
+          __stcs(o + (row + i) * kQuads + q, r);
+        }
+        // the eight lanes of a 128-byte line have their data: drop the line (unless the fp16 tile reads it too)
+        if (!out_tm && (q & 7) == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) l2_discard_128(src + (row + i) * nvq + q);
+        }
+      }
+    }
+    // the constant tail: nothing to read
+    const float4 f4 = make_float4(fill, fill, fill, fill);
+#pragma unroll 1
+    for (int row = 0; row < kRows; ++row) {
+      float4* orow = o + row * kQuads;
+#pragma unroll 4
+      for (int q = nq + tid; q < kQuads; q += kThreadsF) __stcs(orow + q, f4);
+    }
+  }
+  if (out_tm) {
+    // fp16 time-major (3002, 80): rows 0 and 3001 are the conv padding; tiles of 32 frames in turn over the cluster
+    float (*tile)[kTmTileF + 1] = reinterpret_cast<float (*)[kTmTileF + 1]>(r1);
+    __half* o = out_tm + (long long)win * (kFramesOut + 2) * kMels;
+    if (rank == 0 && tid < kMels) {
+      o[tid] = __float2half(0.f);
+      o[(long long)(kFramesOut + 1) * kMels + tid] = __float2half(0.f);
+    }
+    constexpr int kTiles = (kFramesOut + kTmTileF - 1) / kTmTileF;
+    __syncthreads();  // r1 is free (also when no group ran)
+#pragma unroll 1
+    for (int j = rank; j < kTiles; j += kCl) {
+      const int tt = j * kTmTileF;
+      const bool live = tt < n_valid;  // uniform per CTA
+      if (live) {
+        for (int id = tid; id < kMels * kTmTileF; id += kThreadsF) {
+          const int m = id / kTmTileF, f = id - m * kTmTileF;
+          const int t = tt + f;
+          tile[m][f] = (t < n_valid) ? (fmaxf(__ldcg(ls + (long long)m * nvp + t), floor_v) + 4.0f) / 4.0f : fill;
+        }
+        __syncthreads();
+      }
+      for (int id = tid; id < kTmTileF * kMels / 2; id += kThreadsF) {
+        const int f = id / (kMels / 2), m = (id - f * (kMels / 2)) * 2;
+        const int t = tt + f;
+        if (t >= kFramesOut) continue;
+        float a = fill, c = fill;
+        if (live) { a = tile[m][f]; c = tile[m + 1][f]; }
+        *reinterpret_cast<uint32_t*>(o + (long long)(t + 1) * kMels + m) = pack_f16x2(a, c);
+      }
+      if (live) __syncthreads();
+    }
+  }
+}
+
+// Persistent clusters walk the windows.  The finish of window i is deferred until the cluster's transform of window
+// i + 1 is done: barrier.cluster.arrive after the transform, barrier.cluster.wait only then, so no CTA ever idles
+// waiting for its peers' maxima (the wait was 22 % of all warp time when it followed the arrive directly).
+__global__ void __launch_bounds__(kThreadsF, 4) logmel_fused_kernel(const float* __restrict__ pcm, long long pcm_len,
+                                                                   int win_len, long long step, int n_windows,
+                                                                   int nvp, float* __restrict__ logspec,
+                                                                   float* __restrict__ out_f32,
+                                                                   __half* __restrict__ out_tm) {
+  extern __shared__ __align__(16) unsigned char fused_smem[];
+  unsigned char* r1 = fused_smem;                                        // exchange rows / spectrum / transpose tile
+  float* stage = reinterpret_cast<float*>(fused_smem + kR1Bytes);
+  float2* P2 = reinterpret_cast<float2*>(fused_smem + kR1Bytes + kStageWords * 4);
+  float* s_hann = reinterpret_cast<float*>(fused_smem + kR1Bytes + kStageWords * 4 + kPairs * kPP * 8);
+  float2* s_tw = reinterpret_cast<float2*>(s_hann + kNfft);
+  __shared__ float s_red[kThreadsF / 32];
+  __shared__ float s_cmax[3];  // maxima of three windows in flight (a peer may be one transform ahead)
+  float2* E = reinterpret_cast<float2*>(r1);
+  float2* Z = reinterpret_cast<float2*>(r1);
+  const int tid = threadIdx.x;
+  const uint32_t rank = cluster_ctarank();
+  const int n_clusters = gridDim.x / kCl;
+  const int p = tid / 20, b = tid - 20 * p;   // pass 1: (pair, b); pass 2: (pair, c = b)
+
+  for (int i = tid; i < kNfft; i += kThreadsF) s_hann[i] = g_tab.hann[i];
+  for (int i = tid; i < 400; i += kThreadsF) s_tw[i] = g_tab.tw20[i / 20][i % 20];
+  // mel filter of this thread in step 5: filter m for the group's pairs 4 h .. 4 h + 3
+  const int mel_m = tid >> 1, mel_h = tid & 1;
+  const int mel_k0 = __ldg(g_tab.mel_k0 + mel_m), mel_len = __ldg(g_tab.mel_len + mel_m);
+  const float2* mel_w = g_tab.mel_w2[mel_m];
+  const uint64_t keep_policy = l2_keep_policy();
+  __syncthreads();
+
+  int prev_win = -1, slot = 0;
+  for (int win = blockIdx.x / kCl; win < n_windows; win += n_clusters) {
+    long long avail;
+    const int n_valid = window_valid_frames(pcm_len, win, step, win_len, avail);
+    const float* w = pcm + (long long)win * step;
+    const bool aligned8 = ((reinterpret_cast<uintptr_t>(w) & 7) == 0);
+    float* ls = logspec + (long long)win * kMels * nvp;
+
+    // this CTA's share: a contiguous range of frame pairs (a multiple of 4 pairs, so that groups start on 8 frames)
+    const int pairs_total = (n_valid + 1) / 2;
+    const int per = ((pairs_total + kCl - 1) / kCl + 3) & ~3;
+    const int pair_lo = min((int)rank * per, pairs_total), pair_hi = min(pair_lo + per, pairs_total);
+
+    float local_max = -INFINITY;
+    if (pair_lo < pair_hi) {
+      stage_group(stage, w, (long long)kHop * 2 * pair_lo - 200, avail, aligned8, tid);
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    __syncthreads();
+    // Three barriers per group: after the exchange rows, after the spectrum, after the powers.  Step 5 of a group
+    // needs no barrier behind it (it reads only P2 and writes global memory), so warps with short mel filters run
+    // ahead into the next group's pass 1 while the warp with the 14-tap filters finishes.
+    for (int pair0 = pair_lo; pair0 < pair_hi; pair0 += kPairs) {
+      const int np = min(kPairs, pair_hi - pair0);  // live pairs of this group
+      const int t0 = 2 * pair0;
+      const bool pair_on = p < np;
+      // 1. pass 1: window, DFT over a of z[20 a + b], twiddle, store transposed as E[pair][c][b]
+      if (pair_on) {
+        cpx v[20];
+        const float* sa = stage + 2 * kChunkPad * p + b;
+#pragma unroll
+        for (int a = 0; a < 20; ++a) {
+          const int off = 20 * a + 10 * (a >> 3);  // sample 20 a + b of the frame: chunk a / 8 (b < 20)
+          const float h = s_hann[20 * a + b];
+          v[a] = cpx_make(sa[off] * h, sa[off + kChunkPad] * h);
+        }
+        dft20(v);
+        float2* e = E + p * kEP + b;
+        e[0] = cpx_f2(v[0]);
+#pragma unroll
+        for (int c = 1; c < 20; ++c) e[c * kEL] = cmul(cpx_f2(v[c]), s_tw[c * 20 + b]);
+      }
+      __syncthreads();
+      // every thread has its samples: the next group's may land (in flight until the barrier behind step 3)
+      if (pair0 + kPairs < pair_hi) stage_group(stage, w, (long long)kHop * (t0 + kGroup) - 200, avail, aligned8, tid);
+      // 2. pass 2: DFT over b of row c, written back over the same row: Z[pair][c][d] is bin c + 20 d
+      if (pair_on) {
+        cpx v[20];
+        float2* e = E + p * kEP + b * kEL;
+#pragma unroll
+        for (int i = 0; i < 20; ++i) v[i] = cpx_make(e[i].x, e[i].y);
+        dft20(v);
+#pragma unroll
+        for (int d = 0; d < 20; ++d) e[d] = cpx_f2(v[d]);
+      }
+      __syncthreads();
+      // 3. separate the two frames and take the powers (times 4): thread k for every pair, then bins 160..200
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int k = tid + half * kThreadsF;
+        if (k < kBins) {
+          const int k2 = k == 0 ? 0 : kNfft - k;
+          const float2* z1p = Z + (k % 20) * kEL + k / 20;
+          const float2* z2p = Z + (k2 % 20) * kEL + k2 / 20;
+          float2* pw = P2 + k;
+#pragma unroll
+          for (int q = 0; q < kPairs; ++q) {
+            if (q < np) {
+              const float2 z1 = z1p[q * kEP], z2 = z2p[q * kEP];
+              const float ar = z1.x + z2.x, ai = z1.y - z2.y, br = z1.x - z2.x, bi = z1.y + z2.y;
+              pw[q * kPP] = make_float2(fmaf(ar, ar, ai * ai), fmaf(br, br, bi * bi));
+            }
+          }
+        }
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncthreads();
+      // 4. sparse mel filters on (P_A, P_B) pairs + log10: each tap is loaded once for four frame pairs; warps hold
+      //    filters of similar length (the slaney bank widens with m)
+      if (4 * mel_h < np) {
+        uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};  // (0.f, 0.f)
+        const float2* pq = P2 + 4 * mel_h * kPP + mel_k0;
+#pragma unroll 2
+        for (int i = 0; i < mel_len; ++i) {
+          const float2 wv = __ldg(mel_w + i);
+          const uint64_t w2 = f2_pack(wv.x, wv.y);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 pv = pq[j * kPP + i];
+            acc[j] = f2_fma(w2, f2_pack(pv.x, pv.y), acc[j]);
+          }
+        }
+        float* dst = ls + (long long)mel_m * nvp + t0 + 8 * mel_h;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (4 * mel_h + j < np) {
+            float ma, mb;
+            f2_unpack(acc[j], ma, mb);
+            const float va = 0.30102999566398120f * __log2f(fmaxf(ma, 1e-10f));  // log10
+            const float vb = 0.30102999566398120f * __log2f(fmaxf(mb, 1e-10f));
+            SEGMA_DEV_ASSERT(win < n_windows && t0 + 8 * mel_h + 2 * j + 1 < nvp);
+            // a window's last pair may end one frame past n_valid: that frame is all zeros (-10, which the maximum
+            // contains anyway whenever n_valid < 3000) and the finish never reads it
+            st_f32x2_keep(dst + 2 * j, va, vb, keep_policy);
+            local_max = fmaxf(local_max, fmaxf(va, vb));
+          }
+        }
+      }
+    }
+
+    // ---- this CTA's maximum; the finish of the previous window; hand this window to the cluster --------------
+    local_max = warp_max(local_max);
+    if (lane_id() == 0) s_red[tid >> 5] = local_max;
+    __syncthreads();
+    if (tid == 0) {
+      float m = s_red[0];
+      for (int i = 1; i < kThreadsF / 32; ++i) m = fmaxf(m, s_red[i]);
+      s_cmax[slot] = m;
+    }
+    __syncthreads();  // s_cmax[slot] is written; the exchange rows are free for the transpose tile
+    float gmax_prev = -INFINITY;
+    if (prev_win >= 0) {
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // peers finished the previous transform
+      const int pslot = slot == 0 ? 2 : slot - 1;
+#pragma unroll
+      for (uint32_t r = 0; r < kCl; ++r) gmax_prev = fmaxf(gmax_prev, ld_cluster_f32(&s_cmax[pslot], r));
+    }
+    // hand this window to the cluster before the stores of the previous one's finish are issued (a release behind
+    // them would wait for them to drain); the maxima read above are in registers
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    if (prev_win >= 0) {
+      long long pa;
+      const int pv = window_valid_frames(pcm_len, prev_win, step, win_len, pa);
+      finish_window(prev_win, rank, tid, pv, gmax_prev, nvp, logspec + (long long)prev_win * kMels * nvp, out_f32, out_tm, r1);
+    }
+    prev_win = win;
+    slot = slot == 2 ? 0 : slot + 1;
+  }
+  if (prev_win >= 0) {
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    const int pslot = slot == 0 ? 2 : slot - 1;
+    float gmax = -INFINITY;
+#pragma unroll
+    for (uint32_t r = 0; r < kCl; ++r) gmax = fmaxf(gmax, ld_cluster_f32(&s_cmax[pslot], r));
+    long long pa;
+    const int pv = window_valid_frames(pcm_len, prev_win, step, win_len, pa);
+    finish_window(prev_win, rank, tid, pv, gmax, nvp, logspec + (long long)prev_win * kMels * nvp, out_f32, out_tm, r1);
+  }
+  cluster_sync_all();  // no CTA leaves while a peer may still read its maximum
+}
+
 static int max_valid_frames(int win_len) {
   long long nv = ((long long)win_len + 200 + kHop - 1) / kHop;
   if (nv > kFramesOut) nv = kFramesOut;
@@ -503,6 +935,40 @@ int segma_logmel(const float* pcm, int64_t pcm_len, int n_windows, int win_len, 
   const size_t head = ((size_t)n_windows * sizeof(uint32_t) + 255) / 256 * 256;
   uint32_t* win_max = static_cast<uint32_t*>(scratch);
   float* logspec = reinterpret_cast<float*>(static_cast<char*>(scratch) + head);
+  const int groups = nvp / kGroup;
+  static const bool split = [] {
+    const char* e = std::getenv("SEGMA_LOGMEL_SPLIT");
+    return e && e[0] == '1';
+  }();
+  if (!split) {
+    static PerDeviceFlag fused_attr;
+    static int max_clusters[kMaxDevices];
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kThreadsF);
+    cfg.dynamicSmemBytes = kFusedSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int dev = current_device();
+    if (!fused_attr.here()) {
+      SEGMA_CUDA_OK(cudaFuncSetAttribute(logmel_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
+      cfg.gridDim = dim3(kCl * 4 * device_sm_count());
+      int n = 0;
+      SEGMA_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, logmel_fused_kernel, &cfg));
+      SEGMA_REQUIRE(n > 0, "segma_logmel: no cluster of %d CTAs fits on this device", kCl);
+      max_clusters[dev] = n;
+      fused_attr.here() = true;
+    }
+    cfg.gridDim = dim3((unsigned)std::min(n_windows, max_clusters[dev]) * kCl);  // persistent: every cluster is resident
+    SEGMA_CUDA_OK(cudaLaunchKernelEx(&cfg, logmel_fused_kernel, pcm, (long long)pcm_len, win_len, (long long)step,
+                                     n_windows, nvp, logspec, out_f32, static_cast<__half*>(out_tm)));
+    return launch_status("logmel_fused_kernel");
+  }
   SEGMA_CUDA_OK(cudaMemsetAsync(win_max, 0, (size_t)n_windows * sizeof(uint32_t), st));
   const size_t smem = sizeof(float2) * kGroup * kHalf + sizeof(float) * std::max(kStage, kGroup * kBins) + sizeof(SmemTables);
   static PerDeviceFlag attr_set;
@@ -510,7 +976,6 @@ int segma_logmel(const float* pcm, int64_t pcm_len, int n_windows, int win_len, 
     SEGMA_CUDA_OK(cudaFuncSetAttribute(logmel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set.here() = true;
   }
-  const int groups = nvp / kGroup;
   const int grid_a = std::min(n_windows * groups, 4 * device_sm_count());
   logmel_power_kernel<<<grid_a, kThreadsA, smem, st>>>(pcm, pcm_len, win_len, step, n_windows, groups, nvp, logspec,
                                                        win_max);

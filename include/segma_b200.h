@@ -60,7 +60,7 @@ SEGMA_API int segma_pcm_to_f32(const void* src, int format, int64_t n, float* ds
  *   out_f32  [dev] (n_windows, 80, 3000) fp32, or NULL
  *   out_tm   [dev] (n_windows, 3002, 80) fp16 time-major with one zero row before and after each
  *            window (the layout the conv-stem implicit GEMM reads), or NULL
- *   scratch  [dev] segma_logmel_scratch_bytes(n_windows, win_len) bytes
+ *   scratch  [dev] segma_logmel_scratch_bytes(n_windows, win_len) bytes, 128-byte aligned (cudaMalloc is)
  */
 SEGMA_API size_t segma_logmel_scratch_bytes(int n_windows, int win_len);
 SEGMA_API int segma_logmel(const float* pcm, int64_t pcm_len, int n_windows, int win_len, int64_t step, float* out_f32,

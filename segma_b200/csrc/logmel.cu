@@ -6,13 +6,12 @@
 // -> 201-bin power spectrum -> 80 slaney mel bins (391 non-zeros) -> log10(max(., 1e-10))
 // -> max(., window_max - 8) -> (. + 4) / 4, padded with the constant value to 3000 frames.
 //
-// HBM-bound: per window 256 KB of PCM in, 960 KB of features out.  Kernel A stages the overlapping
-// samples of 16 consecutive frames once in shared memory (128-bit loads; each sample is used by 2.5
-// frames), runs a packed real FFT (200-point complex Stockham, radix 8*5*5, in shared memory/registers),
-// applies the sparse mel filters and the log, and reduces the window maximum with one atomic per
-// block.  Kernel B applies the window-global clamp, scales, and streams out the 3000-frame rows
-// (constant beyond the last frame that touches audio), optionally also as the fp16 time-major tile
-// the conv-stem GEMM consumes.
+// Per window 256 KB of PCM in, 960 KB of features out (831 KB of it the constant tail).  One kernel: a cluster of four
+// CTAs per window stages the overlapping samples of 16 frames at a time in shared memory (cp.async, one group ahead),
+// transforms two frames per 400-point complex FFT done as 20 x 20 in registers, applies the sparse mel filters and the
+// log, and keeps the unclamped values in an L2-resident scratch; the cluster's maxima meet through distributed shared
+// memory and each CTA then writes a quarter of the window -- clamp, scale, constant tail, optionally also the fp16
+// time-major tile the conv-stem GEMM consumes -- while the cluster already transforms its next window.
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -25,20 +24,16 @@ namespace segma {
 
 constexpr int kNfft = 400;
 constexpr int kHop = 160;
-constexpr int kHalf = 200;          // complex FFT length (packed real FFT)
 constexpr int kBins = 201;
 constexpr int kMels = SEGMA_MEL_BINS;
 constexpr int kFramesOut = SEGMA_MEL_FRAMES;
 constexpr int kPadSamples = 480000;  // 30 s
-constexpr int kGroup = 16;           // frames per work item (4 CTAs of 160 threads per SM; 8 or 32 frames are slower)
-constexpr int kThreadsA = 160;
+constexpr int kGroup = 16;           // frames per work item: 8 frame pairs x 20 threads
 constexpr int kMaxTaps = 32;         // max contiguous FFT bins per mel filter
-constexpr int kStage = (kGroup - 1) * kHop + kNfft;  // 5360 staged samples per group
+constexpr int kStage = (kGroup - 1) * kHop + kNfft;  // 2800 staged samples per group
 
 struct MelTables {
   float hann[kNfft];
-  float2 tw200[kHalf];       // exp(-2 pi i k / 200)
-  float2 tw400[kBins];       // exp(-2 pi i k / 400)
   int mel_k0[kMels];
   int mel_len[kMels];
   float mel_w[kMels][kMaxTaps];
@@ -81,8 +76,6 @@ static int upload_tables_locked() {
   std::memset(&h, 0, sizeof(h));
   const double two_pi = 6.283185307179586476925286766559;
   for (int n = 0; n < kNfft; ++n) h.hann[n] = (float)(0.5 - 0.5 * std::cos(two_pi * n / kNfft));
-  for (int k = 0; k < kHalf; ++k) h.tw200[k] = make_float2((float)std::cos(two_pi * k / kHalf), (float)-std::sin(two_pi * k / kHalf));
-  for (int k = 0; k < kBins; ++k) h.tw400[k] = make_float2((float)std::cos(two_pi * k / kNfft), (float)-std::sin(two_pi * k / kNfft));
   for (int m = 0; m < kMels; ++m) {
     int first = -1, last = -1;
     for (int k = 0; k < kBins; ++k)
@@ -122,344 +115,12 @@ static int ensure_tables() {
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-// multiply by -i (forward-transform rotation by -90 degrees)
-__device__ __forceinline__ float2 mul_neg_i(float2 a) { return make_float2(a.y, -a.x); }
-
-__device__ __forceinline__ void dft2(float2& a, float2& b) {
-  const float2 t = a;
-  a = cadd(t, b);
-  b = csub(t, b);
-}
-
-// in-place forward DFT of length 8, natural order in and out
-__device__ __forceinline__ void dft8(float2 (&v)[8]) {
-  const float r = 0.70710678118654752440f;
-  // stage 1: pairs (k, k+4)
-  dft2(v[0], v[4]); dft2(v[1], v[5]); dft2(v[2], v[6]); dft2(v[3], v[7]);
-  v[5] = cmul(v[5], make_float2(r, -r));
-  v[6] = mul_neg_i(v[6]);
-  v[7] = cmul(v[7], make_float2(-r, -r));
-  // stage 2
-  dft2(v[0], v[2]); dft2(v[1], v[3]); dft2(v[4], v[6]); dft2(v[5], v[7]);
-  v[3] = mul_neg_i(v[3]);
-  v[7] = mul_neg_i(v[7]);
-  // stage 3
-  dft2(v[0], v[1]); dft2(v[2], v[3]); dft2(v[4], v[5]); dft2(v[6], v[7]);
-  // bit-reversed -> natural: outputs currently at [0,4,2,6,1,5,3,7]
-  float2 t;
-  t = v[1]; v[1] = v[4]; v[4] = t;
-  t = v[3]; v[3] = v[6]; v[6] = t;
-}
-
-// in-place forward DFT of length 5
-__device__ __forceinline__ void dft5(float2 (&v)[5]) {
-  const float c1 = 0.30901699437494742410f;   // cos(2pi/5)
-  const float c2 = -0.80901699437494742410f;  // cos(4pi/5)
-  const float s1 = 0.95105651629515357212f;   // sin(2pi/5)
-  const float s2 = 0.58778525229247312917f;   // sin(4pi/5)
-  const float2 a1 = cadd(v[1], v[4]), b1 = csub(v[1], v[4]);
-  const float2 a2 = cadd(v[2], v[3]), b2 = csub(v[2], v[3]);
-  const float2 x0 = v[0];
-  v[0] = make_float2(x0.x + a1.x + a2.x, x0.y + a1.y + a2.y);
-  const float2 p1 = make_float2(x0.x + c1 * a1.x + c2 * a2.x, x0.y + c1 * a1.y + c2 * a2.y);
-  const float2 p2 = make_float2(x0.x + c2 * a1.x + c1 * a2.x, x0.y + c2 * a1.y + c1 * a2.y);
-  // q = -i * (s1*b1 + s2*b2) etc. (forward transform: exp(-i theta))
-  const float2 q1 = make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
-  const float2 q2 = make_float2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
-  // X1 = p1 - i q1, X4 = p1 + i q1, X2 = p2 - i q2, X3 = p2 + i q2
-  v[1] = make_float2(p1.x + q1.y, p1.y - q1.x);
-  v[4] = make_float2(p1.x - q1.y, p1.y + q1.x);
-  v[2] = make_float2(p2.x + q2.y, p2.y - q2.x);
-  v[3] = make_float2(p2.x - q2.y, p2.y + q2.x);
-}
-
-__device__ __forceinline__ uint32_t float_order_key(float v) {
-  const uint32_t b = __float_as_uint(v);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float float_from_key(uint32_t k) {
-  const uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
-  return __uint_as_float(b);
-}
-
 // padded-window sample n (after torch.stft's reflect padding of the 480000-sample buffer)
 __device__ __forceinline__ float sample_at(const float* __restrict__ w, long long n, long long avail) {
   if (n < 0) n = -n;
   if (n >= kPadSamples) n = 2ll * (kPadSamples - 1) - n;
   return (n < avail) ? __ldg(w + n) : 0.f;
 }
-
-// ---- kernel A: log10 mel power of the frames that touch audio + window max ---------------------------
-// Persistent CTAs walk (window, 32-frame group) work items; the Hann window, both twiddle tables and the
-// compacted mel filters live in shared memory for the lifetime of the CTA.
-constexpr int kMelTapsSmem = 16;  // the slaney bank has at most 14 taps per filter; wider banks read global
-
-struct __align__(16) SmemTables {
-  float hann[kNfft];
-  float2 tw200[kHalf];
-  float2 tw400[kBins + 1];
-  float mel_w[kMels][kMelTapsSmem];
-  short mel_k0[kMels];
-  short mel_len[kMels];
-};
-
-__global__ void __launch_bounds__(kThreadsA, 4) logmel_power_kernel(const float* __restrict__ pcm, long long pcm_len,
-                                                                 int win_len, long long step, int n_windows,
-                                                                 int groups_per_window, int nvp,
-                                                                 float* __restrict__ logspec,
-                                                                 uint32_t* __restrict__ win_max) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* Z = reinterpret_cast<float2*>(smem_raw);                                       // [kGroup][kHalf]
-  float* stage = reinterpret_cast<float*>(smem_raw + sizeof(float2) * kGroup * kHalf);   // samples, later power
-  SmemTables& tab = *reinterpret_cast<SmemTables*>(smem_raw + sizeof(float2) * kGroup * kHalf +
-                                                   sizeof(float) * (kGroup * kBins > kStage ? kGroup * kBins : kStage));
-  __shared__ float s_red[kThreadsA / 32];
-  const int tid = threadIdx.x;
-
-  for (int i = tid; i < kNfft; i += kThreadsA) tab.hann[i] = g_tab.hann[i];
-  for (int i = tid; i < kHalf; i += kThreadsA) tab.tw200[i] = g_tab.tw200[i];
-  for (int i = tid; i < kBins; i += kThreadsA) tab.tw400[i] = g_tab.tw400[i];
-  bool wide_bank = false;
-  for (int m = tid; m < kMels; m += kThreadsA) {
-    tab.mel_k0[m] = static_cast<short>(g_tab.mel_k0[m]);
-    tab.mel_len[m] = static_cast<short>(g_tab.mel_len[m]);
-    for (int i = 0; i < kMelTapsSmem; ++i) tab.mel_w[m][i] = g_tab.mel_w[m][i];
-  }
-  for (int m = 0; m < kMels; ++m) wide_bank |= g_tab.mel_len[m] > kMelTapsSmem;  // uniform across the grid
-  __syncthreads();
-
-  const int n_items = n_windows * groups_per_window;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int win = item / groups_per_window;
-    const int t0 = (item - win * groups_per_window) * kGroup;
-    const long long w_off = (long long)win * step;
-    long long avail = pcm_len - w_off;
-    if (avail > win_len) avail = win_len;
-    if (avail < 0) avail = 0;
-    int n_valid = (int)((avail + 200 + kHop - 1) / kHop);  // frames >= n_valid see only zeros
-    if (avail == 0) n_valid = 0;
-    if (n_valid > kFramesOut) n_valid = kFramesOut;
-    if (t0 >= n_valid) continue;  // whole group is silent padding (uniform per block)
-    const float* w = pcm + w_off;
-
-    // 1. stage samples [160*t0 - 200, +5360) with 128-bit loads where possible
-    {
-      const long long s0 = (long long)kHop * t0 - 200;
-      const bool aligned = ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
-      for (int q = tid; q < kStage / 4; q += kThreadsA) {
-        const long long n = s0 + 4 * q;
-        float4 v;
-        if (aligned && n >= 0 && n + 3 < avail) {
-          v = __ldg(reinterpret_cast<const float4*>(w + n));
-        } else {
-          v.x = sample_at(w, n, avail);
-          v.y = sample_at(w, n + 1, avail);
-          v.z = sample_at(w, n + 2, avail);
-          v.w = sample_at(w, n + 3, avail);
-        }
-        reinterpret_cast<float4*>(stage)[q] = v;
-      }
-    }
-    __syncthreads();
-
-    // 2. FFT stage 1 (radix 8, Ns = 1): z[n] = (x[2n] h[2n], x[2n+1] h[2n+1]); butterfly j takes n = j + 25 t
-    {
-      int f = tid / 25, j = tid - f * 25;  // id = tid + it*160 -> (f, j) advanced incrementally
-#pragma unroll 1
-      for (int it = 0; it < (kGroup * 25 + kThreadsA - 1) / kThreadsA; ++it) {
-        if (f >= kGroup) break;
-        float2 v[8];
-        const float* sp = stage + f * kHop;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const int n = j + 25 * t;
-          const float2 x = *reinterpret_cast<const float2*>(sp + 2 * n);
-          const float2 h = *reinterpret_cast<const float2*>(tab.hann + 2 * n);
-          v[t] = make_float2(x.x * h.x, x.y * h.y);
-        }
-        dft8(v);
-        // Output t of butterfly j is element 8 j + t of the sequence.  Stored transposed, at t * 25 + j: consecutive
-        // threads (consecutive j) then write consecutive 8-byte words -- the natural position 8 j + t puts the 16 lanes
-        // of a half-warp on two bank groups (an 8-way conflict on every store).  The first radix-5 pass reads its
-        // inputs i = jj + 40 s at (i % 8) * 25 + i / 8 = (jj % 8) * 25 + jj / 8 + 5 s.
-        float2* z = Z + f * kHalf + j;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) z[t * 25] = v[t];
-        j += kThreadsA % 25;   // 160 = 6 * 25 + 10
-        f += kThreadsA / 25;
-        if (j >= 25) { j -= 25; ++f; }
-      }
-    }
-    __syncthreads();
-
-    // 3. FFT stages 2 and 3 (radix 5; Ns = 8 then 40), in place: read all, barrier, write all.
-    //    id = tid + it*160 and 160 = 4 * 40, so j = tid % 40 is fixed per thread and f = tid/40 + 4*it.
-    {
-      const int j = tid % 40, fb = tid / 40;
-#pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        const int Ns = pass == 0 ? 8 : 40;
-        const int k = pass == 0 ? (j & 7) : j;
-        const int tw_step = k * (kHalf / (5 * Ns));  // twiddle exp(-2 pi i t k / (5 Ns)) = tw200[t * tw_step]
-        const float2 w1 = tab.tw200[tw_step], w2 = tab.tw200[2 * tw_step], w3 = tab.tw200[3 * tw_step],
-                     w4 = tab.tw200[4 * tw_step];
-        const int out0 = (j / Ns) * Ns * 5 + k;
-        // inputs j + 40 s: pass 0 reads the transposed layout the radix-8 stage wrote, pass 1 the natural one
-        const int in0 = pass == 0 ? (j & 7) * 25 + (j >> 3) : j;
-        const int in_step = pass == 0 ? 5 : 40;
-        constexpr int kIter = (kGroup * 40) / kThreadsA;  // 8 butterflies per thread
-        float2 v[kIter][5];
-#pragma unroll
-        for (int it = 0; it < kIter; ++it) {
-          const float2* z = Z + (fb + 4 * it) * kHalf + in0;
-          v[it][0] = z[0];
-          v[it][1] = cmul(z[in_step], w1);
-          v[it][2] = cmul(z[2 * in_step], w2);
-          v[it][3] = cmul(z[3 * in_step], w3);
-          v[it][4] = cmul(z[4 * in_step], w4);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int it = 0; it < kIter; ++it) {
-          dft5(v[it]);
-          float2* z = Z + (fb + 4 * it) * kHalf + out0;
-#pragma unroll
-          for (int t = 0; t < 5; ++t) z[t * Ns] = v[it][t];
-        }
-        __syncthreads();
-      }
-    }
-
-    // 4. unpack the real FFT and take the power: P[f][k], k = 0..200 (stage buffer is reused)
-    float* P = stage;
-    {
-      int f = 0, k = tid;  // id = tid + it*160 -> (f, k) advanced incrementally (160 < 201)
-      for (int id = tid; id < kGroup * kBins; id += kThreadsA) {
-        const float2* z = Z + f * kHalf;
-        const float2 a = z[k == kHalf ? 0 : k];
-        const float2 bq = z[k == 0 ? 0 : kHalf - k];
-        const float2 b = make_float2(bq.x, -bq.y);                       // conj(Z[200-k])
-        const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
-        const float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
-        const float2 o = mul_neg_i(d);                                   // (Zk - conj(Z[N-k])) / (2i)
-        const float2 x = cadd(e, cmul(tab.tw400[k], o));
-        P[f * kBins + k] = fmaf(x.x, x.x, x.y * x.y);
-        k += kThreadsA;
-        if (k >= kBins) { k -= kBins; ++f; }
-      }
-    }
-    __syncthreads();
-
-    // 5. sparse mel filters + log10; frame index fastest so global stores coalesce along time
-    float local_max = -INFINITY;
-    for (int id = tid; id < kGroup * kMels; id += kThreadsA) {
-      const int m = id / kGroup, f = id - m * kGroup;
-      const int t = t0 + f;
-      if (t < n_valid) {
-        const float* pp = P + f * kBins + tab.mel_k0[m];
-        const int len = tab.mel_len[m];
-        float acc = 0.f;
-        if (!wide_bank) {
-          for (int i = 0; i < len; ++i) acc = fmaf(tab.mel_w[m][i], pp[i], acc);
-        } else {
-          for (int i = 0; i < len; ++i) acc = fmaf(g_tab.mel_w[m][i], pp[i], acc);
-        }
-        const float v = 0.30102999566398120f * __log2f(fmaxf(acc, 1e-10f));  // log10
-        SEGMA_DEV_ASSERT(win < n_windows && m < kMels && t < nvp);
-        logspec[((long long)win * kMels + m) * nvp + t] = v;
-        local_max = fmaxf(local_max, v);
-      }
-    }
-    local_max = warp_max(local_max);
-    if (lane_id() == 0) s_red[tid >> 5] = local_max;
-    __syncthreads();
-    if (tid == 0) {
-      float m = s_red[0];
-      for (int i = 1; i < kThreadsA / 32; ++i) m = fmaxf(m, s_red[i]);
-      atomicMax(win_max + win, float_order_key(m));
-    }
-    // the next item's staging writes `stage`, which every thread has finished reading (barrier above)
-  }
-}
-
-// ---- kernel B: window-global clamp, scale, constant tail ----------------------------------------------
-__device__ __forceinline__ int window_n_valid(long long pcm_len, int win, long long step, int win_len) {
-  long long avail = pcm_len - (long long)win * step;
-  if (avail > win_len) avail = win_len;
-  if (avail <= 0) return 0;
-  long long nv = (avail + 200 + kHop - 1) / kHop;
-  return nv > kFramesOut ? kFramesOut : (int)nv;
-}
-
-__global__ void __launch_bounds__(256) logmel_finish_f32_kernel(const float* __restrict__ logspec,
-                                                                 const uint32_t* __restrict__ win_max,
-                                                                 long long pcm_len, int win_len, long long step,
-                                                                 int nvp, float* __restrict__ out) {
-  const int win = blockIdx.y;
-  const int n_valid = window_n_valid(pcm_len, win, step, win_len);
-  const uint32_t key = win_max[win];
-  float gmax = key ? float_from_key(key) : -10.f;
-  if (n_valid < kFramesOut) gmax = fmaxf(gmax, -10.f);
-  const float floor_v = gmax - 8.0f;
-  const float fill = (fmaxf(-10.f, floor_v) + 4.0f) / 4.0f;
-  constexpr int kQuads = kMels * kFramesOut / 4;
-  float4* o = reinterpret_cast<float4*>(out + (long long)win * kMels * kFramesOut);
-  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < kQuads; q += gridDim.x * blockDim.x) {
-    const int m = q / (kFramesOut / 4);
-    const int t = (q - m * (kFramesOut / 4)) * 4;
-    float4 v = make_float4(fill, fill, fill, fill);
-    if (t < n_valid) {
-      const float* src = logspec + ((long long)win * kMels + m) * nvp + t;
-      float r[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) r[i] = (t + i < n_valid) ? (fmaxf(__ldg(src + i), floor_v) + 4.0f) / 4.0f : fill;
-      v = make_float4(r[0], r[1], r[2], r[3]);
-    }
-    o[q] = v;
-  }
-}
-
-// fp16 time-major (3002, 80) per window: row 0 and row 3001 are the conv padding (zeros)
-constexpr int kTmTile = 32;
-__global__ void __launch_bounds__(256) logmel_finish_tm_kernel(const float* __restrict__ logspec,
-                                                                const uint32_t* __restrict__ win_max,
-                                                                long long pcm_len, int win_len, long long step,
-                                                                int nvp, __half* __restrict__ out) {
-  __shared__ float tile[kMels][kTmTile + 1];
-  const int win = blockIdx.y;
-  const int n_valid = window_n_valid(pcm_len, win, step, win_len);
-  const uint32_t key = win_max[win];
-  float gmax = key ? float_from_key(key) : -10.f;
-  if (n_valid < kFramesOut) gmax = fmaxf(gmax, -10.f);
-  const float floor_v = gmax - 8.0f;
-  const float fill = (fmaxf(-10.f, floor_v) + 4.0f) / 4.0f;
-  __half* o = out + (long long)win * (kFramesOut + 2) * kMels;
-  const int t0 = blockIdx.x * kTmTile;
-  if (blockIdx.x == 0 && threadIdx.x < kMels) {
-    o[threadIdx.x] = __float2half(0.f);
-    o[(long long)(kFramesOut + 1) * kMels + threadIdx.x] = __float2half(0.f);
-  }
-  if (t0 < n_valid) {
-    for (int id = threadIdx.x; id < kMels * kTmTile; id += blockDim.x) {
-      const int m = id / kTmTile, f = id - m * kTmTile;
-      const int t = t0 + f;
-      tile[m][f] = (t < n_valid) ? (fmaxf(__ldg(logspec + ((long long)win * kMels + m) * nvp + t), floor_v) + 4.0f) / 4.0f
-                                 : fill;
-    }
-    __syncthreads();
-  }
-  for (int id = threadIdx.x; id < kTmTile * kMels / 2; id += blockDim.x) {
-    const int f = id / (kMels / 2), m = (id - f * (kMels / 2)) * 2;
-    const int t = t0 + f;
-    if (t >= kFramesOut) continue;
-    float a = fill, b = fill;
-    if (t0 < n_valid) { a = tile[m][f]; b = tile[m + 1][f]; }
-    *reinterpret_cast<uint32_t*>(o + (long long)(t + 1) * kMels + m) = pack_f16x2(a, b);
-  }
-}
-
 
 // ---- fused kernel: one cluster of four CTAs per window ------------------------------------------------------
 // Transform.  Two frames A, B ride one 400-point complex FFT (z = h x_A + i h x_B) done as 20 x 20: with n = 20 a + b
@@ -649,20 +310,24 @@ __device__ __forceinline__ void finish_window(int win, uint32_t rank, int tid, i
           if (t + 3 < n_valid) r.w = (fmaxf(x[i].w, floor_v) + 4.0f) / 4.0f;
           __stcs(o + (row + i) * kQuads + q, r);
         }
-        // the eight lanes of a 128-byte line have their data: drop the line (unless the fp16 tile reads it too)
+        // the eight lanes of a 128-byte line have their data: drop the line (unless the fp16 tile reads it too);
+        // rows are whole lines (nvp % 32 == 0) and belong to one CTA
         if (!out_tm && (q & 7) == 0) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) l2_discard_128(src + (row + i) * nvq + q);
         }
       }
     }
-    // the constant tail: nothing to read
+    // the constant tail: nothing to read; a thread keeps its columns and walks the rows
     const float4 f4 = make_float4(fill, fill, fill, fill);
-#pragma unroll 1
+    constexpr int kTailIt = (kQuads + kThreadsF - 1) / kThreadsF;
+    float4* ocol = o + nq + tid;
+#pragma unroll 2
     for (int row = 0; row < kRows; ++row) {
-      float4* orow = o + row * kQuads;
-#pragma unroll 4
-      for (int q = nq + tid; q < kQuads; q += kThreadsF) __stcs(orow + q, f4);
+#pragma unroll
+      for (int it = 0; it < kTailIt; ++it)
+        if (nq + tid + it * kThreadsF < kQuads) __stcs(ocol + it * kThreadsF, f4);
+      ocol += kQuads;
     }
   }
   if (out_tm) {
@@ -771,8 +436,18 @@ __global__ void __launch_bounds__(kThreadsF, 4) logmel_fused_kernel(const float*
         dft20(v);
         float2* e = E + p * kEP + b;
         e[0] = cpx_f2(v[0]);
+        // twiddles are read in batches ahead of the stores (both live in shared memory: the compiler keeps a load
+        // behind every earlier store, which would put one full load latency in front of each product)
 #pragma unroll
-        for (int c = 1; c < 20; ++c) e[c * kEL] = cmul(cpx_f2(v[c]), s_tw[c * 20 + b]);
+        for (int c0 = 1; c0 < 20; c0 += 5) {
+          float2 tw[5];
+#pragma unroll
+          for (int j = 0; j < 5; ++j)
+            if (c0 + j < 20) tw[j] = s_tw[(c0 + j) * 20 + b];
+#pragma unroll
+          for (int j = 0; j < 5; ++j)
+            if (c0 + j < 20) e[(c0 + j) * kEL] = cmul(cpx_f2(v[c0 + j]), tw[j]);
+        }
       }
       __syncthreads();
       // every thread has its samples: the next group's may land (in flight until the barrier behind step 3)
@@ -797,12 +472,20 @@ __global__ void __launch_bounds__(kThreadsF, 4) logmel_fused_kernel(const float*
           const float2* z1p = Z + (k % 20) * kEL + k / 20;
           const float2* z2p = Z + (k2 % 20) * kEL + k2 / 20;
           float2* pw = P2 + k;
+          // all loads first, then the stores; pairs beyond np hold stale but finite data
+          float2 z1[kPairs], z2[kPairs];
+#pragma unroll
+          for (int q = 0; q < kPairs; ++q) {
+            z1[q] = z1p[q * kEP];
+            z2[q] = z2p[q * kEP];
+          }
 #pragma unroll
           for (int q = 0; q < kPairs; ++q) {
             if (q < np) {
-              const float2 z1 = z1p[q * kEP], z2 = z2p[q * kEP];
-              const float ar = z1.x + z2.x, ai = z1.y - z2.y, br = z1.x - z2.x, bi = z1.y + z2.y;
-              pw[q * kPP] = make_float2(fmaf(ar, ar, ai * ai), fmaf(br, br, bi * bi));
+              float sx, sy, dx, dy;
+              f2_unpack(f2_add(f2_pack(z1[q].x, z1[q].y), f2_pack(z2[q].x, z2[q].y)), sx, sy);
+              f2_unpack(cpx_sub(f2_pack(z1[q].x, z1[q].y), f2_pack(z2[q].x, z2[q].y)), dx, dy);
+              pw[q * kPP] = make_float2(fmaf(sx, sx, dy * dy), fmaf(dx, dx, sy * sy));  // |Z1 + conj Z2|^2, |Z1 - conj Z2|^2
             }
           }
         }
@@ -888,7 +571,9 @@ static int max_valid_frames(int win_len) {
   if (nv > kFramesOut) nv = kFramesOut;
   return (int)nv;
 }
-static int padded_valid(int win_len) { return ceil_div(max_valid_frames(win_len), kGroup) * kGroup; }
+// scratch row length: a multiple of 32 floats, so that every row starts on a 128-byte line (the finish drops whole
+// lines from L2 after reading them: a line shared by two rows would lose the other row's values)
+static int padded_valid(int win_len) { return ceil_div(max_valid_frames(win_len), 32) * 32; }
 
 }  // namespace segma
 
@@ -928,19 +613,14 @@ int segma_logmel(const float* pcm, int64_t pcm_len, int n_windows, int win_len, 
   SEGMA_REQUIRE(step >= 0 && pcm_len >= 0, "segma_logmel: negative step/pcm_len");
   SEGMA_REQUIRE(out_f32 || out_tm, "segma_logmel: no output requested");
   SEGMA_REQUIRE(n_windows <= 65535, "segma_logmel: at most 65535 windows per call");
+  SEGMA_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 127) == 0, "segma_logmel: scratch must be 128-byte aligned");
   int rc = ensure_tables();
   if (rc != SEGMA_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int nvp = padded_valid(win_len);
   const size_t head = ((size_t)n_windows * sizeof(uint32_t) + 255) / 256 * 256;
-  uint32_t* win_max = static_cast<uint32_t*>(scratch);
   float* logspec = reinterpret_cast<float*>(static_cast<char*>(scratch) + head);
-  const int groups = nvp / kGroup;
-  static const bool split = [] {
-    const char* e = std::getenv("SEGMA_LOGMEL_SPLIT");
-    return e && e[0] == '1';
-  }();
-  if (!split) {
+  {
     static PerDeviceFlag fused_attr;
     static int max_clusters[kMaxDevices];
     cudaLaunchConfig_t cfg = {};
@@ -968,31 +648,6 @@ int segma_logmel(const float* pcm, int64_t pcm_len, int n_windows, int win_len, 
     SEGMA_CUDA_OK(cudaLaunchKernelEx(&cfg, logmel_fused_kernel, pcm, (long long)pcm_len, win_len, (long long)step,
                                      n_windows, nvp, logspec, out_f32, static_cast<__half*>(out_tm)));
     return launch_status("logmel_fused_kernel");
-  }
-  SEGMA_CUDA_OK(cudaMemsetAsync(win_max, 0, (size_t)n_windows * sizeof(uint32_t), st));
-  const size_t smem = sizeof(float2) * kGroup * kHalf + sizeof(float) * std::max(kStage, kGroup * kBins) + sizeof(SmemTables);
-  static PerDeviceFlag attr_set;
-  if (!attr_set.here()) {
-    SEGMA_CUDA_OK(cudaFuncSetAttribute(logmel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set.here() = true;
-  }
-  const int grid_a = std::min(n_windows * groups, 4 * device_sm_count());
-  logmel_power_kernel<<<grid_a, kThreadsA, smem, st>>>(pcm, pcm_len, win_len, step, n_windows, groups, nvp, logspec,
-                                                       win_max);
-  rc = launch_status("logmel_power_kernel");
-  if (rc != SEGMA_OK) return rc;
-  if (out_f32) {
-    dim3 grid_b(ceil_div(kMels * kFramesOut / 4, 256 * 4), n_windows);
-    logmel_finish_f32_kernel<<<grid_b, 256, 0, st>>>(logspec, win_max, pcm_len, win_len, step, nvp, out_f32);
-    rc = launch_status("logmel_finish_f32_kernel");
-    if (rc != SEGMA_OK) return rc;
-  }
-  if (out_tm) {
-    dim3 grid_c(ceil_div(kFramesOut, kTmTile), n_windows);
-    logmel_finish_tm_kernel<<<grid_c, 256, 0, st>>>(logspec, win_max, pcm_len, win_len, step, nvp,
-                                                    static_cast<__half*>(out_tm));
-    rc = launch_status("logmel_finish_tm_kernel");
-    if (rc != SEGMA_OK) return rc;
   }
   return SEGMA_OK;
 }

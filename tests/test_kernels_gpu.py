@@ -320,6 +320,32 @@ def test_logmel_tail_and_silence(cuda, L):
     _logmel_close(f32[0], O.whisper_logmel(z), "all-zero window")
 
 
+@pytest.mark.parametrize("step,win", [(1601, 64000), (4000, 32000), (63680, 64000)])
+def test_logmel_many_windows_persistent_clusters(cuda, step, win):
+    """More windows than resident clusters (every cluster walks several windows and finishes window i behind the
+    transform of window i + 1), an odd window step (unaligned windows take the scalar staging path), and an audio
+    buffer that ends inside the batch: partial windows, then windows without any sample."""
+    n_w = 330 if step < 60000 else 40
+    n = step * (n_w - 6) + win // 3
+    pcm = torch.from_numpy(synth.synth_audio(n, 11))
+    dev = pcm.to(cuda)
+    f32, tm = ops.logmel(dev, n_w, win, step, out_f32=True, out_tm=True)
+    picks = sorted({0, 1, 2, 141, 142, 143, 200, n_w - 8, n_w - 7, n_w - 6, n_w - 5, n_w - 1} & set(range(n_w)))
+    for i in picks:
+        chunk = pcm[i * step: i * step + win]
+        if chunk.numel() >= 400:  # the oracle (like the reference) needs a full STFT frame
+            _logmel_close(f32[i], O.whisper_logmel(chunk), f"window {i} of {n_w}")
+        if chunk.numel() == 0:  # past the end of the audio: log10(1e-10) clamped and scaled
+            assert (f32[i] == -1.5).all()
+            continue
+        alone, _ = ops.logmel(dev[i * step:], 1, win, step)
+        assert torch.equal(alone[0], f32[i]), f"window {i}: batch position changes the result"
+    assert torch.equal(tm[:, 1:3001].float(), f32.transpose(1, 2).to(torch.float16).float())
+    assert (tm[:, 0] == 0).all() and (tm[:, 3001] == 0).all()
+    only_f32, _ = ops.logmel(dev, n_w, win, step)  # the scratch rows are dropped from L2 on this path
+    assert torch.equal(only_f32, f32)
+
+
 # ---- stitch + decode ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("F_,sf,nw,tail", [(199, 199, 5, 103), (199, 100, 7, 0), (99, 10, 12, 37), (399, 40, 3, 399)])
 def test_stitch(cuda, F_, sf, nw, tail):

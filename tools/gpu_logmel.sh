@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 timeout -k 5 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q -k "logmel or mel_filters" -p no:cacheprovider 2>&1 | tail -25 > gpurun_out/logmel_tests.log
 echo "== tests exit ${PIPESTATUS[0]}"; tail -25 gpurun_out/logmel_tests.log
-for n in 1024 128; do
+for n in 1024 1136 128; do
   echo "fused $n:"; timeout 120 python tools/run_logmel.py $n 2>&1 | tail -2
   echo "split $n:"; SEGMA_LOGMEL_SPLIT=1 timeout 120 python tools/run_logmel.py $n 2>&1 | tail -2
 done | tee gpurun_out/logmel_timing.txt

@@ -417,17 +417,40 @@ def measure_side_kernels(dev, ctx) -> dict:
     hbm_peak = float(_peaks().get("hbm_gbs", 6650.0))
     dev_pcm, cuts = ctx["dev_pcm"], ctx["cuts"]
 
-    def time_kernel(fn, iters=20):
+    def sm_clock():
+        try:
+            out = subprocess.run(["nvidia-smi", f"--id={dev.index or 0}", "--query-gpu=clocks.sm", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=5).stdout
+            return float(out.strip().splitlines()[0])
+        except Exception:  # noqa: BLE001
+            return None
+
+    clocks_seen = {}
+
+    def time_kernel(fn, iters=20, what=None):
+        """A kernel timed ALONE: the power governor moves the SM clock in steps tens of milliseconds apart, so a
+        measurement that follows the 1 kW model step directly would run at that step's clock (1.39-1.45 GHz) instead of
+        the kernel's own (`tools/logmel_clock_check.py`: the log-mel kernel takes 0.61-0.73 us per window right after
+        3 s of GEMMs and 0.49 from half a second later on, also over 200 launches in a row).  Hence a 1 s pause, a
+        warm-up, and at least 0.25 s of back-to-back launches; the SM clock at the end is reported."""
+        torch.cuda.synchronize()
+        time.sleep(1.0)
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / iters * 1e-3
+        total, n = 0.0, 0
+        while total < 0.25 and n < 50 * iters:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            total += e0.elapsed_time(e1) * 1e-3
+            n += iters
+        if what:
+            clocks_seen[what] = sm_clock()
+        return total / n
 
     side = {}
     lib = ops._lib()
@@ -438,11 +461,11 @@ def measure_side_kernels(dev, ctx) -> dict:
     out_f32 = torch.empty((n_w, 80, 3000), dtype=torch.float32, device=dev)
     scratch = torch.empty(ops.logmel_scratch_bytes(n_w, WIN), dtype=torch.uint8, device=dev)
     t_mel = time_kernel(lambda: lib.segma_logmel(pcm_side.data_ptr(), pcm_side.numel(), n_w, WIN, STEP_SAMPLES,
-                                                 out_f32.data_ptr(), None, scratch.data_ptr(), st))
+                                                 out_f32.data_ptr(), None, scratch.data_ptr(), st), what="logmel")
     mel_bytes = n_w * (4 * WIN + 4 * 80 * 3000)
     side["logmel"] = {"bound": "hbm", "achieved": mel_bytes / t_mel / 1e9, "peak": hbm_peak, "unit": "GB/s",
                       "frac": mel_bytes / t_mel / 1e9 / hbm_peak, "us_per_window": t_mel / n_w * 1e6,
-                      "algorithmic_bytes_per_window": 4 * WIN + 4 * 80 * 3000}
+                      "algorithmic_bytes_per_window": 4 * WIN + 4 * 80 * 3000, "sm_mhz": clocks_seen.get("logmel")}
     del out_f32, scratch
     # wav2vec2 / HuBERT / WavLM front end, layer 0: conv(k=10, s=5) + GroupNorm + GELU, 4*64000 B read and the
     # 2*12799*512 B fp16 activation written per window (SURVEY.md 8d counts the front end's HBM-bound part)
@@ -455,11 +478,11 @@ def measure_side_kernels(dev, ctx) -> dict:
     rows0 = (WIN - 10) // 5 + 1
     act = torch.zeros((n_l0, rows0 + (rows0 & 1), 512), dtype=torch.float16, device=dev)
     ss = torch.empty((n_l0, 512, 2), dtype=torch.float32, device=dev)
-    t_l0 = time_kernel(lambda: ops.w2v2_layer0(dev_pcm[:span0], n_l0, WIN, STEP_SAMPLES, w0, g0, b0, ss, act), iters=10)
+    t_l0 = time_kernel(lambda: ops.w2v2_layer0(dev_pcm[:span0], n_l0, WIN, STEP_SAMPLES, w0, g0, b0, ss, act), iters=10, what="l0")
     l0_bytes = n_l0 * (4 * WIN + 2 * rows0 * 512)
     side["w2v2_layer0"] = {"bound": "hbm", "achieved": l0_bytes / t_l0 / 1e9, "peak": hbm_peak, "unit": "GB/s",
                            "frac": l0_bytes / t_l0 / 1e9 / hbm_peak, "us_per_window": t_l0 / n_l0 * 1e6,
-                           "algorithmic_bytes_per_window": 4 * WIN + 2 * rows0 * 512}
+                           "algorithmic_bytes_per_window": 4 * WIN + 2 * rows0 * 512, "sm_mhz": clocks_seen.get("l0")}
     del act, ss
 
     def speech_like(n_fr):
@@ -525,7 +548,12 @@ def measure_corpus(args, rank: int, world: int, dev):
     model = Models[kind].from_state_dict(sd, le, cfg).to(dev)
     rng = np.random.default_rng(4)
     n_files = args.corpus_files
+    if args.corpus_hours > 0:  # full-size config 4: draw files until the corpus holds that many hours
+        n_files = max(64, int(args.corpus_hours * 3600.0 / (args.corpus_median_s * 1.7)))
     dur_s = np.clip(np.exp(rng.normal(np.log(args.corpus_median_s), 1.3, size=n_files)), min(10.0, args.corpus_median_s), 3600.0)
+    if args.corpus_hours > 0:
+        n_files = int(min(n_files, np.searchsorted(np.cumsum(dur_s), args.corpus_hours * 3600.0) + 1))
+        dur_s = dur_s[:n_files]
     lens = (dur_s * 16_000).astype(np.int64)
     pool = torch.from_numpy(synth.synth_audio(HOUR_SAMPLES, seed=0)).pin_memory()
     offs = rng.integers(0, HOUR_SAMPLES - lens + 1)
@@ -545,7 +573,7 @@ def measure_corpus(args, rank: int, world: int, dev):
         t0 = time.perf_counter()
         e0.record()
         for _ in range(k):
-            out = infer_corpus(files, model, cfg, BATCH, dev, shard=(rank, world), sizes=lens.tolist())
+            out = infer_corpus(files, model, cfg, BATCH, dev, shard=(rank, world), sizes=lens[:len(files)].tolist())
             if to_host:
                 out = out.cpu()
         e1.record()
@@ -556,7 +584,8 @@ def measure_corpus(args, rank: int, world: int, dev):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms[0].item() / 1e3, ms[1].item() / 1e3, out
 
-    timed(dev_files, max(1, min(args.warmup, 1)), False)
+    # one warm-up pass; a corpus of hundreds of hours warms up on its first 256 files
+    timed(dev_files[:256] if args.corpus_hours > 0 else dev_files, max(1, min(args.warmup, 1)), False)
     with ClockSampler(dev.index or 0) as clocks:
         ops.stats.reset()
         dev_s, _, table = timed(dev_files, args.steps, False)
@@ -688,6 +717,8 @@ def main():
                     help="whisper = BASELINE config 2 (the headline, also reports hubert / wavlm = configs 1 and 3 under "
                          "'workloads'); corpus = config 4 in miniature (file-sharded, strong scaling)")
     ap.add_argument("--corpus-files", type=int, default=256, help="files in the corpus workload")
+    ap.add_argument("--corpus-hours", type=float, default=0.0,
+                    help="size the corpus by its total duration instead (1000 = BASELINE config 4 as stated)")
     ap.add_argument("--corpus-model", default="whisper", choices=sorted(WORKLOADS), help="model of the corpus workload")
     ap.add_argument("--corpus-median-s", type=float, default=150.0, help="median file duration of the corpus workload")
     ap.add_argument("--no-side-kernels", action="store_true", help="skip the front-end / decode roofline measurements")
@@ -706,7 +737,8 @@ def main():
                    "--master-addr", "127.0.0.1", "--master-port", "29511", str(Path(__file__).resolve()),
                    "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
                    "--hours", str(args.hours), "--workload", args.workload, "--corpus-files", str(args.corpus_files),
-                   "--corpus-model", args.corpus_model, "--corpus-median-s", str(args.corpus_median_s)]
+                   "--corpus-model", args.corpus_model, "--corpus-median-s", str(args.corpus_median_s),
+                   "--corpus-hours", str(args.corpus_hours)]
             sys.exit(subprocess.call(cmd))
         run_gpu(args)
 

@@ -143,7 +143,8 @@ constexpr int kStageWords = kStageChunks * kChunkPad;
 constexpr int kEL = 21;                        // exchange rows [c][b], odd stride: pass 2 reads columns conflict-free
 constexpr int kEP = 20 * kEL;                  // 420 = 4 mod 16: the 8 pairs of a warp fall on distinct 8-byte banks
 constexpr int kZP = 404;                       // spectrum of a pair, natural order, same residue
-constexpr int kPP = kBins;                     // (P_A, P_B)[k] of a pair
+constexpr int kPP = kBins + 1;                 // (P_A, P_B)[k] of a pair; 4 kPP = 8 mod 16: the two pair groups of a
+                                               // mel filter fall on different banks
 constexpr int kTmTileF = 32;
 constexpr int kR1Bytes = kPairs * kEP * 8;     // stage / exchange / spectrum / transpose tile share one region
 static_assert(kPairs * kZP * 8 <= kR1Bytes && kMels * (kTmTileF + 1) * 4 <= kR1Bytes,

@@ -37,7 +37,8 @@ struct MelTables {
   int mel_k0[kMels];
   int mel_len[kMels];
   float mel_w[kMels][kMaxTaps];
-  float2 tw20[20][20];             // [c][b] = exp(-2 pi i b c / 400): twiddle between the two radix-20 passes
+  float2 tw_b1[20], tw_b4[20];     // exp(-2 pi i b / 400) and its fourth power: the twiddles W400^{b c} between the
+                                   // two radix-20 passes are products of these
   float2 mel_w2[kMels][kMaxTaps];  // (w / 4, w / 4): filter taps for a pair of frames (the 1/4 of the unpacked power)
 };
 
@@ -96,9 +97,10 @@ static int upload_tables_locked() {
       h.mel_w2[m][i] = make_float2(0.25f * h.mel_w[m][i], 0.25f * h.mel_w[m][i]);
     }
   }
-  for (int c = 0; c < 20; ++c)
-    for (int b = 0; b < 20; ++b)
-      h.tw20[c][b] = make_float2((float)std::cos(two_pi * (b * c) / kNfft), (float)-std::sin(two_pi * (b * c) / kNfft));
+  for (int b = 0; b < 20; ++b) {
+    h.tw_b1[b] = make_float2((float)std::cos(two_pi * b / kNfft), (float)-std::sin(two_pi * b / kNfft));
+    h.tw_b4[b] = make_float2((float)std::cos(two_pi * 4 * b / kNfft), (float)-std::sin(two_pi * 4 * b / kNfft));
+  }
   SEGMA_CUDA_OK(cudaMemcpyToSymbol(g_tab, &h, sizeof(h)));
   g_tab_ready.here() = true;
   return SEGMA_OK;
@@ -151,7 +153,8 @@ static_assert(kPairs * kZP * 8 <= kR1Bytes && kMels * (kTmTileF + 1) * 4 <= kR1B
               "shared region too small");
 static_assert(kMels % kCl == 0 && kThreadsF % 20 == 0, "row split");
 static_assert(kR1Bytes % 16 == 0 && (kStageWords * 4) % 16 == 0, "shared-memory carve-up alignment");
-constexpr int kFusedSmem = kR1Bytes + kStageWords * 4 + kPairs * kPP * 8 + kNfft * 4 + 400 * 8;  // + Hann, twiddles
+constexpr int kMelTapsSmem = 15;  // the slaney bank has at most 14 taps per filter; wider banks read global memory
+constexpr int kFusedSmem = kR1Bytes + kStageWords * 4 + kPairs * kPP * 8 + kMels * kMelTapsSmem * 4;
 
 // Complex numbers as packed fp32 pairs (re, im): additions, real scalings and fused multiply-adds of a whole complex
 // number are one FADD2 / FMUL2 / FFMA2 (two fp32 lanes per issue slot on sm_100); multiplications by -i are written on
@@ -297,13 +300,15 @@ __device__ __forceinline__ void finish_window(int win, uint32_t rank, int tid, i
     // frames that touch audio: clamp and scale what the cluster left in the scratch (four rows in flight per thread)
     for (int q = tid; q < nq; q += kThreadsF) {
       const int t = 4 * q;
+      constexpr int kInFlight = 4;  // rows per thread in flight
+      static_assert(kRows % kInFlight == 0, "rows per CTA");
 #pragma unroll 1
-      for (int row = 0; row < kRows; row += 4) {
-        float4 x[4];
+      for (int row = 0; row < kRows; row += kInFlight) {
+        float4 x[kInFlight];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) x[i] = __ldcg(src + (row + i) * nvq + q);
+        for (int i = 0; i < kInFlight; ++i) x[i] = __ldcg(src + (row + i) * nvq + q);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < kInFlight; ++i) {
           float4 r = make_float4(fill, fill, fill, fill);
           r.x = (fmaxf(x[i].x, floor_v) + 4.0f) / 4.0f;
           if (t + 1 < n_valid) r.y = (fmaxf(x[i].y, floor_v) + 4.0f) / 4.0f;
@@ -315,7 +320,7 @@ __device__ __forceinline__ void finish_window(int win, uint32_t rank, int tid, i
         // rows are whole lines (nvp % 32 == 0) and belong to one CTA
         if (!out_tm && (q & 7) == 0) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) l2_discard_128(src + (row + i) * nvq + q);
+          for (int i = 0; i < kInFlight; ++i) l2_discard_128(src + (row + i) * nvq + q);
         }
       }
     }
@@ -378,8 +383,7 @@ __global__ void __launch_bounds__(kThreadsF, 4) logmel_fused_kernel(const float*
   unsigned char* r1 = fused_smem;                                        // exchange rows / spectrum / transpose tile
   float* stage = reinterpret_cast<float*>(fused_smem + kR1Bytes);
   float2* P2 = reinterpret_cast<float2*>(fused_smem + kR1Bytes + kStageWords * 4);
-  float* s_hann = reinterpret_cast<float*>(fused_smem + kR1Bytes + kStageWords * 4 + kPairs * kPP * 8);
-  float2* s_tw = reinterpret_cast<float2*>(s_hann + kNfft);
+  float* s_melw = reinterpret_cast<float*>(fused_smem + kR1Bytes + kStageWords * 4 + kPairs * kPP * 8);
   __shared__ float s_red[kThreadsF / 32];
   __shared__ float s_cmax[3];  // maxima of three windows in flight (a peer may be one transform ahead)
   float2* E = reinterpret_cast<float2*>(r1);
@@ -389,13 +393,16 @@ __global__ void __launch_bounds__(kThreadsF, 4) logmel_fused_kernel(const float*
   const int n_clusters = gridDim.x / kCl;
   const int p = tid / 20, b = tid - 20 * p;   // pass 1: (pair, b); pass 2: (pair, c = b)
 
-  for (int i = tid; i < kNfft; i += kThreadsF) s_hann[i] = g_tab.hann[i];
-  for (int i = tid; i < 400; i += kThreadsF) s_tw[i] = g_tab.tw20[i / 20][i % 20];
+  // the mel taps sit in shared memory (their loads head a dependent chain); the Hann window comes through L1 and the
+  // twiddles are computed: the LSU is the busiest pipe of this kernel
+  for (int i = tid; i < kMels * kMelTapsSmem; i += kThreadsF) s_melw[i] = g_tab.mel_w2[i / kMelTapsSmem][i % kMelTapsSmem].x;
+  const bool wide_bank = __ldg(g_tab.mel_len + (tid >> 1)) > kMelTapsSmem;
   // mel filter of this thread in step 5: filter m for the group's pairs 4 h .. 4 h + 3
   const int mel_m = tid >> 1, mel_h = tid & 1;
   const int mel_k0 = __ldg(g_tab.mel_k0 + mel_m), mel_len = __ldg(g_tab.mel_len + mel_m);
   const float2* mel_w = g_tab.mel_w2[mel_m];
   const uint64_t keep_policy = l2_keep_policy();
+  const float2 tw_b1 = __ldg(&g_tab.tw_b1[b]), tw_b4 = __ldg(&g_tab.tw_b4[b]);
   __syncthreads();
 
   int prev_win = -1, slot = 0;
@@ -431,28 +438,29 @@ __global__ void __launch_bounds__(kThreadsF, 4) logmel_fused_kernel(const float*
 #pragma unroll
         for (int a = 0; a < 20; ++a) {
           const int off = 20 * a + 10 * (a >> 3);  // sample 20 a + b of the frame: chunk a / 8 (b < 20)
-          const float h = s_hann[20 * a + b];
+          const float h = __ldg(g_tab.hann + 20 * a + b);
           v[a] = cpx_make(sa[off] * h, sa[off + kChunkPad] * h);
         }
         dft20(v);
         float2* e = E + p * kEP + b;
         e[0] = cpx_f2(v[0]);
-        // twiddles are read in batches ahead of the stores (both live in shared memory: the compiler keeps a load
-        // behind every earlier store, which would put one full load latency in front of each product)
+        // twiddles W400^{b c} = w^c, w = W400^b, from two table values (w, w^4) by at most three further products
+        // (c = 4 g + r: w^c = (w^4)^g w^r): the LSU is the busiest pipe of this kernel, the FMA pipes are at 15 %
+        const float2 wr[4] = {make_float2(1.f, 0.f), tw_b1, cmul(tw_b1, tw_b1), cmul(cmul(tw_b1, tw_b1), tw_b1)};
+        const float2 w8 = cmul(tw_b4, tw_b4);
+        const float2 wg[5] = {make_float2(1.f, 0.f), tw_b4, w8, cmul(w8, tw_b4), cmul(w8, w8)};
 #pragma unroll
-        for (int c0 = 1; c0 < 20; c0 += 5) {
-          float2 tw[5];
-#pragma unroll
-          for (int j = 0; j < 5; ++j)
-            if (c0 + j < 20) tw[j] = s_tw[(c0 + j) * 20 + b];
-#pragma unroll
-          for (int j = 0; j < 5; ++j)
-            if (c0 + j < 20) e[(c0 + j) * kEL] = cmul(cpx_f2(v[c0 + j]), tw[j]);
+        for (int c = 1; c < 20; ++c) {
+          const int g = c >> 2, r = c & 3;
+          const float2 tw = g == 0 ? wr[r] : (r == 0 ? wg[g] : cmul(wg[g], wr[r]));
+          e[c * kEL] = cmul(cpx_f2(v[c]), tw);
         }
       }
       __syncthreads();
       // every thread has its samples: the next group's may land (in flight until the barrier behind step 3)
-      if (pair0 + kPairs < pair_hi) stage_group(stage, w, (long long)kHop * (t0 + kGroup) - 200, avail, aligned8, tid);
+      const bool more = pair0 + kPairs < pair_hi;
+      const long long s_next = (long long)kHop * (t0 + kGroup) - 200;
+      if (more) stage_group(stage, w, s_next, avail, aligned8, tid);
       // 2. pass 2: DFT over b of row c, written back over the same row: Z[pair][c][d] is bin c + 20 d
       if (pair_on) {
         cpx v[20];
@@ -500,7 +508,8 @@ __global__ void __launch_bounds__(kThreadsF, 4) logmel_fused_kernel(const float*
         const float2* pq = P2 + 4 * mel_h * kPP + mel_k0;
 #pragma unroll 2
         for (int i = 0; i < mel_len; ++i) {
-          const float2 wv = __ldg(mel_w + i);
+          const float wsc = wide_bank ? __ldg(mel_w + i).x : s_melw[mel_m * kMelTapsSmem + i];
+          const float2 wv = make_float2(wsc, wsc);
           const uint64_t w2 = f2_pack(wv.x, wv.y);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {

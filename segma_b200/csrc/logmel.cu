@@ -236,6 +236,11 @@ __device__ __forceinline__ uint64_t l2_keep_policy() {
 __device__ __forceinline__ void st_f32x2_keep(float* p, float a, float b, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(a), "f"(b), "l"(pol) : "memory");
 }
+__device__ __forceinline__ void st_f32x8_keep(float* p, const float (&v)[8], uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;" ::"l"(p), "f"(v[0]), "f"(v[1]),
+               "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void l2_discard_128(const void* p) {
   asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
 }
@@ -518,18 +523,29 @@ __global__ void __launch_bounds__(kThreadsF, 4) logmel_fused_kernel(const float*
           }
         }
         float* dst = ls + (long long)mel_m * nvp + t0 + 8 * mel_h;
+        float lv[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (4 * mel_h + j < np) {
-            float ma, mb;
-            f2_unpack(acc[j], ma, mb);
-            const float va = 0.30102999566398120f * __log2f(fmaxf(ma, 1e-10f));  // log10
-            const float vb = 0.30102999566398120f * __log2f(fmaxf(mb, 1e-10f));
-            SEGMA_DEV_ASSERT(win < n_windows && t0 + 8 * mel_h + 2 * j + 1 < nvp);
-            // a window's last pair may end one frame past n_valid: that frame is all zeros (-10, which the maximum
-            // contains anyway whenever n_valid < 3000) and the finish never reads it
-            st_f32x2_keep(dst + 2 * j, va, vb, keep_policy);
-            local_max = fmaxf(local_max, fmaxf(va, vb));
+          float ma, mb;
+          f2_unpack(acc[j], ma, mb);
+          lv[2 * j] = 0.30102999566398120f * __log2f(fmaxf(ma, 1e-10f));  // log10
+          lv[2 * j + 1] = 0.30102999566398120f * __log2f(fmaxf(mb, 1e-10f));
+        }
+        SEGMA_DEV_ASSERT(win < n_windows && t0 + 8 * mel_h + 7 < nvp);
+        // a window's last pair may end one frame past n_valid: that frame is all zeros (-10, which the maximum
+        // contains anyway whenever n_valid < 3000) and the finish never reads it
+        if (4 * mel_h + 3 < np) {
+          // the thread's eight frames are one 32-byte sector of the row: one 256-bit store
+          st_f32x8_keep(dst, lv, keep_policy);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) local_max = fmaxf(local_max, lv[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (4 * mel_h + j < np) {
+              st_f32x2_keep(dst + 2 * j, lv[2 * j], lv[2 * j + 1], keep_policy);
+              local_max = fmaxf(local_max, fmaxf(lv[2 * j], lv[2 * j + 1]));
+            }
           }
         }
       }

@@ -12,6 +12,7 @@
 // log, and keeps the unclamped values in an L2-resident scratch; the cluster's maxima meet through distributed shared
 // memory and each CTA then writes a quarter of the window -- clamp, scale, constant tail, optionally also the fp16
 // time-major tile the conv-stem GEMM consumes -- while the cluster already transforms its next window.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -36,6 +37,7 @@ struct MelTables {
   float hann[kNfft];
   int mel_k0[kMels];
   int mel_len[kMels];
+  int mel_order[kMels];            // filter of slot s: eight slots in a row have first bins that differ mod 8
   float mel_w[kMels][kMaxTaps];
   float2 tw_b1[20], tw_b4[20];     // exp(-2 pi i b / 400) and its fourth power: the twiddles W400^{b c} between the
                                    // two radix-20 passes are products of these
@@ -97,6 +99,31 @@ static int upload_tables_locked() {
       h.mel_w2[m][i] = make_float2(0.25f * h.mel_w[m][i], 0.25f * h.mel_w[m][i]);
     }
   }
+  // Step 4 of the kernel gives slot s = tid / 2 the filter mel_order[s]; the 8 filters x 2 pair groups of a half-warp
+  // read (P_A, P_B)[k0 + i] in lockstep and collide on an 8-byte bank iff two first bins agree mod 8.  Filters stay
+  // sorted by length (a warp's 16 filters run as long as its longest), but each run of eight is picked, among the next
+  // few candidates, with distinct k0 mod 8.
+  {
+    std::vector<int> cand(kMels);
+    for (int m = 0; m < kMels; ++m) cand[m] = m;
+    std::stable_sort(cand.begin(), cand.end(), [&](int a, int b2) { return h.mel_len[a] < h.mel_len[b2]; });
+    std::vector<bool> used(kMels, false);
+    int n_out = 0;
+    for (int first = 0; first < kMels; ++first) {
+      if (used[first]) continue;
+      bool res[8] = {};
+      int in_group = 0;
+      for (int pass = 0; pass < 2 && in_group < 8; ++pass)
+        for (int c = first; c < std::min(kMels, first + 24) && in_group < 8; ++c) {
+          const int m = cand[c];
+          if (used[c] || (pass == 0 && res[h.mel_k0[m] & 7])) continue;
+          used[c] = true;
+          res[h.mel_k0[m] & 7] = true;
+          h.mel_order[n_out++] = m;
+          ++in_group;
+        }
+    }
+  }
   for (int b = 0; b < 20; ++b) {
     h.tw_b1[b] = make_float2((float)std::cos(two_pi * b / kNfft), (float)-std::sin(two_pi * b / kNfft));
     h.tw_b4[b] = make_float2((float)std::cos(two_pi * 4 * b / kNfft), (float)-std::sin(two_pi * 4 * b / kNfft));
@@ -152,6 +179,7 @@ constexpr int kR1Bytes = kPairs * kEP * 8;     // stage / exchange / spectrum / 
 static_assert(kPairs * kZP * 8 <= kR1Bytes && kMels * (kTmTileF + 1) * 4 <= kR1Bytes,
               "shared region too small");
 static_assert(kMels % kCl == 0 && kThreadsF % 20 == 0, "row split");
+static_assert(kThreadsF == 160 && kBins == 201, "bin mapping of the power pass");
 static_assert(kR1Bytes % 16 == 0 && (kStageWords * 4) % 16 == 0, "shared-memory carve-up alignment");
 constexpr int kMelTapsSmem = 15;  // the slaney bank has at most 14 taps per filter; wider banks read global memory
 constexpr int kFusedSmem = kR1Bytes + kStageWords * 4 + kPairs * kPP * 8 + kMels * kMelTapsSmem * 4;
@@ -401,9 +429,9 @@ __global__ void __launch_bounds__(kThreadsF, 4) logmel_fused_kernel(const float*
   // the mel taps sit in shared memory (their loads head a dependent chain); the Hann window comes through L1 and the
   // twiddles are computed: the LSU is the busiest pipe of this kernel
   for (int i = tid; i < kMels * kMelTapsSmem; i += kThreadsF) s_melw[i] = g_tab.mel_w2[i / kMelTapsSmem][i % kMelTapsSmem].x;
-  const bool wide_bank = __ldg(g_tab.mel_len + (tid >> 1)) > kMelTapsSmem;
-  // mel filter of this thread in step 5: filter m for the group's pairs 4 h .. 4 h + 3
-  const int mel_m = tid >> 1, mel_h = tid & 1;
+  // mel filter of this thread in step 4: filter m for the group's pairs 4 h .. 4 h + 3
+  const int mel_m = __ldg(g_tab.mel_order + (tid >> 1)), mel_h = tid & 1;
+  const bool wide_bank = __ldg(g_tab.mel_len + mel_m) > kMelTapsSmem;
   const int mel_k0 = __ldg(g_tab.mel_k0 + mel_m), mel_len = __ldg(g_tab.mel_len + mel_m);
   const float2* mel_w = g_tab.mel_w2[mel_m];
   const uint64_t keep_policy = l2_keep_policy();
@@ -477,11 +505,13 @@ __global__ void __launch_bounds__(kThreadsF, 4) logmel_fused_kernel(const float*
         for (int d = 0; d < 20; ++d) e[d] = cpx_f2(v[d]);
       }
       __syncthreads();
-      // 3. separate the two frames and take the powers (times 4): thread k for every pair, then bins 160..200
+      // 3. separate the two frames and take the powers (times 4).  Bin k = c + 20 d sits at row c, column d: sixteen
+      //    lanes share d and take c = 0..15 (8-byte bank 5 c + d: conflict-free, also for the mirrored bin); the bins
+      //    with c >= 16 and bin 200 make up a second, short round
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        const int k = tid + half * kThreadsF;
-        if (k < kBins) {
+        const int k = half == 0 ? (tid & 15) + 20 * (tid >> 4) : (tid < 40 ? 16 + (tid & 3) + 20 * (tid >> 2) : 200);
+        if (half == 0 || tid <= 40) {
           const int k2 = k == 0 ? 0 : kNfft - k;
           const float2* z1p = Z + (k % 20) * kEL + k / 20;
           const float2* z2p = Z + (k2 % 20) * kEL + k2 / 20;

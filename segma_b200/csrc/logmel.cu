@@ -31,13 +31,13 @@ constexpr int kFramesOut = SEGMA_MEL_FRAMES;
 constexpr int kPadSamples = 480000;  // 30 s
 constexpr int kGroup = 16;           // frames per work item: 8 frame pairs x 20 threads
 constexpr int kMaxTaps = 32;         // max contiguous FFT bins per mel filter
+constexpr int kMelTapsSmem = 15;     // taps per filter kept in shared memory (the slaney bank has at most 14; wider banks read global memory)
 constexpr int kStage = (kGroup - 1) * kHop + kNfft;  // 2800 staged samples per group
 
 struct MelTables {
   float hann[kNfft];
   int mel_k0[kMels];
   int mel_len[kMels];
-  int mel_order[kMels];            // filter of slot s: eight slots in a row have first bins that differ mod 8
   float mel_w[kMels][kMaxTaps];
   float2 tw_b1[20], tw_b4[20];     // exp(-2 pi i b / 400) and its fourth power: the twiddles W400^{b c} between the
                                    // two radix-20 passes are products of these
@@ -99,29 +99,38 @@ static int upload_tables_locked() {
       h.mel_w2[m][i] = make_float2(0.25f * h.mel_w[m][i], 0.25f * h.mel_w[m][i]);
     }
   }
-  // Step 4 of the kernel gives slot s = tid / 2 the filter mel_order[s]; the 8 filters x 2 pair groups of a half-warp
-  // read (P_A, P_B)[k0 + i] in lockstep and collide on an 8-byte bank iff two first bins agree mod 8.  Filters stay
-  // sorted by length (a warp's 16 filters run as long as its longest), but each run of eight is picked, among the next
-  // few candidates, with distinct k0 mod 8.
-  {
-    std::vector<int> cand(kMels);
-    for (int m = 0; m < kMels; ++m) cand[m] = m;
-    std::stable_sort(cand.begin(), cand.end(), [&](int a, int b2) { return h.mel_len[a] < h.mel_len[b2]; });
-    std::vector<bool> used(kMels, false);
-    int n_out = 0;
-    for (int first = 0; first < kMels; ++first) {
-      if (used[first]) continue;
-      bool res[8] = {};
-      int in_group = 0;
-      for (int pass = 0; pass < 2 && in_group < 8; ++pass)
-        for (int c = first; c < std::min(kMels, first + 24) && in_group < 8; ++c) {
-          const int m = cand[c];
-          if (used[c] || (pass == 0 && res[h.mel_k0[m] & 7])) continue;
-          used[c] = true;
-          res[h.mel_k0[m] & 7] = true;
-          h.mel_order[n_out++] = m;
-          ++in_group;
+  // Step 4 of the kernel: the 8 filters x 2 pair groups of a half-warp read (P_A, P_B)[k0 + i] in lockstep and collide on
+  // an 8-byte bank iff two first bins agree mod 8 (the log-spaced filters do, often).  A filter may start up to a few
+  // bins early with zero taps in front -- free while it stays within its warp's longest filter (+ 1) -- which moves
+  // its bank: longest filters first, each takes the smallest shift that gives it an unused residue.
+  for (int w0 = 0; w0 < kMels; w0 += 16) {
+    int longest = 0;
+    for (int m = w0; m < std::min(kMels, w0 + 16); ++m) longest = std::max(longest, h.mel_len[m]);
+    for (int g0 = w0; g0 < std::min(kMels, w0 + 16); g0 += 8) {
+      int ms[8], n = 0;
+      for (int m = g0; m < std::min(kMels, g0 + 8); ++m) ms[n++] = m;
+      std::stable_sort(ms, ms + n, [&](int a, int b2) { return h.mel_len[a] > h.mel_len[b2]; });
+      bool used[8] = {};
+      for (int i = 0; i < n; ++i) {
+        const int m = ms[i];
+        const int smax = std::min({h.mel_k0[m], longest + 1 - h.mel_len[m], kMelTapsSmem - h.mel_len[m]});
+        int shift = 0;
+        for (int sft = 0; sft <= smax; ++sft)
+          if (!used[(h.mel_k0[m] - sft) & 7]) { shift = sft; break; }
+        if (shift > 0) {
+          for (int t = h.mel_len[m] - 1; t >= 0; --t) {
+            h.mel_w[m][t + shift] = h.mel_w[m][t];
+            h.mel_w2[m][t + shift] = h.mel_w2[m][t];
+          }
+          for (int t = 0; t < shift; ++t) {
+            h.mel_w[m][t] = 0.f;
+            h.mel_w2[m][t] = make_float2(0.f, 0.f);
+          }
+          h.mel_k0[m] -= shift;
+          h.mel_len[m] += shift;
         }
+        used[h.mel_k0[m] & 7] = true;
+      }
     }
   }
   for (int b = 0; b < 20; ++b) {
@@ -181,7 +190,6 @@ static_assert(kPairs * kZP * 8 <= kR1Bytes && kMels * (kTmTileF + 1) * 4 <= kR1B
 static_assert(kMels % kCl == 0 && kThreadsF % 20 == 0, "row split");
 static_assert(kThreadsF == 160 && kBins == 201, "bin mapping of the power pass");
 static_assert(kR1Bytes % 16 == 0 && (kStageWords * 4) % 16 == 0, "shared-memory carve-up alignment");
-constexpr int kMelTapsSmem = 15;  // the slaney bank has at most 14 taps per filter; wider banks read global memory
 constexpr int kFusedSmem = kR1Bytes + kStageWords * 4 + kPairs * kPP * 8 + kMels * kMelTapsSmem * 4;
 
 // Complex numbers as packed fp32 pairs (re, im): additions, real scalings and fused multiply-adds of a whole complex
@@ -430,7 +438,7 @@ __global__ void __launch_bounds__(kThreadsF, 4) logmel_fused_kernel(const float*
   // twiddles are computed: the LSU is the busiest pipe of this kernel
   for (int i = tid; i < kMels * kMelTapsSmem; i += kThreadsF) s_melw[i] = g_tab.mel_w2[i / kMelTapsSmem][i % kMelTapsSmem].x;
   // mel filter of this thread in step 4: filter m for the group's pairs 4 h .. 4 h + 3
-  const int mel_m = __ldg(g_tab.mel_order + (tid >> 1)), mel_h = tid & 1;
+  const int mel_m = tid >> 1, mel_h = tid & 1;
   const bool wide_bank = __ldg(g_tab.mel_len + mel_m) > kMelTapsSmem;
   const int mel_k0 = __ldg(g_tab.mel_k0 + mel_m), mel_len = __ldg(g_tab.mel_len + mel_m);
   const float2* mel_w = g_tab.mel_w2[mel_m];

@@ -268,7 +268,7 @@ def _traffic():
     """DRAM bytes per launch of the dominant kernel from this round's ``ncu --set full`` capture (ncu cannot run inside
     the bench; tools/ncu_full_summary.py writes the file from the capture of the same command)."""
     try:
-        return json.loads((ROOT / "profiles" / "r02_gemm_traffic.json").read_text())
+        return json.loads((ROOT / "profiles" / "r02z_gemm_traffic.json").read_text())
     except Exception:  # noqa: BLE001
         return None
 

@@ -654,9 +654,12 @@ size_t segma_logmel_scratch_bytes(int n_windows, int win_len) {
 int segma_logmel_set_filters(const float* mel_201x80) {
   SEGMA_REQUIRE(mel_201x80 != nullptr, "segma_logmel_set_filters: NULL matrix");
   std::lock_guard<std::mutex> lock(g_tab_mutex);
+  std::vector<float> previous = g_mel_dense;
   g_mel_dense.assign(mel_201x80, mel_201x80 + (size_t)kBins * kMels);
   for (bool& ready : g_tab_ready.done) ready = false;  // other devices pick the new filterbank up on their next call
-  return upload_tables_locked();
+  const int rc = upload_tables_locked();
+  if (rc != SEGMA_OK) g_mel_dense = previous;  // a rejected bank leaves the active one in place (re-uploaded on the next call)
+  return rc;
 }
 
 int segma_logmel_get_filters(float* mel_201x80) {

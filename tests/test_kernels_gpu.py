@@ -346,6 +346,34 @@ def test_logmel_many_windows_persistent_clusters(cuda, step, win):
     assert torch.equal(only_f32, f32)
 
 
+def test_logmel_custom_filterbank(cuda):
+    """`segma_logmel_set_filters`: a bank with filters wider than the 15 taps the kernel keeps in shared memory (those
+    read their taps from global memory), an empty filter and single-bin filters; then back to the built-in bank."""
+    default = ops.mel_filters()
+    rng = np.random.default_rng(3)
+    bank = np.zeros((201, 80), dtype=np.float32)
+    for m in range(80):
+        width = [1, 2, 7, 15, 16, 23, 32][m % 7]
+        lo = int(rng.integers(0, 201 - width + 1))
+        bank[lo:lo + width, m] = rng.uniform(0.01, 0.05, size=width).astype(np.float32)
+    bank[:, 5] = 0.0  # a filter without any bin: log10 of the 1e-10 floor
+    pcm = torch.from_numpy(synth.synth_audio(63680 + 64000, 9))
+    try:
+        ops.set_mel_filters(bank)
+        assert np.array_equal(ops.mel_filters(), bank)
+        f32, _ = ops.logmel(pcm.to(cuda), 2, 64000, 63680)
+        for i in range(2):
+            _logmel_close(f32[i], O.whisper_logmel(pcm[i * 63680: i * 63680 + 64000], bank), f"custom bank, window {i}")
+        too_wide = bank.copy()
+        too_wide[0:40, 7] = 0.01
+        with pytest.raises(Exception):
+            ops.set_mel_filters(too_wide)
+    finally:
+        ops.set_mel_filters(default)
+    f32, _ = ops.logmel(pcm.to(cuda), 1, 64000, 63680)
+    _logmel_close(f32[0], O.whisper_logmel(pcm[:64000]), "built-in bank restored")
+
+
 # ---- stitch + decode ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("F_,sf,nw,tail", [(199, 199, 5, 103), (199, 100, 7, 0), (99, 10, 12, 37), (399, 40, 3, 399)])
 def test_stitch(cuda, F_, sf, nw, tail):

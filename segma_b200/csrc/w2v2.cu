@@ -97,14 +97,21 @@ __global__ void __launch_bounds__(kStatsThreads) w2v2_l0_stats_kernel(
 }
 
 constexpr int kL0TimeTile = 64;
-constexpr int kL0Threads = 256;
+constexpr int kL0Threads = 128;
+constexpr int kL0Row = 12;  // floats staged per time step: x[5 t .. 5 t + 9] and two of padding (48-byte rows: aligned vector loads)
 
-// out[b][t][c] = gelu(conv(x)[t][c] * scale + shift) as fp16, time-major with `out_rows` rows per window
+// out[b][t][c] = gelu(conv(x)[t][c] * scale + shift) as fp16, time-major with `out_rows` rows per window.
+// The kernel is issue bound (ncu: 72 % of the issue slots, ALU 38 % / XU 37 % / FMA 30 %), so what counts is instructions
+// per output: a thread owns FOUR channels (two packed fp32 pairs: the taps are FFMA2 with the sample as a broadcast scalar
+// operand, the affine and the GELU run on pairs), every time step's ten samples arrive as two 128-bit and one 64-bit
+// broadcast load for all four, the four fp16 results leave as one 64-bit store (a warp writes 256 contiguous bytes), and
+// the time loop advances two pointers -- 16.5 instructions per output against 31 with one pair per thread and per-step
+// index arithmetic.
 __global__ void __launch_bounds__(kL0Threads) w2v2_l0_apply_kernel(
     const float* __restrict__ pcm, long long pcm_len, int win_len, long long step,
     const long long* __restrict__ win_offsets, const float* __restrict__ w,
     const float2* __restrict__ scale_shift, int C, __half* __restrict__ out, int out_rows) {
-  __shared__ float s_x[kL0TimeTile * kL0S + kL0K];
+  __shared__ __align__(16) float s_x[kL0TimeTile * kL0Row];
   const int win = blockIdx.y;
   const int t0 = blockIdx.x * kL0TimeTile;
   const long long w_off = win_offsets ? win_offsets[win] : (long long)win * step;
@@ -112,88 +119,113 @@ __global__ void __launch_bounds__(kL0Threads) w2v2_l0_apply_kernel(
   if (avail > win_len) avail = win_len;
   const int T0 = avail >= kL0K ? (int)((avail - kL0K) / kL0S + 1) : 0;
   const float* x = pcm + w_off;
-  for (int i = threadIdx.x; i < kL0TimeTile * kL0S + kL0K; i += kL0Threads) {
-    const long long n = (long long)t0 * kL0S + i;
-    s_x[i] = n < avail ? __ldg(x + n) : 0.f;
+  for (int i = threadIdx.x; i < kL0TimeTile * kL0Row; i += kL0Threads) {
+    const int tt = i / kL0Row, j = i - tt * kL0Row;
+    const long long n = (long long)(t0 + tt) * kL0S + j;
+    s_x[i] = (j < kL0K && n < avail) ? __ldg(x + n) : 0.f;
   }
   __syncthreads();
-  __half* o = out + (long long)win * out_rows * C;
-  for (int c2 = threadIdx.x; c2 < C / 2; c2 += kL0Threads) {
-    const int c = c2 * 2;
-    // the two channels ride in one packed fp32 pair: FFMA2 for the taps and the affine, gelu_erf_pair for the GELU
-    uint64_t w2[kL0K];
+  const int n_rows = min(kL0TimeTile, out_rows - t0);           // rows of this tile that exist
+  const int n_live = max(0, min(kL0TimeTile, T0 - t0));         // of which conv outputs (the rest is zero padding)
+  for (int c = 4 * threadIdx.x; c < C; c += 4 * kL0Threads) {
+    uint64_t wa[kL0K], wb[kL0K];  // taps of the channel pairs (c, c + 1) and (c + 2, c + 3)
 #pragma unroll
-    for (int j = 0; j < kL0K; ++j) w2[j] = f2_pack(__ldg(w + c * kL0K + j), __ldg(w + (c + 1) * kL0K + j));
-    const float2 ssa = scale_shift[(long long)win * C + c], ssb = scale_shift[(long long)win * C + c + 1];
-    const uint64_t sc2 = f2_pack(ssa.x, ssb.x), sh2 = f2_pack(ssa.y, ssb.y);
-    for (int tt = 0; tt < kL0TimeTile; ++tt) {
-      const int t = t0 + tt;
-      if (t >= out_rows) break;
-      float ya = 0.f, yb = 0.f;
-      if (t < T0) {
-        uint64_t y2 = f2_pack(0.f, 0.f);
+    for (int j = 0; j < kL0K; ++j) {
+      wa[j] = f2_pack(__ldg(w + c * kL0K + j), __ldg(w + (c + 1) * kL0K + j));
+      wb[j] = f2_pack(__ldg(w + (c + 2) * kL0K + j), __ldg(w + (c + 3) * kL0K + j));
+    }
+    const float2* ssp = scale_shift + (long long)win * C + c;
+    const float2 s0 = ssp[0], s1 = ssp[1], s2 = ssp[2], s3 = ssp[3];
+    const uint64_t sca = f2_pack(s0.x, s1.x), sha = f2_pack(s0.y, s1.y);
+    const uint64_t scb = f2_pack(s2.x, s3.x), shb = f2_pack(s2.y, s3.y);
+    __half* o = out + ((long long)win * out_rows + t0) * C + c;
+    const float* xs = s_x;
+#pragma unroll 2
+    for (int tt = 0; tt < n_live; ++tt) {
+      const float4 x0 = *reinterpret_cast<const float4*>(xs);
+      const float4 x1 = *reinterpret_cast<const float4*>(xs + 4);
+      const float2 x2 = *reinterpret_cast<const float2*>(xs + 8);
+      const float xv[kL0K] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y};
+      uint64_t ya = f2_pack(0.f, 0.f), yb = f2_pack(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < kL0K; ++j) y2 = f2_fma(w2[j], f2_splat(s_x[tt * kL0S + j]), y2);
-        f2_unpack(gelu_erf_pair(f2_fma(y2, sc2, sh2)), ya, yb);
+      for (int j = 0; j < kL0K; ++j) {
+        ya = f2_fma(wa[j], f2_splat(xv[j]), ya);
+        yb = f2_fma(wb[j], f2_splat(xv[j]), yb);
       }
-      *reinterpret_cast<uint32_t*>(o + (long long)t * C + c) = pack_f16x2(ya, yb);  // rows >= T0 are zero padding
+      float a0, a1, b0, b1;
+      f2_unpack(gelu_erf_pair(f2_fma(ya, sca, sha)), a0, a1);
+      f2_unpack(gelu_erf_pair(f2_fma(yb, scb, shb)), b0, b1);
+      *reinterpret_cast<uint2*>(o) = make_uint2(pack_f16x2(a0, a1), pack_f16x2(b0, b1));
+      o += C;
+      xs += kL0Row;
+    }
+    for (int tt = n_live; tt < n_rows; ++tt) {  // rows >= T0 are zero padding
+      *reinterpret_cast<uint2*>(o) = make_uint2(0u, 0u);
+      o += C;
     }
   }
 }
 
-// gate[(b*H + h)*T + i] = ga * (gb * const_h - 1) + 2, (ga, gb) = sigmoid(sum4(Linear(64 -> 8)(x[b, i, head h])))
-// One warp per row; lane = (head mod 4, output): its 64-long dot products for heads h, h + 4, h + 8, ... share one
-// projection row, read from shared memory once per 4 columns and reused for every head (rows padded to 68 floats:
-// the 8 lanes of a quarter warp read 8 different rows at the same column, which a 64-float pitch would put in the
-// same four banks).  The 8 lanes of a group read the same head slice of x (one broadcast transaction).  The two
-// 4-way sums are two shuffles inside aligned groups of 8 lanes.
-constexpr int kGateMaxPasses = 4;  // up to 16 heads
+// gate[(b*H + h)*T + i] = ga * (gb * const_h - 1) + 2, (ga, gb) = sigmoid(sum4(Linear(64 -> 8)(x[b, i, head h]))).
+// The two 4-way sums commute with the projection: (ga, gb) = sigmoid(x . wa + ba, x . wb + bb) with wa / wb the sums of
+// projection rows 0..3 / 4..7 -- two dot products per head instead of eight.  One warp per row: a lane reads the row's
+// float4 l, l + 32, ... (coalesced; all loads of a row are in flight together), so it always sees columns 4 (l % 16) ..
+// + 3 of heads 2 j + l / 16 and keeps those four (wa, wb) pairs in registers; each partial (a, b) pair is then summed over
+// the 16 lanes of its half-warp with four xor shuffles.  (The first form -- eight outputs per head, every lane walking
+// whole heads -- read 1.2 TB/s, stalled on dependent loads: ncu long-scoreboard 13.8 warp-cycles per issue.)
+constexpr int kGateMaxHeads = 16;
+constexpr int kGateRowsPerWarp = 4;  // consecutive rows per warp: the 32 weight loads of a lane are spread over them
 __global__ void __launch_bounds__(256) wavlm_gate_kernel(const float* __restrict__ x, long long rows, int T, int H,
                                                           const float* __restrict__ gw, const float* __restrict__ gb,
                                                           const float* __restrict__ gconst, float* __restrict__ gate) {
-  constexpr int kPitch = 68;
-  __shared__ __align__(16) float s_w[8 * kPitch];
-  __shared__ float s_b[8];
-  for (int i = threadIdx.x; i < 8 * 64; i += blockDim.x) s_w[(i >> 6) * kPitch + (i & 63)] = gw[i];
-  if (threadIdx.x < 8) s_b[threadIdx.x] = gb[threadIdx.x];
-  __syncthreads();
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int lane = lane_id();
-  const int o = lane & 7, h0 = lane >> 3;
-  const long long b = row / T;
-  const int i = (int)(row - b * T);
-  const float4* xr = reinterpret_cast<const float4*>(x + row * (long long)(H * 64));
-  const float4* wv = reinterpret_cast<const float4*>(s_w + o * kPitch);
-  float acc[kGateMaxPasses];
+  const int kc = lane & 15, half = lane >> 4;
+  uint64_t wab[4];  // (wa, wb)[4 kc + i]
 #pragma unroll
-  for (int p = 0; p < kGateMaxPasses; ++p) acc[p] = 0.f;
-#pragma unroll 4
-  for (int k = 0; k < 16; ++k) {
-    const float4 w4 = wv[k];
+  for (int i = 0; i < 4; ++i) {
+    float wa = 0.f, wb = 0.f;
 #pragma unroll
-    for (int p = 0; p < kGateMaxPasses; ++p) {
-      const int h = h0 + 4 * p;
-      if (h < H) {
-        const float4 a = __ldg(xr + h * 16 + k);
-        acc[p] = fmaf(a.x, w4.x, acc[p]);
-        acc[p] = fmaf(a.y, w4.y, acc[p]);
-        acc[p] = fmaf(a.z, w4.z, acc[p]);
-        acc[p] = fmaf(a.w, w4.w, acc[p]);
-      }
+    for (int o = 0; o < 4; ++o) {
+      wa += __ldg(gw + o * 64 + 4 * kc + i);
+      wb += __ldg(gw + (o + 4) * 64 + 4 * kc + i);
     }
+    wab[i] = f2_pack(wa, wb);
   }
+  const float ba = (__ldg(gb) + __ldg(gb + 1)) + (__ldg(gb + 2) + __ldg(gb + 3));
+  const float bb = (__ldg(gb + 4) + __ldg(gb + 5)) + (__ldg(gb + 6) + __ldg(gb + 7));
+  constexpr int kMaxJ = kGateMaxHeads / 2;
+  const int h = 2 * kc + half;  // lane kc of a half-warp writes head 2 kc + half
+  const float gc = (kc < kMaxJ && h < H) ? __ldg(gconst + h) : 0.f;
+  const long long row0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * kGateRowsPerWarp;
+#pragma unroll 1
+  for (long long row = row0; row < min(rows, row0 + kGateRowsPerWarp); ++row) {
+    const long long b = row / T;
+    const int i = (int)(row - b * T);
+    const float4* xr = reinterpret_cast<const float4*>(x + row * (long long)(H * 64));
+    float4 a[kMaxJ];
 #pragma unroll
-  for (int p = 0; p < kGateMaxPasses; ++p) {
-    const int h = h0 + 4 * p;
-    if (4 * p >= H) break;  // warp-uniform
-    float v = acc[p] + s_b[o];
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);                  // lanes o = 0 and o = 4 hold the two 4-way sums
-    const float other = __shfl_down_sync(0xffffffffu, v, 4);
-    if (h < H && o == 0) {
-      const float ga = 1.0f / (1.0f + expf(-v)), gbv = 1.0f / (1.0f + expf(-other));
-      gate[(b * H + h) * T + i] = ga * (gbv * __ldg(gconst + h) - 1.0f) + 2.0f;
+    for (int j = 0; j < kMaxJ; ++j)
+      a[j] = (2 * j + half < H) ? __ldg(xr + 32 * j + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float mine_a = 0.f, mine_b = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxJ; ++j) {
+      if (2 * j >= H) break;  // warp-uniform
+      uint64_t acc = f2_fma(wab[0], f2_splat(a[j].x), f2_pack(0.f, 0.f));
+      acc = f2_fma(wab[1], f2_splat(a[j].y), acc);
+      acc = f2_fma(wab[2], f2_splat(a[j].z), acc);
+      acc = f2_fma(wab[3], f2_splat(a[j].w), acc);
+      float va, vb;
+      f2_unpack(acc, va, vb);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {  // over the 16 lanes of the half-warp (head 2 j + half)
+        va += __shfl_xor_sync(0xffffffffu, va, o);
+        vb += __shfl_xor_sync(0xffffffffu, vb, o);
+      }
+      if (kc == j) { mine_a = va; mine_b = vb; }
+    }
+    if (kc < kMaxJ && h < H) {
+      const float ga = 1.0f / (1.0f + expf(-(mine_a + ba))), gbv = 1.0f / (1.0f + expf(-(mine_b + bb)));
+      gate[(b * H + h) * T + i] = ga * (gbv * gc - 1.0f) + 2.0f;
     }
   }
 }
@@ -210,7 +242,7 @@ static int w2v2_layer0_impl(const float* pcm, int64_t pcm_len, int n_windows, in
   SEGMA_REQUIRE(n_windows >= 0, "segma_w2v2_layer0: negative n_windows");
   if (n_windows == 0) return SEGMA_OK;
   SEGMA_REQUIRE(pcm && w && gamma && beta && scale_shift && out, "segma_w2v2_layer0: NULL buffer");
-  SEGMA_REQUIRE(channels > 0 && channels % 2 == 0, "segma_w2v2_layer0: channels must be even");
+  SEGMA_REQUIRE(channels > 0 && channels % 4 == 0, "segma_w2v2_layer0: channels must be a multiple of 4");
   SEGMA_REQUIRE(win_len >= kL0K && step >= 0 && pcm_len >= 0, "segma_w2v2_layer0: bad window geometry");
   const int T0 = (win_len - kL0K) / kL0S + 1;
   SEGMA_REQUIRE(out_rows >= T0, "segma_w2v2_layer0: out_rows %d < %d conv outputs", out_rows, T0);
@@ -248,8 +280,8 @@ int segma_wavlm_gate(const float* x, int64_t rows, int T, int n_heads, const flo
   SEGMA_REQUIRE(rows >= 0 && T > 0 && n_heads > 0 && rows % T == 0, "segma_wavlm_gate: bad shape");
   if (rows == 0) return SEGMA_OK;
   SEGMA_REQUIRE(x && gate_w && gate_b && gate_const && gate, "segma_wavlm_gate: NULL buffer");
-  SEGMA_REQUIRE(n_heads <= 4 * kGateMaxPasses, "segma_wavlm_gate: at most %d heads", 4 * kGateMaxPasses);
-  wavlm_gate_kernel<<<(unsigned)ceil_div_ll(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, T, n_heads, gate_w,
+  SEGMA_REQUIRE(n_heads <= kGateMaxHeads, "segma_wavlm_gate: at most %d heads", kGateMaxHeads);
+  wavlm_gate_kernel<<<(unsigned)ceil_div_ll(rows, 8 * kGateRowsPerWarp), 256, 0, (cudaStream_t)stream>>>(x, rows, T, n_heads, gate_w,
                                                                                       gate_b, gate_const, gate);
   return launch_status("wavlm_gate_kernel");
 }

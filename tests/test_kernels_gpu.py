@@ -495,8 +495,9 @@ def test_w2v2_layer0_silence(cuda):
     _close(out[0, :12799], F.gelu(b).expand(12799, C), 1e-3, 1e-3, "silent layer 0")
 
 
-def test_wavlm_gate(cuda):
-    B, T, H = 2, 199, 2
+@pytest.mark.parametrize("H,T", [(2, 199), (12, 199), (16, 50), (5, 33), (1, 7)])
+def test_wavlm_gate(cuda, H, T):
+    B = 2
     x = _rand((B * T, H * 64), 38).to(cuda)
     gw, gb, gc = _rand((8, 64), 39, 0.2).to(cuda), _rand((8,), 40, 0.2).to(cuda), (1 + 0.2 * _rand((H,), 41)).to(cuda)
     gate = torch.empty((B, H, T), device=cuda)

@@ -147,18 +147,26 @@ __device__ __forceinline__ void ex2_poly_pair(uint64_t x2, float& p0, float& p1)
   p1 = __int_as_float(__float_as_int(y1) + (__float_as_int(t1) << 23));
 }
 
+// Exact (erf) GELU:  gelu(x) = max(x, 0) - a Phi(-a),  a = |x|,  and  a Phi(-a) = a 2^{P(a)}  with P the degree-6
+// polynomial fitted to log2(erfc(a / sqrt 2) / 2) on [0, 5.6] (least squares weighted by the product; beyond 5.6 the
+// product is below 6e-8 and a is clamped).  Evaluated in fp32 the product is within 1e-7 and the GELU within 4.9e-7
+// (one ulp at 4) of the erf form, 1.6e-4 relative wherever |gelu| > 1e-4 -- tighter than the Abramowitz-Stegun 7.1.26
+// form used before (6.9e-7 / 2.2e-3) -- with ONE special-function op per element instead of two and 13 instead of 19
+// instructions per pair.  The polynomial runs in -a (coefficients of odd powers negated), so that the last step is one
+// fused multiply-add: max(x, 0) + (-a) 2^P.
+constexpr float kGeluC0 = -9.999896884e-01f, kGeluC1 = 1.151229739e+00f, kGeluC2 = -4.586926103e-01f,
+                kGeluC3 = 5.351120606e-02f, kGeluC4 = 8.142620325e-03f, kGeluC5 = 7.877399912e-04f,
+                kGeluC6 = 3.520013706e-05f;
+constexpr float kGeluClamp = 5.6f;
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = ex2_approx(-1.4426950408889634f * z * z);
-  const float erf_abs = fmaf(-p, e, 1.0f);        // erf(|x| / sqrt 2)
-  const float hx = 0.5f * x;
-  return fmaf(fabsf(hx), erf_abs, hx);            // 0.5 x (1 + sign(x) erf_abs)
+  const float na = fmaxf(-fabsf(x), -kGeluClamp);
+  float p = fmaf(kGeluC6, na, kGeluC5);
+  p = fmaf(p, na, kGeluC4);
+  p = fmaf(p, na, kGeluC3);
+  p = fmaf(p, na, kGeluC2);
+  p = fmaf(p, na, kGeluC1);
+  p = fmaf(p, na, kGeluC0);
+  return fmaf(na, ex2_approx(p), fmaxf(x, 0.f));
 }
 
 __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
@@ -167,29 +175,21 @@ __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
   return r;
 }
 __device__ __forceinline__ uint64_t f2_splat(float v) { return f2_pack(v, v); }
-// gelu_erf on a pair: the same formula with the polynomial, scaling and blend on packed FFMA2 / FMUL2 (two elements
-// per issue slot); only |x|, the reciprocal and the exponential stay scalar
+// gelu_erf on a pair: the polynomial and the final multiply-add on packed FFMA2 (two elements per issue slot); only the
+// clamps and the exponential stay scalar
 __device__ __forceinline__ uint64_t gelu_erf_pair(uint64_t x2) {
   float x0, x1;
   f2_unpack(x2, x0, x1);
-  const uint64_t ax = f2_pack(fabsf(x0), fabsf(x1));
-  const uint64_t d = f2_fma(ax, f2_splat(0.3275911f * 0.70710678118654752440f), f2_splat(1.0f));
-  float d0, d1;
-  f2_unpack(d, d0, d1);
-  const uint64_t t = f2_pack(rcp_approx(d0), rcp_approx(d1));
-  // -(a1 t + a2 t^2 + ... + a5 t^5): negated coefficients so that erf = 1 + p e needs no packed negation
-  uint64_t p = f2_fma(f2_splat(-1.061405429f), t, f2_splat(1.453152027f));
-  p = f2_fma(p, t, f2_splat(-1.421413741f));
-  p = f2_fma(p, t, f2_splat(0.284496736f));
-  p = f2_fma(p, t, f2_splat(-0.254829592f));
-  p = f2_mul(p, t);
-  const uint64_t w = f2_mul(f2_mul(x2, x2), f2_splat(-0.5f * 1.4426950408889634f));  // -(x^2 / 2) log2 e
-  float w0, w1;
-  f2_unpack(w, w0, w1);
-  const uint64_t e = f2_pack(ex2_approx(w0), ex2_approx(w1));
-  const uint64_t erf_abs = f2_fma(p, e, f2_splat(1.0f));  // erf(|x| / sqrt 2)
-  const uint64_t hx = f2_mul(x2, f2_splat(0.5f));
-  return f2_fma(f2_mul(ax, f2_splat(0.5f)), erf_abs, hx);  // 0.5 x (1 + sign(x) erf_abs)
+  const uint64_t na = f2_pack(fmaxf(-fabsf(x0), -kGeluClamp), fmaxf(-fabsf(x1), -kGeluClamp));
+  uint64_t p = f2_fma(f2_splat(kGeluC6), na, f2_splat(kGeluC5));
+  p = f2_fma(p, na, f2_splat(kGeluC4));
+  p = f2_fma(p, na, f2_splat(kGeluC3));
+  p = f2_fma(p, na, f2_splat(kGeluC2));
+  p = f2_fma(p, na, f2_splat(kGeluC1));
+  p = f2_fma(p, na, f2_splat(kGeluC0));
+  float p0, p1;
+  f2_unpack(p, p0, p1);
+  return f2_fma(na, f2_pack(ex2_approx(p0), ex2_approx(p1)), f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
 }
 
 // two fp32 -> packed fp16, round to nearest, saturating to +-65504 instead of overflowing to infinity (an activation

@@ -107,7 +107,10 @@ constexpr int kL0Row = 12;  // floats staged per time step: x[5 t .. 5 t + 9] an
 // broadcast load for all four, the four fp16 results leave as one 64-bit store (a warp writes 256 contiguous bytes), and
 // the time loop advances two pointers -- 16.5 instructions per output against 31 with one pair per thread and per-step
 // index arithmetic.
-__global__ void __launch_bounds__(kL0Threads) w2v2_l0_apply_kernel(
+#ifndef SEGMA_L0_MINB
+#define SEGMA_L0_MINB 1
+#endif
+__global__ void __launch_bounds__(kL0Threads, SEGMA_L0_MINB) w2v2_l0_apply_kernel(
     const float* __restrict__ pcm, long long pcm_len, int win_len, long long step,
     const long long* __restrict__ win_offsets, const float* __restrict__ w,
     const float2* __restrict__ scale_shift, int C, __half* __restrict__ out, int out_rows) {

@@ -108,7 +108,7 @@ constexpr int kL0Row = 12;  // floats staged per time step: x[5 t .. 5 t + 9] an
 // the time loop advances two pointers -- 16.5 instructions per output against 31 with one pair per thread and per-step
 // index arithmetic.
 #ifndef SEGMA_L0_MINB
-#define SEGMA_L0_MINB 1
+#define SEGMA_L0_MINB 6  // 80 registers: 24 warps per SM (A/B: 6.51 us per window at 100 registers, 6.36 at 80 or 72)
 #endif
 __global__ void __launch_bounds__(kL0Threads, SEGMA_L0_MINB) w2v2_l0_apply_kernel(
     const float* __restrict__ pcm, long long pcm_len, int win_len, long long step,

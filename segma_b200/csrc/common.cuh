@@ -158,6 +158,12 @@ constexpr float kGeluC0 = -9.999896884e-01f, kGeluC1 = 1.151229739e+00f, kGeluC2
                 kGeluC3 = 5.351120606e-02f, kGeluC4 = 8.142620325e-03f, kGeluC5 = 7.877399912e-04f,
                 kGeluC6 = 3.520013706e-05f;
 constexpr float kGeluClamp = 5.6f;
+// max(x, 0) that keeps a NaN (fmaxf would return 0 and the GELU of a NaN would come out finite)
+__device__ __forceinline__ float relu_nan(float x) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(0.f));
+  return r;
+}
 __device__ __forceinline__ float gelu_erf(float x) {
   const float na = fmaxf(-fabsf(x), -kGeluClamp);
   float p = fmaf(kGeluC6, na, kGeluC5);
@@ -166,7 +172,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
   p = fmaf(p, na, kGeluC2);
   p = fmaf(p, na, kGeluC1);
   p = fmaf(p, na, kGeluC0);
-  return fmaf(na, ex2_approx(p), fmaxf(x, 0.f));
+  return fmaf(na, ex2_approx(p), relu_nan(x));
 }
 
 __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
@@ -189,7 +195,7 @@ __device__ __forceinline__ uint64_t gelu_erf_pair(uint64_t x2) {
   p = f2_fma(p, na, f2_splat(kGeluC0));
   float p0, p1;
   f2_unpack(p, p0, p1);
-  return f2_fma(na, f2_pack(ex2_approx(p0), ex2_approx(p1)), f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+  return f2_fma(na, f2_pack(ex2_approx(p0), ex2_approx(p1)), f2_pack(relu_nan(x0), relu_nan(x1)));
 }
 
 // two fp32 -> packed fp16, round to nearest, saturating to +-65504 instead of overflowing to infinity (an activation

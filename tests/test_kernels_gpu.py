@@ -495,6 +495,21 @@ def test_w2v2_layer0_silence(cuda):
     _close(out[0, :12799], F.gelu(b).expand(12799, C), 1e-3, 1e-3, "silent layer 0")
 
 
+def test_w2v2_layer0_keeps_nan(cuda):
+    """A NaN sample poisons its window's GroupNorm statistics; the GELU must hand the NaN on (the reference does), not
+    clamp it away, and the neighbouring window stays clean."""
+    C, L = 128, 4000
+    pcm = torch.from_numpy(synth.synth_audio(2 * L, 44))
+    pcm[100] = float("nan")
+    w = _rand((C, 10), 35, 0.5).to(cuda)
+    g, b = (1 + 0.1 * _rand((C,), 36)).to(cuda), (0.3 * _rand((C,), 37)).to(cuda)
+    T0 = (L - 10) // 5 + 1
+    out = torch.zeros((2, T0 + (T0 & 1), C), dtype=torch.float16, device=cuda)
+    ops.w2v2_layer0(pcm.to(cuda), 2, L, L, w, g, b, torch.empty((2, C, 2), device=cuda), out)
+    assert torch.isnan(out[0, :T0]).all()
+    assert torch.isfinite(out[1]).all()
+
+
 @pytest.mark.parametrize("H,T", [(2, 199), (12, 199), (16, 50), (5, 33), (1, 7)])
 def test_wavlm_gate(cuda, H, T):
     B = 2

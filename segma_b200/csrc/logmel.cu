@@ -355,6 +355,7 @@ __device__ __forceinline__ void finish_window(int win, uint32_t rank, int tid, i
           if (t + 1 < n_valid) r.y = (fmaxf(x[i].y, floor_v) + 4.0f) / 4.0f;
           if (t + 2 < n_valid) r.z = (fmaxf(x[i].z, floor_v) + 4.0f) / 4.0f;
           if (t + 3 < n_valid) r.w = (fmaxf(x[i].w, floor_v) + 4.0f) / 4.0f;
+          SEGMA_DEV_ASSERT(rank * kRows + row + i < kMels && q < kQuads && q < nvq);
           __stcs(o + (row + i) * kQuads + q, r);
         }
         // the eight lanes of a 128-byte line have their data: drop the line (unless the fp16 tile reads it too);
@@ -484,6 +485,7 @@ __global__ void __launch_bounds__(kThreadsF, 4) logmel_fused_kernel(const float*
         }
         dft20(v);
         float2* e = E + p * kEP + b;
+        SEGMA_DEV_ASSERT(p < kPairs && b < 20 && (p * kEP + b + 19 * kEL) * 8 < kR1Bytes);
         e[0] = cpx_f2(v[0]);
         // twiddles W400^{b c} = w^c, w = W400^b, from two table values (w, w^4) by at most three further products
         // (c = 4 g + r: w^c = (w^4)^g w^r): the LSU is the busiest pipe of this kernel, the FMA pipes are at 15 %

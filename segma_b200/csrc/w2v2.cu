@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(kL0Threads, SEGMA_L0_MINB) w2v2_l0_apply_kerne
       float a0, a1, b0, b1;
       f2_unpack(gelu_erf_pair(f2_fma(ya, sca, sha)), a0, a1);
       f2_unpack(gelu_erf_pair(f2_fma(yb, scb, shb)), b0, b1);
+      SEGMA_DEV_ASSERT(c + 3 < C && t0 + tt < out_rows && t0 + tt < T0);
       *reinterpret_cast<uint2*>(o) = make_uint2(pack_f16x2(a0, a1), pack_f16x2(b0, b1));
       o += C;
       xs += kL0Row;
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(256) wavlm_gate_kernel(const float* __restrict
     }
     if (kc < kMaxJ && h < H) {
       const float ga = 1.0f / (1.0f + expf(-(mine_a + ba))), gbv = 1.0f / (1.0f + expf(-(mine_b + bb)));
+      SEGMA_DEV_ASSERT(row < rows && h < H && i < T);
       gate[(b * H + h) * T + i] = ga * (gbv * gc - 1.0f) + 2.0f;
     }
   }

@@ -171,7 +171,10 @@ __device__ __forceinline__ float sample_at(const float* __restrict__ w, long lon
 // the (L2-resident) scratch, exchange their maxima through distributed shared memory and then each write a quarter
 // of the window's output -- clamp, scale and the constant tail -- so that one window's stores overlap the other
 // resident clusters' transforms and no second kernel re-reads anything from HBM.
-constexpr int kCl = 4;                         // CTAs per window
+#ifndef SEGMA_LOGMEL_CL
+#define SEGMA_LOGMEL_CL 4
+#endif
+constexpr int kCl = SEGMA_LOGMEL_CL;                         // CTAs per window
 constexpr int kPairs = kGroup / 2;             // frame pairs per group
 constexpr int kThreadsF = kPairs * 20;         // 160
 constexpr int kChunkPad = kHop + 10;           // staged samples: 160-sample chunks 170 words apart, which puts the
@@ -341,7 +344,7 @@ __device__ __forceinline__ void finish_window(int win, uint32_t rank, int tid, i
     // frames that touch audio: clamp and scale what the cluster left in the scratch (four rows in flight per thread)
     for (int q = tid; q < nq; q += kThreadsF) {
       const int t = 4 * q;
-      constexpr int kInFlight = 4;  // rows per thread in flight
+      constexpr int kInFlight = kRows % 4 == 0 ? 4 : (kRows % 5 == 0 ? 5 : 1);  // rows per thread in flight
       static_assert(kRows % kInFlight == 0, "rows per CTA");
 #pragma unroll 1
       for (int row = 0; row < kRows; row += kInFlight) {

@@ -46,6 +46,26 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
     return rank, world, local
 
 
+class UnitQueue:
+    """Work units handed out on demand instead of up front: every rank walks the same longest-first order and claims
+    the next unit with an atomic add on the process group's key-value store (one ~0.1 ms round trip per unit, no
+    collective).  Boards under the same power cap differ by a few percent in speed; with static shares a run ends when
+    the slowest board finishes, with claims the faster boards simply take more units.  ``name`` must be the same on
+    every rank and unique per walk (``infer_corpus`` numbers its calls)."""
+
+    def __init__(self, name: str, n_units: int, store=None):
+        if store is None:
+            from torch.distributed.distributed_c10d import _get_default_store
+
+            store = _get_default_store()
+        self.store, self.key, self.n_units = store, f"segma/unit_queue/{name}", int(n_units)
+
+    def claim(self) -> int | None:
+        """Index (into the common order) of the next unclaimed unit, or None when all are taken."""
+        i = int(self.store.add(self.key, 1)) - 1
+        return i if i < self.n_units else None
+
+
 def all_gather_tables(table: torch.Tensor, group=None) -> torch.Tensor:
     """All-gather variable-length int32 ``(n_i, 4)`` interval tables: one count exchange, then one padded
     ``all_gather_into_tensor``; rows come back ordered by rank, then in each rank's own order.

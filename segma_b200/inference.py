@@ -411,6 +411,11 @@ def infer_file(audio_path, model: BaseSegmentationModel, output_p: Path, config:
     return job.finish(output_p)
 
 
+#: units a rank keeps queued on its GPU before it claims the next one (dynamic walk of `infer_corpus`)
+DYNAMIC_IN_FLIGHT = int(os.environ.get("SEGMA_DYNAMIC_IN_FLIGHT", "3"))
+_CORPUS_WALKS = 0
+
+
 def infer_corpus(audios, model: BaseSegmentationModel, config: Config, batch_size: int = 128, device="cuda",
                  thresholds: None | dict = None, shard: tuple[int, int] | None = None, sizes=None,
                  window_step: int | None = None, gather: bool = True) -> torch.Tensor:
@@ -438,11 +443,25 @@ def infer_corpus(audios, model: BaseSegmentationModel, config: Config, batch_siz
         sizes = [audio_n_samples(a) for a in audios]
     step = Chunkyfier(batch_size, chunk_f, INFERENCE_SETTINGS).step if window_step is None else int(window_step)
     units = plan_work_units(list(sizes), world if window_step is None else 1, chunk_f, batch_size, step, fpw)
-    mine = assign_units(units, world)[shard[0]] if shard is not None else units
+    pack = model.family == "wav2vec2" and window_step is None and os.environ.get("SEGMA_PACK_FILES", "1") != "0"
+    # Units are handed out on demand (distributed.UnitQueue) when several ranks share the corpus: a rank keeps at most
+    # DYNAMIC_IN_FLIGHT units queued on its GPU and claims the next one, longest first, only when one has finished, so
+    # that faster boards take more units.  Packed wav2vec2-family corpora and single ranks keep the static shares.
+    dynamic = (shard is not None and world > 1 and not pack and os.environ.get("SEGMA_DYNAMIC_SHARD", "1") != "0"
+               and torch.distributed.is_available() and torch.distributed.is_initialized())
+    if dynamic:
+        from .distributed import UnitQueue
+
+        global _CORPUS_WALKS
+        _CORPUS_WALKS += 1
+        order = sorted(units, key=lambda u: (-u.n_windows, u.file, u.batch_lo))
+        queue = UnitQueue(f"corpus{_CORPUS_WALKS}", len(order))
+        mine = []
+    else:
+        mine = assign_units(units, world)[shard[0]] if shard is not None else units
     any_split = any(not u.whole_file for u in units)
     cuts = [logit_cut(t) for t in _lower_bounds(thresholds, model.label_encoder.n_labels)]
     results: dict[int, tuple] = {}  # position in `mine` -> (table, count)
-    pack = model.family == "wav2vec2" and window_step is None and os.environ.get("SEGMA_PACK_FILES", "1") != "0"
     if pack:
         # independent windows: whole files are packed across file boundaries into full forward calls
         whole = [k for k, u in enumerate(mine) if u.whole_file]
@@ -459,7 +478,22 @@ def infer_corpus(audios, model: BaseSegmentationModel, config: Config, batch_siz
     for st in lanes:
         st.wait_stream(main)
     turn = 0
-    for k, u in enumerate(mine):
+    in_flight: list = []  # dynamic walk: completion events of the units queued on this GPU
+
+    def walk():
+        if not dynamic:
+            yield from enumerate(mine)
+            return
+        while True:
+            while len(in_flight) >= DYNAMIC_IN_FLIGHT:
+                in_flight.pop(0).synchronize()
+            i = queue.claim()
+            if i is None:
+                return
+            mine.append(order[i])
+            yield len(mine) - 1, order[i]
+
+    for k, u in walk():
         if k in results:
             continue
         small = bool(lanes) and u.n_windows < SMALL_FILE_WINDOWS
@@ -476,8 +510,16 @@ def infer_corpus(audios, model: BaseSegmentationModel, config: Config, batch_siz
             table.record_stream(main)
             count.record_stream(main)
         results[k] = (table, count)
+        if dynamic:
+            done = torch.cuda.Event()
+            done.record(lanes[lane] if small else main)
+            in_flight.append(done)
     for st in lanes:
         main.wait_stream(st)
+    if dynamic:  # claimed in longest-first order: back to (file, batch) order like the static shares
+        perm = sorted(range(len(mine)), key=lambda k: (mine[k].file, mine[k].batch_lo))
+        results = {j: results[k] for j, k in enumerate(perm)}
+        mine = [mine[k] for k in perm]
     offsets = []
     for u in mine:  # first sample of the unit on its file's timeline
         if u.whole_file:

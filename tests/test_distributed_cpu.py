@@ -113,3 +113,34 @@ def test_interval_table_all_gather_world2(tmp_path):
 def test_single_process_gather_is_identity():
     t = torch.arange(12, dtype=torch.int32).reshape(3, 4)
     assert torch.equal(all_gather_tables(t), t)
+
+
+def _queue_worker(rank, world, port, out_dir):
+    import time
+
+    from segma_b200.distributed import UnitQueue
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    got = []
+    for walk, n_units in enumerate([37, 0, 5]):  # three walks over one store: the keys must not collide
+        queue = UnitQueue(f"test{walk}", n_units)
+        mine = []
+        while (i := queue.claim()) is not None:
+            mine.append(i)
+            time.sleep(0.002 if rank == 0 else 0.02)  # rank 1 is the slow board
+        got.append(mine)
+        dist.barrier()
+    torch.save(got, os.path.join(out_dir, f"claims{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_unit_queue_hands_every_unit_out_once_world2(tmp_path):
+    """`distributed.UnitQueue` (the on-demand form of the file / window-batch partition): two ranks claiming from one
+    counter cover every unit exactly once, and the slower rank ends up with fewer."""
+    mp.spawn(_queue_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    a, b = (torch.load(tmp_path / f"claims{r}.pt") for r in range(2))
+    for walk, n_units in enumerate([37, 0, 5]):
+        assert sorted(a[walk] + b[walk]) == list(range(n_units))
+        assert a[walk] == sorted(a[walk]) and b[walk] == sorted(b[walk])  # longest first on every rank
+    assert len(a[0]) > len(b[0])

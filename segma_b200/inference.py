@@ -444,10 +444,13 @@ def infer_corpus(audios, model: BaseSegmentationModel, config: Config, batch_siz
     step = Chunkyfier(batch_size, chunk_f, INFERENCE_SETTINGS).step if window_step is None else int(window_step)
     units = plan_work_units(list(sizes), world if window_step is None else 1, chunk_f, batch_size, step, fpw)
     pack = model.family == "wav2vec2" and window_step is None and os.environ.get("SEGMA_PACK_FILES", "1") != "0"
-    # Units are handed out on demand (distributed.UnitQueue) when several ranks share the corpus: a rank keeps at most
-    # DYNAMIC_IN_FLIGHT units queued on its GPU and claims the next one, longest first, only when one has finished, so
-    # that faster boards take more units.  Packed wav2vec2-family corpora and single ranks keep the static shares.
-    dynamic = (shard is not None and world > 1 and not pack and os.environ.get("SEGMA_DYNAMIC_SHARD", "1") != "0"
+    # SEGMA_DYNAMIC_SHARD=1: units are handed out on demand (distributed.UnitQueue) instead of in static shares: a rank
+    # keeps at most DYNAMIC_IN_FLIGHT units queued on its GPU and claims the next one, longest first, only when one has
+    # finished, so that faster boards take more units.  Off by default: on the 256-file corpus over 8 B200 the static
+    # longest-first shares were 1 % faster (19.9 against 19.6-19.8 audio-h/s, profiles/r02z_dynamic_shard_ab_8gpu.txt) --
+    # waiting on a unit's completion event before the next claim costs more host-side pipelining than the few percent
+    # of board-to-board spread give back at that size.
+    dynamic = (shard is not None and world > 1 and not pack and os.environ.get("SEGMA_DYNAMIC_SHARD", "0") == "1"
                and torch.distributed.is_available() and torch.distributed.is_initialized())
     if dynamic:
         from .distributed import UnitQueue

@@ -7,4 +7,4 @@ for n in 1024 1136 128; do timeout 120 python tools/run_logmel.py $n 2>&1 | tail
 timeout 120 python tools/logmel_clock_check.py 2>&1 | tail -6 | tee -a gpurun_out/logmel_timing.txt
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:logmel -c 1 -s 6 -o gpurun_out/logmel_fused -f python tools/run_logmel.py 1024 > gpurun_out/logmel_ncu.log 2>&1
 echo "ncu exit $?"
-python tools/ncu_source_lines.py gpurun_out/logmel_fused.ncu-rep 0 20 | cut -c1-150
+python tools/ncu_source_lines.py gpurun_out/logmel_fused.ncu-rep 20 | cut -c1-150

@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(kThreadsF, 4) logmel_fused_kernel(const float*
       asm volatile("cp.async.wait_all;" ::: "memory");
     }
     __syncthreads();
-    // Three barriers per group: after the exchange rows, after the spectrum, after the powers.  Step 5 of a group
+    // Three barriers per group: after the exchange rows, after the spectrum, after the powers.  Step 4 of a group
     // needs no barrier behind it (it reads only P2 and writes global memory), so warps with short mel filters run
     // ahead into the next group's pass 1 while the warp with the 14-tap filters finishes.
     for (int pair0 = pair_lo; pair0 < pair_hi; pair0 += kPairs) {
